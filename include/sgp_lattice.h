@@ -1,0 +1,169 @@
+/*
+ * sgp_lattice.h -- C ABI of the B200-native Simplex-GP lattice filter.
+ *
+ * This is the drop-in boundary for the reference's native operator
+ *
+ *     filter(src[N,L], ref[N,d], coeffs[2r+1]) -> out[N,L]
+ *
+ * (pybind11 function exported by gpytorch_lattice_kernel/cpp/lattice.cpp:6-16 and
+ * gpytorch_lattice_kernel/cuda/permutohedral_cuda.cpp:12-22 of the reference, called
+ * from gpytorch_lattice_kernel/bilateral_kernel.py:95,111,119).  The reference rebuilds
+ * the lattice inside every call; here the stages are separate entry points so that a
+ * lattice is built once per hyper-parameter step and reused by every MVM, and
+ * sgp_filter_* keeps the one-call form.
+ *
+ * Conventions
+ *   - plain C, no torch types: raw pointers, sizes, and a cudaStream_t passed as void*.
+ *   - every pointer documented "device" is device memory owned by the caller (PyTorch's
+ *     caching allocator in the Python host); the library never allocates device memory
+ *     except inside sgp_filter_host, which owns a private scratch pool.
+ *   - every function returns an int status: 0 = OK, negative = error; the message of
+ *     the last error on the calling thread is available from sgp_last_error().
+ *     Nothing calls exit() or throws across the boundary (the reference's CUDA path
+ *     exits the process on a CUDA error, permutohedral_cuda_kernel.cu:24-32).
+ *   - all launches go to the given stream and are asynchronous; the only host
+ *     synchronisation is inside sgp_count_points (the caller needs M to size the
+ *     lattice arrays) and sgp_filter_host.
+ *   - fp32 values (the reference CPU path is fp32-only, permutohedral.h:12,17),
+ *     int16 keys, int8 ranks, int32 lattice indices.
+ */
+#ifndef SGP_LATTICE_H
+#define SGP_LATTICE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGP_ABI_VERSION 1
+
+#define SGP_OK 0
+#define SGP_EINVAL (-1)       /* bad argument */
+#define SGP_ERANGE (-2)       /* a lattice coordinate does not fit int16 (reference keys are short) */
+#define SGP_EOVERFLOW (-3)    /* hash table full or an index exceeds 32 bits */
+#define SGP_ECUDA (-4)        /* CUDA runtime error */
+#define SGP_EUNSUPPORTED (-5) /* shape outside what the kernels are built for */
+#define SGP_ENOMEM (-6)       /* host or scratch allocation failed (sgp_filter_host only) */
+
+#define SGP_MAX_DIM 126   /* rank is a signed char in the reference (permutohedral.h:354) */
+#define SGP_MAX_ORDER 7
+
+/* status bits the build kernels OR into *status_flags (device int32) */
+#define SGP_FLAG_KEY_RANGE 1
+#define SGP_FLAG_TABLE_FULL 2
+
+typedef void *sgp_stream_t; /* cudaStream_t */
+
+int sgp_abi_version(void);
+const char *sgp_last_error(void);
+
+/* ---- host-side constants -------------------------------------------------------- */
+
+/* second central moment of the stencil, fp32 sequential (permutohedral.h:203-219) */
+int sgp_stencil_variance(const float *coeffs, int k, float *var_out);
+/* scale_factor[i], i<d (permutohedral.h:372-390) */
+int sgp_scale_factors(int d, float var, float *scale_out);
+/* 1 + 2^-d in fp32, the divisor in slice (permutohedral.h:507) */
+float sgp_slice_divisor(int d);
+
+/* ---- stage 1: lattice construction ---------------------------------------------- */
+
+/* Per-point geometry (permutohedral.h:397-465): elevate, nearest remainder-0 point,
+ * rank sort, barycentric weights.
+ *   x        device [N, ldx] fp32, first d columns used (x is already divided by the lengthscale)
+ *   scale    HOST   [d] from sgp_scale_factors
+ *   greedy   device [N, d+1] int16      rank  device [N, d+1] int8
+ *   replay   device [N, d+1, 2] int32: word 1 receives the weight bits; word 0 (lattice
+ *            index) is written by sgp_number_points
+ *   status_flags device int32, OR-ed with SGP_FLAG_* */
+int sgp_build_points(const float *x, int64_t N, int d, int64_t ldx, const float *scale,
+                     int16_t *greedy, int8_t *rank, int32_t *replay, int32_t *status_flags,
+                     sgp_stream_t stream);
+
+/* number of 64-bit slots to allocate for n_keys insertions (power of two, load <= 1/2) */
+int64_t sgp_hash_capacity(int64_t n_keys);
+
+/* Lock-free find-or-create of the N*(d+1) vertex keys (permutohedral.h:467-474, table
+ * semantics :58-94).  table: device [capacity] uint64, must be filled with 0xFF bytes.
+ * slot_of: device [N*(d+1)] uint32 receives the slot of each point-vertex.
+ * After the call every occupied slot holds the SMALLEST point-vertex id n*(d+1)+rem that
+ * carries its key, which is what makes the numbering below deterministic. */
+int sgp_hash_insert(const int16_t *greedy, const int8_t *rank, int64_t N, int d,
+                    uint64_t *table, int64_t capacity, uint32_t *slot_of,
+                    int32_t *status_flags, sgp_stream_t stream);
+
+/* bytes of device scratch needed by sgp_count_points / sgp_number_points */
+size_t sgp_number_workspace_bytes(int64_t N, int d);
+
+/* First-touch numbering, part 1: marks the point-vertices that create a lattice point
+ * (the owners left by sgp_hash_insert), prefix-sums the marks in point-vertex order and
+ * returns M and the status flags.  Synchronises the stream.  Lattice point i is the i-th
+ * key the reference's sequential scan over (n, rem) would have created (:73-79). */
+int sgp_count_points(const uint64_t *table, int64_t capacity, const uint32_t *slot_of,
+                     int64_t N, int d, void *workspace, size_t workspace_bytes,
+                     const int32_t *status_flags, int64_t *M_out, int32_t *flags_out,
+                     sgp_stream_t stream);
+
+/* First-touch numbering, part 2: writes replay[...,0] (lattice index per point-vertex),
+ * keys [M, d] int16 in first-touch order, and rewrites the table so that each occupied
+ * slot maps key -> lattice index (used by sgp_build_neighbours). */
+int sgp_number_points(uint64_t *table, int64_t capacity, const uint32_t *slot_of,
+                      const int16_t *greedy, const int8_t *rank, int64_t N, int d,
+                      const void *workspace, int64_t M, int32_t *replay, int16_t *keys,
+                      sgp_stream_t stream);
+
+/* Neighbour table of the blur (permutohedral.h:539-545): nbr[j, i, t] = lattice index of
+ * the key "key[i] - o on every stored coordinate, then key[i][j] + o*d on coordinate j when
+ * j < d" (axis j = d only shifts), t enumerating o = -r..-1, 1..r; -1 if absent.
+ * int16 wrap-around as in the reference.  nbr: device [(d+1), M, 2r] int32. */
+int sgp_build_neighbours(const int16_t *keys, int64_t M, int d, int order,
+                         const uint64_t *table, int64_t capacity, int32_t *nbr,
+                         sgp_stream_t stream);
+
+/* Transposed replay table for the gather-form splat: for every lattice point the list of
+ * (point, weight) that touch it, in point-vertex order (= the reference's accumulation
+ * order).  row_ptr: device [M+1] uint32; entries: device [N*(d+1), 2] int32 {n, weight bits};
+ * pv_scratch: device [N*(d+1)] uint32; workspace: device, sgp_csr_workspace_bytes(M). */
+size_t sgp_csr_workspace_bytes(int64_t M);
+int sgp_build_csr(const int32_t *replay, int64_t N, int d, int64_t M, uint32_t *row_ptr,
+                  int32_t *entries, uint32_t *pv_scratch, void *workspace, size_t workspace_bytes,
+                  sgp_stream_t stream);
+
+/* ---- stages 2-4: the MVM on a built lattice -------------------------------------- */
+
+typedef struct sgp_lattice_view {
+    int64_t N;               /* points */
+    int64_t M;               /* lattice points */
+    int32_t d;               /* input dimension */
+    int32_t order;           /* stencil half-width r */
+    const int32_t *replay;   /* device [N, d+1, 2] {lattice index, weight bits} */
+    const int32_t *nbr;      /* device [(d+1), M, 2r] */
+    const uint32_t *csr_ptr; /* device [M+1] or NULL */
+    const int32_t *csr_ent;  /* device [N*(d+1), 2] or NULL */
+} sgp_lattice_view;
+
+#define SGP_SPLAT_AUTO 0
+#define SGP_SPLAT_ATOMIC 1 /* vectorised red.global.add scatter */
+#define SGP_SPLAT_GATHER 2 /* CSR gather, deterministic, reference accumulation order */
+
+/* values[M, L] = sum_{point-vertices} weight * src[n, :]   (permutohedral.h:478-479) */
+int sgp_splat(const sgp_lattice_view *lat, const float *src, int64_t lds, int L,
+              float *values, int mode, sgp_stream_t stream);
+/* d+1 stencil passes (permutohedral.h:526-556), ping-pong between buf0 (input) and buf1.
+ * coeffs: HOST [2r+1].  *result_in_buf1 tells where the blurred values ended. */
+int sgp_blur(const sgp_lattice_view *lat, const float *coeffs, int k, int L,
+             float *buf0, float *buf1, int *result_in_buf1, sgp_stream_t stream);
+/* out[n, :] = sum_rem (w * values[idx, :]) / (1 + 2^-d)   (permutohedral.h:497-510) */
+int sgp_slice(const sgp_lattice_view *lat, const float *values, int L, float *out,
+              int64_t ldo, sgp_stream_t stream);
+/* splat -> blur -> slice; buf0/buf1: device [M, L] fp32 scratch each */
+int sgp_mvm(const sgp_lattice_view *lat, const float *src, int64_t lds, int L,
+            const float *coeffs, int k, float *out, int64_t ldo,
+            float *buf0, float *buf1, int splat_mode, sgp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGP_LATTICE_H */

@@ -1,0 +1,110 @@
+"""ctypes binding of ``include/sgp_lattice.h`` (the C ABI in ``libsgp_lattice.so``).
+
+The library is compiled in-tree by ``csrc/build.py`` (plain nvcc, sm_100a).  There is no
+CPU fallback: if the shared library is missing or fails to load, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libsgp_lattice.so")
+
+SGP_OK = 0
+SGP_SPLAT_AUTO, SGP_SPLAT_ATOMIC, SGP_SPLAT_GATHER = 0, 1, 2
+SGP_MAX_DIM = 126
+SGP_MAX_ORDER = 7
+
+# every symbol include/sgp_lattice.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "sgp_abi_version", "sgp_last_error", "sgp_stencil_variance", "sgp_scale_factors", "sgp_slice_divisor",
+    "sgp_build_points", "sgp_hash_capacity", "sgp_hash_insert", "sgp_number_workspace_bytes",
+    "sgp_count_points", "sgp_number_points", "sgp_build_neighbours", "sgp_csr_workspace_bytes",
+    "sgp_build_csr", "sgp_splat", "sgp_blur", "sgp_slice", "sgp_mvm",
+]
+
+
+class LatticeView(C.Structure):
+    """Mirror of ``struct sgp_lattice_view``."""
+
+    _fields_ = [
+        ("N", C.c_int64),
+        ("M", C.c_int64),
+        ("d", C.c_int32),
+        ("order", C.c_int32),
+        ("replay", C.c_void_p),
+        ("nbr", C.c_void_p),
+        ("csr_ptr", C.c_void_p),
+        ("csr_ent", C.c_void_p),
+    ]
+
+
+class SgpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"sgp_lattice error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library (once). Raises if it has not been built: no fallback path exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python simplex-gp_b200/csrc/build.py` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, sz = C.c_void_p, C.c_int64, C.c_int, C.c_size_t
+    fp = C.POINTER(C.c_float)
+    L.sgp_abi_version.restype = i32
+    L.sgp_abi_version.argtypes = []
+    L.sgp_last_error.restype = C.c_char_p
+    L.sgp_last_error.argtypes = []
+    L.sgp_stencil_variance.restype = i32
+    L.sgp_stencil_variance.argtypes = [fp, i32, fp]
+    L.sgp_scale_factors.restype = i32
+    L.sgp_scale_factors.argtypes = [i32, C.c_float, fp]
+    L.sgp_slice_divisor.restype = C.c_float
+    L.sgp_slice_divisor.argtypes = [i32]
+    L.sgp_build_points.restype = i32
+    L.sgp_build_points.argtypes = [vp, i64, i32, i64, fp, vp, vp, vp, vp, vp]
+    L.sgp_hash_capacity.restype = i64
+    L.sgp_hash_capacity.argtypes = [i64]
+    L.sgp_hash_insert.restype = i32
+    L.sgp_hash_insert.argtypes = [vp, vp, i64, i32, vp, i64, vp, vp, vp]
+    L.sgp_number_workspace_bytes.restype = sz
+    L.sgp_number_workspace_bytes.argtypes = [i64, i32]
+    L.sgp_count_points.restype = i32
+    L.sgp_count_points.argtypes = [vp, i64, vp, i64, i32, vp, sz, vp, C.POINTER(i64), C.POINTER(C.c_int32), vp]
+    L.sgp_number_points.restype = i32
+    L.sgp_number_points.argtypes = [vp, i64, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp]
+    L.sgp_build_neighbours.restype = i32
+    L.sgp_build_neighbours.argtypes = [vp, i64, i32, i32, vp, i64, vp, vp]
+    L.sgp_csr_workspace_bytes.restype = sz
+    L.sgp_csr_workspace_bytes.argtypes = [i64]
+    L.sgp_build_csr.restype = i32
+    L.sgp_build_csr.argtypes = [vp, i64, i32, i64, vp, vp, vp, vp, sz, vp]
+    pv = C.POINTER(LatticeView)
+    L.sgp_splat.restype = i32
+    L.sgp_splat.argtypes = [pv, vp, i64, i32, vp, i32, vp]
+    L.sgp_blur.restype = i32
+    L.sgp_blur.argtypes = [pv, fp, i32, i32, vp, vp, C.POINTER(C.c_int), vp]
+    L.sgp_slice.restype = i32
+    L.sgp_slice.argtypes = [pv, vp, i32, vp, i64, vp]
+    L.sgp_mvm.restype = i32
+    L.sgp_mvm.argtypes = [pv, vp, i64, i32, fp, i32, vp, i64, vp, vp, i32, vp]
+    if L.sgp_abi_version() != 1:
+        raise RuntimeError(f"{LIB_PATH}: ABI version {L.sgp_abi_version()} != 1, rebuild the library")
+    _lib = L
+    return L
+
+
+def check(code: int) -> None:
+    if code != SGP_OK:
+        raise SgpError(code, lib().sgp_last_error().decode("utf-8", "replace"))

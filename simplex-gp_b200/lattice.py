@@ -1,0 +1,285 @@
+"""Host side of the lattice filter: a ``Lattice`` built once per ``(x / lengthscale, stencil)`` and
+reused by every MVM, plus ``lattice_filter`` -- the one-call form with the reference's signature.
+
+Reference being replaced: ``PermutohedralLattice::filter`` (gpytorch_lattice_kernel/cpp/permutohedral.h:259-340),
+reached through ``filter(src, ref, coeffs)`` (cpp/lattice.cpp:6-16, bilateral_kernel.py:95).  The reference
+rebuilds the whole lattice inside every call; here the structure (``replay``, ``keys``, ``nbr``) lives in HBM as
+flat torch tensors and an MVM is splat -> (d+1) x blur -> slice over two ``[M, L]`` ping-pong buffers.
+
+PyTorch is used for device memory and streams only; all compute goes through the C ABI in ``_capi``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import LatticeView, check
+
+__all__ = ["Lattice", "lattice_filter", "stencil_variance", "scale_factors", "slice_divisor"]
+
+
+def _coeffs_np(coeffs) -> np.ndarray:
+    if isinstance(coeffs, torch.Tensor):
+        coeffs = coeffs.detach().to("cpu", torch.float32).numpy()
+    c = np.ascontiguousarray(np.asarray(coeffs, dtype=np.float32))
+    if c.ndim != 1 or c.shape[0] % 2 != 1:
+        raise ValueError(f"stencil coefficients must be a 1-D array of odd length, got shape {c.shape}")
+    if c.shape[0] // 2 > _capi.SGP_MAX_ORDER:
+        raise ValueError(f"stencil order {c.shape[0] // 2} > {_capi.SGP_MAX_ORDER}")
+    return c
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def stencil_variance(coeffs) -> np.float32:
+    """Second central moment of the stencil in index units (permutohedral.h:203-219), fp32."""
+    c = _coeffs_np(coeffs)
+    out = C.c_float(0.0)
+    check(_capi.lib().sgp_stencil_variance(_fp(c), c.shape[0], C.byref(out)))
+    return np.float32(out.value)
+
+
+def scale_factors(d: int, var) -> np.ndarray:
+    """Per-axis scale of the elevation (permutohedral.h:372-390), fp32 ``[d]``."""
+    out = np.empty(d, dtype=np.float32)
+    check(_capi.lib().sgp_scale_factors(int(d), C.c_float(float(var)), _fp(out)))
+    return out
+
+
+def slice_divisor(d: int) -> np.float32:
+    return np.float32(_capi.lib().sgp_slice_divisor(int(d)))
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class Lattice:
+    """Permutohedral lattice of the points ``x[N, d]`` (already divided by the lengthscale).
+
+    Device arrays (all torch tensors on ``x.device``), in the reference's numbering -- lattice point ``i`` is
+    the ``i``-th key the reference's sequential ``splat`` loop would have created:
+
+    ========  ==================  =========================================================================
+    greedy    int16 ``[N, d+1]``   remainder-0 lattice point of each input point (permutohedral.h:404-457)
+    rank      int8  ``[N, d+1]``   simplex permutation (:425-457)
+    replay    int32 ``[N, d+1, 2]`` ``{lattice index, fp32 weight bits}`` per simplex vertex (:482-483)
+    keys      int16 ``[M, d]``     lattice keys in first-touch order (:73-79, :470-471)
+    nbr       int32 ``[d+1, M, 2r]`` blur neighbours, ``t`` over ``o = -r..-1, 1..r``; -1 = absent (:541-545)
+    csr_ptr   uint32 ``[M+1]``     rows of the transposed replay table (gather-form splat), optional
+    csr_ent   int32 ``[N(d+1), 2]`` ``{point, weight bits}`` in point-vertex order within each row
+    ========  ==================  =========================================================================
+    """
+
+    def __init__(self, x: torch.Tensor, coeffs, *, build_csr: bool = True, keep_structure: bool = True,
+                 hash_capacity: Optional[int] = None):
+        if x.dim() != 2:
+            raise ValueError(f"x must be [N, d], got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("Lattice needs a CUDA tensor: this package has no CPU path")
+        if x.dtype != torch.float32:
+            raise TypeError(f"x must be float32 (the reference CPU filter is fp32-only), got {x.dtype}")
+        lib = _capi.lib()
+        x = x.detach().contiguous()
+        self.device = x.device
+        self.N, self.d = int(x.shape[0]), int(x.shape[1])
+        if not (1 <= self.d <= _capi.SGP_MAX_DIM):
+            raise ValueError(f"d={self.d} outside [1, {_capi.SGP_MAX_DIM}]")
+        self.coeffs = _coeffs_np(coeffs)
+        self.order = self.coeffs.shape[0] // 2
+        self.var = stencil_variance(self.coeffs)
+        self.scale = scale_factors(self.d, self.var)
+        N, d, r = self.N, self.d, self.order
+        dev = self.device
+        total = N * (d + 1)
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            self.greedy = torch.empty((N, d + 1), dtype=torch.int16, device=dev)
+            self.rank = torch.empty((N, d + 1), dtype=torch.int8, device=dev)
+            self.replay = torch.empty((N, d + 1, 2), dtype=torch.int32, device=dev)
+            flags = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.M = 0
+            self.keys = torch.empty((0, d), dtype=torch.int16, device=dev)
+            self.nbr = torch.empty((d + 1, 0, 2 * r), dtype=torch.int32, device=dev)
+            self.csr_ptr = None
+            self.csr_ent = None
+            self.hash_capacity = 0
+            if N > 0:
+                check(lib.sgp_build_points(_ptr(x), N, d, x.stride(0), _fp(self.scale), _ptr(self.greedy),
+                                           _ptr(self.rank), _ptr(self.replay), _ptr(flags), st))
+                cap = int(hash_capacity) if hash_capacity else int(lib.sgp_hash_capacity(total))
+                self.hash_capacity = cap
+                table = torch.full((cap,), -1, dtype=torch.int64, device=dev)
+                slot_of = torch.empty(total, dtype=torch.int32, device=dev)
+                check(lib.sgp_hash_insert(_ptr(self.greedy), _ptr(self.rank), N, d, _ptr(table), cap, _ptr(slot_of),
+                                          _ptr(flags), st))
+                ws_bytes = int(lib.sgp_number_workspace_bytes(N, d))
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                M = C.c_int64(0)
+                fl = C.c_int32(0)
+                check(lib.sgp_count_points(_ptr(table), cap, _ptr(slot_of), N, d, _ptr(ws), ws_bytes, _ptr(flags),
+                                           C.byref(M), C.byref(fl), st))
+                self.M = int(M.value)
+                self.keys = torch.empty((self.M, d), dtype=torch.int16, device=dev)
+                check(lib.sgp_number_points(_ptr(table), cap, _ptr(slot_of), _ptr(self.greedy), _ptr(self.rank), N, d,
+                                            _ptr(ws), self.M, _ptr(self.replay), _ptr(self.keys), st))
+                del slot_of, ws
+                self.nbr = torch.empty((d + 1, self.M, 2 * r), dtype=torch.int32, device=dev)
+                check(lib.sgp_build_neighbours(_ptr(self.keys), self.M, d, r, _ptr(table), cap, _ptr(self.nbr), st))
+                del table
+                if build_csr:
+                    self._build_csr()
+            if not keep_structure:
+                self.greedy = None
+                self.rank = None
+        self._bufs = {}
+
+    def _build_csr(self) -> None:
+        lib = _capi.lib()
+        dev, N, d, M = self.device, self.N, self.d, self.M
+        total = N * (d + 1)
+        self.csr_ptr = torch.empty(M + 1, dtype=torch.int32, device=dev)
+        self.csr_ent = torch.empty((total, 2), dtype=torch.int32, device=dev)
+        scratch = torch.empty(total, dtype=torch.int32, device=dev)
+        ws_bytes = int(lib.sgp_csr_workspace_bytes(M))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.sgp_build_csr(_ptr(self.replay), N, d, M, _ptr(self.csr_ptr), _ptr(self.csr_ent), _ptr(scratch),
+                                _ptr(ws), ws_bytes, _stream_ptr(dev)))
+
+    # ---- structure accessors (reference numbering) -------------------------------------------
+    @property
+    def offsets(self) -> torch.Tensor:
+        """int32 ``[N, d+1]``: lattice index of every simplex vertex (reference ``replay[].offset / vd``)."""
+        return self.replay[..., 0]
+
+    @property
+    def weights(self) -> torch.Tensor:
+        """fp32 ``[N, d+1]``: barycentric weight of every simplex vertex (reference ``replay[].weight``)."""
+        return self.replay[..., 1].view(torch.float32)
+
+    def _view(self) -> LatticeView:
+        return LatticeView(self.N, self.M, self.d, self.order, self.replay.data_ptr(),
+                           self.nbr.data_ptr() if self.nbr.numel() else 0,
+                           self.csr_ptr.data_ptr() if self.csr_ptr is not None else 0,
+                           self.csr_ent.data_ptr() if self.csr_ent is not None else 0)
+
+    def _scratch(self, L: int):
+        key = int(L)
+        b = self._bufs.get(key)
+        if b is None:
+            if len(self._bufs) >= 2:
+                self._bufs.clear()
+            b = (torch.empty((max(self.M, 1), L), dtype=torch.float32, device=self.device),
+                 torch.empty((max(self.M, 1), L), dtype=torch.float32, device=self.device))
+            self._bufs[key] = b
+        return b
+
+    def _check_src(self, src: torch.Tensor) -> torch.Tensor:
+        if src.dim() != 2 or src.shape[0] != self.N:
+            raise ValueError(f"Incompatible shapes {tuple(src.shape)}, and {(self.N, self.d)}")
+        if src.device != self.device or src.dtype != torch.float32:
+            raise TypeError("src must be float32 on the lattice's device")
+        if src.stride(1) != 1 and src.shape[1] > 1:
+            src = src.contiguous()
+        return src
+
+    # ---- stages, exposed separately for parity tests ---------------------------------------------
+    def splat(self, src: torch.Tensor, mode: int = _capi.SGP_SPLAT_AUTO) -> torch.Tensor:
+        src = self._check_src(src)
+        L = int(src.shape[1])
+        values = torch.empty((self.M, L), dtype=torch.float32, device=self.device)
+        if self.M == 0 or L == 0:
+            return values
+        v = self._view()
+        with torch.cuda.device(self.device):
+            check(_capi.lib().sgp_splat(C.byref(v), _ptr(src), src.stride(0), L, _ptr(values), mode,
+                                        _stream_ptr(self.device)))
+        return values
+
+    def blur(self, values: torch.Tensor, coeffs=None) -> torch.Tensor:
+        c = self.coeffs if coeffs is None else _coeffs_np(coeffs)
+        L = int(values.shape[1])
+        if self.M == 0 or L == 0:
+            return values.clone()
+        buf0 = values.contiguous().clone()
+        buf1 = torch.empty_like(buf0)
+        v = self._view()
+        where = C.c_int(0)
+        with torch.cuda.device(self.device):
+            check(_capi.lib().sgp_blur(C.byref(v), _fp(c), c.shape[0], L, _ptr(buf0), _ptr(buf1), C.byref(where),
+                                       _stream_ptr(self.device)))
+        return buf1 if where.value else buf0
+
+    def slice(self, values: torch.Tensor) -> torch.Tensor:
+        L = int(values.shape[1])
+        out = torch.empty((self.N, L), dtype=torch.float32, device=self.device)
+        if self.N == 0 or L == 0:
+            return out
+        values = values.contiguous()
+        v = self._view()
+        with torch.cuda.device(self.device):
+            check(_capi.lib().sgp_slice(C.byref(v), _ptr(values), L, _ptr(out), out.stride(0),
+                                        _stream_ptr(self.device)))
+        return out
+
+    # ---- the MVM ------------------------------------------------------------------------------------
+    def mvm(self, src: torch.Tensor, out: Optional[torch.Tensor] = None, coeffs=None,
+            mode: int = _capi.SGP_SPLAT_AUTO) -> torch.Tensor:
+        """``out[N, L] = slice(blur(splat(src[N, L])))`` on the built lattice."""
+        src = self._check_src(src)
+        L = int(src.shape[1])
+        c = self.coeffs if coeffs is None else _coeffs_np(coeffs)
+        if c.shape[0] != 2 * self.order + 1:
+            raise ValueError("stencil length does not match the order this lattice was built for")
+        if out is None:
+            out = torch.empty((self.N, L), dtype=torch.float32, device=self.device)
+        if self.N == 0 or L == 0:
+            return out
+        buf0, buf1 = self._scratch(L)
+        v = self._view()
+        with torch.cuda.device(self.device):
+            check(_capi.lib().sgp_mvm(C.byref(v), _ptr(src), src.stride(0), L, _fp(c), c.shape[0], _ptr(out),
+                                      out.stride(0), _ptr(buf0), _ptr(buf1), mode, _stream_ptr(self.device)))
+        return out
+
+    def algorithmic_bytes(self, L: int) -> int:
+        """Bytes one MVM must move (SURVEY.md section 8d / BASELINE.md section 3)."""
+        N, M, d, r = self.N, self.M, self.d, self.order
+        return 4 * (2 * N * L + 4 * N * (d + 1) + 2 * M * L + (d + 1) * (2 * M * L + 2 * r * M))
+
+
+def lattice_filter(src: torch.Tensor, ref: torch.Tensor, coeffs, *, device=None) -> torch.Tensor:
+    """Drop-in for the reference operator ``filter(src[N,L], ref[N,d], coeffs[2r+1]) -> out[N,L]``.
+
+    Builds the lattice of ``ref`` and applies one MVM, as the reference does on every call
+    (permutohedral.h:259-340).  The result is a fresh tensor with ``src``'s dtype and device.  CPU inputs
+    are staged through pinned memory to the GPU and back: the computation always runs in the CUDA kernels.
+    """
+    assert src.shape[0] == ref.shape[0], "Incompatible shapes {}, and {}".format(src.shape, ref.shape)
+    if src.dtype != torch.float32 or ref.dtype != torch.float32:
+        raise TypeError("filter: float32 tensors required (reference CPU filter is fp32-only)")
+    if src.is_cuda:
+        dev = src.device
+        lat = Lattice(ref.to(dev), coeffs, build_csr=False, keep_structure=False)
+        return lat.mvm(src)
+    if not torch.cuda.is_available():
+        raise RuntimeError("filter: no CUDA device; this package has no CPU path")
+    dev = torch.device(device if device is not None else "cuda")
+    ref_d = ref.contiguous().pin_memory().to(dev, non_blocking=True)
+    src_d = src.contiguous().pin_memory().to(dev, non_blocking=True)
+    lat = Lattice(ref_d, coeffs, build_csr=False, keep_structure=False)
+    out_d = lat.mvm(src_d)
+    out = torch.empty(out_d.shape, dtype=out_d.dtype, pin_memory=True)
+    out.copy_(out_d, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    return out

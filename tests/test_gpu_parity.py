@@ -1,0 +1,84 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars: lattice structure (greedy, rank, keys, vertex offsets, neighbour indices) bit-exact; barycentric weights
+bit-exact; values bit-exact on the deterministic path (gather splat, blur, slice) and within 1e-5 relative on the
+atomic splat path (fp32 atomics reorder the sums).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import MAT15_2, MAT15_3, RBF1, RBF2, bits, make_inputs
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # north_star tolerance for fp32 values
+
+CASES = [
+    # N, d, L, coeffs, dist
+    (4, 2, 1, [0.5, 1.0, 0.5], "randn"),
+    (200, 1, 3, RBF1, "randn"),
+    (1000, 5, 2, [1.0], "randn"),
+    (5000, 3, 4, RBF1, "randn"),
+    (20000, 8, 16, RBF1, "randn"),
+    (20000, 8, 2, RBF1, "rand"),
+    (3000, 18, 11, RBF1, "randn"),
+    (20000, 11, 3, MAT15_2, "randn"),
+    (2000, 24, 2, MAT15_3, "randn"),
+    (777, 7, 5, RBF2, "randn"),
+    (300, 30, 1, RBF1, "randn"),   # generic-d kernels (d > 24)
+]
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / max(np.linalg.norm(b.astype(np.float64)), 1e-30))
+
+
+@pytest.mark.parametrize("N,d,L,coeffs,dist", CASES)
+def test_structure_and_values_match_oracle(sg, oracle, N, d, L, coeffs, dist):
+    x, v = make_inputs(N, d, L, seed=N + d, dist=dist)
+    O = oracle.OracleLattice(x.numpy(), coeffs)
+    lat = sg.Lattice(x.cuda(), coeffs)
+    assert lat.M == O.M
+    assert np.array_equal(lat.scale.view(np.int32), O.scale.view(np.int32))
+    assert np.array_equal(lat.greedy.cpu().numpy(), O.greedy)
+    assert np.array_equal(lat.rank.cpu().numpy(), O.rank)
+    assert np.array_equal(bits(lat.weights.cpu().numpy()), bits(O.weights))
+    assert np.array_equal(lat.offsets.cpu().numpy(), O.offsets)
+    assert np.array_equal(lat.keys.cpu().numpy(), O.keys)
+    if lat.order > 0:
+        assert np.array_equal(lat.nbr.cpu().numpy(), O.nbr)
+
+    out_o, sp_o, bl_o = O.mvm(v.numpy(), return_intermediates=True)
+    vd = v.cuda()
+    # deterministic path: bit-exact at every stage
+    sp = lat.splat(vd, mode=2)
+    assert np.array_equal(bits(sp.cpu().numpy()), bits(sp_o))
+    bl = lat.blur(sp)
+    assert np.array_equal(bits(bl.cpu().numpy()), bits(bl_o))
+    out = lat.slice(bl)
+    assert np.array_equal(bits(out.cpu().numpy()), bits(out_o))
+    assert np.array_equal(bits(lat.mvm(vd, mode=2).cpu().numpy()), bits(out_o))
+    # atomic scatter path: 1e-5 relative
+    sp_a = lat.splat(vd, mode=1)
+    assert _rel(sp_a.cpu().numpy(), sp_o) < REL_TOL
+    out_a = lat.mvm(vd, mode=1)
+    assert _rel(out_a.cpu().numpy(), out_o) < REL_TOL
+
+
+def test_filter_dropin_cpu_and_cuda_inputs(sg, oracle):
+    x, v = make_inputs(3000, 4, 3, seed=5)
+    c = torch.tensor(RBF1)
+    want = oracle.filter(v.numpy(), x.numpy(), c.numpy())
+    got_cpu = sg.filter(v, x, c)
+    assert got_cpu.device.type == "cpu" and got_cpu.shape == v.shape
+    assert _rel(got_cpu.numpy(), want) < REL_TOL
+    got_gpu = sg.filter(v.cuda(), x.cuda(), c.cuda())
+    assert got_gpu.is_cuda
+    assert _rel(got_gpu.cpu().numpy(), want) < REL_TOL
+
+
+def test_key_range_error(sg):
+    x = torch.full((10, 3), 1e6)
+    with pytest.raises(RuntimeError):
+        sg.Lattice(x.cuda(), RBF1)
