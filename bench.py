@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Benchmark of the lattice MVM hot path (BASELINE.json metric): lattice MVM/s at N=1M, d=8, 16 RHS.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one MVM (splat -> (d+1) x blur -> slice) of an [N, 16] RHS block on a PRE-BUILT lattice, inputs
+resident in HBM (north star: the lattice is built once per hyper-parameter step and reused by every CG/Lanczos
+MVM).  At N GPUs the lattice is built on rank 0, NCCL-broadcast, and every rank filters its own 16-column block
+(weak scaling in RHS blocks, no data-path collective); `value` = blocks filtered per second over all ranks.
+
+Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for every key.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "lattice MVM/s (N=1M,d=8,16 RHS)"
+UNIT = "MVM/s"
+WORKLOADS = {
+    # name: (N, d, L, kernel, order)   -- SURVEY.md section 8: config A is the metric's configuration
+    "A": dict(N=1_000_000, d=8, L=16, kernel="rbf", order=1),
+}
+RBF1 = [0.34608543, 1.0, 0.34608543]   # get_coeffs(rbf, 1), tests/golden/coeffs.json
+
+
+def workload_name(w):
+    return f"N={w['N']},d={w['d']},L={w['L']},{w['kernel']} order {w['order']},x~N(0,I),lengthscale 1"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU filter (oracle/_ref when built, else the C port)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_filter():
+    """Returns (callable(src, ref, coeffs) -> out, kind)."""
+    import torch
+    from oracle import build_oracle
+    mod = build_oracle.load_ref(fixed=False)
+    if mod is not None:
+        return (lambda s, r, c: mod.filter(s, r, c)), "reference"
+    from oracle import oracle as port
+
+    def run(s, r, c):
+        return torch.from_numpy(port.filter(s.numpy(), r.numpy(), c.numpy()))
+    return run, "port"
+
+
+def time_cpu_filter(w, n_sample, repeats):
+    """Best-of-`repeats` wall time of the reference filter on the first n_sample points of the workload."""
+    import torch
+    fn, kind = cpu_reference_filter()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n_sample, w["d"], generator=g)
+    v = torch.randn(n_sample, w["L"], generator=g)
+    c = torch.tensor(RBF1)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        fn(v, x, c)
+        best = min(best, time.perf_counter() - t0)
+    return best, kind
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    torch.set_num_threads(1)
+    steps, warm = args.steps, args.warmup
+    # bound the whole run to a few minutes: the -O3 reference needs ~5.7 us per point at this shape
+    budget_s = 150.0 / max(1, steps + warm)
+    n_sample = int(min(w["N"], max(20_000, budget_s / 6.0e-6)))
+    fn, kind = cpu_reference_filter()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n_sample, w["d"], generator=g)
+    v = torch.randn(n_sample, w["L"], generator=g)
+    c = torch.tensor(RBF1)
+    for _ in range(warm):
+        fn(v, x, c)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn(v, x, c)
+    dt = time.perf_counter() - t0
+    per_step = dt / steps
+    # scale the sample linearly to the full N: one full-size MVM costs (N / n_sample) sample filters
+    value = 1.0 / (per_step * (w["N"] / n_sample))
+    sample = (f"{steps} reference filter() calls (lattice rebuilt inside each call, as the reference does) on the first "
+              f"{n_sample} of {w['N']} points, scaled linearly to N")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": per_step * 1e3 * (w["N"] / n_sample), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(w), "device": "cpu"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+
+    import simplex_gp_b200 as sg
+    from simplex_gp_b200 import _capi
+    from simplex_gp_b200.distributed import broadcast_lattice
+    from simplex_gp_b200.lattice import _fp, _ptr, _stream_ptr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world:
+        if rank == 0:
+            print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    N, d, L = w["N"], w["d"], w["L"]
+    coeffs = RBF1
+    steps, warm = args.steps, max(args.warmup, 3)
+    n_rot = 4   # V/out buffer pairs rotated so consecutive steps never re-read the same RHS from L2
+
+    # --- lattice: built once on rank 0 and broadcast (north star) --------------------------------
+    g = torch.Generator().manual_seed(0)
+    x_host = torch.randn(N, d, generator=g)
+    build_ms = bcast_ms = None
+    lat = None
+    if rank == 0:
+        x = x_host.to(dev)
+        sg.Lattice(x, coeffs, build_csr=False)   # warm-up (allocator, module load)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lat = sg.Lattice(x, coeffs, build_csr=False)
+        e1.record()
+        torch.cuda.synchronize()
+        build_ms = e0.elapsed_time(e1)
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lat = broadcast_lattice(lat, src=0, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier()
+        bcast_ms = (time.perf_counter() - t0) * 1e3
+    M = lat.M
+
+    # --- this rank's RHS blocks -----------------------------------------------------------------------
+    gv = torch.Generator(device=dev).manual_seed(1234 + rank)
+    Vs = [torch.randn(N, L, generator=gv, device=dev) for _ in range(n_rot)]
+    outs = [torch.empty(N, L, device=dev) for _ in range(n_rot)]
+    mode = {"atomic": _capi.SGP_SPLAT_ATOMIC, "gather": _capi.SGP_SPLAT_GATHER, "auto": _capi.SGP_SPLAT_AUTO}[args.splat]
+
+    def step(i):
+        lat.mvm(Vs[i % n_rot], out=outs[i % n_rot], mode=mode)
+
+    for i in range(warm):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(elapsed_ms.item())
+    ms_per_step = elapsed_ms / steps
+    value = world * steps / (elapsed_ms * 1e-3)
+
+    # --- per-stage device times (CUDA events on the launching stream), same buffers, rank 0 -----------
+    peak, peak_src = load_peaks()
+    roofline = stages = None
+    if rank == 0:
+        lib = _capi.lib()
+        view = lat._view()
+        buf0, buf1 = lat._scratch(L)
+        cnp = lat.coeffs
+        st = _stream_ptr(dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        acc = [0.0, 0.0, 0.0]
+        reps = max(5, min(steps, 20))
+        where = C.c_int(0)
+        for i in range(reps):
+            V, out = Vs[i % n_rot], outs[i % n_rot]
+            ev[0].record()
+            _capi.check(lib.sgp_splat(C.byref(view), _ptr(V), V.stride(0), L, _ptr(buf0), mode, st))
+            ev[1].record()
+            _capi.check(lib.sgp_blur(C.byref(view), _fp(cnp), cnp.shape[0], L, _ptr(buf0), _ptr(buf1), C.byref(where), st))
+            ev[2].record()
+            _capi.check(lib.sgp_slice(C.byref(view), _ptr(buf1 if where.value else buf0), L, _ptr(out), out.stride(0), st))
+            ev[3].record()
+            torch.cuda.synchronize()
+            for k in range(3):
+                acc[k] += ev[k].elapsed_time(ev[k + 1])
+        t_splat, t_blur, t_slice = (a / reps for a in acc)
+        r = lat.order
+        b_splat = 4 * (N * L + 2 * N * (d + 1) + M * L)
+        b_blur_pass = 4 * (2 * M * L + 2 * r * M)
+        b_slice = 4 * (M * L + 2 * N * (d + 1) + N * L)
+        stages = {
+            "splat": {"ms": t_splat, "launches": 1, "alg_bytes": b_splat, "gbs": b_splat / t_splat / 1e6},
+            "blur": {"ms": t_blur, "launches": d + 1, "alg_bytes": b_blur_pass * (d + 1),
+                     "gbs": b_blur_pass * (d + 1) / t_blur / 1e6},
+            "slice": {"ms": t_slice, "launches": 1, "alg_bytes": b_slice, "gbs": b_slice / t_slice / 1e6},
+        }
+        dom = max(stages, key=lambda k: stages[k]["ms"])
+        kname = {"splat": "sgp_splat_atomic_kernel" if mode != _capi.SGP_SPLAT_GATHER else "sgp_splat_gather_kernel",
+                 "blur": "sgp_blur_kernel", "slice": "sgp_slice_kernel"}[dom]
+        per_launch_bytes = stages[dom]["alg_bytes"] / stages[dom]["launches"]
+        per_launch_ms = stages[dom]["ms"] / stages[dom]["launches"]
+        achieved = per_launch_bytes / per_launch_ms / 1e6
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "alg_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms}
+
+    # --- end-to-end through the reference-facing call, host buffers ----------------------------------
+    e2e = None
+    if args.e2e_steps > 0:
+        x_pin = x_host.pin_memory()
+        gh = torch.Generator().manual_seed(99 + rank)
+        v_pin = torch.randn(N, L, generator=gh).pin_memory()
+        c_t = torch.tensor(coeffs)
+        sg.filter(v_pin, x_pin, c_t, device=dev)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            res = sg.filter(v_pin, x_pin, c_t, device=dev)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * args.e2e_steps / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": 4 * (N * L + N * d), "d2h_bytes_per_step": 4 * N * L,
+               "call": "simplex_gp_b200.filter(src, ref, coeffs) with pinned host tensors: H2D, lattice build, MVM, D2H",
+               "steps": args.e2e_steps, "checksum": float(res.double().sum().item())}
+
+    # --- CPU baseline beside it (rank 0, N=1 only, bounded sample) ------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            t, kind = time_cpu_filter(w, N, repeats=2)
+            cpu_baseline = {"value": 1.0 / t, "unit": UNIT, "cores": 1, "kind": kind,
+                            "sample": f"best of 2 full reference filter() calls at N={N}, d={d}, L={L} (lattice build "
+                                      f"included: the reference rebuilds it in every call); {os.cpu_count()} host cores "
+                                      f"present, the reference code is single-threaded"}
+        except Exception as exc:  # the baseline is reported, never required
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(exc)}
+
+    if rank == 0:
+        alg_bytes = lat.algorithmic_bytes(L)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(w), "M": M, "splat": args.splat,
+                       "sharding": "lattice built on rank 0 + NCCL broadcast; one 16-column RHS block per rank",
+                       "l2": f"working set {(alg_bytes / (d + 1)) / 1e6:.0f}+ MB per step exceeds the 126 MB L2; "
+                             f"V/out rotate over {n_rot} buffer pairs"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": steps * (d + 3),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "mvm_roofline": {"alg_bytes": alg_bytes, "achieved": alg_bytes / ms_per_step / 1e6, "peak": peak,
+                             "unit": "GB/s", "frac": alg_bytes / ms_per_step / 1e6 / peak},
+            "stages": stages, "lattice_build_ms": build_ms, "lattice_broadcast_ms": bcast_ms,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
+    ap.add_argument("--splat", default="atomic", choices=["atomic", "gather", "auto"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference_arm(args, w)
+    return run_ours(args, w)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

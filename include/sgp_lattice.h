@@ -163,6 +163,11 @@ int sgp_mvm(const sgp_lattice_view *lat, const float *src, int64_t lds, int L,
             const float *coeffs, int k, float *out, int64_t ldo,
             float *buf0, float *buf1, int splat_mode, sgp_stream_t stream);
 
+/* Test hook: number of fp32 bit patterns a in [lo, lo+count) for which the division-by-constant
+ * used inside sgp_slice differs from the IEEE division a / sgp_slice_divisor(d).  Must be 0. */
+int sgp_debug_division_mismatches(int d, uint32_t lo, uint32_t count, unsigned long long *mismatches_dev,
+                                  sgp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ SYMBOLS = [
     "sgp_abi_version", "sgp_last_error", "sgp_stencil_variance", "sgp_scale_factors", "sgp_slice_divisor",
     "sgp_build_points", "sgp_hash_capacity", "sgp_hash_insert", "sgp_number_workspace_bytes",
     "sgp_count_points", "sgp_number_points", "sgp_build_neighbours", "sgp_csr_workspace_bytes",
-    "sgp_build_csr", "sgp_splat", "sgp_blur", "sgp_slice", "sgp_mvm",
+    "sgp_build_csr", "sgp_splat", "sgp_blur", "sgp_slice", "sgp_mvm", "sgp_debug_division_mismatches",
 ]
 
 
@@ -99,6 +99,8 @@ def lib() -> C.CDLL:
     L.sgp_slice.argtypes = [pv, vp, i32, vp, i64, vp]
     L.sgp_mvm.restype = i32
     L.sgp_mvm.argtypes = [pv, vp, i64, i32, fp, i32, vp, i64, vp, vp, i32, vp]
+    L.sgp_debug_division_mismatches.restype = i32
+    L.sgp_debug_division_mismatches.argtypes = [i32, C.c_uint32, C.c_uint32, vp, vp]
     if L.sgp_abi_version() != 1:
         raise RuntimeError(f"{LIB_PATH}: ABI version {L.sgp_abi_version()} != 1, rebuild the library")
     _lib = L

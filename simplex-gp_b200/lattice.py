@@ -144,6 +144,30 @@ class Lattice:
                 self.rank = None
         self._bufs = {}
 
+    @classmethod
+    def from_arrays(cls, coeffs, replay: torch.Tensor, keys: torch.Tensor, nbr: torch.Tensor,
+                    build_csr: bool = False) -> "Lattice":
+        """Wrap lattice arrays that were built elsewhere (e.g. received by ``distributed.broadcast_lattice``)."""
+        self = object.__new__(cls)
+        self.device = replay.device
+        self.N, self.d = int(replay.shape[0]), int(replay.shape[1]) - 1
+        self.coeffs = _coeffs_np(coeffs)
+        self.order = self.coeffs.shape[0] // 2
+        self.var = stencil_variance(self.coeffs)
+        self.scale = scale_factors(self.d, self.var)
+        self.M = int(keys.shape[0])
+        if tuple(nbr.shape) != (self.d + 1, self.M, 2 * self.order):
+            raise ValueError(f"nbr shape {tuple(nbr.shape)} does not match (d+1, M, 2r)")
+        self.replay, self.keys, self.nbr = replay.contiguous(), keys.contiguous(), nbr.contiguous()
+        self.greedy = self.rank = None
+        self.csr_ptr = self.csr_ent = None
+        self.hash_capacity = 0
+        self._bufs = {}
+        if build_csr and self.N > 0 and self.M > 0:
+            with torch.cuda.device(self.device):
+                self._build_csr()
+        return self
+
     def _build_csr(self) -> None:
         lib = _capi.lib()
         dev, N, d, M = self.device, self.N, self.d, self.M

@@ -82,3 +82,19 @@ def test_key_range_error(sg):
     x = torch.full((10, 3), 1e6)
     with pytest.raises(RuntimeError):
         sg.Lattice(x.cuda(), RBF1)
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 8, 11, 18, 23, 24, 30])
+def test_exact_division(sg, d):
+    """slice divides by the constant 1 + 2^-d with a 3-instruction Markstein sequence; it must equal the IEEE
+    division (what the reference's `/` compiles to) for every finite fp32 input with |a| >= 2^-100 or a == 0,
+    and be within 1e-37 absolute below that.  Exhaustive over all 2^32 bit patterns."""
+    import ctypes as C
+    from simplex_gp_b200 import _capi
+    lib = _capi.lib()
+    bad = torch.zeros(2, dtype=torch.int64, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    chunk = 1 << 30
+    for k in range(4):
+        _capi.check(lib.sgp_debug_division_mismatches(d, k * chunk, chunk, C.c_void_p(bad.data_ptr()), st))
+    assert bad.tolist() == [0, 0]
