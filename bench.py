@@ -213,11 +213,11 @@ def run_ours(args, w):
     lat = None
     if rank == 0:
         x = x_host.to(dev)
-        sg.Lattice(x, coeffs, build_csr=False)   # warm-up (allocator, module load)
+        sg.Lattice(x, coeffs)   # warm-up (allocator, module load)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        lat = sg.Lattice(x, coeffs, build_csr=False)
+        lat = sg.Lattice(x, coeffs)
         e1.record()
         torch.cuda.synchronize()
         build_ms = e0.elapsed_time(e1)
@@ -235,7 +235,12 @@ def run_ours(args, w):
     gv = torch.Generator(device=dev).manual_seed(1234 + rank)
     Vs = [torch.randn(N, L, generator=gv, device=dev) for _ in range(n_rot)]
     outs = [torch.empty(N, L, device=dev) for _ in range(n_rot)]
-    mode = {"atomic": _capi.SGP_SPLAT_ATOMIC, "gather": _capi.SGP_SPLAT_GATHER, "auto": _capi.SGP_SPLAT_AUTO}[args.splat]
+    mode = {"atomic": _capi.MODE_ATOMIC, "gather": _capi.MODE_GATHER, "tiles": _capi.MODE_TILES,
+            "auto": _capi.MODE_AUTO}[args.splat]
+    if mode == _capi.MODE_AUTO:
+        mode = _capi.MODE_TILES if lat.tiles is not None else _capi.MODE_ATOMIC
+    if mode == _capi.MODE_GATHER and lat.csr_ptr is None:
+        lat._build_csr()
 
     def step(i):
         lat.mvm(Vs[i % n_rot], out=outs[i % n_rot], mode=mode)
@@ -278,14 +283,22 @@ def run_ours(args, w):
         acc = [0.0, 0.0, 0.0]
         reps = max(5, min(steps, 20))
         where = C.c_int(0)
+        tview = lat._tiles_view() if mode == _capi.MODE_TILES else None
         for i in range(reps):
             V, out = Vs[i % n_rot], outs[i % n_rot]
             ev[0].record()
-            _capi.check(lib.sgp_splat(C.byref(view), _ptr(V), V.stride(0), L, _ptr(buf0), mode, st))
+            if tview is not None:
+                _capi.check(lib.sgp_splat_tiles(C.byref(tview), _ptr(V), V.stride(0), L, _ptr(buf0), st))
+            else:
+                _capi.check(lib.sgp_splat(C.byref(view), _ptr(V), V.stride(0), L, _ptr(buf0), mode, st))
             ev[1].record()
             _capi.check(lib.sgp_blur(C.byref(view), _fp(cnp), cnp.shape[0], L, _ptr(buf0), _ptr(buf1), C.byref(where), st))
             ev[2].record()
-            _capi.check(lib.sgp_slice(C.byref(view), _ptr(buf1 if where.value else buf0), L, _ptr(out), out.stride(0), st))
+            res_buf = buf1 if where.value else buf0
+            if tview is not None:
+                _capi.check(lib.sgp_slice_tiles(C.byref(tview), _ptr(res_buf), L, _ptr(out), out.stride(0), st))
+            else:
+                _capi.check(lib.sgp_slice(C.byref(view), _ptr(res_buf), L, _ptr(out), out.stride(0), st))
             ev[3].record()
             torch.cuda.synchronize()
             for k in range(3):
@@ -302,8 +315,10 @@ def run_ours(args, w):
             "slice": {"ms": t_slice, "launches": 1, "alg_bytes": b_slice, "gbs": b_slice / t_slice / 1e6},
         }
         dom = max(stages, key=lambda k: stages[k]["ms"])
-        kname = {"splat": "sgp_splat_atomic_kernel" if mode != _capi.SGP_SPLAT_GATHER else "sgp_splat_gather_kernel",
-                 "blur": "sgp_blur_kernel", "slice": "sgp_slice_kernel"}[dom]
+        kname = {"splat": {_capi.MODE_ATOMIC: "sgp_splat_atomic_kernel", _capi.MODE_GATHER: "sgp_splat_gather_kernel",
+                           _capi.MODE_TILES: "sgp_splat_tiles_kernel"}[mode],
+                 "blur": "sgp_blur_kernel",
+                 "slice": "sgp_slice_tiles_kernel" if mode == _capi.MODE_TILES else "sgp_slice_kernel"}[dom]
         per_launch_bytes = stages[dom]["alg_bytes"] / stages[dom]["launches"]
         per_launch_ms = stages[dom]["ms"] / stages[dom]["launches"]
         achieved = per_launch_bytes / per_launch_ms / 1e6
@@ -352,7 +367,8 @@ def run_ours(args, w):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(w), "M": M, "splat": args.splat,
+            "config": {"workload": workload_name(w), "M": M,
+                       "path": {1: "atomic", 2: "gather", 3: "tiles"}[mode],
                        "sharding": "lattice built on rank 0 + NCCL broadcast; one 16-column RHS block per rank",
                        "l2": f"working set {(alg_bytes / (d + 1)) / 1e6:.0f}+ MB per step exceeds the 126 MB L2; "
                              f"V/out rotate over {n_rot} buffer pairs"},
@@ -376,7 +392,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
-    ap.add_argument("--splat", default="atomic", choices=["atomic", "gather", "auto"])
+    ap.add_argument("--splat", default="auto", choices=["auto", "tiles", "atomic", "gather"],
+                    help="MVM path: locality tiles (default when built), plain atomic scatter, or reference-order gather")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

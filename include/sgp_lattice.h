@@ -163,6 +163,52 @@ int sgp_mvm(const sgp_lattice_view *lat, const float *src, int64_t lds, int L,
             const float *coeffs, int k, float *out, int64_t ldo,
             float *buf0, float *buf1, int splat_mode, sgp_stream_t stream);
 
+/* ---- locality tiles: shared-memory staged splat and slice ------------------------------
+ *
+ * Points are sorted so that points sharing lattice vertices are adjacent and cut into tiles of
+ * tile_points points.  Per tile, the distinct lattice rows it touches form its dictionary
+ * (seg_row[tile_seg_ptr[t] .. tile_seg_ptr[t+1])) and its point-vertices are grouped by dictionary
+ * entry into segments (seg_ptr / seg_ent).  See simplex-gp_b200/csrc/sgp_tiles.cu.  This is an
+ * internal acceleration structure; the observable lattice (replay, keys, nbr) is unchanged. */
+typedef struct sgp_tiles_view {
+    int64_t N;                    /* points */
+    int64_t M;                    /* lattice points */
+    int64_t S;                    /* segments = sum of dictionary sizes */
+    int32_t d;
+    int32_t tile_points;          /* T */
+    int32_t max_dict;             /* largest dictionary */
+    int32_t reserved;
+    const uint32_t *perm;         /* device [N]: sorted position -> point */
+    const uint32_t *tile_seg_ptr; /* device [n_tiles+1] */
+    const uint32_t *seg_ptr;      /* device [S+1] into seg_ent */
+    const int32_t *seg_row;       /* device [S] lattice index */
+    const int32_t *seg_ent;       /* device [N*(d+1), 2] {point index inside its tile, weight bits} */
+    const uint16_t *lidx;         /* device [N*(d+1)] dictionary index of each sorted point-vertex */
+    const float *tile_w;          /* device [N*(d+1)] weight of each sorted point-vertex */
+} sgp_tiles_view;
+
+size_t sgp_tiles_workspace_bytes(int64_t N, int d);
+/* sort + segment count; synchronises the stream; perm: device [N]; returns S */
+int sgp_tiles_prepare(const int32_t *replay, int64_t N, int d, int64_t M, int tile_points,
+                      uint32_t *perm, void *workspace, size_t workspace_bytes, int64_t *S_out,
+                      sgp_stream_t stream);
+/* fills the tile arrays (sizes as in sgp_tiles_view) from the workspace left by sgp_tiles_prepare;
+ * synchronises the stream; *max_dict_out = largest dictionary */
+int sgp_tiles_finalize(const int32_t *replay, const uint32_t *perm, int64_t N, int d, int tile_points,
+                       int64_t S, void *workspace, size_t workspace_bytes, uint32_t *seg_ptr,
+                       int32_t *seg_row, int32_t *seg_ent, uint32_t *tile_seg_ptr, uint16_t *lidx,
+                       float *tile_w, int32_t *max_dict_out, sgp_stream_t stream);
+/* values[M, L] = splat(src) with one vector reduction per segment (values is zeroed inside) */
+int sgp_splat_tiles(const sgp_tiles_view *tiles, const float *src, int64_t lds, int L, float *values,
+                    sgp_stream_t stream);
+/* out = slice(values), dictionary rows staged in shared memory; same arithmetic as sgp_slice */
+int sgp_slice_tiles(const sgp_tiles_view *tiles, const float *values, int L, float *out, int64_t ldo,
+                    sgp_stream_t stream);
+/* splat_tiles -> blur -> slice_tiles */
+int sgp_mvm_tiles(const sgp_lattice_view *lat, const sgp_tiles_view *tiles, const float *src, int64_t lds,
+                  int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1,
+                  sgp_stream_t stream);
+
 /* Test hook: number of fp32 bit patterns a in [lo, lo+count) for which the division-by-constant
  * used inside sgp_slice differs from the IEEE division a / sgp_slice_divisor(d).  Must be 0. */
 int sgp_debug_division_mismatches(int d, uint32_t lo, uint32_t count, unsigned long long *mismatches_dev,

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libsgp_lattice.so")
 
 SGP_OK = 0
 SGP_SPLAT_AUTO, SGP_SPLAT_ATOMIC, SGP_SPLAT_GATHER = 0, 1, 2
+MODE_AUTO, MODE_ATOMIC, MODE_GATHER, MODE_TILES = 0, 1, 2, 3   # Lattice.mvm(mode=...)
 SGP_MAX_DIM = 126
 SGP_MAX_ORDER = 7
 
@@ -22,6 +23,8 @@ SYMBOLS = [
     "sgp_build_points", "sgp_hash_capacity", "sgp_hash_insert", "sgp_number_workspace_bytes",
     "sgp_count_points", "sgp_number_points", "sgp_build_neighbours", "sgp_csr_workspace_bytes",
     "sgp_build_csr", "sgp_splat", "sgp_blur", "sgp_slice", "sgp_mvm", "sgp_debug_division_mismatches",
+    "sgp_tiles_workspace_bytes", "sgp_tiles_prepare", "sgp_tiles_finalize", "sgp_splat_tiles", "sgp_slice_tiles",
+    "sgp_mvm_tiles",
 ]
 
 
@@ -37,6 +40,27 @@ class LatticeView(C.Structure):
         ("nbr", C.c_void_p),
         ("csr_ptr", C.c_void_p),
         ("csr_ent", C.c_void_p),
+    ]
+
+
+class TilesView(C.Structure):
+    """Mirror of ``struct sgp_tiles_view``."""
+
+    _fields_ = [
+        ("N", C.c_int64),
+        ("M", C.c_int64),
+        ("S", C.c_int64),
+        ("d", C.c_int32),
+        ("tile_points", C.c_int32),
+        ("max_dict", C.c_int32),
+        ("reserved", C.c_int32),
+        ("perm", C.c_void_p),
+        ("tile_seg_ptr", C.c_void_p),
+        ("seg_ptr", C.c_void_p),
+        ("seg_row", C.c_void_p),
+        ("seg_ent", C.c_void_p),
+        ("lidx", C.c_void_p),
+        ("tile_w", C.c_void_p),
     ]
 
 
@@ -99,6 +123,19 @@ def lib() -> C.CDLL:
     L.sgp_slice.argtypes = [pv, vp, i32, vp, i64, vp]
     L.sgp_mvm.restype = i32
     L.sgp_mvm.argtypes = [pv, vp, i64, i32, fp, i32, vp, i64, vp, vp, i32, vp]
+    pt = C.POINTER(TilesView)
+    L.sgp_tiles_workspace_bytes.restype = sz
+    L.sgp_tiles_workspace_bytes.argtypes = [i64, i32]
+    L.sgp_tiles_prepare.restype = i32
+    L.sgp_tiles_prepare.argtypes = [vp, i64, i32, i64, i32, vp, vp, sz, C.POINTER(i64), vp]
+    L.sgp_tiles_finalize.restype = i32
+    L.sgp_tiles_finalize.argtypes = [vp, vp, i64, i32, i32, i64, vp, sz, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int32), vp]
+    L.sgp_splat_tiles.restype = i32
+    L.sgp_splat_tiles.argtypes = [pt, vp, i64, i32, vp, vp]
+    L.sgp_slice_tiles.restype = i32
+    L.sgp_slice_tiles.argtypes = [pt, vp, i32, vp, i64, vp]
+    L.sgp_mvm_tiles.restype = i32
+    L.sgp_mvm_tiles.argtypes = [pv, pt, vp, i64, i32, fp, i32, vp, i64, vp, vp, vp]
     L.sgp_debug_division_mismatches.restype = i32
     L.sgp_debug_division_mismatches.argtypes = [i32, C.c_uint32, C.c_uint32, vp, vp]
     if L.sgp_abi_version() != 1:

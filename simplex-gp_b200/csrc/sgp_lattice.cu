@@ -24,13 +24,14 @@
 #include <string.h>
 
 #include "sgp_lattice.h"
+#include "sgp_common.cuh"
 
 // ------------------------------------------------------------------------------------
-// error plumbing
+// error plumbing (declared in sgp_common.cuh, shared with sgp_tiles.cu)
 // ------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char *fmt, ...)
+int sgp_fail(int code, const char *fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -39,19 +40,15 @@ static int fail(int code, const char *fmt, ...)
     return code;
 }
 
-#define CUDA_TRY(expr)                                                                        \
-    do {                                                                                      \
-        cudaError_t _e = (expr);                                                              \
-        if (_e != cudaSuccess)                                                                \
-            return fail(SGP_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));          \
-    } while (0)
-
-static int launch_ok(const char *what)
+int sgp_launch_ok(const char *what)
 {
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(SGP_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    if (e != cudaSuccess) return sgp_fail(SGP_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
     return SGP_OK;
 }
+
+#define fail sgp_fail
+#define launch_ok sgp_launch_ok
 
 extern "C" int sgp_abi_version(void) { return SGP_ABI_VERSION; }
 extern "C" const char *sgp_last_error(void) { return g_err; }
@@ -444,8 +441,8 @@ sgp_scan_down_kernel(uint32_t *__restrict__ data, int64_t n, const uint32_t *__r
 }
 
 // exclusive scan of data[n] in place; tile_sums: scratch of ceil(n/SCAN_TILE) uint32; total -> device uint64
-static int exclusive_scan_u32(uint32_t *data, int64_t n, uint32_t *tile_sums, unsigned long long *total_dev,
-                              cudaStream_t st)
+int sgp_exclusive_scan_u32(uint32_t *data, int64_t n, uint32_t *tile_sums, unsigned long long *total_dev,
+                             cudaStream_t st)
 {
     const int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (n_tiles == 0) {
@@ -592,35 +589,6 @@ sgp_csr_order_kernel(const int32_t *__restrict__ replay, int64_t total, int dp1,
 // stages 2-4: splat / blur / slice.  Thread = (row, chunk of VEC channels); a row's
 // channels are adjacent so one row of L=16 fp32 is 4 lanes x float4 = 64 contiguous bytes.
 // ------------------------------------------------------------------------------------
-template <int VEC> struct Vec;
-template <> struct Vec<1> {
-    float v[1];
-    __device__ __forceinline__ void load(const float *p) { v[0] = __ldg(p); }
-    __device__ __forceinline__ void load_cg(const float *p) { v[0] = __ldcg(p); }
-    __device__ __forceinline__ void store(float *p) const { *p = v[0]; }
-    __device__ __forceinline__ void red(float *p) const { atomicAdd(p, v[0]); }
-};
-template <> struct Vec<2> {
-    float v[2];
-    __device__ __forceinline__ void load(const float *p) { float2 t = __ldg((const float2 *)p); v[0] = t.x; v[1] = t.y; }
-    __device__ __forceinline__ void load_cg(const float *p) { float2 t = __ldcg((const float2 *)p); v[0] = t.x; v[1] = t.y; }
-    __device__ __forceinline__ void store(float *p) const { *(float2 *)p = make_float2(v[0], v[1]); }
-    __device__ __forceinline__ void red(float *p) const
-    {
-        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
-    }
-};
-template <> struct Vec<4> {
-    float v[4];
-    __device__ __forceinline__ void load(const float *p) { float4 t = __ldg((const float4 *)p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-    __device__ __forceinline__ void load_cg(const float *p) { float4 t = __ldcg((const float4 *)p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-    __device__ __forceinline__ void store(float *p) const { *(float4 *)p = make_float4(v[0], v[1], v[2], v[3]); }
-    __device__ __forceinline__ void red(float *p) const
-    {
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
-    }
-};
-
 #define SLICE_BATCH 9
 // splat, scatter form: thread = (point n, chunk); (d+1) vector reductions into the lattice
 template <int VEC>
@@ -742,19 +710,6 @@ sgp_blur_kernel(const int32_t *__restrict__ nbr_j, const float *__restrict__ in,
         }
         acc.store(out + i * L + c0);
     }
-}
-
-// a / b for a fixed divisor b whose reciprocal rb = RN(1/b) was computed on the host (Markstein:
-// q0 = RN(a*rb), rem = a - q0*b exactly by FMA, q = RN(q0 + rem*rb)).  Equal to the IEEE division
-// bit for bit for every finite |a| >= 2^-100 and for a = 0 (sign of zero aside, which cannot reach
-// the sum); below 2^-100 the remainder may be inexact and q can be off by one denormal-range ulp
-// (absolute error < 1e-37).  tests/test_gpu_parity.py::test_exact_division checks both claims over
-// all 2^32 bit patterns.  Five issue slots per term instead of the ~12 of __fdiv_rn.
-__device__ __forceinline__ float exact_div(float a, float b, float rb)
-{
-    const float q0 = __fmul_rn(a, rb);
-    const float rem = __fmaf_rn(-q0, b, a);
-    return __fmaf_rn(rem, rb, q0);
 }
 
 // counts[0]: mismatches with |a| in [2^-100, inf) or a == 0 (must be 0);
@@ -949,7 +904,7 @@ extern "C" int sgp_count_points(const uint64_t *table, int64_t capacity, const u
     sgp_mark_kernel<<<grid_for(total, 256), 256, 0, st>>>((const unsigned long long *)table, slot_of, total, marks);
     rc = launch_ok("sgp_mark_kernel");
     if (rc) return rc;
-    rc = exclusive_scan_u32(marks, total, tiles, total_dev, st);
+    rc = sgp_exclusive_scan_u32(marks, total, tiles, total_dev, st);
     if (rc) return rc;
     unsigned long long m_host = 0;
     int32_t f_host = 0;
@@ -1035,7 +990,7 @@ extern "C" int sgp_build_csr(const int32_t *replay, int64_t N, int d, int64_t M,
     sgp_csr_count_kernel<<<grid_for(total, 256), 256, 0, st>>>(replay, total, row_ptr);
     rc = launch_ok("sgp_csr_count_kernel");
     if (rc) return rc;
-    rc = exclusive_scan_u32(row_ptr, M + 1, tiles, total_dev, st);
+    rc = sgp_exclusive_scan_u32(row_ptr, M + 1, tiles, total_dev, st);
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(uint32_t) * (size_t)(M + 1), st));
     sgp_csr_fill_kernel<<<grid_for(total, 256), 256, 0, st>>>(replay, total, row_ptr, cursor, pv_scratch);

@@ -1,0 +1,468 @@
+// sgp_tiles.cu -- locality tiles for splat and slice (B200, sm_100a).
+//
+// Why: at the metric configuration (N=1M, d=8, 16 RHS, M=0.4M) a lattice point is touched by 22
+// point-vertices on average and by ~9000 at the centre of the data.  The plain scatter splat
+// therefore sends 9M x 64 B vector reductions to L2 (L1TEX and the L2 atomic units are the
+// limiter, and same-address reductions serialise), and the plain slice gathers 9M x 64 B rows
+// from L2.  Both are bounded by L2 traffic, not HBM.
+//
+// What: points are sorted once per lattice so that points sharing lattice vertices are adjacent
+// (key = lattice index of their remainder-0 vertex), and cut into tiles of T points.  For every
+// tile the distinct lattice rows its T*(d+1) point-vertices touch form the tile's DICTIONARY
+// (`seg_row`), and the point-vertices are grouped by dictionary entry into SEGMENTS (`seg_ptr`,
+// `seg_ent`).  Then
+//   splat: one CTA per tile stages the tile's T RHS rows in shared memory, sums every segment
+//          in registers (deterministic order) and issues ONE vector reduction per segment;
+//   slice: one CTA per tile stages the tile's dictionary rows in shared memory once and every
+//          point combines its d+1 vertices from shared memory.
+// L2 traffic per stage drops from N(d+1) rows to S rows (S = number of segments, ~3.3x fewer at
+// the metric configuration).
+//
+// Sorting uses cub::DeviceRadixSort (CUDA toolkit header library) -- plumbing of the build
+// phase; every kernel on the MVM path is hand-written below.
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "sgp_common.cuh"
+#include "sgp_lattice.h"
+
+#define fail sgp_fail
+#define launch_ok sgp_launch_ok
+#define grid_for sgp_grid_for
+
+// ------------------------------------------------------------------------------------
+// build
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sgp_tile_pointkeys_kernel(const int32_t *__restrict__ replay, int64_t N, int dp1, uint32_t *__restrict__ keys,
+                          uint32_t *__restrict__ vals)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    keys[n] = (uint32_t)replay[n * dp1 * 2];   // lattice index of the remainder-0 vertex
+    vals[n] = (uint32_t)n;
+}
+
+// composite key of every sorted point-vertex q = p*(d+1)+r: (tile of p) << 32 | lattice index
+__global__ void __launch_bounds__(256)
+sgp_tile_pvkeys_kernel(const int32_t *__restrict__ replay, const uint32_t *__restrict__ perm, int64_t total, int dp1,
+                       int T, unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total) return;
+    const int64_t p = q / dp1;
+    const int r = (int)(q - p * dp1);
+    const int64_t n = perm[p];
+    const uint32_t idx = (uint32_t)replay[(n * dp1 + r) * 2];
+    keys[q] = ((unsigned long long)(p / T) << 32) | idx;
+    vals[q] = (uint32_t)q;
+}
+
+__global__ void __launch_bounds__(256)
+sgp_tile_heads_kernel(const unsigned long long *__restrict__ keys, int64_t total, uint32_t *__restrict__ heads)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    heads[k] = (k == 0 || keys[k] != keys[k - 1]) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+sgp_tile_fill_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals,
+                     const uint32_t *__restrict__ excl, int64_t total, const int32_t *__restrict__ replay,
+                     const uint32_t *__restrict__ perm, int dp1, int T, int64_t n_tiles, int64_t S,
+                     uint32_t *__restrict__ seg_ptr, int32_t *__restrict__ seg_row, int2 *__restrict__ seg_ent,
+                     uint32_t *__restrict__ tile_seg_ptr, uint32_t *__restrict__ seg_of_q,
+                     float *__restrict__ tile_w)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    const unsigned long long key = keys[k];
+    const bool head = (k == 0) || (key != keys[k - 1]);
+    const uint32_t s = excl[k] + (head ? 1u : 0u) - 1u;
+    const uint32_t q = vals[k];
+    const int64_t p = q / (uint32_t)dp1;
+    const int r = (int)(q - p * dp1);
+    const int64_t n = perm[p];
+    const int32_t wbits = replay[(n * dp1 + r) * 2 + 1];
+    const int64_t tile = (int64_t)(key >> 32);
+    seg_ent[k] = make_int2((int)(p - tile * T), wbits);   // {point index inside the tile, weight bits}
+    seg_of_q[q] = s;
+    tile_w[q] = __int_as_float(wbits);
+    if (head) {
+        seg_ptr[s] = (uint32_t)k;
+        seg_row[s] = (int32_t)(uint32_t)key;
+        if (k == 0 || (int64_t)(keys[k - 1] >> 32) != tile) tile_seg_ptr[tile] = s;
+    }
+    if (k == total - 1) {
+        seg_ptr[S] = (uint32_t)total;
+        tile_seg_ptr[n_tiles] = (uint32_t)S;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sgp_tile_lidx_kernel(const uint32_t *__restrict__ seg_of_q, const uint32_t *__restrict__ tile_seg_ptr, int64_t total,
+                     int dp1, int T, uint16_t *__restrict__ lidx)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total) return;
+    const int64_t tile = (q / dp1) / T;
+    lidx[q] = (uint16_t)(seg_of_q[q] - tile_seg_ptr[tile]);
+}
+
+// per-tile dictionary size -> max (for the slice kernel's shared-memory budget)
+__global__ void __launch_bounds__(256)
+sgp_tile_maxdict_kernel(const uint32_t *__restrict__ tile_seg_ptr, int64_t n_tiles, uint32_t *__restrict__ max_out)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    atomicMax(max_out, tile_seg_ptr[t + 1] - tile_seg_ptr[t]);
+}
+
+// workspace layout (bytes, every block 256-aligned):
+//   k64a, k64b : total * 8     composite keys (double buffer; also used as 2 x uint32 buffers for the point sort)
+//   v32a, v32b : total * 4     payloads
+//   heads      : total * 4     head flags -> exclusive scan
+//   seg_of_q   : total * 4
+//   scan tiles : sgp_scan_tiles(total) * 4
+//   total_dev  : 16
+//   cub temp   : max of the two sorts
+struct TilesWs {
+    size_t k64a, k64b, v32a, v32b, heads, seg_of_q, scan_tiles, total_dev, cub, cub_bytes, bytes;
+};
+
+static int tiles_ws_layout(int64_t N, int d, TilesWs *w)
+{
+    const int64_t total = N * (int64_t)(d + 1);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o = 0;
+    w->k64a = o; o += al((size_t)total * 8);
+    w->k64b = o; o += al((size_t)total * 8);
+    w->v32a = o; o += al((size_t)total * 4);
+    w->v32b = o; o += al((size_t)total * 4);
+    w->heads = o; o += al((size_t)total * 4);
+    w->seg_of_q = o; o += al((size_t)total * 4);
+    w->scan_tiles = o; o += al((size_t)sgp_scan_tiles(total) * 4);
+    w->total_dev = o; o += 256;
+    size_t t1 = 0, t2 = 0;
+    cudaError_t e1 = cub::DeviceRadixSort::SortPairs(nullptr, t1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                     (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)N, 0, 32);
+    cudaError_t e2 = cub::DeviceRadixSort::SortPairs(nullptr, t2, (const unsigned long long *)nullptr,
+                                                     (unsigned long long *)nullptr, (const uint32_t *)nullptr,
+                                                     (uint32_t *)nullptr, (int64_t)total, 0, 64);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return sgp_fail(SGP_ECUDA, "cub temp-size query failed");
+    w->cub_bytes = t1 > t2 ? t1 : t2;
+    w->cub = o; o += al(w->cub_bytes);
+    w->bytes = o;
+    return SGP_OK;
+}
+
+extern "C" size_t sgp_tiles_workspace_bytes(int64_t N, int d)
+{
+    TilesWs w;
+    if (N <= 0 || d < 1 || tiles_ws_layout(N, d, &w) != SGP_OK) return 0;
+    return w.bytes;
+}
+
+static int bits_for(uint64_t v)
+{
+    int b = 1;
+    while (b < 64 && (v >> b) != 0) ++b;
+    return b;
+}
+
+extern "C" int sgp_tiles_prepare(const int32_t *replay, int64_t N, int d, int64_t M, int tile_points,
+                                 uint32_t *perm, void *workspace, size_t workspace_bytes, int64_t *S_out,
+                                 sgp_stream_t stream)
+{
+    if (!replay || !perm || !workspace || !S_out || N <= 0 || M <= 0 || d < 1 || d > SGP_MAX_DIM)
+        return fail(SGP_EINVAL, "sgp_tiles_prepare: bad argument");
+    if (tile_points < 1 || (int64_t)tile_points * (d + 1) > 65535)
+        return fail(SGP_EINVAL, "tile_points*(d+1) must fit 16 bits (got %d*%d)", tile_points, d + 1);
+    TilesWs w;
+    int rc = tiles_ws_layout(N, d, &w);
+    if (rc) return rc;
+    if (workspace_bytes < w.bytes) return fail(SGP_EINVAL, "tiles workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    char *base = (char *)workspace;
+    const int dp1 = d + 1;
+    const int64_t total = N * dp1;
+    const int64_t n_tiles = (N + tile_points - 1) / tile_points;
+    unsigned long long *k64a = (unsigned long long *)(base + w.k64a), *k64b = (unsigned long long *)(base + w.k64b);
+    uint32_t *v32a = (uint32_t *)(base + w.v32a), *v32b = (uint32_t *)(base + w.v32b);
+    uint32_t *heads = (uint32_t *)(base + w.heads);
+    uint32_t *scan_tiles = (uint32_t *)(base + w.scan_tiles);
+    unsigned long long *total_dev = (unsigned long long *)(base + w.total_dev);
+    void *cub_tmp = base + w.cub;
+    size_t cub_bytes = w.cub_bytes;
+
+    // 1. sort points by the lattice index of their remainder-0 vertex (stable: ties keep input order)
+    uint32_t *pk_in = (uint32_t *)k64a, *pk_out = (uint32_t *)k64b;
+    sgp_tile_pointkeys_kernel<<<grid_for(N, 256), 256, 0, st>>>(replay, N, dp1, pk_in, v32a);
+    rc = launch_ok("sgp_tile_pointkeys_kernel");
+    if (rc) return rc;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, pk_in, pk_out, v32a, perm, (int64_t)N, 0,
+                                             bits_for((uint64_t)M), st));
+    // 2. sort point-vertices by (tile, lattice index); stable, so a segment keeps sorted-point order
+    sgp_tile_pvkeys_kernel<<<grid_for(total, 256), 256, 0, st>>>(replay, perm, total, dp1, tile_points, k64a, v32a);
+    rc = launch_ok("sgp_tile_pvkeys_kernel");
+    if (rc) return rc;
+    cub_bytes = w.cub_bytes;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, k64a, k64b, v32a, v32b, (int64_t)total, 0,
+                                             32 + bits_for((uint64_t)n_tiles), st));
+    // 3. segment heads -> exclusive scan -> S
+    sgp_tile_heads_kernel<<<grid_for(total, 256), 256, 0, st>>>(k64b, total, heads);
+    rc = launch_ok("sgp_tile_heads_kernel");
+    if (rc) return rc;
+    rc = sgp_exclusive_scan_u32(heads, total, scan_tiles, total_dev, st);
+    if (rc) return rc;
+    unsigned long long s_host = 0;
+    CUDA_TRY(cudaMemcpyAsync(&s_host, total_dev, sizeof(s_host), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *S_out = (int64_t)s_host;
+    return SGP_OK;
+}
+
+extern "C" int sgp_tiles_finalize(const int32_t *replay, const uint32_t *perm, int64_t N, int d, int tile_points,
+                                  int64_t S, void *workspace, size_t workspace_bytes, uint32_t *seg_ptr,
+                                  int32_t *seg_row, int32_t *seg_ent, uint32_t *tile_seg_ptr, uint16_t *lidx,
+                                  float *tile_w, int32_t *max_dict_out, sgp_stream_t stream)
+{
+    if (!replay || !perm || !workspace || !seg_ptr || !seg_row || !seg_ent || !tile_seg_ptr || !lidx || !tile_w ||
+        !max_dict_out || N <= 0 || S <= 0)
+        return fail(SGP_EINVAL, "sgp_tiles_finalize: bad argument");
+    TilesWs w;
+    int rc = tiles_ws_layout(N, d, &w);
+    if (rc) return rc;
+    if (workspace_bytes < w.bytes) return fail(SGP_EINVAL, "tiles workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *base = (char *)workspace;
+    const int dp1 = d + 1;
+    const int64_t total = N * dp1;
+    const int64_t n_tiles = (N + tile_points - 1) / tile_points;
+    const unsigned long long *keys = (const unsigned long long *)(base + w.k64b);
+    const uint32_t *vals = (const uint32_t *)(base + w.v32b);
+    const uint32_t *excl = (const uint32_t *)(base + w.heads);
+    uint32_t *seg_of_q = (uint32_t *)(base + w.seg_of_q);
+    uint32_t *max_dev = (uint32_t *)(base + w.total_dev);
+    sgp_tile_fill_kernel<<<grid_for(total, 256), 256, 0, st>>>(keys, vals, excl, total, replay, perm, dp1, tile_points,
+                                                                n_tiles, S, seg_ptr, seg_row, (int2 *)seg_ent,
+                                                                tile_seg_ptr, seg_of_q, tile_w);
+    rc = launch_ok("sgp_tile_fill_kernel");
+    if (rc) return rc;
+    sgp_tile_lidx_kernel<<<grid_for(total, 256), 256, 0, st>>>(seg_of_q, tile_seg_ptr, total, dp1, tile_points, lidx);
+    rc = launch_ok("sgp_tile_lidx_kernel");
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(max_dev, 0, sizeof(uint32_t), st));
+    sgp_tile_maxdict_kernel<<<grid_for(n_tiles, 256), 256, 0, st>>>(tile_seg_ptr, n_tiles, max_dev);
+    rc = launch_ok("sgp_tile_maxdict_kernel");
+    if (rc) return rc;
+    uint32_t mx = 0;
+    CUDA_TRY(cudaMemcpyAsync(&mx, max_dev, sizeof(mx), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *max_dict_out = (int32_t)mx;
+    return SGP_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// MVM kernels on tiles.  CB = channels staged per CTA (<= 16 fp32 = one 64-byte row piece).
+// ------------------------------------------------------------------------------------
+#define TILE_THREADS 256
+
+// splat: CTA = (tile, channel block).  Stage the tile's RHS rows, reduce every segment in
+// registers in sorted-point order, one vector reduction per segment.
+template <int VEC>
+__global__ void __launch_bounds__(TILE_THREADS)
+sgp_splat_tiles_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ tile_seg_ptr,
+                       const uint32_t *__restrict__ seg_ptr, const int32_t *__restrict__ seg_row,
+                       const int2 *__restrict__ seg_ent, const float *__restrict__ src, int64_t lds, int64_t N,
+                       int T, int L, int CB, float *__restrict__ values)
+{
+    extern __shared__ __align__(16) float smem[];   // [T][CB]
+    const int64_t tile = blockIdx.x;
+    const int cb0 = blockIdx.y * CB;
+    const int cb = min(CB, L - cb0);                // channels of this block (multiple of VEC)
+    const int chunks = cb / VEC;
+    const int64_t p0 = tile * T;
+    const int np = (int)min((int64_t)T, N - p0);
+
+    for (int w = threadIdx.x; w < np * chunks; w += TILE_THREADS) {
+        const int lp = w / chunks, c = (w - lp * chunks) * VEC;
+        Vec<VEC> v;
+        v.load(src + (int64_t)perm[p0 + lp] * lds + cb0 + c);
+        v.store(smem + lp * CB + c);
+    }
+    __syncthreads();
+
+    const uint32_t s0 = tile_seg_ptr[tile], s1 = tile_seg_ptr[tile + 1];
+    const int nseg = (int)(s1 - s0);
+    for (int w = threadIdx.x; w < nseg * chunks; w += TILE_THREADS) {
+        const int ls = w / chunks, c = (w - ls * chunks) * VEC;
+        const uint32_t a = seg_ptr[s0 + ls], b = seg_ptr[s0 + ls + 1];
+        const int64_t row = seg_row[s0 + ls];
+        Vec<VEC> acc;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
+        for (uint32_t e = a; e < b; ++e) {
+            const int2 ent = __ldg(seg_ent + e);
+            const float wgt = __int_as_float(ent.y);
+            Vec<VEC> sv;
+            sv.load_plain(smem + ent.x * CB + c);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(wgt, sv.v[k]));
+        }
+        acc.red(values + row * L + cb0 + c);
+    }
+}
+
+// slice: CTA = (tile, channel block).  Stage the tile's dictionary rows once, then every point
+// combines its d+1 vertices from shared memory in vertex order (same arithmetic as sgp_slice_kernel).
+// Tiles whose dictionary exceeds `cap` rows (no reuse to exploit) read the lattice directly.
+template <int VEC>
+__global__ void __launch_bounds__(TILE_THREADS)
+sgp_slice_tiles_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ tile_seg_ptr,
+                       const int32_t *__restrict__ seg_row, const uint16_t *__restrict__ lidx,
+                       const float *__restrict__ tile_w, const float *__restrict__ values, int64_t N, int T, int dp1,
+                       int L, int CB, int cap, float divisor, float rdivisor, float *__restrict__ out, int64_t ldo)
+{
+    extern __shared__ __align__(16) float smem[];   // [cap][CB]
+    const int64_t tile = blockIdx.x;
+    const int cb0 = blockIdx.y * CB;
+    const int cb = min(CB, L - cb0);
+    const int chunks = cb / VEC;
+    const int64_t p0 = tile * T;
+    const int np = (int)min((int64_t)T, N - p0);
+    const uint32_t s0 = tile_seg_ptr[tile];
+    const int nloc = (int)(tile_seg_ptr[tile + 1] - s0);
+    const bool staged = nloc <= cap;
+
+    if (staged) {
+        for (int w = threadIdx.x; w < nloc * chunks; w += TILE_THREADS) {
+            const int lr = w / chunks, c = (w - lr * chunks) * VEC;
+            Vec<VEC> v;
+            v.load(values + (int64_t)seg_row[s0 + lr] * L + cb0 + c);
+            v.store(smem + lr * CB + c);
+        }
+        __syncthreads();
+    }
+    for (int w = threadIdx.x; w < np * chunks; w += TILE_THREADS) {
+        const int lp = w / chunks, c = (w - lp * chunks) * VEC;
+        const int64_t q0 = (p0 + lp) * dp1;
+        Vec<VEC> acc;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
+        if (staged) {
+            for (int r = 0; r < dp1; ++r) {
+                const float wgt = __ldg(tile_w + q0 + r);
+                Vec<VEC> sv;
+                sv.load_plain(smem + (int)__ldg(lidx + q0 + r) * CB + c);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    acc.v[k] = __fadd_rn(acc.v[k], exact_div(__fmul_rn(wgt, sv.v[k]), divisor, rdivisor));
+            }
+        } else {
+            for (int r = 0; r < dp1; ++r) {
+                const float wgt = __ldg(tile_w + q0 + r);
+                Vec<VEC> v;
+                v.load(values + (int64_t)seg_row[s0 + __ldg(lidx + q0 + r)] * L + cb0 + c);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    acc.v[k] = __fadd_rn(acc.v[k], exact_div(__fmul_rn(wgt, v.v[k]), divisor, rdivisor));
+            }
+        }
+        acc.store(out + (int64_t)perm[p0 + lp] * ldo + cb0 + c);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------
+static int tile_vec(int L, int CB, int64_t ld_a, const void *p0, const void *p1)
+{
+    auto al = [](const void *p, int bytes) { return ((uintptr_t)p % bytes) == 0; };
+    if (L % 4 == 0 && CB % 4 == 0 && ld_a % 4 == 0 && al(p0, 16) && al(p1, 16)) return 4;
+    if (L % 2 == 0 && CB % 2 == 0 && ld_a % 2 == 0 && al(p0, 8) && al(p1, 8)) return 2;
+    return 1;
+}
+
+static int check_tiles(const sgp_tiles_view *t, int L)
+{
+    if (!t || !t->perm || !t->tile_seg_ptr || !t->seg_ptr || !t->seg_row || !t->seg_ent || !t->lidx || !t->tile_w)
+        return fail(SGP_EINVAL, "null tiles view");
+    if (t->N <= 0 || t->M <= 0 || t->S <= 0 || t->d < 1 || t->tile_points < 1 || L < 1)
+        return fail(SGP_EINVAL, "bad tiles view");
+    return SGP_OK;
+}
+
+extern "C" int sgp_splat_tiles(const sgp_tiles_view *t, const float *src, int64_t lds, int L, float *values,
+                               sgp_stream_t stream)
+{
+    int rc = check_tiles(t, L);
+    if (rc) return rc;
+    if (!src || !values || lds < L) return fail(SGP_EINVAL, "sgp_splat_tiles: null pointer or lds < L");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int CB = L < 16 ? L : 16;
+    const int vec = tile_vec(L, CB, lds, src, values);
+    const int64_t n_tiles = (t->N + t->tile_points - 1) / t->tile_points;
+    const unsigned ncb = (unsigned)((L + CB - 1) / CB);
+    const size_t smem = (size_t)t->tile_points * CB * sizeof(float);
+    CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)t->M * (size_t)L, st));
+    dim3 grid((unsigned)n_tiles, ncb);
+#define SGP_LAUNCH_SPLAT_TILES(VV)                                                                                   \
+    sgp_splat_tiles_kernel<VV><<<grid, TILE_THREADS, smem, st>>>(t->perm, t->tile_seg_ptr, t->seg_ptr, t->seg_row,  \
+                                                                 (const int2 *)t->seg_ent, src, lds, t->N,           \
+                                                                 t->tile_points, L, CB, values)
+    if (vec == 4) SGP_LAUNCH_SPLAT_TILES(4);
+    else if (vec == 2) SGP_LAUNCH_SPLAT_TILES(2);
+    else SGP_LAUNCH_SPLAT_TILES(1);
+    return launch_ok("sgp_splat_tiles_kernel");
+}
+
+extern "C" int sgp_slice_tiles(const sgp_tiles_view *t, const float *values, int L, float *out, int64_t ldo,
+                               sgp_stream_t stream)
+{
+    int rc = check_tiles(t, L);
+    if (rc) return rc;
+    if (!values || !out || ldo < L) return fail(SGP_EINVAL, "sgp_slice_tiles: null pointer or ldo < L");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int CB = L < 16 ? L : 16;
+    const int vec = tile_vec(L, CB, ldo, values, out);
+    const int64_t n_tiles = (t->N + t->tile_points - 1) / t->tile_points;
+    const unsigned ncb = (unsigned)((L + CB - 1) / CB);
+    // dictionary rows staged per CTA: bounded so that >= 3 CTAs fit one SM (227 KB)
+    int cap = t->max_dict;
+    const int cap_limit = (72 * 1024) / (CB * (int)sizeof(float));
+    if (cap > cap_limit) cap = cap_limit;
+    if (cap < 1) cap = 1;
+    const size_t smem = (size_t)cap * CB * sizeof(float);
+    const float divisor = sgp_slice_divisor(t->d);
+    volatile float rdivisor = 1.0f / divisor;
+    dim3 grid((unsigned)n_tiles, ncb);
+#define SGP_LAUNCH_SLICE_TILES(VV)                                                                                   \
+    do {                                                                                                             \
+        if (smem > 48 * 1024)                                                                                        \
+            CUDA_TRY(cudaFuncSetAttribute(sgp_slice_tiles_kernel<VV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                          (int)smem));                                                               \
+        sgp_slice_tiles_kernel<VV><<<grid, TILE_THREADS, smem, st>>>(t->perm, t->tile_seg_ptr, t->seg_row, t->lidx,  \
+                                                                     t->tile_w, values, t->N, t->tile_points,        \
+                                                                     t->d + 1, L, CB, cap, divisor, rdivisor, out,  \
+                                                                     ldo);                                           \
+    } while (0)
+    if (vec == 4) SGP_LAUNCH_SLICE_TILES(4);
+    else if (vec == 2) SGP_LAUNCH_SLICE_TILES(2);
+    else SGP_LAUNCH_SLICE_TILES(1);
+    return launch_ok("sgp_slice_tiles_kernel");
+}
+
+extern "C" int sgp_mvm_tiles(const sgp_lattice_view *lat, const sgp_tiles_view *tiles, const float *src, int64_t lds,
+                             int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1,
+                             sgp_stream_t stream)
+{
+    int rc = sgp_splat_tiles(tiles, src, lds, L, buf0, stream);
+    if (rc) return rc;
+    int in1 = 0;
+    rc = sgp_blur(lat, coeffs, k, L, buf0, buf1, &in1, stream);
+    if (rc) return rc;
+    return sgp_slice_tiles(tiles, in1 ? buf1 : buf0, L, out, ldo, stream);
+}

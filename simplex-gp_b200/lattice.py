@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._capi import LatticeView, check
+from ._capi import LatticeView, TilesView, check
 
 __all__ = ["Lattice", "lattice_filter", "stencil_variance", "scale_factors", "slice_divisor"]
 
@@ -81,8 +81,8 @@ class Lattice:
     ========  ==================  =========================================================================
     """
 
-    def __init__(self, x: torch.Tensor, coeffs, *, build_csr: bool = True, keep_structure: bool = True,
-                 hash_capacity: Optional[int] = None):
+    def __init__(self, x: torch.Tensor, coeffs, *, build_csr: bool = False, build_tiles: bool = False,
+                 tile_points: int = 256, keep_structure: bool = True, hash_capacity: Optional[int] = None):
         if x.dim() != 2:
             raise ValueError(f"x must be [N, d], got {tuple(x.shape)}")
         if not x.is_cuda:
@@ -113,6 +113,7 @@ class Lattice:
             self.nbr = torch.empty((d + 1, 0, 2 * r), dtype=torch.int32, device=dev)
             self.csr_ptr = None
             self.csr_ent = None
+            self.tiles = None
             self.hash_capacity = 0
             if N > 0:
                 check(lib.sgp_build_points(_ptr(x), N, d, x.stride(0), _fp(self.scale), _ptr(self.greedy),
@@ -139,6 +140,8 @@ class Lattice:
                 del table
                 if build_csr:
                     self._build_csr()
+                if build_tiles:
+                    self._build_tiles(tile_points)
             if not keep_structure:
                 self.greedy = None
                 self.rank = None
@@ -146,7 +149,7 @@ class Lattice:
 
     @classmethod
     def from_arrays(cls, coeffs, replay: torch.Tensor, keys: torch.Tensor, nbr: torch.Tensor,
-                    build_csr: bool = False) -> "Lattice":
+                    build_csr: bool = False, build_tiles: bool = False, tile_points: int = 256) -> "Lattice":
         """Wrap lattice arrays that were built elsewhere (e.g. received by ``distributed.broadcast_lattice``)."""
         self = object.__new__(cls)
         self.device = replay.device
@@ -161,12 +164,54 @@ class Lattice:
         self.replay, self.keys, self.nbr = replay.contiguous(), keys.contiguous(), nbr.contiguous()
         self.greedy = self.rank = None
         self.csr_ptr = self.csr_ent = None
+        self.tiles = None
         self.hash_capacity = 0
         self._bufs = {}
-        if build_csr and self.N > 0 and self.M > 0:
+        if self.N > 0 and self.M > 0:
             with torch.cuda.device(self.device):
-                self._build_csr()
+                if build_csr:
+                    self._build_csr()
+                if build_tiles:
+                    self._build_tiles(tile_points)
         return self
+
+    def _build_tiles(self, tile_points: int = 256) -> None:
+        """Locality tiles for the shared-memory staged splat / slice (csrc/sgp_tiles.cu)."""
+        lib = _capi.lib()
+        dev, N, d, M = self.device, self.N, self.d, self.M
+        total = N * (d + 1)
+        T = int(tile_points)
+        while T > 1 and T * (d + 1) > 65535:
+            T //= 2
+        n_tiles = (N + T - 1) // T
+        st = _stream_ptr(dev)
+        ws_bytes = int(lib.sgp_tiles_workspace_bytes(N, d))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        perm = torch.empty(N, dtype=torch.int32, device=dev)
+        S = C.c_int64(0)
+        check(lib.sgp_tiles_prepare(_ptr(self.replay), N, d, M, T, _ptr(perm), _ptr(ws), ws_bytes, C.byref(S), st))
+        S = int(S.value)
+        t = {
+            "T": T, "S": S, "perm": perm,
+            "seg_ptr": torch.empty(S + 1, dtype=torch.int32, device=dev),
+            "seg_row": torch.empty(S, dtype=torch.int32, device=dev),
+            "seg_ent": torch.empty((total, 2), dtype=torch.int32, device=dev),
+            "tile_seg_ptr": torch.empty(n_tiles + 1, dtype=torch.int32, device=dev),
+            "lidx": torch.empty(total, dtype=torch.int16, device=dev),
+            "tile_w": torch.empty(total, dtype=torch.float32, device=dev),
+        }
+        mx = C.c_int32(0)
+        check(lib.sgp_tiles_finalize(_ptr(self.replay), _ptr(perm), N, d, T, S, _ptr(ws), ws_bytes, _ptr(t["seg_ptr"]),
+                                     _ptr(t["seg_row"]), _ptr(t["seg_ent"]), _ptr(t["tile_seg_ptr"]), _ptr(t["lidx"]),
+                                     _ptr(t["tile_w"]), C.byref(mx), st))
+        t["max_dict"] = int(mx.value)
+        self.tiles = t
+
+    def _tiles_view(self) -> TilesView:
+        t = self.tiles
+        return TilesView(self.N, self.M, t["S"], self.d, t["T"], t["max_dict"], 0, t["perm"].data_ptr(),
+                         t["tile_seg_ptr"].data_ptr(), t["seg_ptr"].data_ptr(), t["seg_row"].data_ptr(),
+                         t["seg_ent"].data_ptr(), t["lidx"].data_ptr(), t["tile_w"].data_ptr())
 
     def _build_csr(self) -> None:
         lib = _capi.lib()
@@ -224,10 +269,15 @@ class Lattice:
         values = torch.empty((self.M, L), dtype=torch.float32, device=self.device)
         if self.M == 0 or L == 0:
             return values
-        v = self._view()
         with torch.cuda.device(self.device):
-            check(_capi.lib().sgp_splat(C.byref(v), _ptr(src), src.stride(0), L, _ptr(values), mode,
-                                        _stream_ptr(self.device)))
+            if mode == _capi.MODE_TILES or (mode == _capi.MODE_AUTO and self.tiles is not None):
+                tv = self._tiles_view()
+                check(_capi.lib().sgp_splat_tiles(C.byref(tv), _ptr(src), src.stride(0), L, _ptr(values),
+                                                  _stream_ptr(self.device)))
+            else:
+                v = self._view()
+                check(_capi.lib().sgp_splat(C.byref(v), _ptr(src), src.stride(0), L, _ptr(values), mode,
+                                            _stream_ptr(self.device)))
         return values
 
     def blur(self, values: torch.Tensor, coeffs=None) -> torch.Tensor:
@@ -244,22 +294,30 @@ class Lattice:
                                        _stream_ptr(self.device)))
         return buf1 if where.value else buf0
 
-    def slice(self, values: torch.Tensor) -> torch.Tensor:
+    def slice(self, values: torch.Tensor, mode: int = _capi.MODE_AUTO) -> torch.Tensor:
         L = int(values.shape[1])
         out = torch.empty((self.N, L), dtype=torch.float32, device=self.device)
         if self.N == 0 or L == 0:
             return out
         values = values.contiguous()
-        v = self._view()
         with torch.cuda.device(self.device):
-            check(_capi.lib().sgp_slice(C.byref(v), _ptr(values), L, _ptr(out), out.stride(0),
-                                        _stream_ptr(self.device)))
+            if mode == _capi.MODE_TILES or (mode == _capi.MODE_AUTO and self.tiles is not None):
+                tv = self._tiles_view()
+                check(_capi.lib().sgp_slice_tiles(C.byref(tv), _ptr(values), L, _ptr(out), out.stride(0),
+                                                  _stream_ptr(self.device)))
+            else:
+                v = self._view()
+                check(_capi.lib().sgp_slice(C.byref(v), _ptr(values), L, _ptr(out), out.stride(0),
+                                            _stream_ptr(self.device)))
         return out
 
     # ---- the MVM ------------------------------------------------------------------------------------
     def mvm(self, src: torch.Tensor, out: Optional[torch.Tensor] = None, coeffs=None,
             mode: int = _capi.SGP_SPLAT_AUTO) -> torch.Tensor:
-        """``out[N, L] = slice(blur(splat(src[N, L])))`` on the built lattice."""
+        """``out[N, L] = slice(blur(splat(src[N, L])))`` on the built lattice.
+
+        ``mode``: 0 auto (locality tiles when built, else atomic scatter), 1 atomic scatter splat + direct slice,
+        2 gather splat in the reference's accumulation order (bit-exact, needs ``build_csr=True``), 3 tiles."""
         src = self._check_src(src)
         L = int(src.shape[1])
         c = self.coeffs if coeffs is None else _coeffs_np(coeffs)
@@ -272,8 +330,16 @@ class Lattice:
         buf0, buf1 = self._scratch(L)
         v = self._view()
         with torch.cuda.device(self.device):
-            check(_capi.lib().sgp_mvm(C.byref(v), _ptr(src), src.stride(0), L, _fp(c), c.shape[0], _ptr(out),
-                                      out.stride(0), _ptr(buf0), _ptr(buf1), mode, _stream_ptr(self.device)))
+            if mode == _capi.MODE_TILES or (mode == _capi.MODE_AUTO and self.tiles is not None):
+                if self.tiles is None:
+                    raise RuntimeError("tiles were not built for this lattice (build_tiles=False)")
+                tv = self._tiles_view()
+                check(_capi.lib().sgp_mvm_tiles(C.byref(v), C.byref(tv), _ptr(src), src.stride(0), L, _fp(c),
+                                                c.shape[0], _ptr(out), out.stride(0), _ptr(buf0), _ptr(buf1),
+                                                _stream_ptr(self.device)))
+            else:
+                check(_capi.lib().sgp_mvm(C.byref(v), _ptr(src), src.stride(0), L, _fp(c), c.shape[0], _ptr(out),
+                                          out.stride(0), _ptr(buf0), _ptr(buf1), mode, _stream_ptr(self.device)))
         return out
 
     def algorithmic_bytes(self, L: int) -> int:
@@ -294,14 +360,14 @@ def lattice_filter(src: torch.Tensor, ref: torch.Tensor, coeffs, *, device=None)
         raise TypeError("filter: float32 tensors required (reference CPU filter is fp32-only)")
     if src.is_cuda:
         dev = src.device
-        lat = Lattice(ref.to(dev), coeffs, build_csr=False, keep_structure=False)
+        lat = Lattice(ref.to(dev), coeffs, build_csr=False, build_tiles=False, keep_structure=False)
         return lat.mvm(src)
     if not torch.cuda.is_available():
         raise RuntimeError("filter: no CUDA device; this package has no CPU path")
     dev = torch.device(device if device is not None else "cuda")
     ref_d = ref.contiguous().pin_memory().to(dev, non_blocking=True)
     src_d = src.contiguous().pin_memory().to(dev, non_blocking=True)
-    lat = Lattice(ref_d, coeffs, build_csr=False, keep_structure=False)
+    lat = Lattice(ref_d, coeffs, build_csr=False, build_tiles=False, keep_structure=False)
     out_d = lat.mvm(src_d)
     out = torch.empty(out_d.shape, dtype=out_d.dtype, pin_memory=True)
     out.copy_(out_d, non_blocking=True)

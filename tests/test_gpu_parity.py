@@ -38,7 +38,7 @@ def _rel(a, b):
 def test_structure_and_values_match_oracle(sg, oracle, N, d, L, coeffs, dist):
     x, v = make_inputs(N, d, L, seed=N + d, dist=dist)
     O = oracle.OracleLattice(x.numpy(), coeffs)
-    lat = sg.Lattice(x.cuda(), coeffs)
+    lat = sg.Lattice(x.cuda(), coeffs, build_csr=True, build_tiles=True)
     assert lat.M == O.M
     assert np.array_equal(lat.scale.view(np.int32), O.scale.view(np.int32))
     assert np.array_equal(lat.greedy.cpu().numpy(), O.greedy)
@@ -56,9 +56,17 @@ def test_structure_and_values_match_oracle(sg, oracle, N, d, L, coeffs, dist):
     assert np.array_equal(bits(sp.cpu().numpy()), bits(sp_o))
     bl = lat.blur(sp)
     assert np.array_equal(bits(bl.cpu().numpy()), bits(bl_o))
-    out = lat.slice(bl)
+    out = lat.slice(bl, mode=1)
     assert np.array_equal(bits(out.cpu().numpy()), bits(out_o))
     assert np.array_equal(bits(lat.mvm(vd, mode=2).cpu().numpy()), bits(out_o))
+    # locality tiles: slice is the same arithmetic staged through shared memory (bit-exact on the same lattice
+    # values); splat sums per-tile partials, then one reduction per segment (1e-5 relative)
+    out_t = lat.slice(bl, mode=3)
+    assert np.array_equal(bits(out_t.cpu().numpy()), bits(out_o))
+    sp_t = lat.splat(vd, mode=3)
+    assert _rel(sp_t.cpu().numpy(), sp_o) < REL_TOL
+    assert _rel(lat.mvm(vd, mode=3).cpu().numpy(), out_o) < REL_TOL
+    assert _rel(lat.mvm(vd).cpu().numpy(), out_o) < REL_TOL
     # atomic scatter path: 1e-5 relative
     sp_a = lat.splat(vd, mode=1)
     assert _rel(sp_a.cpu().numpy(), sp_o) < REL_TOL
