@@ -20,7 +20,8 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_columns", "shard_points", "broadcast_lattice_arrays", "broadcast_lattice", "lattice_arrays"]
+__all__ = ["shard_columns", "shard_points", "broadcast_lattice_arrays", "broadcast_lattice", "lattice_arrays",
+           "all_gather_columns", "allreduce_lattice_values"]
 
 
 def shard_columns(L: int, world: int, rank: int) -> Tuple[int, int]:
@@ -70,7 +71,8 @@ def broadcast_lattice_arrays(arrays: Optional[dict], meta: Optional[dict], src: 
         else:
             t = torch.empty(shapes[name], dtype=dtype, device=device)
         if t.numel() > 0:
-            dist.broadcast(t, src=src, group=group)
+            # as bytes: neither NCCL nor gloo has an int16 type, and a broadcast moves bits anyway
+            dist.broadcast(t.view(-1).view(torch.uint8), src=src, group=group)
         out[name] = t
     return out, meta
 
@@ -89,3 +91,29 @@ def broadcast_lattice(lat, src: int = 0, device=None, group=None, build_csr: boo
     if rank == src:
         return lat
     return Lattice.from_arrays(meta["coeffs"], arrays["replay"], arrays["keys"], arrays["nbr"], build_csr=build_csr)
+
+
+def all_gather_columns(mine: torch.Tensor, L: int, group=None) -> torch.Tensor:
+    """Reassemble ``[N, L]`` from per-rank column blocks laid out by ``shard_columns`` (ragged blocks allowed).
+
+    Column-sharded MVMs need this only when the caller wants the full block on every rank; CG keeps its RHS
+    column-sharded and all-reduces ``L`` dot products instead."""
+    world = dist.get_world_size(group)
+    N = mine.shape[0]
+    widths = [hi - lo for lo, hi in (shard_columns(L, world, r) for r in range(world))]
+    wmax = max(widths) if widths else 0
+    if wmax == 0:
+        return mine.new_empty((N, 0))
+    pad = mine.new_zeros((N, wmax))
+    pad[:, : mine.shape[1]] = mine
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad.contiguous(), group=group)
+    return torch.cat([p[:, :w] for p, w in zip(parts, widths)], dim=1)
+
+
+def allreduce_lattice_values(values: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the per-rank splatted lattice values ``[M, L]`` in place (point sharding: the one exchange step of the
+    MVM, between splat and blur; ``M*L*4`` bytes over NVLink with the NCCL backend)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(values, op=dist.ReduceOp.SUM, group=group)
+    return values
