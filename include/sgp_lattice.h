@@ -209,6 +209,25 @@ int sgp_mvm_tiles(const sgp_lattice_view *lat, const sgp_tiles_view *tiles, cons
                   int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1,
                   sgp_stream_t stream);
 
+/* ---- stage 5: lengthscale-gradient pass (bilateral_kernel.py:97-124) -------------------
+ *
+ * The reference filters one N x 2L(1+d) block [g | g(x)x | v | v(x)x] with the derivative stencil and
+ * contracts it into grad_x (:113-122).  Channels are independent under the filter, so they are grouped
+ * per RHS column l -- block(l) = [g_l, g_l x_1..x_d, v_l, v_l x_1..x_d], 2(1+d) channels -- and
+ * processed nl columns at a time: sgp_grad_pack -> sgp_mvm (derivative stencil, lattice built with
+ * that stencil's variance) -> sgp_grad_contract.  See simplex-gp_b200/csrc/sgp_grad.cu. */
+int sgp_grad_channels(int d, int nl); /* 2(1+d)*nl */
+/* packed[N, ldp] <- blocks of columns [l0, l0+nl) of g[N, ldg], v[N, ldv] with x[N, ldx] (all device) */
+int sgp_grad_pack(const float *g, int64_t ldg, const float *v, int64_t ldv, const float *x, int64_t ldx,
+                  int64_t N, int d, int l0, int nl, float *packed, int64_t ldp, sgp_stream_t stream);
+/* grad_x[N, ldgx] (+)= sum over the chunk's columns of the reference expression (:122); first != 0
+ * starts the sum at zero, last != 0 applies the factor -2.  Chunks must be visited in increasing l0.
+ * grad_src (device [N, ldgs], may be NULL) receives the filtered g columns (:123). */
+int sgp_grad_contract(const float *filtered, int64_t ldp, const float *g, int64_t ldg, const float *v,
+                      int64_t ldv, const float *x, int64_t ldx, int64_t N, int d, int l0, int nl,
+                      int first, int last, float *grad_x, int64_t ldgx, float *grad_src, int64_t ldgs,
+                      sgp_stream_t stream);
+
 /* Test hook: number of fp32 bit patterns a in [lo, lo+count) for which the division-by-constant
  * used inside sgp_slice differs from the IEEE division a / sgp_slice_divisor(d).  Must be 0. */
 int sgp_debug_division_mismatches(int d, uint32_t lo, uint32_t count, unsigned long long *mismatches_dev,

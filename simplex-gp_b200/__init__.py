@@ -9,6 +9,9 @@ The directory name contains a hyphen, so the importable name is ``simplex_gp_b20
 at the repository root).
 """
 from .coeffs import DiscretizedKernelFN, Matern, get_coeffs, matern, rbf
+from .function import LatticeCache, LatticeFilterGeneral, lattice_cache, lattice_filter_grad
+from .kernels import (BilateralKernel, LatticeAccelerated, MaternLattice, RBFLattice, RectangularLazyLattice,
+                      SquareLazyLattice)
 from .lattice import Lattice, lattice_filter, scale_factors, slice_divisor, stencil_variance
 
 filter = lattice_filter  # the reference's operator name (cpp/lattice.cpp:14-16)
@@ -16,4 +19,7 @@ filter = lattice_filter  # the reference's operator name (cpp/lattice.cpp:14-16)
 __all__ = [
     "Lattice", "lattice_filter", "filter", "stencil_variance", "scale_factors", "slice_divisor",
     "get_coeffs", "DiscretizedKernelFN", "rbf", "matern", "Matern",
+    "LatticeFilterGeneral", "LatticeCache", "lattice_cache", "lattice_filter_grad",
+    "RBFLattice", "MaternLattice", "BilateralKernel", "LatticeAccelerated", "SquareLazyLattice",
+    "RectangularLazyLattice",
 ]

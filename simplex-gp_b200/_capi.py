@@ -24,7 +24,7 @@ SYMBOLS = [
     "sgp_count_points", "sgp_number_points", "sgp_build_neighbours", "sgp_csr_workspace_bytes",
     "sgp_build_csr", "sgp_splat", "sgp_blur", "sgp_slice", "sgp_mvm", "sgp_debug_division_mismatches",
     "sgp_tiles_workspace_bytes", "sgp_tiles_prepare", "sgp_tiles_finalize", "sgp_splat_tiles", "sgp_slice_tiles",
-    "sgp_mvm_tiles",
+    "sgp_mvm_tiles", "sgp_grad_channels", "sgp_grad_pack", "sgp_grad_contract",
 ]
 
 
@@ -136,6 +136,12 @@ def lib() -> C.CDLL:
     L.sgp_slice_tiles.argtypes = [pt, vp, i32, vp, i64, vp]
     L.sgp_mvm_tiles.restype = i32
     L.sgp_mvm_tiles.argtypes = [pv, pt, vp, i64, i32, fp, i32, vp, i64, vp, vp, vp]
+    L.sgp_grad_channels.restype = i32
+    L.sgp_grad_channels.argtypes = [i32, i32]
+    L.sgp_grad_pack.restype = i32
+    L.sgp_grad_pack.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, vp, i64, vp]
+    L.sgp_grad_contract.restype = i32
+    L.sgp_grad_contract.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, i32, i32, vp, i64, vp, i64, vp]
     L.sgp_debug_division_mismatches.restype = i32
     L.sgp_debug_division_mismatches.argtypes = [i32, C.c_uint32, C.c_uint32, vp, vp]
     if L.sgp_abi_version() != 1:

