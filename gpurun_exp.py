@@ -1,4 +1,4 @@
-import sys, time, torch, numpy as np, ctypes as C
+import sys, time, torch, numpy as np, ctypes as C, os
 sys.path.insert(0, '/root/repo')
 import simplex_gp_b200 as sg
 from simplex_gp_b200 import _capi
@@ -7,41 +7,25 @@ torch.manual_seed(0)
 N,d,L=1_000_000,8,16
 x=torch.randn(N,d,device='cuda'); v=torch.randn(N,L,device='cuda')
 c=[0.34608543,1,0.34608543]
-def stages(lat, v, mode, reps=20):
-    lib=_capi.lib(); view=lat._view(); buf0,buf1=lat._scratch(L); cnp=lat.coeffs; st=_stream_ptr(lat.device)
-    out=torch.empty(N,L,device='cuda'); where=C.c_int(0)
-    ev=[torch.cuda.Event(enable_timing=True) for _ in range(4)]; acc=[0,0,0]
-    for i in range(reps+3):
-        ev[0].record(); _capi.check(lib.sgp_splat(C.byref(view), _ptr(v), v.stride(0), L, _ptr(buf0), mode, st))
-        ev[1].record(); _capi.check(lib.sgp_blur(C.byref(view), _fp(cnp), 3, L, _ptr(buf0), _ptr(buf1), C.byref(where), st))
-        ev[2].record(); _capi.check(lib.sgp_slice(C.byref(view), _ptr(buf1 if where.value else buf0), L, _ptr(out), out.stride(0), st))
-        ev[3].record(); torch.cuda.synchronize()
-        if i>=3:
-            for k in range(3): acc[k]+=ev[k].elapsed_time(ev[k+1])
-    return [a/reps*1000 for a in acc]
-def stages_tiles(lat, v, reps=20):
-    lib=_capi.lib(); view=lat._view(); tv=lat._tiles_view(); buf0,buf1=lat._scratch(L); cnp=lat.coeffs; st=_stream_ptr(lat.device)
-    out=torch.empty(N,L,device='cuda'); where=C.c_int(0)
-    ev=[torch.cuda.Event(enable_timing=True) for _ in range(4)]; acc=[0,0,0]
-    for i in range(reps+3):
-        ev[0].record(); _capi.check(lib.sgp_splat_tiles(C.byref(tv), _ptr(v), v.stride(0), L, _ptr(buf0), st))
-        ev[1].record(); _capi.check(lib.sgp_blur(C.byref(view), _fp(cnp), 3, L, _ptr(buf0), _ptr(buf1), C.byref(where), st))
-        ev[2].record(); _capi.check(lib.sgp_slice_tiles(C.byref(tv), _ptr(buf1 if where.value else buf0), L, _ptr(out), out.stride(0), st))
-        ev[3].record(); torch.cuda.synchronize()
-        if i>=3:
-            for k in range(3): acc[k]+=ev[k].elapsed_time(ev[k+1])
-    return [a/reps*1000 for a in acc]
-import time
-for T in (128,256,512):
-    torch.cuda.synchronize(); t0=time.time(); lat=sg.Lattice(x,c,tile_points=T); torch.cuda.synchronize(); bt=time.time()-t0
-    print('T',T,'build s',bt,'S',lat.tiles['S'],'S/pv',lat.tiles['S']/(N*(d+1)),'max_dict',lat.tiles['max_dict'],'tiles: splat/blur/slice us', stages_tiles(lat,v))
-print('atomic', stages(lat,v,1))
-sys.exit(0)
-# sort points lexicographically by greedy
-g=lat.greedy.cpu().numpy().astype(np.int32)
-order=torch.from_numpy(np.lexsort(g[:, ::-1].T)).cuda()
-xs=x[order].contiguous(); vs=v[order].contiguous()
-lat2=sg.Lattice(xs,c)
-print('sorted pts: splat/blur/slice us atomic', stages(lat2,vs,1), 'gather', stages(lat2,vs,2))
-cnt=torch.bincount(lat.offsets.reshape(-1).long(), minlength=lat.M)
-print('max row', cnt.max().item())
+def timeit(fn, reps=20, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1)/reps*1000
+for ga, gr in ((3,512),(3,384),(2,512),(4,1500),(5,1600),(1,512)):
+    torch.cuda.synchronize(); t0=time.time()
+    lat=sg.Lattice(x,c,group_axes=ga,group_rows=gr); torch.cuda.synchronize(); bt=time.time()-t0
+    if lat.groups is None: print('no groups', ga, gr); continue
+    gl=lat.groups['list']
+    lib=_capi.lib(); buf0,buf1=lat._scratch(L); st=_stream_ptr(lat.device); where=C.c_int(0); arr=lat.groups['array']; cnp=lat.coeffs
+    view=lat._view()
+    t_g=timeit(lambda: _capi.check(lib.sgp_blur_groups(arr,len(arr),lat.M,1,_fp(cnp),3,L,_ptr(buf0),_ptr(buf1),C.byref(where),st)))
+    t_a=timeit(lambda: _capi.check(lib.sgp_blur(C.byref(view),_fp(cnp),3,L,_ptr(buf0),_ptr(buf1),C.byref(where),st)))
+    out=torch.empty(N,L,device='cuda')
+    t_mg=timeit(lambda: lat.mvm(v,out=out,mode=1,blur='groups'))
+    t_ma=timeit(lambda: lat.mvm(v,out=out,mode=1,blur='axis'))
+    print(f'axes {ga} rows {gr}: build {bt*1e3:.1f} ms groups', [(g['j0'],g['j1'],g['max_class'],g['rows_cap'],g['n_batches']) for g in gl],
+          f'blur groups {t_g:.1f} us, axis {t_a:.1f} us; mvm groups {t_mg:.1f} us, axis {t_ma:.1f} us')

@@ -209,6 +209,47 @@ int sgp_mvm_tiles(const sgp_lattice_view *lat, const sgp_tiles_view *tiles, cons
                   int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1,
                   sgp_stream_t stream);
 
+/* ---- blur groups: several axes per launch, staged through shared memory ------------------
+ *
+ * For a range of consecutive axes [j0, j1) the lattice points split into classes that the passes of those
+ * axes never leave; a CTA holding whole classes in shared memory runs all j1-j0 passes on chip (see
+ * simplex-gp_b200/csrc/sgp_groups.cu).  A lattice's axes 0..d are covered by a chain of groups; stage g
+ * gathers its input rows from stage g-1's output order (src) and writes its own order contiguously.
+ * The arithmetic per pass is that of sgp_blur, so values are bit-identical to the per-axis path.  The slice
+ * after the last stage reads through a replay table remapped to that stage's order (sgp_remap_replay). */
+typedef struct sgp_blur_group {
+    int32_t j0, j1;              /* axis range [j0, j1) */
+    int32_t rows_cap;            /* largest number of rows of one CTA batch (sizes the shared memory) */
+    int32_t reserved;
+    int64_t n_batches;
+    const uint32_t *batch_begin; /* device [n_batches+1] positions */
+    const int32_t *src;          /* device [M] input row of every position */
+    const uint16_t *lnb;         /* device [M, j1-j0, 2r] batch-local neighbour positions, 0xFFFF = absent */
+} sgp_blur_group;
+
+size_t sgp_group_workspace_bytes(int64_t M);
+/* Sort the lattice points by class of the axis range: order[p] (device [M]) = lattice index at position p,
+ * pos = its inverse, class_start[p] = first position of p's class.  Synchronises; *max_class_out = largest class. */
+int sgp_group_prepare(const int16_t *keys, int64_t M, int d, int j0, int j1, uint32_t *order, uint32_t *pos,
+                      uint32_t *class_start, void *workspace, size_t workspace_bytes, int64_t *max_class_out,
+                      sgp_stream_t stream);
+/* Cut the sorted positions into CTA batches (batch b owns the classes starting in [b*window, (b+1)*window),
+ * n_batches = ceil(M/window), so a batch has fewer than window + max_class rows) and fill the group tables.
+ * prev_pos: pos of the previous stage (NULL for the first stage, whose input is in lattice-index order).
+ * Synchronises; *max_rows_out = rows of the largest batch. */
+int sgp_group_finalize(const int32_t *nbr, int64_t M, int order, int j0, int j1, const uint32_t *order_of,
+                       const uint32_t *pos, const uint32_t *class_start, const uint32_t *prev_pos,
+                       int64_t window, int64_t n_batches, uint32_t *batch_begin, int32_t *src, uint16_t *lnb,
+                       void *workspace, size_t workspace_bytes, int32_t *max_rows_out, sgp_stream_t stream);
+/* replay_out[q] = {pos[replay[q].index], replay[q].weight bits}, q < total */
+int sgp_remap_replay(const int32_t *replay, int64_t total, const uint32_t *pos, int32_t *replay_out,
+                     sgp_stream_t stream);
+/* channels staged per CTA for L channels */
+int sgp_blur_groups_channel_block(int L);
+/* run the chain: buf0 (lattice-index order) -> ... ; *result_in_buf1 tells where the last stage wrote */
+int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64_t M, int order, const float *coeffs,
+                    int k, int L, float *buf0, float *buf1, int *result_in_buf1, sgp_stream_t stream);
+
 /* ---- stage 5: lengthscale-gradient pass (bilateral_kernel.py:97-124) -------------------
  *
  * The reference filters one N x 2L(1+d) block [g | g(x)x | v | v(x)x] with the derivative stencil and

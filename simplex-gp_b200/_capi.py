@@ -25,6 +25,8 @@ SYMBOLS = [
     "sgp_build_csr", "sgp_splat", "sgp_blur", "sgp_slice", "sgp_mvm", "sgp_debug_division_mismatches",
     "sgp_tiles_workspace_bytes", "sgp_tiles_prepare", "sgp_tiles_finalize", "sgp_splat_tiles", "sgp_slice_tiles",
     "sgp_mvm_tiles", "sgp_grad_channels", "sgp_grad_pack", "sgp_grad_contract",
+    "sgp_group_workspace_bytes", "sgp_group_prepare", "sgp_group_finalize", "sgp_remap_replay",
+    "sgp_blur_groups_channel_block", "sgp_blur_groups",
 ]
 
 
@@ -61,6 +63,21 @@ class TilesView(C.Structure):
         ("seg_ent", C.c_void_p),
         ("lidx", C.c_void_p),
         ("tile_w", C.c_void_p),
+    ]
+
+
+class BlurGroup(C.Structure):
+    """Mirror of ``struct sgp_blur_group``."""
+
+    _fields_ = [
+        ("j0", C.c_int32),
+        ("j1", C.c_int32),
+        ("rows_cap", C.c_int32),
+        ("reserved", C.c_int32),
+        ("n_batches", C.c_int64),
+        ("batch_begin", C.c_void_p),
+        ("src", C.c_void_p),
+        ("lnb", C.c_void_p),
     ]
 
 
@@ -142,6 +159,19 @@ def lib() -> C.CDLL:
     L.sgp_grad_pack.argtypes = [vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, vp, i64, vp]
     L.sgp_grad_contract.restype = i32
     L.sgp_grad_contract.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, i32, i32, vp, i64, vp, i64, vp]
+    L.sgp_group_workspace_bytes.restype = sz
+    L.sgp_group_workspace_bytes.argtypes = [i64]
+    L.sgp_group_prepare.restype = i32
+    L.sgp_group_prepare.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, sz, C.POINTER(i64), vp]
+    L.sgp_group_finalize.restype = i32
+    L.sgp_group_finalize.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, sz,
+                                     C.POINTER(C.c_int32), vp]
+    L.sgp_remap_replay.restype = i32
+    L.sgp_remap_replay.argtypes = [vp, i64, vp, vp, vp]
+    L.sgp_blur_groups_channel_block.restype = i32
+    L.sgp_blur_groups_channel_block.argtypes = [i32]
+    L.sgp_blur_groups.restype = i32
+    L.sgp_blur_groups.argtypes = [C.POINTER(BlurGroup), i32, i64, i32, fp, i32, i32, vp, vp, C.POINTER(C.c_int), vp]
     L.sgp_debug_division_mismatches.restype = i32
     L.sgp_debug_division_mismatches.argtypes = [i32, C.c_uint32, C.c_uint32, vp, vp]
     if L.sgp_abi_version() != 1:

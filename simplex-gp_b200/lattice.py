@@ -82,6 +82,7 @@ class Lattice:
     """
 
     def __init__(self, x: torch.Tensor, coeffs, *, build_csr: bool = False, build_tiles: bool = False,
+                 build_groups: bool = True, group_axes: int = 3, group_rows: int = 512,
                  tile_points: int = 256, keep_structure: bool = True, hash_capacity: Optional[int] = None):
         if x.dim() != 2:
             raise ValueError(f"x must be [N, d], got {tuple(x.shape)}")
@@ -114,6 +115,7 @@ class Lattice:
             self.csr_ptr = None
             self.csr_ent = None
             self.tiles = None
+            self.groups = None
             self.hash_capacity = 0
             if N > 0:
                 check(lib.sgp_build_points(_ptr(x), N, d, x.stride(0), _fp(self.scale), _ptr(self.greedy),
@@ -142,6 +144,8 @@ class Lattice:
                     self._build_csr()
                 if build_tiles:
                     self._build_tiles(tile_points)
+                if build_groups and r >= 1 and self.M > 0:
+                    self._build_groups(group_axes, group_rows)
             if not keep_structure:
                 self.greedy = None
                 self.rank = None
@@ -149,7 +153,8 @@ class Lattice:
 
     @classmethod
     def from_arrays(cls, coeffs, replay: torch.Tensor, keys: torch.Tensor, nbr: torch.Tensor,
-                    build_csr: bool = False, build_tiles: bool = False, tile_points: int = 256) -> "Lattice":
+                    build_csr: bool = False, build_tiles: bool = False, tile_points: int = 256,
+                    build_groups: bool = True, group_axes: int = 3, group_rows: int = 512) -> "Lattice":
         """Wrap lattice arrays that were built elsewhere (e.g. received by ``distributed.broadcast_lattice``)."""
         self = object.__new__(cls)
         self.device = replay.device
@@ -165,6 +170,7 @@ class Lattice:
         self.greedy = self.rank = None
         self.csr_ptr = self.csr_ent = None
         self.tiles = None
+        self.groups = None
         self.hash_capacity = 0
         self._bufs = {}
         if self.N > 0 and self.M > 0:
@@ -173,7 +179,63 @@ class Lattice:
                     self._build_csr()
                 if build_tiles:
                     self._build_tiles(tile_points)
+                if build_groups and self.order >= 1:
+                    self._build_groups(group_axes, group_rows)
         return self
+
+    def _build_groups(self, group_axes: int = 3, group_rows: int = 512) -> None:
+        """Blur groups (csrc/sgp_groups.cu): cover axes 0..d with ranges of up to ``group_axes`` consecutive axes whose
+        classes fit ``group_rows`` rows of one CTA.  A range is shortened until its largest class fits; if even a
+        single axis does not fit (a long 1-D line), no groups are built and the per-axis blur is used."""
+        lib = _capi.lib()
+        dev, d, M, r = self.device, self.d, self.M, self.order
+        CB = int(lib.sgp_blur_groups_channel_block(16))
+        rows_limit = min(int(group_rows), (200 * 1024) // (2 * CB * 4), 0xFFFF - 1)
+        st = _stream_ptr(dev)
+        ws_bytes = int(lib.sgp_group_workspace_bytes(M))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        groups, keep = [], []
+        prev_pos = None
+        j0 = 0
+        while j0 <= d:
+            j1 = min(j0 + max(1, int(group_axes)), d + 1)
+            while True:
+                order_of = torch.empty(M, dtype=torch.int32, device=dev)
+                pos = torch.empty(M, dtype=torch.int32, device=dev)
+                cstart = torch.empty(M, dtype=torch.int32, device=dev)
+                mx = C.c_int64(0)
+                check(lib.sgp_group_prepare(_ptr(self.keys), M, d, j0, j1, _ptr(order_of), _ptr(pos), _ptr(cstart),
+                                            _ptr(ws), ws_bytes, C.byref(mx), st))
+                if mx.value <= rows_limit or j1 - j0 == 1:
+                    break
+                j1 -= 1
+            if mx.value > rows_limit:
+                self.groups = None
+                return
+            window = max(1, rows_limit - int(mx.value) + 1)
+            n_batches = (M + window - 1) // window
+            g = {
+                "j0": j0, "j1": j1, "n_batches": n_batches, "max_class": int(mx.value),
+                "batch_begin": torch.empty(n_batches + 1, dtype=torch.int32, device=dev),
+                "src": torch.empty(M, dtype=torch.int32, device=dev),
+                "lnb": torch.empty((M, j1 - j0, 2 * r), dtype=torch.int16, device=dev),
+            }
+            rows = C.c_int32(0)
+            check(lib.sgp_group_finalize(_ptr(self.nbr), M, r, j0, j1, _ptr(order_of), _ptr(pos), _ptr(cstart),
+                                         _ptr(prev_pos), window, n_batches, _ptr(g["batch_begin"]), _ptr(g["src"]),
+                                         _ptr(g["lnb"]), _ptr(ws), ws_bytes, C.byref(rows), st))
+            g["rows_cap"] = int(rows.value)
+            groups.append(g)
+            prev_pos = pos
+            keep.append(pos)
+            j0 = j1
+        replay_out = torch.empty_like(self.replay)
+        check(lib.sgp_remap_replay(_ptr(self.replay), self.N * (d + 1), _ptr(prev_pos), _ptr(replay_out), st))
+        arr = (_capi.BlurGroup * len(groups))()
+        for k, g in enumerate(groups):
+            arr[k] = _capi.BlurGroup(g["j0"], g["j1"], g["rows_cap"], 0, g["n_batches"], g["batch_begin"].data_ptr(),
+                                     g["src"].data_ptr(), g["lnb"].data_ptr())
+        self.groups = {"list": groups, "array": arr, "replay_out": replay_out, "final_pos": prev_pos}
 
     def _build_tiles(self, tile_points: int = 256) -> None:
         """Locality tiles for the shared-memory staged splat / slice (csrc/sgp_tiles.cu)."""
@@ -280,7 +342,9 @@ class Lattice:
                                             _stream_ptr(self.device)))
         return values
 
-    def blur(self, values: torch.Tensor, coeffs=None) -> torch.Tensor:
+    def blur(self, values: torch.Tensor, coeffs=None, groups: bool = False) -> torch.Tensor:
+        """Blurred lattice values in lattice-index order.  ``groups=True`` runs the shared-memory group chain (whose
+        output order is its last stage's) and permutes the result back, for comparison with the per-axis path."""
         c = self.coeffs if coeffs is None else _coeffs_np(coeffs)
         L = int(values.shape[1])
         if self.M == 0 or L == 0:
@@ -290,6 +354,14 @@ class Lattice:
         v = self._view()
         where = C.c_int(0)
         with torch.cuda.device(self.device):
+            if groups:
+                if self.groups is None:
+                    raise RuntimeError("blur groups were not built for this lattice")
+                arr = self.groups["array"]
+                check(_capi.lib().sgp_blur_groups(arr, len(arr), self.M, self.order, _fp(c), c.shape[0], L, _ptr(buf0),
+                                                  _ptr(buf1), C.byref(where), _stream_ptr(self.device)))
+                res = buf1 if where.value else buf0
+                return res[self.groups["final_pos"].long()]
             check(_capi.lib().sgp_blur(C.byref(v), _fp(c), c.shape[0], L, _ptr(buf0), _ptr(buf1), C.byref(where),
                                        _stream_ptr(self.device)))
         return buf1 if where.value else buf0
@@ -313,11 +385,13 @@ class Lattice:
 
     # ---- the MVM ------------------------------------------------------------------------------------
     def mvm(self, src: torch.Tensor, out: Optional[torch.Tensor] = None, coeffs=None,
-            mode: int = _capi.SGP_SPLAT_AUTO) -> torch.Tensor:
+            mode: int = _capi.SGP_SPLAT_AUTO, blur: str = "auto") -> torch.Tensor:
         """``out[N, L] = slice(blur(splat(src[N, L])))`` on the built lattice.
 
         ``mode``: 0 auto (locality tiles when built, else atomic scatter), 1 atomic scatter splat + direct slice,
-        2 gather splat in the reference's accumulation order (bit-exact, needs ``build_csr=True``), 3 tiles."""
+        2 gather splat in the reference's accumulation order (bit-exact, needs ``build_csr=True``), 3 tiles.
+        ``blur``: "groups" (several axes per launch through shared memory), "axis" (one launch per axis) or "auto"
+        (groups when they were built and the splat/slice path is not the tile path)."""
         src = self._check_src(src)
         L = int(src.shape[1])
         c = self.coeffs if coeffs is None else _coeffs_np(coeffs)
@@ -329,8 +403,24 @@ class Lattice:
             return out
         buf0, buf1 = self._scratch(L)
         v = self._view()
+        tiles = mode == _capi.MODE_TILES or (mode == _capi.MODE_AUTO and self.tiles is not None)
+        use_groups = blur == "groups" or (blur == "auto" and self.groups is not None and not tiles)
+        if use_groups:
+            if self.groups is None or tiles:
+                raise RuntimeError("blur groups are not available on this path")
+            lib, st = _capi.lib(), _stream_ptr(self.device)
+            where = C.c_int(0)
+            arr = self.groups["array"]
+            with torch.cuda.device(self.device):
+                check(lib.sgp_splat(C.byref(v), _ptr(src), src.stride(0), L, _ptr(buf0), mode, st))
+                check(lib.sgp_blur_groups(arr, len(arr), self.M, self.order, _fp(c), c.shape[0], L, _ptr(buf0),
+                                          _ptr(buf1), C.byref(where), st))
+                v2 = self._view()
+                v2.replay = self.groups["replay_out"].data_ptr()
+                check(lib.sgp_slice(C.byref(v2), _ptr(buf1 if where.value else buf0), L, _ptr(out), out.stride(0), st))
+            return out
         with torch.cuda.device(self.device):
-            if mode == _capi.MODE_TILES or (mode == _capi.MODE_AUTO and self.tiles is not None):
+            if tiles:
                 if self.tiles is None:
                     raise RuntimeError("tiles were not built for this lattice (build_tiles=False)")
                 tv = self._tiles_view()
@@ -360,14 +450,14 @@ def lattice_filter(src: torch.Tensor, ref: torch.Tensor, coeffs, *, device=None)
         raise TypeError("filter: float32 tensors required (reference CPU filter is fp32-only)")
     if src.is_cuda:
         dev = src.device
-        lat = Lattice(ref.to(dev), coeffs, build_csr=False, build_tiles=False, keep_structure=False)
+        lat = Lattice(ref.to(dev), coeffs, build_csr=False, build_tiles=False, build_groups=False, keep_structure=False)
         return lat.mvm(src)
     if not torch.cuda.is_available():
         raise RuntimeError("filter: no CUDA device; this package has no CPU path")
     dev = torch.device(device if device is not None else "cuda")
     ref_d = ref.contiguous().pin_memory().to(dev, non_blocking=True)
     src_d = src.contiguous().pin_memory().to(dev, non_blocking=True)
-    lat = Lattice(ref_d, coeffs, build_csr=False, build_tiles=False, keep_structure=False)
+    lat = Lattice(ref_d, coeffs, build_csr=False, build_tiles=False, build_groups=False, keep_structure=False)
     out_d = lat.mvm(src_d)
     out = torch.empty(out_d.shape, dtype=out_d.dtype, pin_memory=True)
     out.copy_(out_d, non_blocking=True)

@@ -59,6 +59,13 @@ def test_structure_and_values_match_oracle(sg, oracle, N, d, L, coeffs, dist):
     out = lat.slice(bl, mode=1)
     assert np.array_equal(bits(out.cpu().numpy()), bits(out_o))
     assert np.array_equal(bits(lat.mvm(vd, mode=2).cpu().numpy()), bits(out_o))
+    # blur groups (several axes per launch through shared memory): same arithmetic per pass, bit-exact
+    if lat.order > 0:
+        assert lat.groups is not None
+        bl_g = lat.blur(sp, groups=True)
+        assert np.array_equal(bits(bl_g.cpu().numpy()), bits(bl_o))
+        assert np.array_equal(bits(lat.mvm(vd, mode=2, blur="groups").cpu().numpy()), bits(out_o))
+        assert np.array_equal(bits(lat.mvm(vd, mode=2, blur="axis").cpu().numpy()), bits(out_o))
     # locality tiles: slice is the same arithmetic staged through shared memory (bit-exact on the same lattice
     # values); splat sums per-tile partials, then one reduction per segment (1e-5 relative)
     out_t = lat.slice(bl, mode=3)
@@ -72,6 +79,34 @@ def test_structure_and_values_match_oracle(sg, oracle, N, d, L, coeffs, dist):
     assert _rel(sp_a.cpu().numpy(), sp_o) < REL_TOL
     out_a = lat.mvm(vd, mode=1)
     assert _rel(out_a.cpu().numpy(), out_o) < REL_TOL
+
+
+@pytest.mark.parametrize("group_axes,group_rows", [(1, 512), (2, 64), (4, 512), (9, 1500), (3, 16)])
+def test_blur_group_partitions(sg, oracle, group_axes, group_rows):
+    """Any partition of the axes into groups gives the per-axis result bit for bit; ranges whose classes do not fit
+    are shortened, and a lattice whose single-axis lines do not fit falls back to the per-axis blur."""
+    x, v = make_inputs(6000, 8, 8, seed=41)
+    O = oracle.OracleLattice(x.numpy(), RBF2)
+    out_o, sp_o, bl_o = O.mvm(v.numpy(), return_intermediates=True)
+    lat = sg.Lattice(x.cuda(), RBF2, build_csr=True, group_axes=group_axes, group_rows=group_rows)
+    sp = lat.splat(v.cuda(), mode=2)
+    if lat.groups is None:
+        assert group_rows == 16   # lines longer than 16 lattice points exist here
+        assert np.array_equal(bits(lat.mvm(v.cuda(), mode=2).cpu().numpy()), bits(out_o))
+        return
+    covered = [(g["j0"], g["j1"]) for g in lat.groups["list"]]
+    assert covered[0][0] == 0 and covered[-1][1] == 9 and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    assert all(g["rows_cap"] <= group_rows for g in lat.groups["list"])
+    assert np.array_equal(bits(lat.blur(sp, groups=True).cpu().numpy()), bits(bl_o))
+    assert np.array_equal(bits(lat.mvm(v.cuda(), mode=2, blur="groups").cpu().numpy()), bits(out_o))
+
+
+def test_long_line_falls_back_to_axis_blur(sg, oracle):
+    x, v = make_inputs(20000, 1, 2, seed=42, scale=200.0)   # d = 1: one lattice line holds every point
+    lat = sg.Lattice(x.cuda(), RBF1, build_csr=True)
+    O = oracle.OracleLattice(x.numpy(), RBF1)
+    assert lat.M == O.M and lat.M > 2000 and lat.groups is None
+    assert np.array_equal(bits(lat.mvm(v.cuda(), mode=2).cpu().numpy()), bits(O.mvm(v.numpy())))
 
 
 def test_filter_dropin_cpu_and_cuda_inputs(sg, oracle):
