@@ -15,17 +15,18 @@ def timeit(fn, reps=20, warm=3):
     for _ in range(reps): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1)/reps*1000
-for ga, gr in ((3,512),(3,384),(2,512),(4,1500),(5,1600),(1,512)):
-    torch.cuda.synchronize(); t0=time.time()
-    lat=sg.Lattice(x,c,group_axes=ga,group_rows=gr); torch.cuda.synchronize(); bt=time.time()-t0
-    if lat.groups is None: print('no groups', ga, gr); continue
-    gl=lat.groups['list']
-    lib=_capi.lib(); buf0,buf1=lat._scratch(L); st=_stream_ptr(lat.device); where=C.c_int(0); arr=lat.groups['array']; cnp=lat.coeffs
-    view=lat._view()
-    t_g=timeit(lambda: _capi.check(lib.sgp_blur_groups(arr,len(arr),lat.M,1,_fp(cnp),3,L,_ptr(buf0),_ptr(buf1),C.byref(where),st)))
-    t_a=timeit(lambda: _capi.check(lib.sgp_blur(C.byref(view),_fp(cnp),3,L,_ptr(buf0),_ptr(buf1),C.byref(where),st)))
-    out=torch.empty(N,L,device='cuda')
-    t_mg=timeit(lambda: lat.mvm(v,out=out,mode=1,blur='groups'))
-    t_ma=timeit(lambda: lat.mvm(v,out=out,mode=1,blur='axis'))
-    print(f'axes {ga} rows {gr}: build {bt*1e3:.1f} ms groups', [(g['j0'],g['j1'],g['max_class'],g['rows_cap'],g['n_batches']) for g in gl],
-          f'blur groups {t_g:.1f} us, axis {t_a:.1f} us; mvm groups {t_mg:.1f} us, axis {t_ma:.1f} us')
+torch.cuda.synchronize(); t0=time.time()
+lat=sg.Lattice(x,c); torch.cuda.synchronize(); print('build ms', (time.time()-t0)*1e3)
+t0=time.time(); lat=sg.Lattice(x,c); torch.cuda.synchronize(); print('build ms (2nd)', (time.time()-t0)*1e3)
+lib=_capi.lib(); buf0,buf1=lat._scratch(L); st=_stream_ptr(lat.device); where=C.c_int(0); arr=lat.groups['array']; cnp=lat.coeffs
+out=torch.empty(N,L,device='cuda')
+for srt in (False, True):
+    for ex in (True, False):
+        vi = lat._view(lat.sorted['replay'], lat.sorted['perm'], ex) if srt else lat._view(exact=ex)
+        vo = lat._view(lat.sorted['replay_out'], lat.sorted['perm'], ex) if srt else lat._view(lat.groups['replay_out'], None, ex)
+        t_sp=timeit(lambda: _capi.check(lib.sgp_splat(C.byref(vi),_ptr(v),v.stride(0),L,_ptr(buf0),1,st)))
+        t_bg=timeit(lambda: _capi.check(lib.sgp_blur_groups(arr,len(arr),lat.M,1,_fp(cnp),3,L,_ptr(buf0),_ptr(buf1),C.byref(where),0 if ex else 1,st)))
+        t_ba=timeit(lambda: _capi.check(lib.sgp_blur(C.byref(vi),_fp(cnp),3,L,_ptr(buf0),_ptr(buf1),C.byref(where),st)))
+        t_sl=timeit(lambda: _capi.check(lib.sgp_slice(C.byref(vo),_ptr(buf1),L,_ptr(out),out.stride(0),st)))
+        t_m=timeit(lambda: lat.mvm(v,out=out,sorted=srt,exact=ex))
+        print(f'sorted={srt} exact={ex}: splat {t_sp:.1f} blur groups {t_bg:.1f} axis {t_ba:.1f} slice {t_sl:.1f} | mvm {t_m:.1f} us -> {1e6/t_m:.0f} MVM/s')

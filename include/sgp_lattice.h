@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SGP_ABI_VERSION 1
+#define SGP_ABI_VERSION 2
 
 #define SGP_OK 0
 #define SGP_EINVAL (-1)       /* bad argument */
@@ -142,6 +142,12 @@ typedef struct sgp_lattice_view {
     const int32_t *nbr;      /* device [(d+1), M, 2r] */
     const uint32_t *csr_ptr; /* device [M+1] or NULL */
     const int32_t *csr_ent;  /* device [N*(d+1), 2] or NULL */
+    const uint32_t *perm;    /* device [N] or NULL.  When set, row p of replay describes point perm[p]: splat and
+                                slice walk the points in that (locality) order and address src / out rows through it */
+    int32_t fast;            /* 0: the reference's arithmetic, one rounding per product and per sum (bit-exact on the
+                                deterministic path); 1: fused multiply-adds and one division per output in slice
+                                (differs by rounding only, ~1e-7 relative) */
+    int32_t reserved;
 } sgp_lattice_view;
 
 #define SGP_SPLAT_AUTO 0
@@ -233,22 +239,25 @@ size_t sgp_group_workspace_bytes(int64_t M);
 int sgp_group_prepare(const int16_t *keys, int64_t M, int d, int j0, int j1, uint32_t *order, uint32_t *pos,
                       uint32_t *class_start, void *workspace, size_t workspace_bytes, int64_t *max_class_out,
                       sgp_stream_t stream);
-/* Cut the sorted positions into CTA batches (batch b owns the classes starting in [b*window, (b+1)*window),
- * n_batches = ceil(M/window), so a batch has fewer than window + max_class rows) and fill the group tables.
- * prev_pos: pos of the previous stage (NULL for the first stage, whose input is in lattice-index order).
- * Synchronises; *max_rows_out = rows of the largest batch. */
+/* Pack whole classes greedily into CTA batches of at most `cap` rows and fill the group tables.
+ * batch_begin: device [sgp_group_max_batches(M, cap, max_class) + 1].  prev_pos: pos of the previous stage
+ * (NULL for the first stage, whose input is in lattice-index order).  Synchronises; *n_batches_out = batches
+ * used, *max_rows_out = rows of the largest batch. */
+int64_t sgp_group_max_batches(int64_t M, int64_t cap, int64_t max_class);
 int sgp_group_finalize(const int32_t *nbr, int64_t M, int order, int j0, int j1, const uint32_t *order_of,
                        const uint32_t *pos, const uint32_t *class_start, const uint32_t *prev_pos,
-                       int64_t window, int64_t n_batches, uint32_t *batch_begin, int32_t *src, uint16_t *lnb,
-                       void *workspace, size_t workspace_bytes, int32_t *max_rows_out, sgp_stream_t stream);
+                       int64_t cap, int64_t max_batches, uint32_t *batch_begin, int32_t *src, uint16_t *lnb,
+                       void *workspace, size_t workspace_bytes, int64_t *n_batches_out, int32_t *max_rows_out,
+                       sgp_stream_t stream);
 /* replay_out[q] = {pos[replay[q].index], replay[q].weight bits}, q < total */
 int sgp_remap_replay(const int32_t *replay, int64_t total, const uint32_t *pos, int32_t *replay_out,
                      sgp_stream_t stream);
 /* channels staged per CTA for L channels */
 int sgp_blur_groups_channel_block(int L);
-/* run the chain: buf0 (lattice-index order) -> ... ; *result_in_buf1 tells where the last stage wrote */
+/* run the chain: buf0 (lattice-index order) -> ... ; *result_in_buf1 tells where the last stage wrote;
+ * fast as in sgp_lattice_view */
 int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64_t M, int order, const float *coeffs,
-                    int k, int L, float *buf0, float *buf1, int *result_in_buf1, sgp_stream_t stream);
+                    int k, int L, float *buf0, float *buf1, int *result_in_buf1, int fast, sgp_stream_t stream);
 
 /* ---- stage 5: lengthscale-gradient pass (bilateral_kernel.py:97-124) -------------------
  *
@@ -268,6 +277,17 @@ int sgp_grad_contract(const float *filtered, int64_t ldp, const float *g, int64_
                       int64_t ldv, const float *x, int64_t ldx, int64_t N, int d, int l0, int nl,
                       int first, int last, float *grad_x, int64_t ldgx, float *grad_src, int64_t ldgs,
                       sgp_stream_t stream);
+
+/* ---- locality order of the points --------------------------------------------------------
+ * perm (device [N]): the points in lexicographic order of their remainder-0 lattice point, so that points sharing
+ * lattice vertices are adjacent.  A replay table re-ordered with sgp_permute_replay plus sgp_lattice_view.perm makes
+ * splat and slice walk the points in that order (neighbouring threads then touch the same lattice rows). */
+size_t sgp_sort_points_workspace_bytes(int64_t N);
+int sgp_sort_points(const int16_t *greedy, int64_t N, int d, uint32_t *perm, void *workspace,
+                    size_t workspace_bytes, sgp_stream_t stream);
+/* replay_out[p, r] = {pos ? pos[replay[perm[p], r].index] : that index, weight bits}; pos may be NULL */
+int sgp_permute_replay(const int32_t *replay, const uint32_t *perm, const uint32_t *pos, int64_t N, int d,
+                       int32_t *replay_out, sgp_stream_t stream);
 
 /* Test hook: number of fp32 bit patterns a in [lo, lo+count) for which the division-by-constant
  * used inside sgp_slice differs from the IEEE division a / sgp_slice_divisor(d).  Must be 0. */

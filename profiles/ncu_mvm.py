@@ -15,9 +15,10 @@ mode = int(os.environ.get("SGP_SPLAT", 1))
 torch.manual_seed(0)
 x = torch.randn(N, d, device="cuda")
 v = torch.randn(N, L, device="cuda")
+blur = os.environ.get("SGP_BLUR", "auto")
 lat = sg.Lattice(x, [0.34608543, 1.0, 0.34608543], build_csr=(mode == 2))
 out = torch.empty(N, L, device="cuda")
 for _ in range(int(os.environ.get("SGP_REPS", 3))):
-    lat.mvm(v, out=out, mode=mode)
+    lat.mvm(v, out=out, mode=mode, blur=blur)
 torch.cuda.synchronize()
 print("M", lat.M, "checksum", float(out.double().sum()))

@@ -25,8 +25,10 @@ SYMBOLS = [
     "sgp_build_csr", "sgp_splat", "sgp_blur", "sgp_slice", "sgp_mvm", "sgp_debug_division_mismatches",
     "sgp_tiles_workspace_bytes", "sgp_tiles_prepare", "sgp_tiles_finalize", "sgp_splat_tiles", "sgp_slice_tiles",
     "sgp_mvm_tiles", "sgp_grad_channels", "sgp_grad_pack", "sgp_grad_contract",
-    "sgp_group_workspace_bytes", "sgp_group_prepare", "sgp_group_finalize", "sgp_remap_replay",
-    "sgp_blur_groups_channel_block", "sgp_blur_groups",
+    "sgp_group_workspace_bytes", "sgp_group_prepare", "sgp_group_max_batches", "sgp_group_finalize",
+    "sgp_remap_replay",
+    "sgp_blur_groups_channel_block", "sgp_blur_groups", "sgp_sort_points_workspace_bytes", "sgp_sort_points",
+    "sgp_permute_replay",
 ]
 
 
@@ -42,6 +44,9 @@ class LatticeView(C.Structure):
         ("nbr", C.c_void_p),
         ("csr_ptr", C.c_void_p),
         ("csr_ent", C.c_void_p),
+        ("perm", C.c_void_p),
+        ("fast", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -165,17 +170,25 @@ def lib() -> C.CDLL:
     L.sgp_group_prepare.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, sz, C.POINTER(i64), vp]
     L.sgp_group_finalize.restype = i32
     L.sgp_group_finalize.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, sz,
-                                     C.POINTER(C.c_int32), vp]
+                                     C.POINTER(i64), C.POINTER(C.c_int32), vp]
+    L.sgp_group_max_batches.restype = i64
+    L.sgp_group_max_batches.argtypes = [i64, i64, i64]
     L.sgp_remap_replay.restype = i32
     L.sgp_remap_replay.argtypes = [vp, i64, vp, vp, vp]
     L.sgp_blur_groups_channel_block.restype = i32
     L.sgp_blur_groups_channel_block.argtypes = [i32]
     L.sgp_blur_groups.restype = i32
-    L.sgp_blur_groups.argtypes = [C.POINTER(BlurGroup), i32, i64, i32, fp, i32, i32, vp, vp, C.POINTER(C.c_int), vp]
+    L.sgp_blur_groups.argtypes = [C.POINTER(BlurGroup), i32, i64, i32, fp, i32, i32, vp, vp, C.POINTER(C.c_int), i32, vp]
+    L.sgp_sort_points_workspace_bytes.restype = sz
+    L.sgp_sort_points_workspace_bytes.argtypes = [i64]
+    L.sgp_sort_points.restype = i32
+    L.sgp_sort_points.argtypes = [vp, i64, i32, vp, vp, sz, vp]
+    L.sgp_permute_replay.restype = i32
+    L.sgp_permute_replay.argtypes = [vp, vp, vp, i64, i32, vp, vp]
     L.sgp_debug_division_mismatches.restype = i32
     L.sgp_debug_division_mismatches.argtypes = [i32, C.c_uint32, C.c_uint32, vp, vp]
-    if L.sgp_abi_version() != 1:
-        raise RuntimeError(f"{LIB_PATH}: ABI version {L.sgp_abi_version()} != 1, rebuild the library")
+    if L.sgp_abi_version() != 2:
+        raise RuntimeError(f"{LIB_PATH}: ABI version {L.sgp_abi_version()} != 2, rebuild the library")
     _lib = L
     return L
 

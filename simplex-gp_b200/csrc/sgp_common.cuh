@@ -60,6 +60,13 @@ template <> struct Vec<4> {
 };
 
 
+// acc + a*b: the reference's two roundings (EXACT) or one fused multiply-add (FAST; differs by rounding only, far
+// inside the 1e-5 relative tolerance of the value path)
+template <bool FAST> __device__ __forceinline__ float madd(float a, float b, float acc)
+{
+    return FAST ? __fmaf_rn(a, b, acc) : __fadd_rn(acc, __fmul_rn(a, b));
+}
+
 // a / b for a fixed divisor b whose reciprocal rb = RN(1/b) was computed on the host (Markstein:
 // q0 = RN(a*rb), rem = a - q0*b exactly by FMA, q = RN(q0 + rem*rb)).  Equal to the IEEE division
 // bit for bit for every finite |a| >= 2^-100 and for a = 0 (sign of zero aside, which cannot reach

@@ -25,6 +25,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "sgp_common.cuh"
@@ -34,7 +35,6 @@
 #define launch_ok sgp_launch_ok
 #define grid_for sgp_grid_for
 
-#define GROUP_THREADS 512
 #define LNB_ABSENT 0xFFFFu
 
 // ------------------------------------------------------------------------------------
@@ -99,33 +99,42 @@ sgp_group_pos_kernel(const uint32_t *__restrict__ order, const uint32_t *__restr
     if (p == M - 1 || class_start[p + 1] != class_start[p]) atomicMax(max_class, (uint32_t)(p - class_start[p] + 1));
 }
 
-// batch b owns the classes that START in [b*window, (b+1)*window): batch_begin[b] = first p with class_start[p] >= b*window
-__global__ void __launch_bounds__(256)
-sgp_group_batches_kernel(const uint32_t *__restrict__ class_start, int64_t M, int64_t window, int64_t n_batches,
-                         uint32_t *__restrict__ batch_begin, uint32_t *__restrict__ max_rows)
+// Greedy packing of whole classes into CTA batches of at most `cap` rows: a batch starts where the previous one ended
+// and extends to the last class boundary within cap rows.  Sequential over batches (one thread; a binary search
+// over the monotone class_start array per batch), which is a few thousand steps at the metric configuration.
+// out[0] = n_batches, out[1] = rows of the largest batch.
+__global__ void sgp_group_pack_kernel(const uint32_t *__restrict__ class_start, int64_t M, int64_t cap,
+                                      int64_t max_batches, uint32_t *__restrict__ batch_begin,
+                                      uint32_t *__restrict__ out)
 {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > n_batches) return;
-    auto lower = [&](int64_t target) {
-        int64_t lo = 0, hi = M;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if ((int64_t)class_start[mid] >= target) hi = mid; else lo = mid + 1;
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int64_t begin = 0, nb = 0;
+    uint32_t max_rows = 0;
+    while (begin < M && nb < max_batches) {
+        batch_begin[nb++] = (uint32_t)begin;
+        int64_t end = begin + cap;
+        if (end >= M) {
+            end = M;
+        } else {
+            end = class_start[end];          // start of the class that position begin+cap falls into
+            if (end <= begin) {              // a class larger than cap: cannot happen (checked by the caller)
+                out[2] = 1;
+                end = begin + cap;
+            }
         }
-        return lo;
-    };
-    const int64_t begin = (b == n_batches) ? M : lower(b * window);
-    batch_begin[b] = (uint32_t)begin;
-    if (b < n_batches) {
-        const int64_t end = (b + 1 == n_batches) ? M : lower((b + 1) * window);
-        atomicMax(max_rows, (uint32_t)(end - begin));
+        if ((uint32_t)(end - begin) > max_rows) max_rows = (uint32_t)(end - begin);
+        begin = end;
     }
+    if (begin < M) out[2] = 1;
+    batch_begin[nb] = (uint32_t)M;
+    out[0] = (uint32_t)nb;
+    out[1] = max_rows;
 }
 
 __global__ void __launch_bounds__(256)
 sgp_group_tables_kernel(const int32_t *__restrict__ nbr, int64_t M, int order_r, int j0, int j1,
                         const uint32_t *__restrict__ order, const uint32_t *__restrict__ pos,
-                        const uint32_t *__restrict__ class_start, const uint32_t *__restrict__ prev_pos, int64_t window,
+                        const uint32_t *__restrict__ prev_pos, int64_t n_batches,
                         const uint32_t *__restrict__ batch_begin, int32_t *__restrict__ src, uint16_t *__restrict__ lnb,
                         int32_t *__restrict__ flags)
 {
@@ -133,7 +142,13 @@ sgp_group_tables_kernel(const int32_t *__restrict__ nbr, int64_t M, int order_r,
     if (p >= M) return;
     const uint32_t row = order[p];
     src[p] = prev_pos ? (int32_t)prev_pos[row] : (int32_t)row;
-    const uint32_t base = batch_begin[class_start[p] / window];
+    // batch of position p: last b with batch_begin[b] <= p
+    int64_t lo = 0, hi = n_batches;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)batch_begin[mid] <= p) lo = mid; else hi = mid;
+    }
+    const uint32_t base = batch_begin[lo], limit = batch_begin[lo + 1];
     const int nax = j1 - j0, w = 2 * order_r;
     for (int a = 0; a < nax; ++a) {
         const int32_t *np = nbr + ((int64_t)(j0 + a) * M + row) * w;
@@ -143,7 +158,7 @@ sgp_group_tables_kernel(const int32_t *__restrict__ nbr, int64_t M, int order_r,
             if (nb >= 0) {
                 const uint32_t q = pos[nb];
                 local = q - base;
-                if (q < base || local >= LNB_ABSENT) {   // neighbour outside the CTA's rows: must not happen
+                if (q < base || q >= limit || local >= LNB_ABSENT) {   // neighbour outside the CTA's rows: must not happen
                     atomicOr(flags, 4);
                     local = LNB_ABSENT;
                 }
@@ -235,13 +250,21 @@ extern "C" int sgp_group_prepare(const int16_t *keys, int64_t M, int d, int j0, 
     return SGP_OK;
 }
 
+extern "C" int64_t sgp_group_max_batches(int64_t M, int64_t cap, int64_t max_class)
+{
+    if (M <= 0 || cap < 1 || max_class > cap) return 0;
+    return M / (cap - max_class + 1) + 2;   // every batch but the last holds more than cap - max_class rows
+}
+
 extern "C" int sgp_group_finalize(const int32_t *nbr, int64_t M, int order_r, int j0, int j1, const uint32_t *order,
                                   const uint32_t *pos, const uint32_t *class_start, const uint32_t *prev_pos,
-                                  int64_t window, int64_t n_batches, uint32_t *batch_begin, int32_t *src, uint16_t *lnb,
-                                  void *workspace, size_t workspace_bytes, int32_t *max_rows_out, sgp_stream_t stream)
+                                  int64_t cap, int64_t max_batches, uint32_t *batch_begin, int32_t *src, uint16_t *lnb,
+                                  void *workspace, size_t workspace_bytes, int64_t *n_batches_out, int32_t *max_rows_out,
+                                  sgp_stream_t stream)
 {
-    if (!nbr || !order || !pos || !class_start || !batch_begin || !src || !lnb || !workspace || !max_rows_out || M <= 0 ||
-        order_r < 1 || order_r > SGP_MAX_ORDER || j1 <= j0 || window < 1 || n_batches != (M + window - 1) / window)
+    if (!nbr || !order || !pos || !class_start || !batch_begin || !src || !lnb || !workspace || !max_rows_out ||
+        !n_batches_out || M <= 0 || order_r < 1 || order_r > SGP_MAX_ORDER || j1 <= j0 || cap < 1 || cap >= LNB_ABSENT ||
+        max_batches < 1)
         return fail(SGP_EINVAL, "sgp_group_finalize: bad argument");
     GroupWs w;
     int rc = group_ws_layout(M, &w);
@@ -249,20 +272,25 @@ extern "C" int sgp_group_finalize(const int32_t *nbr, int64_t M, int order_r, in
     if (workspace_bytes < w.bytes) return fail(SGP_EINVAL, "group workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t *small = (uint32_t *)((char *)workspace + w.small);
-    CUDA_TRY(cudaMemsetAsync(small, 0, 16, st));
-    sgp_group_batches_kernel<<<grid_for(n_batches + 1, 256), 256, 0, st>>>(class_start, M, window, n_batches, batch_begin,
-                                                                            small);
-    rc = launch_ok("sgp_group_batches_kernel");
+    CUDA_TRY(cudaMemsetAsync(small, 0, 32, st));
+    sgp_group_pack_kernel<<<1, 32, 0, st>>>(class_start, M, cap, max_batches, batch_begin, small);
+    rc = launch_ok("sgp_group_pack_kernel");
     if (rc) return rc;
-    sgp_group_tables_kernel<<<grid_for(M, 256), 256, 0, st>>>(nbr, M, order_r, j0, j1, order, pos, class_start, prev_pos,
-                                                               window, batch_begin, src, lnb, (int32_t *)(small + 1));
-    rc = launch_ok("sgp_group_tables_kernel");
-    if (rc) return rc;
-    uint32_t host[2] = {0, 0};
+    uint32_t host[4] = {0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(host, small, sizeof(host), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (host[1] != 0) return fail(SGP_EINVAL, "blur group [%d,%d): a neighbour fell outside its CTA batch", j0, j1);
-    *max_rows_out = (int32_t)host[0];
+    if (host[2] != 0) return fail(SGP_EINVAL, "blur group [%d,%d): classes do not fit %lld rows", j0, j1, (long long)cap);
+    const int64_t n_batches = host[0];
+    sgp_group_tables_kernel<<<grid_for(M, 256), 256, 0, st>>>(nbr, M, order_r, j0, j1, order, pos, prev_pos, n_batches,
+                                                               batch_begin, src, lnb, (int32_t *)(small + 4));
+    rc = launch_ok("sgp_group_tables_kernel");
+    if (rc) return rc;
+    uint32_t flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, small + 4, sizeof(flag), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (flag != 0) return fail(SGP_EINVAL, "blur group [%d,%d): a neighbour fell outside its CTA batch", j0, j1);
+    *n_batches_out = n_batches;
+    *max_rows_out = (int32_t)host[1];
     return SGP_OK;
 }
 
@@ -277,7 +305,7 @@ extern "C" int sgp_remap_replay(const int32_t *replay, int64_t total, const uint
 }
 
 // ------------------------------------------------------------------------------------
-// the MVM kernel: one CTA per batch (x one block of CB channels)
+// the MVM kernel: one CTA per batch (x one block of CHUNKS*VEC channels)
 // ------------------------------------------------------------------------------------
 struct GroupCoeffs {
     float c[2 * SGP_MAX_ORDER + 1];
@@ -285,110 +313,138 @@ struct GroupCoeffs {
 
 #define STAGE_UNROLL 4
 
-template <int VEC, int R>
-__global__ void __launch_bounds__(GROUP_THREADS)
+// Shared memory: A[rows_cap][CBT] | B[rows_cap][CBT] | nbs[rows_cap][nax][2r] (uint16), CBT = CHUNKS*VEC channels.
+// A thread owns one channel chunk (c) and the rows lr0, lr0+RSTEP, ... of the batch for the whole kernel, so the
+// index arithmetic is hoisted out of every loop.
+template <int VEC, int R, int CHUNKS, int THREADS, bool FAST>
+__global__ void __launch_bounds__(THREADS)
 sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *__restrict__ src,
                       const uint16_t *__restrict__ lnb, const float *__restrict__ in, float *__restrict__ out, int L,
-                      int CB, int rows_cap, int nax, int order_rt, GroupCoeffs cf)
+                      int rows_cap, int nax, int order_rt, GroupCoeffs cf)
 {
     constexpr int RR = R > 0 ? R : SGP_MAX_ORDER;
+    constexpr int CBT = CHUNKS * VEC;
+    constexpr int RSTEP = THREADS / CHUNKS;
     const int r = R > 0 ? R : order_rt;
+    const int w2 = 2 * r;
     extern __shared__ __align__(16) float smem[];
-    float *A = smem, *B = smem + (size_t)rows_cap * CB;
+    float *A = smem, *B = smem + rows_cap * CBT;
+    uint16_t *nbs = (uint16_t *)(smem + 2 * rows_cap * CBT);
     const uint32_t p0 = batch_begin[blockIdx.x];
     const int rows = (int)(batch_begin[blockIdx.x + 1] - p0);
     if (rows == 0) return;
-    const int cb0 = blockIdx.y * CB;
-    const int cb = min(CB, L - cb0);
-    const int chunks = cb / VEC;
-    const int items = rows * chunks;
+    const int c = (threadIdx.x % CHUNKS) * VEC;
+    const int lr0 = threadIdx.x / CHUNKS;
+    const int cg = blockIdx.y * CBT + c;          // first global channel of this thread
+    const bool live = cg < L;                      // the last channel block may be partial (L % CBT != 0)
 
-    // stage: gather the batch's rows from the previous stage's order; STAGE_UNROLL independent row loads in flight
-    for (int w0 = threadIdx.x; w0 < items; w0 += GROUP_THREADS * STAGE_UNROLL) {
-        int srow[STAGE_UNROLL];
-        Vec<VEC> v[STAGE_UNROLL];
+    // stage the neighbour table of the batch (contiguous) ...
+    {
+        const int n32 = (rows * nax * w2) >> 1;    // w2 is even: whole 32-bit words
+        const uint32_t *g32 = (const uint32_t *)(lnb + (int64_t)p0 * nax * w2);
+        uint32_t *s32 = (uint32_t *)nbs;
+        for (int i = threadIdx.x; i < n32; i += THREADS) s32[i] = __ldg(g32 + i);
+    }
+    // ... and gather the batch's rows from the previous stage's order, STAGE_UNROLL independent loads in flight
+    if (live) {
+        for (int lr = lr0; lr < rows; lr += RSTEP * STAGE_UNROLL) {
+            int srow[STAGE_UNROLL];
+            Vec<VEC> v[STAGE_UNROLL];
 #pragma unroll
-        for (int u = 0; u < STAGE_UNROLL; ++u) {
-            const int w = w0 + u * GROUP_THREADS;
-            srow[u] = (w < items) ? __ldg(src + p0 + w / chunks) : -1;
-        }
+            for (int u = 0; u < STAGE_UNROLL; ++u) srow[u] = (lr + u * RSTEP < rows) ? __ldg(src + p0 + lr + u * RSTEP) : -1;
 #pragma unroll
-        for (int u = 0; u < STAGE_UNROLL; ++u) {
-            const int w = w0 + u * GROUP_THREADS;
-            if (srow[u] >= 0) v[u].load_cg(in + (int64_t)srow[u] * L + cb0 + (w % chunks) * VEC);
-        }
+            for (int u = 0; u < STAGE_UNROLL; ++u)
+                if (srow[u] >= 0) v[u].load_cg(in + (int64_t)srow[u] * L + cg);
 #pragma unroll
-        for (int u = 0; u < STAGE_UNROLL; ++u) {
-            const int w = w0 + u * GROUP_THREADS;
-            if (srow[u] >= 0) v[u].store(A + (w / chunks) * CB + (w % chunks) * VEC);
+            for (int u = 0; u < STAGE_UNROLL; ++u)
+                if (srow[u] >= 0) v[u].store(A + (lr + u * RSTEP) * CBT + c);
         }
     }
     __syncthreads();
 
-    const int w2 = 2 * r;
     for (int a = 0; a < nax; ++a) {
-        for (int w = threadIdx.x; w < items; w += GROUP_THREADS) {
-            const int lr = w / chunks, c = (w - lr * chunks) * VEC;
-            const uint16_t *nb = lnb + ((int64_t)(p0 + lr) * nax + a) * w2;
-            uint32_t ni[2 * RR];
+        if (live) {
+            for (int lr = lr0; lr < rows; lr += RSTEP) {
+                const uint16_t *nb = nbs + (lr * nax + a) * w2;
+                uint32_t ni[2 * RR];
+                if (R == 1) {
+                    const uint32_t both = *(const uint32_t *)nb;
+                    ni[0] = both & 0xFFFFu;
+                    ni[1] = both >> 16;
+                } else {
 #pragma unroll
-            for (int t = 0; t < 2 * RR; ++t) ni[t] = (t < w2) ? (uint32_t)__ldg(nb + t) : LNB_ABSENT;
-            Vec<VEC> acc;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
-            // reference order: o = -r..-1, 0, 1..r
-#pragma unroll
-            for (int t = 0; t < RR; ++t) {
-                if (t < r && ni[t] != LNB_ABSENT) {
-                    Vec<VEC> v;
-                    v.load_plain(A + ni[t] * CB + c);
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(cf.c[t], v.v[k]));
+                    for (int t = 0; t < 2 * RR; ++t) ni[t] = (t < w2) ? (uint32_t)nb[t] : LNB_ABSENT;
                 }
-            }
-            {
-                Vec<VEC> v;
-                v.load_plain(A + lr * CB + c);
+                Vec<VEC> acc;
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(cf.c[r], v.v[k]));
-            }
+                for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
+                // reference order: o = -r..-1, 0, 1..r
 #pragma unroll
-            for (int t = 0; t < RR; ++t) {
-                if (t < r && ni[r + t] != LNB_ABSENT) {
-                    Vec<VEC> v;
-                    v.load_plain(A + ni[r + t] * CB + c);
+                for (int t = 0; t < RR; ++t) {
+                    if (t < r && ni[t] != LNB_ABSENT) {
+                        Vec<VEC> v;
+                        v.load_plain(A + ni[t] * CBT + c);
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(cf.c[r + 1 + t], v.v[k]));
+                        for (int k = 0; k < VEC; ++k) acc.v[k] = madd<FAST>(cf.c[t], v.v[k], acc.v[k]);
+                    }
                 }
+                {
+                    Vec<VEC> v;
+                    v.load_plain(A + lr * CBT + c);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) acc.v[k] = madd<FAST>(cf.c[r], v.v[k], acc.v[k]);
+                }
+#pragma unroll
+                for (int t = 0; t < RR; ++t) {
+                    if (t < r && ni[r + t] != LNB_ABSENT) {
+                        Vec<VEC> v;
+                        v.load_plain(A + ni[r + t] * CBT + c);
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) acc.v[k] = madd<FAST>(cf.c[r + 1 + t], v.v[k], acc.v[k]);
+                    }
+                }
+                acc.store(B + lr * CBT + c);
             }
-            acc.store(B + lr * CB + c);
         }
         __syncthreads();
         float *t = A; A = B; B = t;
     }
 
-    for (int w = threadIdx.x; w < items; w += GROUP_THREADS) {
-        const int lr = w / chunks, c = (w - lr * chunks) * VEC;
-        Vec<VEC> v;
-        v.load_plain(A + lr * CB + c);
-        v.store(out + (int64_t)(p0 + lr) * L + cb0 + c);
+    if (live) {
+        for (int lr = lr0; lr < rows; lr += RSTEP) {
+            Vec<VEC> v;
+            v.load_plain(A + lr * CBT + c);
+            v.store(out + (int64_t)(p0 + lr) * L + cg);
+        }
     }
 }
 
-template <int VEC>
-static int launch_group(const sgp_blur_group *g, int order, const GroupCoeffs &cf, int L, int CB, const float *in,
-                        float *out, cudaStream_t st)
+static size_t group_smem_bytes(int rows_cap, int cbt, int nax, int order)
 {
-    const size_t smem = (size_t)2 * g->rows_cap * CB * sizeof(float);
-    dim3 grid((unsigned)g->n_batches, (unsigned)((L + CB - 1) / CB));
+    return (size_t)2 * rows_cap * cbt * sizeof(float) + (((size_t)rows_cap * nax * 2 * order * sizeof(uint16_t) + 15) & ~(size_t)15);
+}
+
+template <int VEC, int CHUNKS, int THREADS, bool FAST>
+static int launch_group(const sgp_blur_group *g, int order, const GroupCoeffs &cf, int L, const float *in, float *out,
+                        cudaStream_t st)
+{
+    constexpr int CBT = VEC * CHUNKS;
     const int nax = g->j1 - g->j0;
+    const size_t smem = group_smem_bytes(g->rows_cap, CBT, nax, order);
+    if (smem > 227 * 1024)
+        return fail(SGP_EUNSUPPORTED, "blur group needs %zu bytes of shared memory (%d rows x %d channels)", smem,
+                    g->rows_cap, CBT);
+    dim3 grid((unsigned)g->n_batches, (unsigned)((L + CBT - 1) / CBT));
 #define SGP_LAUNCH_GROUP(RR)                                                                                          \
     do {                                                                                                              \
-        if (smem > 48 * 1024)                                                                                         \
-            CUDA_TRY(cudaFuncSetAttribute(sgp_blur_group_kernel<VEC, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)smem));                                                                \
-        sgp_blur_group_kernel<VEC, RR><<<grid, GROUP_THREADS, smem, st>>>(g->batch_begin, g->src, g->lnb, in, out, L,   \
-                                                                         CB, g->rows_cap, nax, order, cf);            \
+        static size_t granted = 48 * 1024;   /* per instantiation: raise the dynamic shared-memory limit once */         \
+        if (smem > granted) {                                                                                         \
+            CUDA_TRY(cudaFuncSetAttribute(sgp_blur_group_kernel<VEC, RR, CHUNKS, THREADS, FAST>,                            \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
+            granted = smem;                                                                                           \
+        }                                                                                                             \
+        sgp_blur_group_kernel<VEC, RR, CHUNKS, THREADS, FAST><<<grid, THREADS, smem, st>>>(                                  \
+            g->batch_begin, g->src, g->lnb, in, out, L, g->rows_cap, nax, order, cf);                                 \
     } while (0)
     if (order == 1) SGP_LAUNCH_GROUP(1);
     else if (order == 2) SGP_LAUNCH_GROUP(2);
@@ -398,10 +454,24 @@ static int launch_group(const sgp_blur_group *g, int order, const GroupCoeffs &c
     return launch_ok("sgp_blur_group_kernel");
 }
 
-extern "C" int sgp_blur_groups_channel_block(int L) { return L < 16 ? L : 16; }
+// channels staged per CTA: whole 64-byte row pieces when the rows are that wide
+extern "C" int sgp_blur_groups_channel_block(int L)
+{
+    static int cb_env = -1;   // tuning hook: SGP_GROUP_CB=8 stages 32-byte row pieces (more CTAs per SM)
+    if (cb_env < 0) {
+        const char *e = getenv("SGP_GROUP_CB");
+        cb_env = e ? atoi(e) : 0;
+    }
+    if (L % 4 == 0) {
+        if (cb_env == 8 && L >= 8) return 8;
+        return L >= 16 ? 16 : (L >= 8 ? 8 : 4);
+    }
+    if (L % 2 == 0) return L >= 8 ? 8 : (L >= 4 ? 4 : 2);
+    return L >= 4 ? 4 : (L >= 2 ? 2 : 1);
+}
 
 extern "C" int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64_t M, int order, const float *coeffs,
-                               int k, int L, float *buf0, float *buf1, int *result_in_buf1, sgp_stream_t stream)
+                               int k, int L, float *buf0, float *buf1, int *result_in_buf1, int fast, sgp_stream_t stream)
 {
     if (!groups || n_groups < 1 || M < 0 || L < 1 || !coeffs || k != 2 * order + 1 || order < 1 || order > SGP_MAX_ORDER)
         return fail(SGP_EINVAL, "sgp_blur_groups: bad argument");
@@ -415,19 +485,37 @@ extern "C" int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64
     const int CB = sgp_blur_groups_channel_block(L);
     auto al = [](const void *p, int bytes) { return ((uintptr_t)p % bytes) == 0; };
     int vec = 1;
-    if (L % 4 == 0 && CB % 4 == 0 && al(buf0, 16) && al(buf1, 16)) vec = 4;
-    else if (L % 2 == 0 && CB % 2 == 0 && al(buf0, 8) && al(buf1, 8)) vec = 2;
+    if (L % 4 == 0 && al(buf0, 16) && al(buf1, 16)) vec = 4;
+    else if (L % 2 == 0 && al(buf0, 8) && al(buf1, 8)) vec = 2;
+    const int chunks = CB / vec;   // 1, 2 or 4 by construction of CB
+    static int threads_env = 0;    // tuning hook: SGP_GROUP_THREADS=256|512
+    if (threads_env == 0) {
+        const char *e = getenv("SGP_GROUP_THREADS");
+        threads_env = (e && atoi(e) == 512) ? 512 : 256;
+    }
     float *in = buf0, *out = buf1;
     for (int gi = 0; gi < n_groups; ++gi) {
         const sgp_blur_group *g = groups + gi;
         if (!g->batch_begin || !g->src || !g->lnb || g->rows_cap < 1 || g->n_batches < 1 || g->j1 <= g->j0)
             return fail(SGP_EINVAL, "sgp_blur_groups: group %d is not built", gi);
-        if ((size_t)2 * g->rows_cap * CB * sizeof(float) > 227 * 1024)
-            return fail(SGP_EUNSUPPORTED, "blur group %d needs %d rows x %d channels of shared memory", gi, g->rows_cap, CB);
-        int rc;
-        if (vec == 4) rc = launch_group<4>(g, order, cf, L, CB, in, out, st);
-        else if (vec == 2) rc = launch_group<2>(g, order, cf, L, CB, in, out, st);
-        else rc = launch_group<1>(g, order, cf, L, CB, in, out, st);
+        int rc = SGP_EUNSUPPORTED;
+#define SGP_GROUP_CASE(VV, CC)                                                                          \
+    if (vec == VV && chunks == CC)                                                                      \
+        rc = fast ? ((threads_env == 512) ? launch_group<VV, CC, 512, true>(g, order, cf, L, in, out, st)   \
+                                          : launch_group<VV, CC, 256, true>(g, order, cf, L, in, out, st))  \
+                  : ((threads_env == 512) ? launch_group<VV, CC, 512, false>(g, order, cf, L, in, out, st)  \
+                                          : launch_group<VV, CC, 256, false>(g, order, cf, L, in, out, st))
+        SGP_GROUP_CASE(4, 4);
+        else SGP_GROUP_CASE(4, 2);
+        else SGP_GROUP_CASE(4, 1);
+        else SGP_GROUP_CASE(2, 4);
+        else SGP_GROUP_CASE(2, 2);
+        else SGP_GROUP_CASE(2, 1);
+        else SGP_GROUP_CASE(1, 4);
+        else SGP_GROUP_CASE(1, 2);
+        else SGP_GROUP_CASE(1, 1);
+        else return fail(SGP_EUNSUPPORTED, "sgp_blur_groups: no kernel for vec=%d chunks=%d", vec, chunks);
+#undef SGP_GROUP_CASE
         if (rc) return rc;
         float *t = in; in = out; out = t;
     }

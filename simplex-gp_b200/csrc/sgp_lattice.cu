@@ -593,15 +593,16 @@ sgp_csr_order_kernel(const int32_t *__restrict__ replay, int64_t total, int dp1,
 // splat, scatter form: thread = (point n, chunk); (d+1) vector reductions into the lattice
 template <int VEC>
 __global__ void __launch_bounds__(256)
-sgp_splat_atomic_kernel(const int2 *__restrict__ replay, const float *__restrict__ src, int64_t lds,
-                        int64_t N, int dp1, int L, int chunks, float *__restrict__ values)
+sgp_splat_atomic_kernel(const int2 *__restrict__ replay, const uint32_t *__restrict__ perm,
+                        const float *__restrict__ src, int64_t lds, int64_t N, int dp1, int L, int chunks,
+                        float *__restrict__ values)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n = tid / chunks;
     if (n >= N) return;
     const int c0 = (int)(tid - n * chunks) * VEC;
     Vec<VEC> v;
-    v.load(src + n * lds + c0);
+    v.load(src + (perm ? (int64_t)__ldg(perm + n) : n) * lds + c0);   // replay is in processing order, src in caller order
     const int2 *rp = replay + n * dp1;
     for (int r0 = 0; r0 < dp1; r0 += SLICE_BATCH) {
         int2 e[SLICE_BATCH];
@@ -654,7 +655,7 @@ struct CoeffParam {
 // one blur pass along axis j: thread = (ROWS lattice points, one chunk).  All neighbour indices of the
 // thread's rows are loaded first, then all (2r+1)*ROWS lattice rows, so that several dependent
 // index->row load chains overlap (the pass is latency-bound otherwise: M*L/4 threads is only ~5 waves).
-template <int VEC, int R, int ROWS>
+template <int VEC, int R, int ROWS, bool FAST>
 __global__ void __launch_bounds__(256)
 sgp_blur_kernel(const int32_t *__restrict__ nbr_j, const float *__restrict__ in, float *__restrict__ out,
                 int64_t M, int L, int chunks, int order_rt, CoeffParam cf)
@@ -695,17 +696,17 @@ sgp_blur_kernel(const int32_t *__restrict__ nbr_j, const float *__restrict__ in,
         for (int t = 0; t < RR; ++t) {
             if (t < r && nb[q][t] >= 0) {
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(cf.c[t], v[q][t].v[k]));
+                for (int k = 0; k < VEC; ++k) acc.v[k] = madd<FAST>(cf.c[t], v[q][t].v[k], acc.v[k]);
             }
         }
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(cf.c[r], v[q][2 * RR].v[k]));
+        for (int k = 0; k < VEC; ++k) acc.v[k] = madd<FAST>(cf.c[r], v[q][2 * RR].v[k], acc.v[k]);
 #pragma unroll
         for (int t = 0; t < RR; ++t) {
             if (t < r && nb[q][r + t] >= 0) {
 #pragma unroll
                 for (int k = 0; k < VEC; ++k)
-                    acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(cf.c[r + 1 + t], v[q][r + t].v[k]));
+                    acc.v[k] = madd<FAST>(cf.c[r + 1 + t], v[q][r + t].v[k], acc.v[k]);
             }
         }
         acc.store(out + i * L + c0);
@@ -734,10 +735,11 @@ sgp_exact_div_check_kernel(float b, float rb, uint32_t lo, uint32_t count, unsig
 // slice: thread = (point n, chunk).  Vertices are processed in batches of BATCH with all
 // replay entries, then all lattice rows, in flight together (two dependent latencies per batch
 // instead of two per vertex); the sum itself stays in vertex order.
-template <int VEC, int BATCH>
+template <int VEC, int BATCH, bool FAST>
 __global__ void __launch_bounds__(256)
-sgp_slice_kernel(const int2 *__restrict__ replay, const float *__restrict__ values, int64_t N, int dp1,
-                 int L, int chunks, float divisor, float rdivisor, float *__restrict__ out, int64_t ldo)
+sgp_slice_kernel(const int2 *__restrict__ replay, const uint32_t *__restrict__ perm, const float *__restrict__ values,
+                 int64_t N, int dp1, int L, int chunks, float divisor, float rdivisor, float *__restrict__ out,
+                 int64_t ldo)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n = tid / chunks;
@@ -760,7 +762,8 @@ sgp_slice_kernel(const int2 *__restrict__ replay, const float *__restrict__ valu
             const float w = __int_as_float(e[b].y);
 #pragma unroll
             for (int k = 0; k < VEC; ++k)
-                acc.v[k] = __fadd_rn(acc.v[k], exact_div(__fmul_rn(w, v[b].v[k]), divisor, rdivisor));
+                acc.v[k] = FAST ? __fmaf_rn(w, v[b].v[k], acc.v[k])
+                                : __fadd_rn(acc.v[k], exact_div(__fmul_rn(w, v[b].v[k]), divisor, rdivisor));
         }
     }
     for (; r0 < dp1; ++r0) {
@@ -769,9 +772,15 @@ sgp_slice_kernel(const int2 *__restrict__ replay, const float *__restrict__ valu
         Vec<VEC> v;
         v.load(values + (int64_t)e.x * L + c0);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], exact_div(__fmul_rn(w, v.v[k]), divisor, rdivisor));
+        for (int k = 0; k < VEC; ++k)
+            acc.v[k] = FAST ? __fmaf_rn(w, v.v[k], acc.v[k])
+                            : __fadd_rn(acc.v[k], exact_div(__fmul_rn(w, v.v[k]), divisor, rdivisor));
     }
-    acc.store(out + n * ldo + c0);
+    if (FAST) {   // one division of the sum instead of one per term (differs from the reference by rounding only)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc.v[k] = __fdiv_rn(acc.v[k], divisor);
+    }
+    acc.store(out + (perm ? (int64_t)__ldg(perm + n) : n) * ldo + c0);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1050,7 +1059,7 @@ extern "C" int sgp_splat(const sgp_lattice_view *lat, const float *src, int64_t 
     CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)lat->M * (size_t)L, st));
     const int64_t work = lat->N * chunks;
     SGP_DISPATCH_VEC(vec, (sgp_splat_atomic_kernel<VV><<<grid_for(work, 256), 256, 0, st>>>(
-                              (const int2 *)lat->replay, src, lds, lat->N, lat->d + 1, L, chunks, values)));
+                              (const int2 *)lat->replay, lat->perm, src, lds, lat->N, lat->d + 1, L, chunks, values)));
     return launch_ok("sgp_splat_atomic_kernel");
 }
 
@@ -1086,24 +1095,32 @@ extern "C" int sgp_blur(const sgp_lattice_view *lat, const float *coeffs, int k,
     }
     const int rows = (r == 1) ? rows_env : 1;
     const unsigned grid = (unsigned)((lat->M + (int64_t)rows_per_block * rows - 1) / ((int64_t)rows_per_block * rows));
+#define SGP_BLUR_LAUNCH(RR_, ROWS_)                                                                                     \
+    do {                                                                                                                \
+        if (lat->fast) {                                                                                                \
+            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, RR_, ROWS_, true><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf))); \
+        } else {                                                                                                        \
+            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, RR_, ROWS_, false><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf))); \
+        }                                                                                                               \
+    } while (0)
     float *in = buf0, *out = buf1;
     for (int j = 0; j <= lat->d; ++j) {
         const int32_t *nbr_j = lat->nbr + (int64_t)j * lat->M * (2 * r);
         if (r == 0) {
             // order-0 stencil: out = c[0] * in
-            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 0, 1><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf)));
+            SGP_BLUR_LAUNCH(0, 1);
         } else if (r == 1 && rows == 4) {
-            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 1, 4><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf)));
+            SGP_BLUR_LAUNCH(1, 4);
         } else if (r == 1 && rows == 2) {
-            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 1, 2><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf)));
+            SGP_BLUR_LAUNCH(1, 2);
         } else if (r == 1) {
-            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 1, 1><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf)));
+            SGP_BLUR_LAUNCH(1, 1);
         } else if (r == 2) {
-            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 2, 1><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf)));
+            SGP_BLUR_LAUNCH(2, 1);
         } else if (r == 3) {
-            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 3, 1><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf)));
+            SGP_BLUR_LAUNCH(3, 1);
         } else {
-            SGP_DISPATCH_VEC(vec, (sgp_blur_kernel<VV, 0, 1><<<grid, block, 0, st>>>(nbr_j, in, out, lat->M, L, chunks, r, cf)));
+            SGP_BLUR_LAUNCH(0, 1);
         }
         float *t = in; in = out; out = t;
     }
@@ -1129,15 +1146,16 @@ extern "C" int sgp_slice(const sgp_lattice_view *lat, const float *values, int L
         const char *e = getenv("SGP_SLICE_BATCH");
         batch = (e && atoi(e) == 3) ? 3 : 9;
     }
+#define SGP_SLICE_LAUNCH(BB, FF)                                                                                       \
+    SGP_DISPATCH_VEC(vec, (sgp_slice_kernel<VV, BB, FF><<<grid_for(work, 256), 256, 0, st>>>(                          \
+                              (const int2 *)lat->replay, lat->perm, values, lat->N, lat->d + 1, L, chunks, divisor,    \
+                              rdivisor, out, ldo)))
     if (batch == 3) {
-        SGP_DISPATCH_VEC(vec, (sgp_slice_kernel<VV, 3><<<grid_for(work, 256), 256, 0, st>>>(
-                                  (const int2 *)lat->replay, values, lat->N, lat->d + 1, L, chunks, divisor, rdivisor, out,
-                                  ldo)));
+        if (lat->fast) { SGP_SLICE_LAUNCH(3, true); } else { SGP_SLICE_LAUNCH(3, false); }
     } else {
-        SGP_DISPATCH_VEC(vec, (sgp_slice_kernel<VV, 9><<<grid_for(work, 256), 256, 0, st>>>(
-                                  (const int2 *)lat->replay, values, lat->N, lat->d + 1, L, chunks, divisor, rdivisor, out,
-                                  ldo)));
+        if (lat->fast) { SGP_SLICE_LAUNCH(9, true); } else { SGP_SLICE_LAUNCH(9, false); }
     }
+#undef SGP_SLICE_LAUNCH
     return launch_ok("sgp_slice_kernel");
 }
 

@@ -266,6 +266,93 @@ extern "C" int sgp_tiles_finalize(const int32_t *replay, const uint32_t *perm, i
 }
 
 // ------------------------------------------------------------------------------------
+// locality order of the points: lexicographic by the remainder-0 lattice point (greedy), so that points of one
+// lattice cell -- and, mostly, of neighbouring cells -- are adjacent.  LSD radix sort, four 16-bit coordinates per pass.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sgp_pointsort_keys_kernel(const int16_t *__restrict__ greedy, const uint32_t *__restrict__ perm_in, int64_t N, int dp1,
+                          int c_hi, unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const uint32_t n = perm_in ? perm_in[p] : (uint32_t)p;
+    const int16_t *g = greedy + (int64_t)n * dp1;
+    unsigned long long k = 0;
+    // coordinates c_hi-3 .. c_hi, most significant first (c_hi-3 is the more significant axis)
+    for (int c = c_hi - 3; c <= c_hi; ++c) {
+        const uint32_t v = (c >= 0) ? (uint32_t)(uint16_t)(g[c] + 32768) : 0u;
+        k = (k << 16) | v;
+    }
+    keys[p] = k;
+    vals[p] = n;
+}
+
+extern "C" size_t sgp_sort_points_workspace_bytes(int64_t N)
+{
+    if (N <= 0) return 0;
+    size_t t = 0;
+    if (cub::DeviceRadixSort::SortPairs(nullptr, t, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)N, 0, 64) != cudaSuccess)
+        return 0;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    return al((size_t)N * 8) * 2 + al((size_t)N * 4) * 2 + al(t);
+}
+
+extern "C" int sgp_sort_points(const int16_t *greedy, int64_t N, int d, uint32_t *perm, void *workspace,
+                               size_t workspace_bytes, sgp_stream_t stream)
+{
+    if (!greedy || !perm || !workspace || N <= 0 || d < 1 || d > SGP_MAX_DIM) return fail(SGP_EINVAL, "sgp_sort_points: bad argument");
+    if (workspace_bytes < sgp_sort_points_workspace_bytes(N)) return fail(SGP_EINVAL, "sgp_sort_points: workspace too small");
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    char *base = (char *)workspace;
+    unsigned long long *ka = (unsigned long long *)base, *kb = (unsigned long long *)(base + al((size_t)N * 8));
+    uint32_t *va = (uint32_t *)(base + 2 * al((size_t)N * 8)), *vb = va + al((size_t)N * 4) / 4;
+    void *tmp = (char *)(vb) + al((size_t)N * 4);
+    size_t tmp_bytes = workspace_bytes - (size_t)((char *)tmp - base);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int dp1 = d + 1;
+    const uint32_t *cur = nullptr;   // identity
+    // least significant group of coordinates first; sorts are stable, so the final order is lexicographic in 0..d
+    for (int c_hi = d; c_hi >= 0; c_hi -= 4) {
+        sgp_pointsort_keys_kernel<<<grid_for(N, 256), 256, 0, st>>>(greedy, cur, N, dp1, c_hi, ka, va);
+        int rc = launch_ok("sgp_pointsort_keys_kernel");
+        if (rc) return rc;
+        uint32_t *dst = (c_hi - 4 < 0) ? perm : vb;
+        size_t tb = tmp_bytes;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb, ka, kb, va, dst, (int64_t)N, 0, 64, st));
+        if (dst != perm) {   // next pass reads its input permutation from vb
+            cur = vb;
+        }
+    }
+    return SGP_OK;
+}
+
+// out[p, r] = {pos ? pos[replay[perm[p], r].index] : replay[perm[p], r].index, weight bits}
+__global__ void __launch_bounds__(256)
+sgp_permute_replay_kernel(const int2 *__restrict__ replay, const uint32_t *__restrict__ perm,
+                          const uint32_t *__restrict__ pos, int64_t total, int dp1, int2 *__restrict__ out)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total) return;
+    const int64_t p = q / dp1;
+    const int r = (int)(q - p * dp1);
+    int2 e = replay[(int64_t)perm[p] * dp1 + r];
+    if (pos) e.x = (int)pos[e.x];
+    out[q] = e;
+}
+
+extern "C" int sgp_permute_replay(const int32_t *replay, const uint32_t *perm, const uint32_t *pos, int64_t N, int d,
+                                  int32_t *replay_out, sgp_stream_t stream)
+{
+    if (N == 0) return SGP_OK;
+    if (!replay || !perm || !replay_out || N < 0 || d < 1) return fail(SGP_EINVAL, "sgp_permute_replay: bad argument");
+    const int64_t total = N * (int64_t)(d + 1);
+    sgp_permute_replay_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const int2 *)replay, perm, pos, total,
+                                                                                       d + 1, (int2 *)replay_out);
+    return launch_ok("sgp_permute_replay_kernel");
+}
+
+// ------------------------------------------------------------------------------------
 // MVM kernels on tiles.  CB = channels staged per CTA (<= 16 fp32 = one 64-byte row piece).
 // ------------------------------------------------------------------------------------
 #define TILE_THREADS 256

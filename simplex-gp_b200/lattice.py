@@ -83,6 +83,7 @@ class Lattice:
 
     def __init__(self, x: torch.Tensor, coeffs, *, build_csr: bool = False, build_tiles: bool = False,
                  build_groups: bool = True, group_axes: int = 3, group_rows: int = 512,
+                 sort_points: bool = True, exact: bool = False,
                  tile_points: int = 256, keep_structure: bool = True, hash_capacity: Optional[int] = None):
         if x.dim() != 2:
             raise ValueError(f"x must be [N, d], got {tuple(x.shape)}")
@@ -100,6 +101,7 @@ class Lattice:
         self.order = self.coeffs.shape[0] // 2
         self.var = stencil_variance(self.coeffs)
         self.scale = scale_factors(self.d, self.var)
+        self.exact = bool(exact)
         N, d, r = self.N, self.d, self.order
         dev = self.device
         total = N * (d + 1)
@@ -116,6 +118,7 @@ class Lattice:
             self.csr_ent = None
             self.tiles = None
             self.groups = None
+            self.sorted = None
             self.hash_capacity = 0
             if N > 0:
                 check(lib.sgp_build_points(_ptr(x), N, d, x.stride(0), _fp(self.scale), _ptr(self.greedy),
@@ -146,6 +149,8 @@ class Lattice:
                     self._build_tiles(tile_points)
                 if build_groups and r >= 1 and self.M > 0:
                     self._build_groups(group_axes, group_rows)
+                if sort_points and self.M > 0:
+                    self._sort_points()
             if not keep_structure:
                 self.greedy = None
                 self.rank = None
@@ -154,7 +159,8 @@ class Lattice:
     @classmethod
     def from_arrays(cls, coeffs, replay: torch.Tensor, keys: torch.Tensor, nbr: torch.Tensor,
                     build_csr: bool = False, build_tiles: bool = False, tile_points: int = 256,
-                    build_groups: bool = True, group_axes: int = 3, group_rows: int = 512) -> "Lattice":
+                    build_groups: bool = True, group_axes: int = 3, group_rows: int = 512,
+                    exact: bool = False) -> "Lattice":
         """Wrap lattice arrays that were built elsewhere (e.g. received by ``distributed.broadcast_lattice``)."""
         self = object.__new__(cls)
         self.device = replay.device
@@ -171,6 +177,8 @@ class Lattice:
         self.csr_ptr = self.csr_ent = None
         self.tiles = None
         self.groups = None
+        self.sorted = None      # the locality order needs greedy, which does not travel with the arrays
+        self.exact = bool(exact)
         self.hash_capacity = 0
         self._bufs = {}
         if self.N > 0 and self.M > 0:
@@ -189,8 +197,7 @@ class Lattice:
         single axis does not fit (a long 1-D line), no groups are built and the per-axis blur is used."""
         lib = _capi.lib()
         dev, d, M, r = self.device, self.d, self.M, self.order
-        CB = int(lib.sgp_blur_groups_channel_block(16))
-        rows_limit = min(int(group_rows), (200 * 1024) // (2 * CB * 4), 0xFFFF - 1)
+        rows_limit = min(int(group_rows), (160 * 1024) // (2 * 16 * 4), 0xFFFF - 1)
         st = _stream_ptr(dev)
         ws_bytes = int(lib.sgp_group_workspace_bytes(M))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -212,18 +219,18 @@ class Lattice:
             if mx.value > rows_limit:
                 self.groups = None
                 return
-            window = max(1, rows_limit - int(mx.value) + 1)
-            n_batches = (M + window - 1) // window
+            max_batches = int(lib.sgp_group_max_batches(M, rows_limit, int(mx.value)))
             g = {
-                "j0": j0, "j1": j1, "n_batches": n_batches, "max_class": int(mx.value),
-                "batch_begin": torch.empty(n_batches + 1, dtype=torch.int32, device=dev),
+                "j0": j0, "j1": j1, "max_class": int(mx.value),
+                "batch_begin": torch.empty(max_batches + 1, dtype=torch.int32, device=dev),
                 "src": torch.empty(M, dtype=torch.int32, device=dev),
                 "lnb": torch.empty((M, j1 - j0, 2 * r), dtype=torch.int16, device=dev),
             }
-            rows = C.c_int32(0)
+            rows, nb = C.c_int32(0), C.c_int64(0)
             check(lib.sgp_group_finalize(_ptr(self.nbr), M, r, j0, j1, _ptr(order_of), _ptr(pos), _ptr(cstart),
-                                         _ptr(prev_pos), window, n_batches, _ptr(g["batch_begin"]), _ptr(g["src"]),
-                                         _ptr(g["lnb"]), _ptr(ws), ws_bytes, C.byref(rows), st))
+                                         _ptr(prev_pos), rows_limit, max_batches, _ptr(g["batch_begin"]), _ptr(g["src"]),
+                                         _ptr(g["lnb"]), _ptr(ws), ws_bytes, C.byref(nb), C.byref(rows), st))
+            g["n_batches"] = int(nb.value)
             g["rows_cap"] = int(rows.value)
             groups.append(g)
             prev_pos = pos
@@ -236,6 +243,25 @@ class Lattice:
             arr[k] = _capi.BlurGroup(g["j0"], g["j1"], g["rows_cap"], 0, g["n_batches"], g["batch_begin"].data_ptr(),
                                      g["src"].data_ptr(), g["lnb"].data_ptr())
         self.groups = {"list": groups, "array": arr, "replay_out": replay_out, "final_pos": prev_pos}
+
+    def _sort_points(self) -> None:
+        """Locality order of the points (csrc/sgp_tiles.cu, sgp_sort_points) and the replay tables re-ordered with it:
+        ``replay`` for the splat (lattice-index rows) and ``replay_out`` for the slice (rows in the order the last blur
+        stage leaves them)."""
+        lib = _capi.lib()
+        dev, N, d = self.device, self.N, self.d
+        st = _stream_ptr(dev)
+        ws_bytes = int(lib.sgp_sort_points_workspace_bytes(N))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        perm = torch.empty(N, dtype=torch.int32, device=dev)
+        check(lib.sgp_sort_points(_ptr(self.greedy), N, d, _ptr(perm), _ptr(ws), ws_bytes, st))
+        rp = torch.empty_like(self.replay)
+        check(lib.sgp_permute_replay(_ptr(self.replay), _ptr(perm), None, N, d, _ptr(rp), st))
+        out = rp
+        if self.groups is not None:
+            out = torch.empty_like(self.replay)
+            check(lib.sgp_permute_replay(_ptr(self.replay), _ptr(perm), _ptr(self.groups["final_pos"]), N, d, _ptr(out), st))
+        self.sorted = {"perm": perm, "replay": rp, "replay_out": out}
 
     def _build_tiles(self, tile_points: int = 256) -> None:
         """Locality tiles for the shared-memory staged splat / slice (csrc/sgp_tiles.cu)."""
@@ -298,11 +324,14 @@ class Lattice:
         """fp32 ``[N, d+1]``: barycentric weight of every simplex vertex (reference ``replay[].weight``)."""
         return self.replay[..., 1].view(torch.float32)
 
-    def _view(self) -> LatticeView:
-        return LatticeView(self.N, self.M, self.d, self.order, self.replay.data_ptr(),
+    def _view(self, replay: Optional[torch.Tensor] = None, perm: Optional[torch.Tensor] = None,
+              exact: Optional[bool] = None) -> LatticeView:
+        exact = self.exact if exact is None else exact
+        return LatticeView(self.N, self.M, self.d, self.order, (self.replay if replay is None else replay).data_ptr(),
                            self.nbr.data_ptr() if self.nbr.numel() else 0,
                            self.csr_ptr.data_ptr() if self.csr_ptr is not None else 0,
-                           self.csr_ent.data_ptr() if self.csr_ent is not None else 0)
+                           self.csr_ent.data_ptr() if self.csr_ent is not None else 0,
+                           0 if perm is None else perm.data_ptr(), 0 if exact else 1, 0)
 
     def _scratch(self, L: int):
         key = int(L)
@@ -325,24 +354,30 @@ class Lattice:
         return src
 
     # ---- stages, exposed separately for parity tests ---------------------------------------------
-    def splat(self, src: torch.Tensor, mode: int = _capi.SGP_SPLAT_AUTO) -> torch.Tensor:
+    # Stage methods take and return lattice values in LATTICE-INDEX order (the reference's numbering) and default to
+    # the reference's arithmetic (exact=True); `mvm` is the production path and defaults to the lattice's setting.
+    def splat(self, src: torch.Tensor, mode: int = _capi.SGP_SPLAT_AUTO, sorted: bool = False) -> torch.Tensor:
         src = self._check_src(src)
         L = int(src.shape[1])
         values = torch.empty((self.M, L), dtype=torch.float32, device=self.device)
         if self.M == 0 or L == 0:
             return values
         with torch.cuda.device(self.device):
-            if mode == _capi.MODE_TILES or (mode == _capi.MODE_AUTO and self.tiles is not None):
+            if mode == _capi.MODE_TILES:
                 tv = self._tiles_view()
                 check(_capi.lib().sgp_splat_tiles(C.byref(tv), _ptr(src), src.stride(0), L, _ptr(values),
                                                   _stream_ptr(self.device)))
             else:
+                if mode == _capi.MODE_AUTO:
+                    mode = _capi.MODE_GATHER if self.csr_ptr is not None else _capi.MODE_ATOMIC
                 v = self._view()
+                if sorted and mode == _capi.MODE_ATOMIC:
+                    v = self._view(self.sorted["replay"], self.sorted["perm"])
                 check(_capi.lib().sgp_splat(C.byref(v), _ptr(src), src.stride(0), L, _ptr(values), mode,
                                             _stream_ptr(self.device)))
         return values
 
-    def blur(self, values: torch.Tensor, coeffs=None, groups: bool = False) -> torch.Tensor:
+    def blur(self, values: torch.Tensor, coeffs=None, groups: bool = False, exact: bool = True) -> torch.Tensor:
         """Blurred lattice values in lattice-index order.  ``groups=True`` runs the shared-memory group chain (whose
         output order is its last stage's) and permutes the result back, for comparison with the per-axis path."""
         c = self.coeffs if coeffs is None else _coeffs_np(coeffs)
@@ -351,7 +386,6 @@ class Lattice:
             return values.clone()
         buf0 = values.contiguous().clone()
         buf1 = torch.empty_like(buf0)
-        v = self._view()
         where = C.c_int(0)
         with torch.cuda.device(self.device):
             if groups:
@@ -359,39 +393,48 @@ class Lattice:
                     raise RuntimeError("blur groups were not built for this lattice")
                 arr = self.groups["array"]
                 check(_capi.lib().sgp_blur_groups(arr, len(arr), self.M, self.order, _fp(c), c.shape[0], L, _ptr(buf0),
-                                                  _ptr(buf1), C.byref(where), _stream_ptr(self.device)))
+                                                  _ptr(buf1), C.byref(where), 0 if exact else 1,
+                                                  _stream_ptr(self.device)))
                 res = buf1 if where.value else buf0
                 return res[self.groups["final_pos"].long()]
+            v = self._view(exact=exact)
             check(_capi.lib().sgp_blur(C.byref(v), _fp(c), c.shape[0], L, _ptr(buf0), _ptr(buf1), C.byref(where),
                                        _stream_ptr(self.device)))
         return buf1 if where.value else buf0
 
-    def slice(self, values: torch.Tensor, mode: int = _capi.MODE_AUTO) -> torch.Tensor:
+    def slice(self, values: torch.Tensor, mode: int = _capi.MODE_AUTO, sorted: bool = False,
+              exact: bool = True) -> torch.Tensor:
         L = int(values.shape[1])
         out = torch.empty((self.N, L), dtype=torch.float32, device=self.device)
         if self.N == 0 or L == 0:
             return out
         values = values.contiguous()
         with torch.cuda.device(self.device):
-            if mode == _capi.MODE_TILES or (mode == _capi.MODE_AUTO and self.tiles is not None):
+            if mode == _capi.MODE_TILES:
                 tv = self._tiles_view()
                 check(_capi.lib().sgp_slice_tiles(C.byref(tv), _ptr(values), L, _ptr(out), out.stride(0),
                                                   _stream_ptr(self.device)))
             else:
-                v = self._view()
+                v = self._view(self.sorted["replay"], self.sorted["perm"], exact) if sorted else self._view(exact=exact)
                 check(_capi.lib().sgp_slice(C.byref(v), _ptr(values), L, _ptr(out), out.stride(0),
                                             _stream_ptr(self.device)))
         return out
 
     # ---- the MVM ------------------------------------------------------------------------------------
     def mvm(self, src: torch.Tensor, out: Optional[torch.Tensor] = None, coeffs=None,
-            mode: int = _capi.SGP_SPLAT_AUTO, blur: str = "auto") -> torch.Tensor:
+            mode: int = _capi.SGP_SPLAT_AUTO, blur: str = "auto", sorted: Optional[bool] = None,
+            exact: Optional[bool] = None) -> torch.Tensor:
         """``out[N, L] = slice(blur(splat(src[N, L])))`` on the built lattice.
 
-        ``mode``: 0 auto (locality tiles when built, else atomic scatter), 1 atomic scatter splat + direct slice,
-        2 gather splat in the reference's accumulation order (bit-exact, needs ``build_csr=True``), 3 tiles.
-        ``blur``: "groups" (several axes per launch through shared memory), "axis" (one launch per axis) or "auto"
-        (groups when they were built and the splat/slice path is not the tile path)."""
+        ``mode``   splat form: 0 auto (atomic scatter), 1 atomic scatter (``red.global.add.v4.f32``), 2 gather in the
+                   reference's accumulation order (deterministic; needs ``build_csr=True``), 3 locality tiles
+                   (needs ``build_tiles=True``; implies the tile slice and the per-axis blur).
+        ``blur``   "groups" (several axes per launch through shared memory), "axis" (one launch per axis) or "auto"
+                   (groups when they were built).
+        ``sorted`` walk the points in the locality order in splat and slice (default: when it was built).
+        ``exact``  the reference's arithmetic (one rounding per product and sum, one division per slice term) instead
+                   of fused multiply-adds; with ``mode=2`` the result is then bit-identical to the reference's.
+                   Default: the lattice's ``exact`` attribute (False)."""
         src = self._check_src(src)
         L = int(src.shape[1])
         c = self.coeffs if coeffs is None else _coeffs_np(coeffs)
@@ -401,35 +444,45 @@ class Lattice:
             out = torch.empty((self.N, L), dtype=torch.float32, device=self.device)
         if self.N == 0 or L == 0:
             return out
+        exact = self.exact if exact is None else bool(exact)
         buf0, buf1 = self._scratch(L)
-        v = self._view()
-        tiles = mode == _capi.MODE_TILES or (mode == _capi.MODE_AUTO and self.tiles is not None)
-        use_groups = blur == "groups" or (blur == "auto" and self.groups is not None and not tiles)
-        if use_groups:
-            if self.groups is None or tiles:
-                raise RuntimeError("blur groups are not available on this path")
-            lib, st = _capi.lib(), _stream_ptr(self.device)
-            where = C.c_int(0)
-            arr = self.groups["array"]
+        lib, st = _capi.lib(), _stream_ptr(self.device)
+        if mode == _capi.MODE_TILES:
+            if self.tiles is None:
+                raise RuntimeError("tiles were not built for this lattice (build_tiles=True)")
+            v, tv = self._view(exact=exact), self._tiles_view()
             with torch.cuda.device(self.device):
-                check(lib.sgp_splat(C.byref(v), _ptr(src), src.stride(0), L, _ptr(buf0), mode, st))
-                check(lib.sgp_blur_groups(arr, len(arr), self.M, self.order, _fp(c), c.shape[0], L, _ptr(buf0),
-                                          _ptr(buf1), C.byref(where), st))
-                v2 = self._view()
-                v2.replay = self.groups["replay_out"].data_ptr()
-                check(lib.sgp_slice(C.byref(v2), _ptr(buf1 if where.value else buf0), L, _ptr(out), out.stride(0), st))
+                check(lib.sgp_mvm_tiles(C.byref(v), C.byref(tv), _ptr(src), src.stride(0), L, _fp(c), c.shape[0],
+                                        _ptr(out), out.stride(0), _ptr(buf0), _ptr(buf1), st))
             return out
+        if mode == _capi.MODE_AUTO:
+            mode = _capi.MODE_ATOMIC
+        use_sorted = (self.sorted is not None) if sorted is None else bool(sorted)
+        if use_sorted and self.sorted is None:
+            raise RuntimeError("the locality order was not built for this lattice (sort_points=True)")
+        use_groups = (self.groups is not None) if blur == "auto" else (blur == "groups")
+        if use_groups and self.groups is None:
+            raise RuntimeError("blur groups were not built for this lattice")
+        where = C.c_int(0)
         with torch.cuda.device(self.device):
-            if tiles:
-                if self.tiles is None:
-                    raise RuntimeError("tiles were not built for this lattice (build_tiles=False)")
-                tv = self._tiles_view()
-                check(_capi.lib().sgp_mvm_tiles(C.byref(v), C.byref(tv), _ptr(src), src.stride(0), L, _fp(c),
-                                                c.shape[0], _ptr(out), out.stride(0), _ptr(buf0), _ptr(buf1),
-                                                _stream_ptr(self.device)))
+            if mode == _capi.MODE_GATHER or not use_sorted:
+                v_in = self._view(exact=exact)
             else:
-                check(_capi.lib().sgp_mvm(C.byref(v), _ptr(src), src.stride(0), L, _fp(c), c.shape[0], _ptr(out),
-                                          out.stride(0), _ptr(buf0), _ptr(buf1), mode, _stream_ptr(self.device)))
+                v_in = self._view(self.sorted["replay"], self.sorted["perm"], exact)
+            check(lib.sgp_splat(C.byref(v_in), _ptr(src), src.stride(0), L, _ptr(buf0), mode, st))
+            if use_groups:
+                arr = self.groups["array"]
+                check(lib.sgp_blur_groups(arr, len(arr), self.M, self.order, _fp(c), c.shape[0], L, _ptr(buf0),
+                                          _ptr(buf1), C.byref(where), 0 if exact else 1, st))
+            else:
+                vb = self._view(exact=exact)
+                check(lib.sgp_blur(C.byref(vb), _fp(c), c.shape[0], L, _ptr(buf0), _ptr(buf1), C.byref(where), st))
+            if use_sorted:
+                rp = self.sorted["replay_out"] if use_groups else self.sorted["replay"]
+                v_out = self._view(rp, self.sorted["perm"], exact)
+            else:
+                v_out = self._view(self.groups["replay_out"] if use_groups else None, None, exact)
+            check(lib.sgp_slice(C.byref(v_out), _ptr(buf1 if where.value else buf0), L, _ptr(out), out.stride(0), st))
         return out
 
     def algorithmic_bytes(self, L: int) -> int:
@@ -450,14 +503,14 @@ def lattice_filter(src: torch.Tensor, ref: torch.Tensor, coeffs, *, device=None)
         raise TypeError("filter: float32 tensors required (reference CPU filter is fp32-only)")
     if src.is_cuda:
         dev = src.device
-        lat = Lattice(ref.to(dev), coeffs, build_csr=False, build_tiles=False, build_groups=False, keep_structure=False)
+        lat = Lattice(ref.to(dev), coeffs, build_csr=False, build_tiles=False, build_groups=False, sort_points=False, keep_structure=False)
         return lat.mvm(src)
     if not torch.cuda.is_available():
         raise RuntimeError("filter: no CUDA device; this package has no CPU path")
     dev = torch.device(device if device is not None else "cuda")
     ref_d = ref.contiguous().pin_memory().to(dev, non_blocking=True)
     src_d = src.contiguous().pin_memory().to(dev, non_blocking=True)
-    lat = Lattice(ref_d, coeffs, build_csr=False, build_tiles=False, build_groups=False, keep_structure=False)
+    lat = Lattice(ref_d, coeffs, build_csr=False, build_tiles=False, build_groups=False, sort_points=False, keep_structure=False)
     out_d = lat.mvm(src_d)
     out = torch.empty(out_d.shape, dtype=out_d.dtype, pin_memory=True)
     out.copy_(out_d, non_blocking=True)
