@@ -147,7 +147,8 @@ typedef struct sgp_lattice_view {
     int32_t fast;            /* 0: the reference's arithmetic, one rounding per product and per sum (bit-exact on the
                                 deterministic path); 1: fused multiply-adds and one division per output in slice
                                 (differs by rounding only, ~1e-7 relative) */
-    int32_t reserved;
+    int32_t replay_transposed; /* 0: replay is [N, d+1, 2]; 1: [d+1, N, 2] (what sgp_permute_replay can produce: the
+                                  points of a warp then read one contiguous run per vertex) */
 } sgp_lattice_view;
 
 #define SGP_SPLAT_AUTO 0
@@ -177,26 +178,32 @@ int sgp_mvm(const sgp_lattice_view *lat, const float *src, int64_t lds, int L,
  * entry into segments (seg_ptr / seg_ent).  See simplex-gp_b200/csrc/sgp_tiles.cu.  This is an
  * internal acceleration structure; the observable lattice (replay, keys, nbr) is unchanged. */
 typedef struct sgp_tiles_view {
-    int64_t N;                    /* points */
-    int64_t M;                    /* lattice points */
-    int64_t S;                    /* segments = sum of dictionary sizes */
+    int64_t N;                      /* points */
+    int64_t M;                      /* lattice points */
+    int64_t S;                      /* segments = sum of dictionary sizes */
+    int64_t P;                      /* splat pieces (segments cut into runs of at most 8 entries) */
     int32_t d;
-    int32_t tile_points;          /* T */
-    int32_t max_dict;             /* largest dictionary */
+    int32_t tile_points;            /* T */
+    int32_t dict_cap;               /* largest dictionary */
     int32_t reserved;
-    const uint32_t *perm;         /* device [N]: sorted position -> point */
-    const uint32_t *tile_seg_ptr; /* device [n_tiles+1] */
-    const uint32_t *seg_ptr;      /* device [S+1] into seg_ent */
-    const int32_t *seg_row;       /* device [S] lattice index */
-    const int32_t *seg_ent;       /* device [N*(d+1), 2] {point index inside its tile, weight bits} */
-    const uint16_t *lidx;         /* device [N*(d+1)] dictionary index of each sorted point-vertex */
-    const float *tile_w;          /* device [N*(d+1)] weight of each sorted point-vertex */
+    const uint32_t *perm;           /* device [N]: sorted position -> point (sgp_sort_points) */
+    const uint32_t *tile_seg_ptr;   /* device [n_tiles+1]                                    (slice) */
+    const int32_t *seg_row;         /* device [S] lattice row of each dictionary entry, in the order in which the
+                                       stage addresses the lattice values                     (slice) */
+    const uint16_t *lidx;           /* device [N*(d+1)] dictionary index of each sorted point-vertex (slice) */
+    const float *tile_w;            /* device [N*(d+1)] weight of each sorted point-vertex    (slice) */
+    const int32_t *seg_ent;         /* device [N*(d+1), 2] {point index inside its tile, weight bits}, grouped by
+                                       segment                                                (splat) */
+    const uint32_t *tile_piece_ptr; /* device [n_tiles+1]                                     (splat) */
+    const uint32_t *piece_ptr;      /* device [P+1] entry range of each piece                 (splat) */
+    const int32_t *piece_row;       /* device [P] lattice row of each piece                   (splat) */
 } sgp_tiles_view;
 
 size_t sgp_tiles_workspace_bytes(int64_t N, int d);
-/* sort + segment count; synchronises the stream; perm: device [N]; returns S */
+/* segment count of the tiling of the points in the order perm (device [N], from sgp_sort_points);
+ * synchronises the stream; returns S */
 int sgp_tiles_prepare(const int32_t *replay, int64_t N, int d, int64_t M, int tile_points,
-                      uint32_t *perm, void *workspace, size_t workspace_bytes, int64_t *S_out,
+                      const uint32_t *perm, void *workspace, size_t workspace_bytes, int64_t *S_out,
                       sgp_stream_t stream);
 /* fills the tile arrays (sizes as in sgp_tiles_view) from the workspace left by sgp_tiles_prepare;
  * synchronises the stream; *max_dict_out = largest dictionary */
@@ -204,16 +211,12 @@ int sgp_tiles_finalize(const int32_t *replay, const uint32_t *perm, int64_t N, i
                        int64_t S, void *workspace, size_t workspace_bytes, uint32_t *seg_ptr,
                        int32_t *seg_row, int32_t *seg_ent, uint32_t *tile_seg_ptr, uint16_t *lidx,
                        float *tile_w, int32_t *max_dict_out, sgp_stream_t stream);
-/* values[M, L] = splat(src) with one vector reduction per segment (values is zeroed inside) */
+/* values[M, L] = splat(src): one vector reduction per piece (values is zeroed inside) */
 int sgp_splat_tiles(const sgp_tiles_view *tiles, const float *src, int64_t lds, int L, float *values,
                     sgp_stream_t stream);
-/* out = slice(values), dictionary rows staged in shared memory; same arithmetic as sgp_slice */
+/* out = slice(values), dictionary rows staged in shared memory; fast as in sgp_lattice_view */
 int sgp_slice_tiles(const sgp_tiles_view *tiles, const float *values, int L, float *out, int64_t ldo,
-                    sgp_stream_t stream);
-/* splat_tiles -> blur -> slice_tiles */
-int sgp_mvm_tiles(const sgp_lattice_view *lat, const sgp_tiles_view *tiles, const float *src, int64_t lds,
-                  int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1,
-                  sgp_stream_t stream);
+                    int fast, sgp_stream_t stream);
 
 /* ---- blur groups: several axes per launch, staged through shared memory ------------------
  *
@@ -278,6 +281,18 @@ int sgp_grad_contract(const float *filtered, int64_t ldp, const float *g, int64_
                       int first, int last, float *grad_x, int64_t ldgx, float *grad_src, int64_t ldgs,
                       sgp_stream_t stream);
 
+/* ---- row-sorted splat ("segmented gather") -------------------------------------------------
+ * ent (device [sgp_rowsort_padded(N,d), 2] int32 {point, weight bits}) and ent_row (device [same] int32 lattice
+ * row): the point-vertices sorted by lattice row, point-vertex order within a row (the reference's accumulation
+ * order), padded with zero-weight entries to a multiple of 8.  sgp_splat_rows gives every thread 8 consecutive
+ * entries: balanced whatever the row lengths, one vector reduction per run of equal rows (values is zeroed inside). */
+size_t sgp_rowsort_workspace_bytes(int64_t N, int d);
+int64_t sgp_rowsort_padded(int64_t N, int d);
+int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int64_t M, int32_t *ent, int32_t *ent_row,
+                        void *workspace, size_t workspace_bytes, sgp_stream_t stream);
+int sgp_splat_rows(const int32_t *ent, const int32_t *ent_row, int64_t N, int d, int64_t M, const float *src,
+                   int64_t lds, int L, float *values, sgp_stream_t stream);
+
 /* ---- locality order of the points --------------------------------------------------------
  * perm (device [N]): the points in lexicographic order of their remainder-0 lattice point, so that points sharing
  * lattice vertices are adjacent.  A replay table re-ordered with sgp_permute_replay plus sgp_lattice_view.perm makes
@@ -285,9 +300,10 @@ int sgp_grad_contract(const float *filtered, int64_t ldp, const float *g, int64_
 size_t sgp_sort_points_workspace_bytes(int64_t N);
 int sgp_sort_points(const int16_t *greedy, int64_t N, int d, uint32_t *perm, void *workspace,
                     size_t workspace_bytes, sgp_stream_t stream);
-/* replay_out[p, r] = {pos ? pos[replay[perm[p], r].index] : that index, weight bits}; pos may be NULL */
+/* replay_out[p, r] (or [r, p] when transposed != 0) = {pos ? pos[replay[perm ? perm[p] : p, r].index] : that index,
+ * weight bits}; perm and pos may be NULL */
 int sgp_permute_replay(const int32_t *replay, const uint32_t *perm, const uint32_t *pos, int64_t N, int d,
-                       int32_t *replay_out, sgp_stream_t stream);
+                       int transposed, int32_t *replay_out, sgp_stream_t stream);
 
 /* Test hook: number of fp32 bit patterns a in [lo, lo+count) for which the division-by-constant
  * used inside sgp_slice differs from the IEEE division a / sgp_slice_divisor(d).  Must be 0. */

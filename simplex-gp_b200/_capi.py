@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libsgp_lattice.so")
 
 SGP_OK = 0
 SGP_SPLAT_AUTO, SGP_SPLAT_ATOMIC, SGP_SPLAT_GATHER = 0, 1, 2
-MODE_AUTO, MODE_ATOMIC, MODE_GATHER, MODE_TILES = 0, 1, 2, 3   # Lattice.mvm(mode=...)
+MODE_AUTO, MODE_ATOMIC, MODE_GATHER, MODE_TILES, MODE_ROWS = 0, 1, 2, 3, 4   # Lattice.mvm(mode=...)
 SGP_MAX_DIM = 126
 SGP_MAX_ORDER = 7
 
@@ -24,11 +24,12 @@ SYMBOLS = [
     "sgp_count_points", "sgp_number_points", "sgp_build_neighbours", "sgp_csr_workspace_bytes",
     "sgp_build_csr", "sgp_splat", "sgp_blur", "sgp_slice", "sgp_mvm", "sgp_debug_division_mismatches",
     "sgp_tiles_workspace_bytes", "sgp_tiles_prepare", "sgp_tiles_finalize", "sgp_splat_tiles", "sgp_slice_tiles",
-    "sgp_mvm_tiles", "sgp_grad_channels", "sgp_grad_pack", "sgp_grad_contract",
+    "sgp_grad_channels", "sgp_grad_pack", "sgp_grad_contract",
     "sgp_group_workspace_bytes", "sgp_group_prepare", "sgp_group_max_batches", "sgp_group_finalize",
     "sgp_remap_replay",
     "sgp_blur_groups_channel_block", "sgp_blur_groups", "sgp_sort_points_workspace_bytes", "sgp_sort_points",
-    "sgp_permute_replay",
+    "sgp_permute_replay", "sgp_rowsort_workspace_bytes", "sgp_rowsort_padded", "sgp_build_rowsorted",
+    "sgp_splat_rows",
 ]
 
 
@@ -46,7 +47,7 @@ class LatticeView(C.Structure):
         ("csr_ent", C.c_void_p),
         ("perm", C.c_void_p),
         ("fast", C.c_int32),
-        ("reserved", C.c_int32),
+        ("replay_transposed", C.c_int32),
     ]
 
 
@@ -57,17 +58,20 @@ class TilesView(C.Structure):
         ("N", C.c_int64),
         ("M", C.c_int64),
         ("S", C.c_int64),
+        ("P", C.c_int64),
         ("d", C.c_int32),
         ("tile_points", C.c_int32),
-        ("max_dict", C.c_int32),
+        ("dict_cap", C.c_int32),
         ("reserved", C.c_int32),
         ("perm", C.c_void_p),
         ("tile_seg_ptr", C.c_void_p),
-        ("seg_ptr", C.c_void_p),
         ("seg_row", C.c_void_p),
-        ("seg_ent", C.c_void_p),
         ("lidx", C.c_void_p),
         ("tile_w", C.c_void_p),
+        ("seg_ent", C.c_void_p),
+        ("tile_piece_ptr", C.c_void_p),
+        ("piece_ptr", C.c_void_p),
+        ("piece_row", C.c_void_p),
     ]
 
 
@@ -155,9 +159,7 @@ def lib() -> C.CDLL:
     L.sgp_splat_tiles.restype = i32
     L.sgp_splat_tiles.argtypes = [pt, vp, i64, i32, vp, vp]
     L.sgp_slice_tiles.restype = i32
-    L.sgp_slice_tiles.argtypes = [pt, vp, i32, vp, i64, vp]
-    L.sgp_mvm_tiles.restype = i32
-    L.sgp_mvm_tiles.argtypes = [pv, pt, vp, i64, i32, fp, i32, vp, i64, vp, vp, vp]
+    L.sgp_slice_tiles.argtypes = [pt, vp, i32, vp, i64, i32, vp]
     L.sgp_grad_channels.restype = i32
     L.sgp_grad_channels.argtypes = [i32, i32]
     L.sgp_grad_pack.restype = i32
@@ -184,7 +186,15 @@ def lib() -> C.CDLL:
     L.sgp_sort_points.restype = i32
     L.sgp_sort_points.argtypes = [vp, i64, i32, vp, vp, sz, vp]
     L.sgp_permute_replay.restype = i32
-    L.sgp_permute_replay.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+    L.sgp_permute_replay.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
+    L.sgp_rowsort_workspace_bytes.restype = sz
+    L.sgp_rowsort_workspace_bytes.argtypes = [i64, i32]
+    L.sgp_rowsort_padded.restype = i64
+    L.sgp_rowsort_padded.argtypes = [i64, i32]
+    L.sgp_build_rowsorted.restype = i32
+    L.sgp_build_rowsorted.argtypes = [vp, i64, i32, i64, vp, vp, vp, sz, vp]
+    L.sgp_splat_rows.restype = i32
+    L.sgp_splat_rows.argtypes = [vp, vp, i64, i32, i64, vp, i64, i32, vp, vp]
     L.sgp_debug_division_mismatches.restype = i32
     L.sgp_debug_division_mismatches.argtypes = [i32, C.c_uint32, C.c_uint32, vp, vp]
     if L.sgp_abi_version() != 2:

@@ -26,12 +26,41 @@ int sgp_exclusive_scan_u32(uint32_t *data, int64_t n, uint32_t *tile_sums, unsig
 
 static inline unsigned sgp_grid_for(int64_t work, int block) { return (unsigned)((work + block - 1) / block); }
 
+// Loads whose ISSUE ORDER matters (a batch of index loads, then a batch of dependent row loads, so that a thread has
+// several independent memory round trips in flight): volatile asm statements keep their relative order, whereas
+// plain __ldg calls get interleaved with their consumers by the compiler.
+__device__ __forceinline__ int2 ldg_ordered_int2(const int2 *p)
+{
+    int2 v;
+    asm volatile("ld.global.nc.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_ordered_f4(const float *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ldg_ordered_f2(const float *p)
+{
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_ordered_f1(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // ---- vector of VEC channels of one row ------------------------------------------------------
 template <int VEC> struct Vec;
 template <> struct Vec<1> {
     float v[1];
     __device__ __forceinline__ void load(const float *p) { v[0] = __ldg(p); }
     __device__ __forceinline__ void load_cg(const float *p) { v[0] = __ldcg(p); }
+    __device__ __forceinline__ void load_ordered(const float *p) { v[0] = ldg_ordered_f1(p); }
     __device__ __forceinline__ void load_plain(const float *p) { v[0] = *p; }
     __device__ __forceinline__ void store(float *p) const { *p = v[0]; }
     __device__ __forceinline__ void red(float *p) const { atomicAdd(p, v[0]); }
@@ -40,6 +69,7 @@ template <> struct Vec<2> {
     float v[2];
     __device__ __forceinline__ void load(const float *p) { float2 t = __ldg((const float2 *)p); v[0] = t.x; v[1] = t.y; }
     __device__ __forceinline__ void load_cg(const float *p) { float2 t = __ldcg((const float2 *)p); v[0] = t.x; v[1] = t.y; }
+    __device__ __forceinline__ void load_ordered(const float *p) { float2 t = ldg_ordered_f2(p); v[0] = t.x; v[1] = t.y; }
     __device__ __forceinline__ void load_plain(const float *p) { float2 t = *(const float2 *)p; v[0] = t.x; v[1] = t.y; }
     __device__ __forceinline__ void store(float *p) const { *(float2 *)p = make_float2(v[0], v[1]); }
     __device__ __forceinline__ void red(float *p) const
@@ -51,6 +81,7 @@ template <> struct Vec<4> {
     float v[4];
     __device__ __forceinline__ void load(const float *p) { float4 t = __ldg((const float4 *)p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     __device__ __forceinline__ void load_cg(const float *p) { float4 t = __ldcg((const float4 *)p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    __device__ __forceinline__ void load_ordered(const float *p) { float4 t = ldg_ordered_f4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     __device__ __forceinline__ void load_plain(const float *p) { float4 t = *(const float4 *)p; v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     __device__ __forceinline__ void store(float *p) const { *(float4 *)p = make_float4(v[0], v[1], v[2], v[3]); }
     __device__ __forceinline__ void red(float *p) const
@@ -65,6 +96,40 @@ template <> struct Vec<4> {
 template <bool FAST> __device__ __forceinline__ float madd(float a, float b, float acc)
 {
     return FAST ? __fmaf_rn(a, b, acc) : __fadd_rn(acc, __fmul_rn(a, b));
+}
+
+// ---- asynchronous global -> shared row gathers (LDGSTS) --------------------------------------------
+// A gather "index -> row" is two dependent memory round trips.  Warps issue in order, so a loop of such pairs
+// serialises them; instead the index list is staged in shared memory first and the rows are then fetched with
+// cp.async, which costs no registers and never blocks the issuing warp: every row of a CTA's batch is in flight at once.
+template <int VEC> __device__ __forceinline__ void cp_async_vec(float *smem_dst, const float *gsrc)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if (VEC == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    else if (VEC == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+// Cooperative asynchronous copy of nbytes (a multiple of 4; both pointers 4-byte aligned, the shared one 16-byte
+// aligned) by the whole CTA: 16-byte pieces when the global pointer allows it, 4-byte pieces otherwise.
+// Never "smem[i] = global[i]" in a loop: each iteration would stall the warp for a full memory round trip.
+__device__ __forceinline__ void cta_copy_async(void *smem_dst, const void *gsrc, int nbytes, int tid, int nthreads)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const char *g = (const char *)gsrc;
+    int done = 0;
+    if ((((uintptr_t)g) & 15) == 0) {
+        const int n16 = nbytes >> 4;
+        for (int i = tid; i < n16; i += nthreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * i), "l"(g + 16 * (size_t)i) : "memory");
+        done = n16 << 4;
+    }
+    const int n4 = (nbytes - done) >> 2;
+    for (int i = tid; i < n4; i += nthreads)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + done + 4u * i), "l"(g + done + 4 * (size_t)i) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 // a / b for a fixed divisor b whose reciprocal rb = RN(1/b) was computed on the host (Markstein:

@@ -328,8 +328,9 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
     const int r = R > 0 ? R : order_rt;
     const int w2 = 2 * r;
     extern __shared__ __align__(16) float smem[];
-    float *A = smem, *B = smem + rows_cap * CBT;
-    uint16_t *nbs = (uint16_t *)(smem + 2 * rows_cap * CBT);
+    const int buf_floats = (rows_cap * CBT + 3) & ~3;   // every array starts 16-byte aligned
+    float *A = smem, *B = smem + buf_floats;
+    uint16_t *nbs = (uint16_t *)(smem + 2 * buf_floats);
     const uint32_t p0 = batch_begin[blockIdx.x];
     const int rows = (int)(batch_begin[blockIdx.x + 1] - p0);
     if (rows == 0) return;
@@ -338,28 +339,17 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
     const int cg = blockIdx.y * CBT + c;          // first global channel of this thread
     const bool live = cg < L;                      // the last channel block may be partial (L % CBT != 0)
 
-    // stage the neighbour table of the batch (contiguous) ...
-    {
-        const int n32 = (rows * nax * w2) >> 1;    // w2 is even: whole 32-bit words
-        const uint32_t *g32 = (const uint32_t *)(lnb + (int64_t)p0 * nax * w2);
-        uint32_t *s32 = (uint32_t *)nbs;
-        for (int i = threadIdx.x; i < n32; i += THREADS) s32[i] = __ldg(g32 + i);
-    }
-    // ... and gather the batch's rows from the previous stage's order, STAGE_UNROLL independent loads in flight
+    // stage the batch's neighbour table and its slice of the gather list (plain range copies, asynchronous) ...
+    int32_t *SRC = (int32_t *)(nbs + (((size_t)rows_cap * nax * w2 + 7) & ~(size_t)7));
+    cta_copy_async(nbs, lnb + (int64_t)p0 * nax * w2, rows * nax * w2 * 2, threadIdx.x, THREADS);   // w2 even: whole words
+    cta_copy_async(SRC, src + p0, rows * 4, threadIdx.x, THREADS);
+    cp_async_wait_all();
+    __syncthreads();
+    // ... and the rows themselves, gathered from the previous stage's order, all in flight at once (cp.async)
     if (live) {
-        for (int lr = lr0; lr < rows; lr += RSTEP * STAGE_UNROLL) {
-            int srow[STAGE_UNROLL];
-            Vec<VEC> v[STAGE_UNROLL];
-#pragma unroll
-            for (int u = 0; u < STAGE_UNROLL; ++u) srow[u] = (lr + u * RSTEP < rows) ? __ldg(src + p0 + lr + u * RSTEP) : -1;
-#pragma unroll
-            for (int u = 0; u < STAGE_UNROLL; ++u)
-                if (srow[u] >= 0) v[u].load_cg(in + (int64_t)srow[u] * L + cg);
-#pragma unroll
-            for (int u = 0; u < STAGE_UNROLL; ++u)
-                if (srow[u] >= 0) v[u].store(A + (lr + u * RSTEP) * CBT + c);
-        }
+        for (int lr = lr0; lr < rows; lr += RSTEP) cp_async_vec<VEC>(A + lr * CBT + c, in + (int64_t)SRC[lr] * L + cg);
     }
+    cp_async_wait_all();
     __syncthreads();
 
     for (int a = 0; a < nax; ++a) {
@@ -421,7 +411,8 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
 
 static size_t group_smem_bytes(int rows_cap, int cbt, int nax, int order)
 {
-    return (size_t)2 * rows_cap * cbt * sizeof(float) + (((size_t)rows_cap * nax * 2 * order * sizeof(uint16_t) + 15) & ~(size_t)15);
+    return (size_t)2 * (((size_t)rows_cap * cbt + 3) & ~(size_t)3) * sizeof(float) +
+           (((size_t)rows_cap * nax * 2 * order * sizeof(uint16_t) + 15) & ~(size_t)15) + (size_t)rows_cap * sizeof(int32_t);
 }
 
 template <int VEC, int CHUNKS, int THREADS, bool FAST>

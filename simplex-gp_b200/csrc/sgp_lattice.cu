@@ -593,9 +593,9 @@ sgp_csr_order_kernel(const int32_t *__restrict__ replay, int64_t total, int dp1,
 // splat, scatter form: thread = (point n, chunk); (d+1) vector reductions into the lattice
 template <int VEC>
 __global__ void __launch_bounds__(256)
-sgp_splat_atomic_kernel(const int2 *__restrict__ replay, const uint32_t *__restrict__ perm,
-                        const float *__restrict__ src, int64_t lds, int64_t N, int dp1, int L, int chunks,
-                        float *__restrict__ values)
+sgp_splat_atomic_kernel(const int2 *__restrict__ replay, int64_t pstride, int64_t rstride,
+                        const uint32_t *__restrict__ perm, const float *__restrict__ src, int64_t lds, int64_t N,
+                        int dp1, int L, int chunks, float *__restrict__ values)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n = tid / chunks;
@@ -603,11 +603,14 @@ sgp_splat_atomic_kernel(const int2 *__restrict__ replay, const uint32_t *__restr
     const int c0 = (int)(tid - n * chunks) * VEC;
     Vec<VEC> v;
     v.load(src + (perm ? (int64_t)__ldg(perm + n) : n) * lds + c0);   // replay is in processing order, src in caller order
-    const int2 *rp = replay + n * dp1;
+    // entry (n, r) lives at replay[n*pstride + r*rstride]: [N, d+1] (pstride = d+1, rstride = 1) or the transposed
+    // [d+1, N] (pstride = 1, rstride = N), for which the 8 points of a warp read one 64-byte run per vertex
+    const int2 *rp = replay + n * pstride;
     for (int r0 = 0; r0 < dp1; r0 += SLICE_BATCH) {
         int2 e[SLICE_BATCH];
 #pragma unroll
-        for (int b = 0; b < SLICE_BATCH; ++b) e[b] = (r0 + b < dp1) ? __ldg(rp + r0 + b) : make_int2(0, 0);
+        for (int b = 0; b < SLICE_BATCH; ++b)
+            e[b] = (r0 + b < dp1) ? ldg_ordered_int2(rp + (r0 + b) * rstride) : make_int2(0, 0);
 #pragma unroll
         for (int b = 0; b < SLICE_BATCH; ++b) {
             if (r0 + b < dp1) {
@@ -737,15 +740,15 @@ sgp_exact_div_check_kernel(float b, float rb, uint32_t lo, uint32_t count, unsig
 // instead of two per vertex); the sum itself stays in vertex order.
 template <int VEC, int BATCH, bool FAST>
 __global__ void __launch_bounds__(256)
-sgp_slice_kernel(const int2 *__restrict__ replay, const uint32_t *__restrict__ perm, const float *__restrict__ values,
-                 int64_t N, int dp1, int L, int chunks, float divisor, float rdivisor, float *__restrict__ out,
-                 int64_t ldo)
+sgp_slice_kernel(const int2 *__restrict__ replay, int64_t pstride, int64_t rstride,
+                 const uint32_t *__restrict__ perm, const float *__restrict__ values, int64_t N, int dp1, int L,
+                 int chunks, float divisor, float rdivisor, float *__restrict__ out, int64_t ldo)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n = tid / chunks;
     if (n >= N) return;
     const int c0 = (int)(tid - n * chunks) * VEC;
-    const int2 *rp = replay + n * dp1;
+    const int2 *rp = replay + n * pstride;
     Vec<VEC> acc;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
@@ -754,20 +757,28 @@ sgp_slice_kernel(const int2 *__restrict__ replay, const uint32_t *__restrict__ p
         int2 e[BATCH];
         Vec<VEC> v[BATCH];
 #pragma unroll
-        for (int b = 0; b < BATCH; ++b) e[b] = __ldg(rp + r0 + b);
+        for (int b = 0; b < BATCH; ++b) e[b] = ldg_ordered_int2(rp + (r0 + b) * rstride);
+        // A warp issues in order, so a row load placed before a later index load would make the warp wait a full
+        // memory round trip with that index load not yet issued.  Lattice indices are never negative: branching on
+        // all of them keeps every index load ahead of every row load (two round trips per batch, not up to BATCH).
+        int lowest = e[0].x;
 #pragma unroll
-        for (int b = 0; b < BATCH; ++b) v[b].load(values + (int64_t)e[b].x * L + c0);
+        for (int b = 1; b < BATCH; ++b) lowest = min(lowest, e[b].x);
+        if (lowest >= 0) {
 #pragma unroll
-        for (int b = 0; b < BATCH; ++b) {
-            const float w = __int_as_float(e[b].y);
+            for (int b = 0; b < BATCH; ++b) v[b].load_ordered(values + (int64_t)e[b].x * L + c0);
 #pragma unroll
-            for (int k = 0; k < VEC; ++k)
-                acc.v[k] = FAST ? __fmaf_rn(w, v[b].v[k], acc.v[k])
-                                : __fadd_rn(acc.v[k], exact_div(__fmul_rn(w, v[b].v[k]), divisor, rdivisor));
+            for (int b = 0; b < BATCH; ++b) {
+                const float w = __int_as_float(e[b].y);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    acc.v[k] = FAST ? __fmaf_rn(w, v[b].v[k], acc.v[k])
+                                    : __fadd_rn(acc.v[k], exact_div(__fmul_rn(w, v[b].v[k]), divisor, rdivisor));
+            }
         }
     }
     for (; r0 < dp1; ++r0) {
-        const int2 e = __ldg(rp + r0);
+        const int2 e = __ldg(rp + r0 * rstride);
         const float w = __int_as_float(e.y);
         Vec<VEC> v;
         v.load(values + (int64_t)e.x * L + c0);
@@ -778,7 +789,7 @@ sgp_slice_kernel(const int2 *__restrict__ replay, const uint32_t *__restrict__ p
     }
     if (FAST) {   // one division of the sum instead of one per term (differs from the reference by rounding only)
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) acc.v[k] = __fdiv_rn(acc.v[k], divisor);
+        for (int k = 0; k < VEC; ++k) acc.v[k] = exact_div(acc.v[k], divisor, rdivisor);
     }
     acc.store(out + (perm ? (int64_t)__ldg(perm + n) : n) * ldo + c0);
 }
@@ -1059,7 +1070,9 @@ extern "C" int sgp_splat(const sgp_lattice_view *lat, const float *src, int64_t 
     CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)lat->M * (size_t)L, st));
     const int64_t work = lat->N * chunks;
     SGP_DISPATCH_VEC(vec, (sgp_splat_atomic_kernel<VV><<<grid_for(work, 256), 256, 0, st>>>(
-                              (const int2 *)lat->replay, lat->perm, src, lds, lat->N, lat->d + 1, L, chunks, values)));
+                              (const int2 *)lat->replay, lat->replay_transposed ? 1 : lat->d + 1,
+                              lat->replay_transposed ? lat->N : 1, lat->perm, src, lds, lat->N, lat->d + 1, L, chunks,
+                              values)));
     return launch_ok("sgp_splat_atomic_kernel");
 }
 
@@ -1148,8 +1161,9 @@ extern "C" int sgp_slice(const sgp_lattice_view *lat, const float *values, int L
     }
 #define SGP_SLICE_LAUNCH(BB, FF)                                                                                       \
     SGP_DISPATCH_VEC(vec, (sgp_slice_kernel<VV, BB, FF><<<grid_for(work, 256), 256, 0, st>>>(                          \
-                              (const int2 *)lat->replay, lat->perm, values, lat->N, lat->d + 1, L, chunks, divisor,    \
-                              rdivisor, out, ldo)))
+                              (const int2 *)lat->replay, lat->replay_transposed ? 1 : lat->d + 1,                      \
+                              lat->replay_transposed ? lat->N : 1, lat->perm, values, lat->N, lat->d + 1, L, chunks,    \
+                              divisor, rdivisor, out, ldo)))
     if (batch == 3) {
         if (lat->fast) { SGP_SLICE_LAUNCH(3, true); } else { SGP_SLICE_LAUNCH(3, false); }
     } else {

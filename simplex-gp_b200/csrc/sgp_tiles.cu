@@ -7,7 +7,7 @@
 // from L2.  Both are bounded by L2 traffic, not HBM.
 //
 // What: points are sorted once per lattice so that points sharing lattice vertices are adjacent
-// (key = lattice index of their remainder-0 vertex), and cut into tiles of T points.  For every
+// (sgp_sort_points: lexicographic order of their remainder-0 lattice point), and cut into tiles of T points.  For every
 // tile the distinct lattice rows its T*(d+1) point-vertices touch form the tile's DICTIONARY
 // (`seg_row`), and the point-vertices are grouped by dictionary entry into SEGMENTS (`seg_ptr`,
 // `seg_ent`).  Then
@@ -173,7 +173,7 @@ static int bits_for(uint64_t v)
 }
 
 extern "C" int sgp_tiles_prepare(const int32_t *replay, int64_t N, int d, int64_t M, int tile_points,
-                                 uint32_t *perm, void *workspace, size_t workspace_bytes, int64_t *S_out,
+                                 const uint32_t *perm, void *workspace, size_t workspace_bytes, int64_t *S_out,
                                  sgp_stream_t stream)
 {
     if (!replay || !perm || !workspace || !S_out || N <= 0 || M <= 0 || d < 1 || d > SGP_MAX_DIM)
@@ -197,13 +197,7 @@ extern "C" int sgp_tiles_prepare(const int32_t *replay, int64_t N, int d, int64_
     void *cub_tmp = base + w.cub;
     size_t cub_bytes = w.cub_bytes;
 
-    // 1. sort points by the lattice index of their remainder-0 vertex (stable: ties keep input order)
-    uint32_t *pk_in = (uint32_t *)k64a, *pk_out = (uint32_t *)k64b;
-    sgp_tile_pointkeys_kernel<<<grid_for(N, 256), 256, 0, st>>>(replay, N, dp1, pk_in, v32a);
-    rc = launch_ok("sgp_tile_pointkeys_kernel");
-    if (rc) return rc;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, pk_in, pk_out, v32a, perm, (int64_t)N, 0,
-                                             bits_for((uint64_t)M), st));
+    // 1. the points arrive sorted (perm from sgp_sort_points)
     // 2. sort point-vertices by (tile, lattice index); stable, so a segment keeps sorted-point order
     sgp_tile_pvkeys_kernel<<<grid_for(total, 256), 256, 0, st>>>(replay, perm, total, dp1, tile_points, k64a, v32a);
     rc = launch_ok("sgp_tile_pvkeys_kernel");
@@ -330,135 +324,331 @@ extern "C" int sgp_sort_points(const int16_t *greedy, int64_t N, int d, uint32_t
 // out[p, r] = {pos ? pos[replay[perm[p], r].index] : replay[perm[p], r].index, weight bits}
 __global__ void __launch_bounds__(256)
 sgp_permute_replay_kernel(const int2 *__restrict__ replay, const uint32_t *__restrict__ perm,
-                          const uint32_t *__restrict__ pos, int64_t total, int dp1, int2 *__restrict__ out)
+                          const uint32_t *__restrict__ pos, int64_t N, int dp1, int transposed, int2 *__restrict__ out)
 {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= total) return;
-    const int64_t p = q / dp1;
-    const int r = (int)(q - p * dp1);
-    int2 e = replay[(int64_t)perm[p] * dp1 + r];
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // output index
+    if (q >= N * dp1) return;
+    int64_t p;
+    int r;
+    if (transposed) {
+        r = (int)(q / N);
+        p = q - (int64_t)r * N;
+    } else {
+        p = q / dp1;
+        r = (int)(q - p * dp1);
+    }
+    int2 e = replay[(perm ? (int64_t)perm[p] : p) * dp1 + r];
     if (pos) e.x = (int)pos[e.x];
     out[q] = e;
 }
 
 extern "C" int sgp_permute_replay(const int32_t *replay, const uint32_t *perm, const uint32_t *pos, int64_t N, int d,
-                                  int32_t *replay_out, sgp_stream_t stream)
+                                  int transposed, int32_t *replay_out, sgp_stream_t stream)
 {
     if (N == 0) return SGP_OK;
-    if (!replay || !perm || !replay_out || N < 0 || d < 1) return fail(SGP_EINVAL, "sgp_permute_replay: bad argument");
+    if (!replay || !replay_out || N < 0 || d < 1) return fail(SGP_EINVAL, "sgp_permute_replay: bad argument");
     const int64_t total = N * (int64_t)(d + 1);
-    sgp_permute_replay_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const int2 *)replay, perm, pos, total,
-                                                                                       d + 1, (int2 *)replay_out);
+    sgp_permute_replay_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const int2 *)replay, perm, pos, N,
+                                                                                       d + 1, transposed, (int2 *)replay_out);
     return launch_ok("sgp_permute_replay_kernel");
 }
 
 // ------------------------------------------------------------------------------------
-// MVM kernels on tiles.  CB = channels staged per CTA (<= 16 fp32 = one 64-byte row piece).
+// Row-sorted splat ("segmented gather").  The point-vertices are sorted once per lattice by the lattice row they
+// touch (stable radix sort: within a row they stay in point-vertex order, the reference's accumulation order).  A
+// thread then owns ROWSEG consecutive entries and one channel chunk: it issues the ROWSEG RHS-row loads together,
+// accumulates runs of equal row in registers and issues one vector reduction per run.  Work is perfectly balanced
+// whatever the row lengths (1 to ~10^4 touches per lattice point at the metric configuration); reductions drop from
+// one per point-vertex to one per (row, thread) run; and the gather side moves through L2 as plain loads, which the
+// scatter form's same-address reductions do not.
 // ------------------------------------------------------------------------------------
-#define TILE_THREADS 256
+#define ROWSEG 8
 
-// splat: CTA = (tile, channel block).  Stage the tile's RHS rows, reduce every segment in
-// registers in sorted-point order, one vector reduction per segment.
-template <int VEC>
-__global__ void __launch_bounds__(TILE_THREADS)
-sgp_splat_tiles_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ tile_seg_ptr,
-                       const uint32_t *__restrict__ seg_ptr, const int32_t *__restrict__ seg_row,
-                       const int2 *__restrict__ seg_ent, const float *__restrict__ src, int64_t lds, int64_t N,
-                       int T, int L, int CB, float *__restrict__ values)
+__global__ void __launch_bounds__(256)
+sgp_rowsort_keys_kernel(const int2 *__restrict__ replay, int64_t total, uint32_t *__restrict__ keys,
+                        uint32_t *__restrict__ vals)
 {
-    extern __shared__ __align__(16) float smem[];   // [T][CB]
-    const int64_t tile = blockIdx.x;
-    const int cb0 = blockIdx.y * CB;
-    const int cb = min(CB, L - cb0);                // channels of this block (multiple of VEC)
-    const int chunks = cb / VEC;
-    const int64_t p0 = tile * T;
-    const int np = (int)min((int64_t)T, N - p0);
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total) return;
+    keys[q] = (uint32_t)replay[q].x;
+    vals[q] = (uint32_t)q;
+}
 
-    for (int w = threadIdx.x; w < np * chunks; w += TILE_THREADS) {
-        const int lp = w / chunks, c = (w - lp * chunks) * VEC;
-        Vec<VEC> v;
-        v.load(src + (int64_t)perm[p0 + lp] * lds + cb0 + c);
-        v.store(smem + lp * CB + c);
-    }
-    __syncthreads();
-
-    const uint32_t s0 = tile_seg_ptr[tile], s1 = tile_seg_ptr[tile + 1];
-    const int nseg = (int)(s1 - s0);
-    for (int w = threadIdx.x; w < nseg * chunks; w += TILE_THREADS) {
-        const int ls = w / chunks, c = (w - ls * chunks) * VEC;
-        const uint32_t a = seg_ptr[s0 + ls], b = seg_ptr[s0 + ls + 1];
-        const int64_t row = seg_row[s0 + ls];
-        Vec<VEC> acc;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
-        for (uint32_t e = a; e < b; ++e) {
-            const int2 ent = __ldg(seg_ent + e);
-            const float wgt = __int_as_float(ent.y);
-            Vec<VEC> sv;
-            sv.load_plain(smem + ent.x * CB + c);
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(wgt, sv.v[k]));
-        }
-        acc.red(values + row * L + cb0 + c);
+__global__ void __launch_bounds__(256)
+sgp_rowsort_fill_kernel(const int2 *__restrict__ replay, const uint32_t *__restrict__ sorted_row,
+                        const uint32_t *__restrict__ sorted_pv, int64_t total, int64_t padded, int dp1,
+                        int2 *__restrict__ ent, int32_t *__restrict__ ent_row)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= padded) return;
+    if (k < total) {
+        const uint32_t q = sorted_pv[k];
+        ent[k] = make_int2((int)(q / (uint32_t)dp1), replay[q].y);
+        ent_row[k] = (int32_t)sorted_row[k];
+    } else {   // padding: weight 0 on the last row
+        ent[k] = make_int2(0, 0);
+        ent_row[k] = (int32_t)sorted_row[total - 1];
     }
 }
 
-// slice: CTA = (tile, channel block).  Stage the tile's dictionary rows once, then every point
-// combines its d+1 vertices from shared memory in vertex order (same arithmetic as sgp_slice_kernel).
-// Tiles whose dictionary exceeds `cap` rows (no reuse to exploit) read the lattice directly.
+extern "C" size_t sgp_rowsort_workspace_bytes(int64_t N, int d)
+{
+    const int64_t total = N * (int64_t)(d + 1);
+    if (total <= 0) return 0;
+    size_t t = 0;
+    if (cub::DeviceRadixSort::SortPairs(nullptr, t, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
+                                        (uint32_t *)nullptr, (int64_t)total, 0, 32) != cudaSuccess)
+        return 0;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    return al((size_t)total * 4) * 4 + al(t);
+}
+
+extern "C" int64_t sgp_rowsort_padded(int64_t N, int d)
+{
+    const int64_t total = N * (int64_t)(d + 1);
+    return (total + ROWSEG - 1) / ROWSEG * ROWSEG;
+}
+
+extern "C" int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int64_t M, int32_t *ent, int32_t *ent_row,
+                                   void *workspace, size_t workspace_bytes, sgp_stream_t stream)
+{
+    if (!replay || !ent || !ent_row || !workspace || N <= 0 || M <= 0 || d < 1) return fail(SGP_EINVAL, "sgp_build_rowsorted: bad argument");
+    if (workspace_bytes < sgp_rowsort_workspace_bytes(N, d)) return fail(SGP_EINVAL, "sgp_build_rowsorted: workspace too small");
+    const int64_t total = N * (int64_t)(d + 1);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    char *base = (char *)workspace;
+    const size_t blk = al((size_t)total * 4);
+    uint32_t *ka = (uint32_t *)base, *kb = (uint32_t *)(base + blk), *va = (uint32_t *)(base + 2 * blk),
+             *vb = (uint32_t *)(base + 3 * blk);
+    void *tmp = base + 4 * blk;
+    size_t tmp_bytes = workspace_bytes - 4 * blk;
+    cudaStream_t st = (cudaStream_t)stream;
+    sgp_rowsort_keys_kernel<<<grid_for(total, 256), 256, 0, st>>>((const int2 *)replay, total, ka, va);
+    int rc = launch_ok("sgp_rowsort_keys_kernel");
+    if (rc) return rc;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ka, kb, va, vb, (int64_t)total, 0, bits_for((uint64_t)M), st));
+    const int64_t padded = sgp_rowsort_padded(N, d);
+    sgp_rowsort_fill_kernel<<<grid_for(padded, 256), 256, 0, st>>>((const int2 *)replay, kb, vb, total, padded, d + 1,
+                                                                  (int2 *)ent, ent_row);
+    return launch_ok("sgp_rowsort_fill_kernel");
+}
+
+// thread = (segment of ROWSEG entries, channel chunk)
+template <int VEC>
+__global__ void __launch_bounds__(256)
+sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ ent_row, int64_t n_seg,
+                      const float *__restrict__ src, int64_t lds, int L, int chunks, float *__restrict__ values)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t seg = tid / chunks;
+    if (seg >= n_seg) return;
+    const int c0 = (int)(tid - seg * chunks) * VEC;
+    int2 e[ROWSEG];
+    int row[ROWSEG];
+    Vec<VEC> v[ROWSEG];
+    const int4 *ep = (const int4 *)(ent + seg * ROWSEG);     // ROWSEG entries = ROWSEG/2 16-byte loads
+    const int4 *rp = (const int4 *)(ent_row + seg * ROWSEG);
+#pragma unroll
+    for (int i = 0; i < ROWSEG / 2; ++i) {
+        const int4 t = __ldg(ep + i);
+        e[2 * i] = make_int2(t.x, t.y);
+        e[2 * i + 1] = make_int2(t.z, t.w);
+    }
+#pragma unroll
+    for (int i = 0; i < ROWSEG / 4; ++i) {
+        const int4 t = __ldg(rp + i);
+        row[4 * i] = t.x; row[4 * i + 1] = t.y; row[4 * i + 2] = t.z; row[4 * i + 3] = t.w;
+    }
+    // point indices are never negative: the branch keeps every entry load ahead of every row load (in-order issue)
+    int lowest = e[0].x;
+#pragma unroll
+    for (int i = 1; i < ROWSEG; ++i) lowest = min(lowest, e[i].x);
+    if (lowest < 0) return;
+#pragma unroll
+    for (int i = 0; i < ROWSEG; ++i) v[i].load_ordered(src + (int64_t)e[i].x * lds + c0);
+    Vec<VEC> acc;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < ROWSEG; ++i) {
+        const float w = __int_as_float(e[i].y);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc.v[k] = __fmaf_rn(w, v[i].v[k], acc.v[k]);
+        if (i == ROWSEG - 1 || row[i + 1] != row[i]) {
+            acc.red(values + (int64_t)row[i] * L + c0);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
+        }
+    }
+}
+
+extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *ent_row, int64_t N, int d, int64_t M, const float *src,
+                              int64_t lds, int L, float *values, sgp_stream_t stream)
+{
+    if (N == 0 || M == 0) return SGP_OK;
+    if (!ent || !ent_row || !src || !values || N < 0 || M < 0 || d < 1 || L < 1 || lds < L)
+        return fail(SGP_EINVAL, "sgp_splat_rows: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_seg = sgp_rowsort_padded(N, d) / ROWSEG;
+    auto al = [](const void *p, int bytes) { return ((uintptr_t)p % bytes) == 0; };
+    int vec = 1;
+    if (L % 4 == 0 && lds % 4 == 0 && al(src, 16) && al(values, 16)) vec = 4;
+    else if (L % 2 == 0 && lds % 2 == 0 && al(src, 8) && al(values, 8)) vec = 2;
+    const int chunks = L / vec;
+    CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)M * (size_t)L, st));
+    const int64_t work = n_seg * chunks;
+    if (vec == 4) sgp_splat_rows_kernel<4><<<grid_for(work, 256), 256, 0, st>>>((const int2 *)ent, ent_row, n_seg, src, lds, L, chunks, values);
+    else if (vec == 2) sgp_splat_rows_kernel<2><<<grid_for(work, 256), 256, 0, st>>>((const int2 *)ent, ent_row, n_seg, src, lds, L, chunks, values);
+    else sgp_splat_rows_kernel<1><<<grid_for(work, 256), 256, 0, st>>>((const int2 *)ent, ent_row, n_seg, src, lds, L, chunks, values);
+    return launch_ok("sgp_splat_rows_kernel");
+}
+
+// ------------------------------------------------------------------------------------
+// MVM kernels on tiles.  One CTA per tile and per block of CB channels (CB*4 = one 64-byte row piece for L >= 16).
+// Every global read of a tile happens in a first phase of independent, coalesced (or row-gather) loads into shared
+// memory; the second phase works out of shared memory only, so L2 sees one row transfer per dictionary entry
+// (slice) or per piece (splat) instead of one per point-vertex.
+// ------------------------------------------------------------------------------------
+#define TILE_THREADS 256
+#define TILE_PIECE 8   /* entries per splat piece: bounds the work of one thread and the length of one dependent chain */
+
+// splat.  Shared memory: V[T][CB] rows of the tile's points | E[T*dp1] {local point, weight} grouped by piece |
+// PP[pieces+1] piece bounds (relative to the tile's first entry) | PR[pieces] lattice row of each piece.
 template <int VEC>
 __global__ void __launch_bounds__(TILE_THREADS)
-sgp_slice_tiles_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ tile_seg_ptr,
-                       const int32_t *__restrict__ seg_row, const uint16_t *__restrict__ lidx,
-                       const float *__restrict__ tile_w, const float *__restrict__ values, int64_t N, int T, int dp1,
-                       int L, int CB, int cap, float divisor, float rdivisor, float *__restrict__ out, int64_t ldo)
+sgp_splat_tiles_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ tile_piece_ptr,
+                       const uint32_t *__restrict__ piece_ptr, const int32_t *__restrict__ piece_row,
+                       const int2 *__restrict__ seg_ent, const float *__restrict__ src, int64_t lds, int64_t N, int T,
+                       int dp1, int L, int CB, float *__restrict__ values)
 {
-    extern __shared__ __align__(16) float smem[];   // [cap][CB]
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // T is a multiple of 8, so every array below starts 16-byte aligned
+    float *V = (float *)smem_raw;
+    int2 *E = (int2 *)(V + (size_t)T * CB);
+    uint32_t *PP = (uint32_t *)(E + (size_t)T * dp1);
+    int32_t *PR = (int32_t *)(PP + (size_t)T * dp1 + 8);
+    uint32_t *PM = (uint32_t *)(PR + (size_t)T * dp1);   // the tile's slice of perm
     const int64_t tile = blockIdx.x;
     const int cb0 = blockIdx.y * CB;
     const int cb = min(CB, L - cb0);
     const int chunks = cb / VEC;
     const int64_t p0 = tile * T;
     const int np = (int)min((int64_t)T, N - p0);
+    const int64_t e0 = p0 * dp1;
+    const uint32_t j0 = tile_piece_ptr[tile];
+    const int npieces = (int)(tile_piece_ptr[tile + 1] - j0);
+
+    // phase 0a: everything that is a plain range copy, asynchronously (perm slice, entries, piece bounds and rows)
+    cta_copy_async(PM, perm + p0, np * 4, threadIdx.x, TILE_THREADS);
+    cta_copy_async(E, seg_ent + e0, np * dp1 * 8, threadIdx.x, TILE_THREADS);
+    cta_copy_async(PP, piece_ptr + j0, (npieces + 1) * 4, threadIdx.x, TILE_THREADS);
+    cta_copy_async(PR, piece_row + j0, npieces * 4, threadIdx.x, TILE_THREADS);
+    cp_async_wait_all();
+    __syncthreads();
+    // phase 0b: the RHS rows of the tile's points, gathered through perm
+    for (int w = threadIdx.x; w < np * chunks; w += TILE_THREADS) {
+        const int lp = w / chunks, c = (w - lp * chunks) * VEC;
+        cp_async_vec<VEC>(V + lp * CB + c, src + (int64_t)PM[lp] * lds + cb0 + c);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    for (int w = threadIdx.x; w < npieces * chunks; w += TILE_THREADS) {
+        const int j = w / chunks, c = (w - j * chunks) * VEC;
+        const uint32_t a = PP[j] - (uint32_t)e0, b = PP[j + 1] - (uint32_t)e0;
+        Vec<VEC> acc;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
+#pragma unroll 4
+        for (uint32_t e = a; e < b; ++e) {
+            const int2 ent = E[e];
+            const float wgt = __int_as_float(ent.y);
+            Vec<VEC> sv;
+            sv.load_plain(V + ent.x * CB + c);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc.v[k] = __fmaf_rn(wgt, sv.v[k], acc.v[k]);
+        }
+        acc.red(values + (int64_t)PR[j] * L + cb0 + c);
+    }
+}
+
+// slice.  Shared memory: D[cap][CB] dictionary rows | W[T*dp1] weights | LI[T*dp1] dictionary index per point-vertex.
+// Tiles whose dictionary exceeds cap rows (sparse regions: no reuse to exploit) read the lattice directly.
+template <int VEC, bool FAST>
+__global__ void __launch_bounds__(TILE_THREADS)
+sgp_slice_tiles_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ tile_seg_ptr,
+                       const int32_t *__restrict__ seg_row, const uint16_t *__restrict__ lidx,
+                       const float *__restrict__ tile_w, const float *__restrict__ values, int64_t N, int T, int dp1,
+                       int L, int CB, int cap, float divisor, float rdivisor, float *__restrict__ out, int64_t ldo)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *D = (float *)smem_raw;
+    float *W = D + (((size_t)cap * CB + 3) & ~(size_t)3);
+    int32_t *IDX = (int32_t *)(W + (size_t)T * dp1);          // the tile's dictionary (lattice rows)
+    uint32_t *PM = (uint32_t *)(IDX + ((cap + 3) & ~3));      // the tile's slice of perm
+    uint16_t *LI = (uint16_t *)(PM + T);
+    const int64_t tile = blockIdx.x;
+    const int cb0 = blockIdx.y * CB;
+    const int cb = min(CB, L - cb0);
+    const int chunks = cb / VEC;
+    const int64_t p0 = tile * T;
+    const int np = (int)min((int64_t)T, N - p0);
+    const int64_t q0 = p0 * dp1;
     const uint32_t s0 = tile_seg_ptr[tile];
     const int nloc = (int)(tile_seg_ptr[tile + 1] - s0);
     const bool staged = nloc <= cap;
 
+    // phase 0a: plain range copies, asynchronously (dictionary, weights, dictionary indices, perm slice)
+    if (staged) cta_copy_async(IDX, seg_row + s0, nloc * 4, threadIdx.x, TILE_THREADS);
+    cta_copy_async(W, tile_w + q0, np * dp1 * 4, threadIdx.x, TILE_THREADS);
+    cta_copy_async(LI, lidx + q0, (np * dp1 * 2 + 3) & ~3, threadIdx.x, TILE_THREADS);   // lidx is padded by the builder
+    cta_copy_async(PM, perm + p0, np * 4, threadIdx.x, TILE_THREADS);
+    cp_async_wait_all();
+    __syncthreads();
+    // phase 0b: the dictionary rows, all in flight at once
     if (staged) {
         for (int w = threadIdx.x; w < nloc * chunks; w += TILE_THREADS) {
             const int lr = w / chunks, c = (w - lr * chunks) * VEC;
-            Vec<VEC> v;
-            v.load(values + (int64_t)seg_row[s0 + lr] * L + cb0 + c);
-            v.store(smem + lr * CB + c);
+            cp_async_vec<VEC>(D + lr * CB + c, values + (int64_t)IDX[lr] * L + cb0 + c);
         }
+        cp_async_wait_all();
         __syncthreads();
     }
+
     for (int w = threadIdx.x; w < np * chunks; w += TILE_THREADS) {
         const int lp = w / chunks, c = (w - lp * chunks) * VEC;
-        const int64_t q0 = (p0 + lp) * dp1;
+        const float *wp = W + lp * dp1;
+        const uint16_t *lp_i = LI + lp * dp1;
         Vec<VEC> acc;
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
         if (staged) {
+#pragma unroll 3
             for (int r = 0; r < dp1; ++r) {
-                const float wgt = __ldg(tile_w + q0 + r);
+                const float wgt = wp[r];
                 Vec<VEC> sv;
-                sv.load_plain(smem + (int)__ldg(lidx + q0 + r) * CB + c);
+                sv.load_plain(D + (int)lp_i[r] * CB + c);
 #pragma unroll
                 for (int k = 0; k < VEC; ++k)
-                    acc.v[k] = __fadd_rn(acc.v[k], exact_div(__fmul_rn(wgt, sv.v[k]), divisor, rdivisor));
+                    acc.v[k] = FAST ? __fmaf_rn(wgt, sv.v[k], acc.v[k])
+                                    : __fadd_rn(acc.v[k], exact_div(__fmul_rn(wgt, sv.v[k]), divisor, rdivisor));
             }
         } else {
             for (int r = 0; r < dp1; ++r) {
-                const float wgt = __ldg(tile_w + q0 + r);
+                const float wgt = wp[r];
                 Vec<VEC> v;
-                v.load(values + (int64_t)seg_row[s0 + __ldg(lidx + q0 + r)] * L + cb0 + c);
+                v.load(values + (int64_t)__ldg(seg_row + s0 + lp_i[r]) * L + cb0 + c);
 #pragma unroll
                 for (int k = 0; k < VEC; ++k)
-                    acc.v[k] = __fadd_rn(acc.v[k], exact_div(__fmul_rn(wgt, v.v[k]), divisor, rdivisor));
+                    acc.v[k] = FAST ? __fmaf_rn(wgt, v.v[k], acc.v[k])
+                                    : __fadd_rn(acc.v[k], exact_div(__fmul_rn(wgt, v.v[k]), divisor, rdivisor));
             }
         }
-        acc.store(out + (int64_t)perm[p0 + lp] * ldo + cb0 + c);
+        if (FAST) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc.v[k] = exact_div(acc.v[k], divisor, rdivisor);
+        }
+        acc.store(out + (int64_t)PM[lp] * ldo + cb0 + c);
     }
 }
 
@@ -475,8 +665,7 @@ static int tile_vec(int L, int CB, int64_t ld_a, const void *p0, const void *p1)
 
 static int check_tiles(const sgp_tiles_view *t, int L)
 {
-    if (!t || !t->perm || !t->tile_seg_ptr || !t->seg_ptr || !t->seg_row || !t->seg_ent || !t->lidx || !t->tile_w)
-        return fail(SGP_EINVAL, "null tiles view");
+    if (!t || !t->perm) return fail(SGP_EINVAL, "null tiles view");
     if (t->N <= 0 || t->M <= 0 || t->S <= 0 || t->d < 1 || t->tile_points < 1 || L < 1)
         return fail(SGP_EINVAL, "bad tiles view");
     return SGP_OK;
@@ -487,69 +676,86 @@ extern "C" int sgp_splat_tiles(const sgp_tiles_view *t, const float *src, int64_
 {
     int rc = check_tiles(t, L);
     if (rc) return rc;
-    if (!src || !values || lds < L) return fail(SGP_EINVAL, "sgp_splat_tiles: null pointer or lds < L");
+    if (!src || !values || lds < L || !t->tile_piece_ptr || !t->piece_ptr || !t->piece_row || !t->seg_ent)
+        return fail(SGP_EINVAL, "sgp_splat_tiles: null pointer or lds < L");
     cudaStream_t st = (cudaStream_t)stream;
     const int CB = L < 16 ? L : 16;
     const int vec = tile_vec(L, CB, lds, src, values);
-    const int64_t n_tiles = (t->N + t->tile_points - 1) / t->tile_points;
+    const int T = t->tile_points, dp1 = t->d + 1;
+    const int64_t n_tiles = (t->N + T - 1) / T;
     const unsigned ncb = (unsigned)((L + CB - 1) / CB);
-    const size_t smem = (size_t)t->tile_points * CB * sizeof(float);
+    const size_t smem = (size_t)T * CB * 4 + (size_t)T * dp1 * 8 + ((size_t)T * dp1 + 8) * 4 + (size_t)T * dp1 * 4 + (size_t)T * 4;
+    if (smem > 227 * 1024) return fail(SGP_EUNSUPPORTED, "splat tiles need %zu bytes of shared memory", smem);
     CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)t->M * (size_t)L, st));
     dim3 grid((unsigned)n_tiles, ncb);
 #define SGP_LAUNCH_SPLAT_TILES(VV)                                                                                   \
-    sgp_splat_tiles_kernel<VV><<<grid, TILE_THREADS, smem, st>>>(t->perm, t->tile_seg_ptr, t->seg_ptr, t->seg_row,  \
-                                                                 (const int2 *)t->seg_ent, src, lds, t->N,           \
-                                                                 t->tile_points, L, CB, values)
+    do {                                                                                                             \
+        static size_t granted = 48 * 1024;                                                                           \
+        if (smem > granted) {                                                                                        \
+            CUDA_TRY(cudaFuncSetAttribute(sgp_splat_tiles_kernel<VV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                          (int)smem));                                                               \
+            granted = smem;                                                                                          \
+        }                                                                                                            \
+        sgp_splat_tiles_kernel<VV><<<grid, TILE_THREADS, smem, st>>>(t->perm, t->tile_piece_ptr, t->piece_ptr,      \
+                                                                     t->piece_row, (const int2 *)t->seg_ent, src,    \
+                                                                     lds, t->N, T, dp1, L, CB, values);              \
+    } while (0)
     if (vec == 4) SGP_LAUNCH_SPLAT_TILES(4);
     else if (vec == 2) SGP_LAUNCH_SPLAT_TILES(2);
     else SGP_LAUNCH_SPLAT_TILES(1);
+#undef SGP_LAUNCH_SPLAT_TILES
     return launch_ok("sgp_splat_tiles_kernel");
 }
 
 extern "C" int sgp_slice_tiles(const sgp_tiles_view *t, const float *values, int L, float *out, int64_t ldo,
-                               sgp_stream_t stream)
+                               int fast, sgp_stream_t stream)
 {
     int rc = check_tiles(t, L);
     if (rc) return rc;
-    if (!values || !out || ldo < L) return fail(SGP_EINVAL, "sgp_slice_tiles: null pointer or ldo < L");
+    if (!values || !out || ldo < L || !t->tile_seg_ptr || !t->seg_row || !t->lidx || !t->tile_w)
+        return fail(SGP_EINVAL, "sgp_slice_tiles: null pointer or ldo < L");
     cudaStream_t st = (cudaStream_t)stream;
     const int CB = L < 16 ? L : 16;
     const int vec = tile_vec(L, CB, ldo, values, out);
-    const int64_t n_tiles = (t->N + t->tile_points - 1) / t->tile_points;
+    const int T = t->tile_points, dp1 = t->d + 1;
+    const int64_t n_tiles = (t->N + T - 1) / T;
     const unsigned ncb = (unsigned)((L + CB - 1) / CB);
-    // dictionary rows staged per CTA: bounded so that >= 3 CTAs fit one SM (227 KB)
-    int cap = t->max_dict;
-    const int cap_limit = (72 * 1024) / (CB * (int)sizeof(float));
-    if (cap > cap_limit) cap = cap_limit;
+    // dictionary rows staged per CTA (tiles with more read the lattice directly)
+    static int cap_env = 0;   // tuning hook: SGP_TILE_DICT_CAP
+    if (cap_env == 0) {
+        const char *e = getenv("SGP_TILE_DICT_CAP");
+        cap_env = e ? atoi(e) : 768;
+        if (cap_env < 1) cap_env = 768;
+    }
+    int cap = t->dict_cap < cap_env ? t->dict_cap : cap_env;
     if (cap < 1) cap = 1;
-    const size_t smem = (size_t)cap * CB * sizeof(float);
+    const size_t smem = (((size_t)cap * CB + 3) & ~(size_t)3) * 4 + (size_t)T * dp1 * 4 + (size_t)((cap + 3) & ~3) * 4 + (size_t)T * 4 +
+                        (((size_t)T * dp1 * 2 + 15) & ~(size_t)15);
+    if (smem > 227 * 1024) return fail(SGP_EUNSUPPORTED, "slice tiles need %zu bytes of shared memory", smem);
     const float divisor = sgp_slice_divisor(t->d);
     volatile float rdivisor = 1.0f / divisor;
     dim3 grid((unsigned)n_tiles, ncb);
-#define SGP_LAUNCH_SLICE_TILES(VV)                                                                                   \
+#define SGP_LAUNCH_SLICE_TILES(VV, FF)                                                                               \
     do {                                                                                                             \
-        if (smem > 48 * 1024)                                                                                        \
-            CUDA_TRY(cudaFuncSetAttribute(sgp_slice_tiles_kernel<VV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                          (int)smem));                                                               \
-        sgp_slice_tiles_kernel<VV><<<grid, TILE_THREADS, smem, st>>>(t->perm, t->tile_seg_ptr, t->seg_row, t->lidx,  \
-                                                                     t->tile_w, values, t->N, t->tile_points,        \
-                                                                     t->d + 1, L, CB, cap, divisor, rdivisor, out,  \
-                                                                     ldo);                                           \
+        static size_t granted = 48 * 1024;                                                                           \
+        if (smem > granted) {                                                                                        \
+            CUDA_TRY(cudaFuncSetAttribute(sgp_slice_tiles_kernel<VV, FF>,                                            \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+            granted = smem;                                                                                          \
+        }                                                                                                            \
+        sgp_slice_tiles_kernel<VV, FF><<<grid, TILE_THREADS, smem, st>>>(t->perm, t->tile_seg_ptr, t->seg_row,      \
+                                                                         t->lidx, t->tile_w, values, t->N, T, dp1,   \
+                                                                         L, CB, cap, divisor, rdivisor, out, ldo);   \
     } while (0)
-    if (vec == 4) SGP_LAUNCH_SLICE_TILES(4);
-    else if (vec == 2) SGP_LAUNCH_SLICE_TILES(2);
-    else SGP_LAUNCH_SLICE_TILES(1);
+    if (fast) {
+        if (vec == 4) SGP_LAUNCH_SLICE_TILES(4, true);
+        else if (vec == 2) SGP_LAUNCH_SLICE_TILES(2, true);
+        else SGP_LAUNCH_SLICE_TILES(1, true);
+    } else {
+        if (vec == 4) SGP_LAUNCH_SLICE_TILES(4, false);
+        else if (vec == 2) SGP_LAUNCH_SLICE_TILES(2, false);
+        else SGP_LAUNCH_SLICE_TILES(1, false);
+    }
+#undef SGP_LAUNCH_SLICE_TILES
     return launch_ok("sgp_slice_tiles_kernel");
-}
-
-extern "C" int sgp_mvm_tiles(const sgp_lattice_view *lat, const sgp_tiles_view *tiles, const float *src, int64_t lds,
-                             int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1,
-                             sgp_stream_t stream)
-{
-    int rc = sgp_splat_tiles(tiles, src, lds, L, buf0, stream);
-    if (rc) return rc;
-    int in1 = 0;
-    rc = sgp_blur(lat, coeffs, k, L, buf0, buf1, &in1, stream);
-    if (rc) return rc;
-    return sgp_slice_tiles(tiles, in1 ? buf1 : buf0, L, out, ldo, stream);
 }

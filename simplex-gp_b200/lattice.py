@@ -83,7 +83,7 @@ class Lattice:
 
     def __init__(self, x: torch.Tensor, coeffs, *, build_csr: bool = False, build_tiles: bool = False,
                  build_groups: bool = True, group_axes: int = 3, group_rows: int = 512,
-                 sort_points: bool = True, exact: bool = False,
+                 sort_points: bool = False, build_rows: bool = True, exact: bool = False,
                  tile_points: int = 256, keep_structure: bool = True, hash_capacity: Optional[int] = None):
         if x.dim() != 2:
             raise ValueError(f"x must be [N, d], got {tuple(x.shape)}")
@@ -119,6 +119,7 @@ class Lattice:
             self.tiles = None
             self.groups = None
             self.sorted = None
+            self.rows = None
             self.hash_capacity = 0
             if N > 0:
                 check(lib.sgp_build_points(_ptr(x), N, d, x.stride(0), _fp(self.scale), _ptr(self.greedy),
@@ -145,16 +146,19 @@ class Lattice:
                 del table
                 if build_csr:
                     self._build_csr()
-                if build_tiles:
-                    self._build_tiles(tile_points)
                 if build_groups and r >= 1 and self.M > 0:
                     self._build_groups(group_axes, group_rows)
-                if sort_points and self.M > 0:
+                if (sort_points or build_tiles) and self.M > 0:
                     self._sort_points()
+                if build_tiles and self.M > 0:
+                    self._build_tiles(tile_points)
+                if build_rows and self.M > 0:
+                    self._build_rows()
             if not keep_structure:
                 self.greedy = None
                 self.rank = None
         self._bufs = {}
+        self._tables = {}
 
     @classmethod
     def from_arrays(cls, coeffs, replay: torch.Tensor, keys: torch.Tensor, nbr: torch.Tensor,
@@ -178,17 +182,18 @@ class Lattice:
         self.tiles = None
         self.groups = None
         self.sorted = None      # the locality order needs greedy, which does not travel with the arrays
+        self.rows = None
         self.exact = bool(exact)
         self.hash_capacity = 0
         self._bufs = {}
+        self._tables = {}
         if self.N > 0 and self.M > 0:
             with torch.cuda.device(self.device):
                 if build_csr:
                     self._build_csr()
-                if build_tiles:
-                    self._build_tiles(tile_points)
                 if build_groups and self.order >= 1:
                     self._build_groups(group_axes, group_rows)
+                self._build_rows()
         return self
 
     def _build_groups(self, group_axes: int = 3, group_rows: int = 512) -> None:
@@ -236,18 +241,28 @@ class Lattice:
             prev_pos = pos
             keep.append(pos)
             j0 = j1
-        replay_out = torch.empty_like(self.replay)
-        check(lib.sgp_remap_replay(_ptr(self.replay), self.N * (d + 1), _ptr(prev_pos), _ptr(replay_out), st))
         arr = (_capi.BlurGroup * len(groups))()
         for k, g in enumerate(groups):
             arr[k] = _capi.BlurGroup(g["j0"], g["j1"], g["rows_cap"], 0, g["n_batches"], g["batch_begin"].data_ptr(),
                                      g["src"].data_ptr(), g["lnb"].data_ptr())
-        self.groups = {"list": groups, "array": arr, "replay_out": replay_out, "final_pos": prev_pos}
+        self.groups = {"list": groups, "array": arr, "final_pos": prev_pos}
+
+    def _build_rows(self) -> None:
+        """Point-vertices sorted by lattice row for the segmented-gather splat (csrc/sgp_tiles.cu, sgp_build_rowsorted)."""
+        lib = _capi.lib()
+        dev, N, d, M = self.device, self.N, self.d, self.M
+        st = _stream_ptr(dev)
+        padded = int(lib.sgp_rowsort_padded(N, d))
+        ws_bytes = int(lib.sgp_rowsort_workspace_bytes(N, d))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ent = torch.empty((padded, 2), dtype=torch.int32, device=dev)
+        ent_row = torch.empty(padded, dtype=torch.int32, device=dev)
+        check(lib.sgp_build_rowsorted(_ptr(self.replay), N, d, M, _ptr(ent), _ptr(ent_row), _ptr(ws), ws_bytes, st))
+        self.rows = {"ent": ent, "ent_row": ent_row}
 
     def _sort_points(self) -> None:
-        """Locality order of the points (csrc/sgp_tiles.cu, sgp_sort_points) and the replay tables re-ordered with it:
-        ``replay`` for the splat (lattice-index rows) and ``replay_out`` for the slice (rows in the order the last blur
-        stage leaves them)."""
+        """Locality order of the points (csrc/sgp_tiles.cu, sgp_sort_points); the replay tables re-ordered with it are
+        made on first use by ``_table``."""
         lib = _capi.lib()
         dev, N, d = self.device, self.N, self.d
         st = _stream_ptr(dev)
@@ -255,51 +270,75 @@ class Lattice:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         perm = torch.empty(N, dtype=torch.int32, device=dev)
         check(lib.sgp_sort_points(_ptr(self.greedy), N, d, _ptr(perm), _ptr(ws), ws_bytes, st))
-        rp = torch.empty_like(self.replay)
-        check(lib.sgp_permute_replay(_ptr(self.replay), _ptr(perm), None, N, d, _ptr(rp), st))
-        out = rp
-        if self.groups is not None:
-            out = torch.empty_like(self.replay)
-            check(lib.sgp_permute_replay(_ptr(self.replay), _ptr(perm), _ptr(self.groups["final_pos"]), N, d, _ptr(out), st))
-        self.sorted = {"perm": perm, "replay": rp, "replay_out": out}
+        self.sorted = {"perm": perm}
 
     def _build_tiles(self, tile_points: int = 256) -> None:
-        """Locality tiles for the shared-memory staged splat / slice (csrc/sgp_tiles.cu)."""
+        """Locality tiles for the shared-memory staged splat / slice (csrc/sgp_tiles.cu): the points in locality
+        order are cut into tiles of ``tile_points``; per tile, the distinct lattice rows it touches (its dictionary)
+        and its point-vertices grouped by row into segments, the segments cut into pieces of at most 8 entries."""
         lib = _capi.lib()
         dev, N, d, M = self.device, self.N, self.d, self.M
+        if self.sorted is None:
+            self._sort_points()
+        perm = self.sorted["perm"]
         total = N * (d + 1)
-        T = int(tile_points)
-        while T > 1 and T * (d + 1) > 65535:
+        T = max(8, int(tile_points) // 8 * 8)
+        while T > 8 and T * (d + 1) > 65535:
             T //= 2
         n_tiles = (N + T - 1) // T
         st = _stream_ptr(dev)
         ws_bytes = int(lib.sgp_tiles_workspace_bytes(N, d))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        perm = torch.empty(N, dtype=torch.int32, device=dev)
         S = C.c_int64(0)
         check(lib.sgp_tiles_prepare(_ptr(self.replay), N, d, M, T, _ptr(perm), _ptr(ws), ws_bytes, C.byref(S), st))
         S = int(S.value)
+        seg_ptr = torch.empty(S + 1, dtype=torch.int32, device=dev)
         t = {
-            "T": T, "S": S, "perm": perm,
-            "seg_ptr": torch.empty(S + 1, dtype=torch.int32, device=dev),
+            "T": T, "S": S,
             "seg_row": torch.empty(S, dtype=torch.int32, device=dev),
             "seg_ent": torch.empty((total, 2), dtype=torch.int32, device=dev),
             "tile_seg_ptr": torch.empty(n_tiles + 1, dtype=torch.int32, device=dev),
-            "lidx": torch.empty(total, dtype=torch.int16, device=dev),
+            "lidx": torch.zeros(total + 8, dtype=torch.int16, device=dev),   # padded: copied in 4-byte pieces
             "tile_w": torch.empty(total, dtype=torch.float32, device=dev),
         }
         mx = C.c_int32(0)
-        check(lib.sgp_tiles_finalize(_ptr(self.replay), _ptr(perm), N, d, T, S, _ptr(ws), ws_bytes, _ptr(t["seg_ptr"]),
+        check(lib.sgp_tiles_finalize(_ptr(self.replay), _ptr(perm), N, d, T, S, _ptr(ws), ws_bytes, _ptr(seg_ptr),
                                      _ptr(t["seg_row"]), _ptr(t["seg_ent"]), _ptr(t["tile_seg_ptr"]), _ptr(t["lidx"]),
                                      _ptr(t["tile_w"]), C.byref(mx), st))
         t["max_dict"] = int(mx.value)
+        del ws
+        # splat pieces: every segment cut into runs of at most 8 entries (index plumbing of the build, torch ops)
+        PIECE = 8
+        sp = seg_ptr.long()
+        lens = sp[1:] - sp[:-1]
+        npc = (lens + (PIECE - 1)) // PIECE
+        first = torch.cumsum(npc, 0) - npc
+        P = int(npc.sum().item())
+        seg_of_piece = torch.repeat_interleave(torch.arange(S, device=dev), npc, output_size=P)
+        k_in_seg = torch.arange(P, device=dev) - first[seg_of_piece]
+        start = sp[:-1][seg_of_piece] + PIECE * k_in_seg
+        piece_ptr = torch.empty(P + 1, dtype=torch.int32, device=dev)
+        piece_ptr[:P] = start.to(torch.int32)
+        piece_ptr[P] = total
+        t["P"] = P
+        t["piece_ptr"] = piece_ptr
+        t["piece_row"] = t["seg_row"][seg_of_piece].contiguous()
+        tsp = t["tile_seg_ptr"].long()
+        first_ext = torch.cat([first, first.new_tensor([P])])
+        t["tile_piece_ptr"] = first_ext[tsp].to(torch.int32).contiguous()
+        # the slice after a blur-group chain reads the lattice values in the last stage's order
+        t["seg_row_out"] = t["seg_row"]
+        if self.groups is not None:
+            t["seg_row_out"] = self.groups["final_pos"][t["seg_row"].long()].contiguous()
         self.tiles = t
 
-    def _tiles_view(self) -> TilesView:
+    def _tiles_view(self, final: bool = False) -> TilesView:
         t = self.tiles
-        return TilesView(self.N, self.M, t["S"], self.d, t["T"], t["max_dict"], 0, t["perm"].data_ptr(),
-                         t["tile_seg_ptr"].data_ptr(), t["seg_ptr"].data_ptr(), t["seg_row"].data_ptr(),
-                         t["seg_ent"].data_ptr(), t["lidx"].data_ptr(), t["tile_w"].data_ptr())
+        rows = t["seg_row_out"] if final else t["seg_row"]
+        return TilesView(self.N, self.M, t["S"], t["P"], self.d, t["T"], t["max_dict"], 0,
+                         self.sorted["perm"].data_ptr(), t["tile_seg_ptr"].data_ptr(), rows.data_ptr(),
+                         t["lidx"].data_ptr(), t["tile_w"].data_ptr(), t["seg_ent"].data_ptr(),
+                         t["tile_piece_ptr"].data_ptr(), t["piece_ptr"].data_ptr(), t["piece_row"].data_ptr())
 
     def _build_csr(self) -> None:
         lib = _capi.lib()
@@ -324,14 +363,30 @@ class Lattice:
         """fp32 ``[N, d+1]``: barycentric weight of every simplex vertex (reference ``replay[].weight``)."""
         return self.replay[..., 1].view(torch.float32)
 
+    def _table(self, sorted: bool, final: bool) -> torch.Tensor:
+        """Internal replay table ``[d+1, N, 2]`` (transposed: the points of a warp read one contiguous run per
+        vertex), built on first use: rows in the locality order when ``sorted``; lattice indices mapped to the order
+        the last blur-group stage leaves the lattice values in when ``final``."""
+        key = (bool(sorted), bool(final))
+        t = self._tables.get(key)
+        if t is None:
+            t = torch.empty((self.d + 1, self.N, 2), dtype=torch.int32, device=self.device)
+            perm = self.sorted["perm"] if sorted else None
+            pos = self.groups["final_pos"] if final else None
+            with torch.cuda.device(self.device):
+                check(_capi.lib().sgp_permute_replay(_ptr(self.replay), _ptr(perm), _ptr(pos), self.N, self.d, 1, _ptr(t),
+                                                     _stream_ptr(self.device)))
+            self._tables[key] = t
+        return t
+
     def _view(self, replay: Optional[torch.Tensor] = None, perm: Optional[torch.Tensor] = None,
-              exact: Optional[bool] = None) -> LatticeView:
+              exact: Optional[bool] = None, transposed: bool = False) -> LatticeView:
         exact = self.exact if exact is None else exact
         return LatticeView(self.N, self.M, self.d, self.order, (self.replay if replay is None else replay).data_ptr(),
                            self.nbr.data_ptr() if self.nbr.numel() else 0,
                            self.csr_ptr.data_ptr() if self.csr_ptr is not None else 0,
                            self.csr_ent.data_ptr() if self.csr_ent is not None else 0,
-                           0 if perm is None else perm.data_ptr(), 0 if exact else 1, 0)
+                           0 if perm is None else perm.data_ptr(), 0 if exact else 1, 1 if transposed else 0)
 
     def _scratch(self, L: int):
         key = int(L)
@@ -367,12 +422,16 @@ class Lattice:
                 tv = self._tiles_view()
                 check(_capi.lib().sgp_splat_tiles(C.byref(tv), _ptr(src), src.stride(0), L, _ptr(values),
                                                   _stream_ptr(self.device)))
+            elif mode == _capi.MODE_ROWS:
+                check(_capi.lib().sgp_splat_rows(_ptr(self.rows["ent"]), _ptr(self.rows["ent_row"]), self.N, self.d,
+                                                 self.M, _ptr(src), src.stride(0), L, _ptr(values),
+                                                 _stream_ptr(self.device)))
             else:
                 if mode == _capi.MODE_AUTO:
                     mode = _capi.MODE_GATHER if self.csr_ptr is not None else _capi.MODE_ATOMIC
                 v = self._view()
                 if sorted and mode == _capi.MODE_ATOMIC:
-                    v = self._view(self.sorted["replay"], self.sorted["perm"])
+                    v = self._view(self._table(True, False), self.sorted["perm"], transposed=True)
                 check(_capi.lib().sgp_splat(C.byref(v), _ptr(src), src.stride(0), L, _ptr(values), mode,
                                             _stream_ptr(self.device)))
         return values
@@ -413,9 +472,10 @@ class Lattice:
             if mode == _capi.MODE_TILES:
                 tv = self._tiles_view()
                 check(_capi.lib().sgp_slice_tiles(C.byref(tv), _ptr(values), L, _ptr(out), out.stride(0),
-                                                  _stream_ptr(self.device)))
+                                                  0 if exact else 1, _stream_ptr(self.device)))
             else:
-                v = self._view(self.sorted["replay"], self.sorted["perm"], exact) if sorted else self._view(exact=exact)
+                v = self._view(self._table(True, False), self.sorted["perm"], exact, True) if sorted \
+                    else self._view(exact=exact)
                 check(_capi.lib().sgp_slice(C.byref(v), _ptr(values), L, _ptr(out), out.stride(0),
                                             _stream_ptr(self.device)))
         return out
@@ -426,9 +486,10 @@ class Lattice:
             exact: Optional[bool] = None) -> torch.Tensor:
         """``out[N, L] = slice(blur(splat(src[N, L])))`` on the built lattice.
 
-        ``mode``   splat form: 0 auto (atomic scatter), 1 atomic scatter (``red.global.add.v4.f32``), 2 gather in the
-                   reference's accumulation order (deterministic; needs ``build_csr=True``), 3 locality tiles
-                   (needs ``build_tiles=True``; implies the tile slice and the per-axis blur).
+        ``mode``   splat form: 0 auto (row-sorted segmented gather when built, else atomic scatter), 1 atomic scatter
+                   (``red.global.add.v4.f32`` per point-vertex), 2 gather in the reference's accumulation order
+                   (deterministic; needs ``build_csr=True``), 3 locality tiles (needs ``build_tiles=True``; implies the
+                   tile slice), 4 row-sorted segmented gather (``build_rows=True``).
         ``blur``   "groups" (several axes per launch through shared memory), "axis" (one launch per axis) or "auto"
                    (groups when they were built).
         ``sorted`` walk the points in the locality order in splat and slice (default: when it was built).
@@ -447,17 +508,14 @@ class Lattice:
         exact = self.exact if exact is None else bool(exact)
         buf0, buf1 = self._scratch(L)
         lib, st = _capi.lib(), _stream_ptr(self.device)
-        if mode == _capi.MODE_TILES:
-            if self.tiles is None:
-                raise RuntimeError("tiles were not built for this lattice (build_tiles=True)")
-            v, tv = self._view(exact=exact), self._tiles_view()
-            with torch.cuda.device(self.device):
-                check(lib.sgp_mvm_tiles(C.byref(v), C.byref(tv), _ptr(src), src.stride(0), L, _fp(c), c.shape[0],
-                                        _ptr(out), out.stride(0), _ptr(buf0), _ptr(buf1), st))
-            return out
+        use_tiles = mode == _capi.MODE_TILES
+        if use_tiles and self.tiles is None:
+            raise RuntimeError("tiles were not built for this lattice (build_tiles=True)")
         if mode == _capi.MODE_AUTO:
-            mode = _capi.MODE_ATOMIC
-        use_sorted = (self.sorted is not None) if sorted is None else bool(sorted)
+            mode = _capi.MODE_ROWS if self.rows is not None else _capi.MODE_ATOMIC
+        if mode == _capi.MODE_ROWS and self.rows is None:
+            raise RuntimeError("the row-sorted entries were not built for this lattice (build_rows=True)")
+        use_sorted = False if sorted is None else bool(sorted)   # measured slower than the input order on B200
         if use_sorted and self.sorted is None:
             raise RuntimeError("the locality order was not built for this lattice (sort_points=True)")
         use_groups = (self.groups is not None) if blur == "auto" else (blur == "groups")
@@ -465,11 +523,19 @@ class Lattice:
             raise RuntimeError("blur groups were not built for this lattice")
         where = C.c_int(0)
         with torch.cuda.device(self.device):
-            if mode == _capi.MODE_GATHER or not use_sorted:
-                v_in = self._view(exact=exact)
+            perm = self.sorted["perm"] if use_sorted else None
+            if use_tiles:
+                tv = self._tiles_view(False)
+                check(lib.sgp_splat_tiles(C.byref(tv), _ptr(src), src.stride(0), L, _ptr(buf0), st))
+            elif mode == _capi.MODE_ROWS:
+                check(lib.sgp_splat_rows(_ptr(self.rows["ent"]), _ptr(self.rows["ent_row"]), self.N, self.d, self.M,
+                                         _ptr(src), src.stride(0), L, _ptr(buf0), st))
             else:
-                v_in = self._view(self.sorted["replay"], self.sorted["perm"], exact)
-            check(lib.sgp_splat(C.byref(v_in), _ptr(src), src.stride(0), L, _ptr(buf0), mode, st))
+                if mode == _capi.MODE_GATHER:
+                    v_in = self._view(exact=exact)
+                else:
+                    v_in = self._view(self._table(use_sorted, False), perm, exact, True)
+                check(lib.sgp_splat(C.byref(v_in), _ptr(src), src.stride(0), L, _ptr(buf0), mode, st))
             if use_groups:
                 arr = self.groups["array"]
                 check(lib.sgp_blur_groups(arr, len(arr), self.M, self.order, _fp(c), c.shape[0], L, _ptr(buf0),
@@ -477,12 +543,13 @@ class Lattice:
             else:
                 vb = self._view(exact=exact)
                 check(lib.sgp_blur(C.byref(vb), _fp(c), c.shape[0], L, _ptr(buf0), _ptr(buf1), C.byref(where), st))
-            if use_sorted:
-                rp = self.sorted["replay_out"] if use_groups else self.sorted["replay"]
-                v_out = self._view(rp, self.sorted["perm"], exact)
+            res = buf1 if where.value else buf0
+            if use_tiles:
+                tv = self._tiles_view(use_groups)
+                check(lib.sgp_slice_tiles(C.byref(tv), _ptr(res), L, _ptr(out), out.stride(0), 0 if exact else 1, st))
             else:
-                v_out = self._view(self.groups["replay_out"] if use_groups else None, None, exact)
-            check(lib.sgp_slice(C.byref(v_out), _ptr(buf1 if where.value else buf0), L, _ptr(out), out.stride(0), st))
+                v_out = self._view(self._table(use_sorted, use_groups), perm, exact, True)
+                check(lib.sgp_slice(C.byref(v_out), _ptr(res), L, _ptr(out), out.stride(0), st))
         return out
 
     def algorithmic_bytes(self, L: int) -> int:
@@ -503,14 +570,16 @@ def lattice_filter(src: torch.Tensor, ref: torch.Tensor, coeffs, *, device=None)
         raise TypeError("filter: float32 tensors required (reference CPU filter is fp32-only)")
     if src.is_cuda:
         dev = src.device
-        lat = Lattice(ref.to(dev), coeffs, build_csr=False, build_tiles=False, build_groups=False, sort_points=False, keep_structure=False)
+        lat = Lattice(ref.to(dev), coeffs, build_csr=False, build_tiles=False, build_groups=False, sort_points=False, build_rows=False,
+                      keep_structure=False)
         return lat.mvm(src)
     if not torch.cuda.is_available():
         raise RuntimeError("filter: no CUDA device; this package has no CPU path")
     dev = torch.device(device if device is not None else "cuda")
     ref_d = ref.contiguous().pin_memory().to(dev, non_blocking=True)
     src_d = src.contiguous().pin_memory().to(dev, non_blocking=True)
-    lat = Lattice(ref_d, coeffs, build_csr=False, build_tiles=False, build_groups=False, sort_points=False, keep_structure=False)
+    lat = Lattice(ref_d, coeffs, build_csr=False, build_tiles=False, build_groups=False, sort_points=False, build_rows=False,
+                      keep_structure=False)
     out_d = lat.mvm(src_d)
     out = torch.empty(out_d.shape, dtype=out_d.dtype, pin_memory=True)
     out.copy_(out_d, non_blocking=True)

@@ -38,7 +38,7 @@ def _rel(a, b):
 def test_structure_and_values_match_oracle(sg, oracle, N, d, L, coeffs, dist):
     x, v = make_inputs(N, d, L, seed=N + d, dist=dist)
     O = oracle.OracleLattice(x.numpy(), coeffs)
-    lat = sg.Lattice(x.cuda(), coeffs, build_csr=True, build_tiles=True)
+    lat = sg.Lattice(x.cuda(), coeffs, build_csr=True, build_tiles=True, sort_points=True)
     assert lat.M == O.M
     assert np.array_equal(lat.scale.view(np.int32), O.scale.view(np.int32))
     assert np.array_equal(lat.greedy.cpu().numpy(), O.greedy)
@@ -68,8 +68,13 @@ def test_structure_and_values_match_oracle(sg, oracle, N, d, L, coeffs, dist):
     assert _rel(lat.mvm(vd).cpu().numpy(), out_o) < REL_TOL
     assert _rel(lat.mvm(vd, blur="axis").cpu().numpy(), out_o) < REL_TOL
     assert _rel(lat.mvm(vd, sorted=False).cpu().numpy(), out_o) < REL_TOL
+    assert _rel(lat.mvm(vd, sorted=False, blur="axis", exact=True).cpu().numpy(), out_o) < REL_TOL
     assert _rel(lat.slice(bl, mode=1, exact=False).cpu().numpy(), out_o) < 1e-6
     assert _rel(lat.blur(sp, exact=False).cpu().numpy(), bl_o) < 1e-6
+    # row-sorted segmented-gather splat (the production splat)
+    assert _rel(lat.splat(vd, mode=4).cpu().numpy(), sp_o) < REL_TOL
+    assert _rel(lat.mvm(vd, mode=4).cpu().numpy(), out_o) < REL_TOL
+    assert _rel(lat.mvm(vd, mode=1).cpu().numpy(), out_o) < REL_TOL
     # blur groups (several axes per launch through shared memory): same arithmetic per pass, bit-exact
     if lat.order > 0:
         assert lat.groups is not None
@@ -81,9 +86,11 @@ def test_structure_and_values_match_oracle(sg, oracle, N, d, L, coeffs, dist):
     # values); splat sums per-tile partials, then one reduction per segment (1e-5 relative)
     out_t = lat.slice(bl, mode=3)
     assert np.array_equal(bits(out_t.cpu().numpy()), bits(out_o))
+    assert _rel(lat.slice(bl, mode=3, exact=False).cpu().numpy(), out_o) < 1e-6
     sp_t = lat.splat(vd, mode=3)
     assert _rel(sp_t.cpu().numpy(), sp_o) < REL_TOL
     assert _rel(lat.mvm(vd, mode=3).cpu().numpy(), out_o) < REL_TOL
+    assert _rel(lat.mvm(vd, mode=3, blur="axis", exact=True).cpu().numpy(), out_o) < REL_TOL
     # atomic scatter path: 1e-5 relative
     sp_a = lat.splat(vd, mode=1)
     assert _rel(sp_a.cpu().numpy(), sp_o) < REL_TOL
