@@ -34,6 +34,11 @@ WORKLOADS = {
     "A": dict(N=1_000_000, d=8, L=16, kernel="rbf", order=1),
 }
 RBF1 = [0.34608543, 1.0, 0.34608543]   # get_coeffs(rbf, 1), tests/golden/coeffs.json
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/),
+# cold-cache replays of the same command; None until a capture exists for the kernel
+TRAFFIC_NCU = {   # profiles/r1_mvm_full.txt
+    "sgp_splat_rows_kernel": 275.0e6, "sgp_blur_group_kernel": 32.3e6, "sgp_slice_kernel": 140.0e6,
+}
 
 
 def workload_name(w):
@@ -236,14 +241,17 @@ def run_ours(args, w):
     Vs = [torch.randn(N, L, generator=gv, device=dev) for _ in range(n_rot)]
     outs = [torch.empty(N, L, device=dev) for _ in range(n_rot)]
     mode = {"atomic": _capi.MODE_ATOMIC, "gather": _capi.MODE_GATHER, "tiles": _capi.MODE_TILES,
-            "auto": _capi.MODE_AUTO}[args.splat]
+            "rows": _capi.MODE_ROWS, "auto": _capi.MODE_AUTO}[args.splat]
     if mode == _capi.MODE_AUTO:
-        mode = _capi.MODE_TILES if lat.tiles is not None else _capi.MODE_ATOMIC
+        mode = _capi.MODE_ROWS if lat.rows is not None else _capi.MODE_ATOMIC
     if mode == _capi.MODE_GATHER and lat.csr_ptr is None:
         lat._build_csr()
+    if mode == _capi.MODE_TILES and lat.tiles is None:
+        lat._build_tiles()
+    use_groups = lat.groups is not None and args.blur != "axis"
 
     def step(i):
-        lat.mvm(Vs[i % n_rot], out=outs[i % n_rot], mode=mode)
+        lat.mvm(Vs[i % n_rot], out=outs[i % n_rot], mode=mode, blur="groups" if use_groups else "axis")
 
     for i in range(warm):
         step(i)
@@ -275,7 +283,6 @@ def run_ours(args, w):
     roofline = stages = None
     if rank == 0:
         lib = _capi.lib()
-        view = lat._view()
         buf0, buf1 = lat._scratch(L)
         cnp = lat.coeffs
         st = _stream_ptr(dev)
@@ -283,48 +290,66 @@ def run_ours(args, w):
         acc = [0.0, 0.0, 0.0]
         reps = max(5, min(steps, 20))
         where = C.c_int(0)
-        tview = lat._tiles_view() if mode == _capi.MODE_TILES else None
+        fast = 0 if lat.exact else 1
+        v_in = lat._view(lat._table(False, False), None, lat.exact, True)
+        v_axis = lat._view(exact=lat.exact)
+        v_out = lat._view(lat._table(False, use_groups), None, lat.exact, True)
+        tv_in = lat._tiles_view(False) if mode == _capi.MODE_TILES else None
+        tv_out = lat._tiles_view(use_groups) if mode == _capi.MODE_TILES else None
+        garr = lat.groups["array"] if use_groups else None
         for i in range(reps):
             V, out = Vs[i % n_rot], outs[i % n_rot]
             ev[0].record()
-            if tview is not None:
-                _capi.check(lib.sgp_splat_tiles(C.byref(tview), _ptr(V), V.stride(0), L, _ptr(buf0), st))
+            if mode == _capi.MODE_TILES:
+                _capi.check(lib.sgp_splat_tiles(C.byref(tv_in), _ptr(V), V.stride(0), L, _ptr(buf0), st))
+            elif mode == _capi.MODE_ROWS:
+                _capi.check(lib.sgp_splat_rows(_ptr(lat.rows["ent"]), _ptr(lat.rows["ent_row"]), N, d, M, _ptr(V),
+                                               V.stride(0), L, _ptr(buf0), st))
             else:
-                _capi.check(lib.sgp_splat(C.byref(view), _ptr(V), V.stride(0), L, _ptr(buf0), mode, st))
+                _capi.check(lib.sgp_splat(C.byref(v_in if mode == _capi.MODE_ATOMIC else v_axis), _ptr(V), V.stride(0), L,
+                                          _ptr(buf0), mode, st))
             ev[1].record()
-            _capi.check(lib.sgp_blur(C.byref(view), _fp(cnp), cnp.shape[0], L, _ptr(buf0), _ptr(buf1), C.byref(where), st))
+            if use_groups:
+                _capi.check(lib.sgp_blur_groups(garr, len(garr), M, lat.order, _fp(cnp), cnp.shape[0], L, _ptr(buf0),
+                                                _ptr(buf1), C.byref(where), fast, st))
+            else:
+                _capi.check(lib.sgp_blur(C.byref(v_axis), _fp(cnp), cnp.shape[0], L, _ptr(buf0), _ptr(buf1),
+                                         C.byref(where), st))
             ev[2].record()
             res_buf = buf1 if where.value else buf0
-            if tview is not None:
-                _capi.check(lib.sgp_slice_tiles(C.byref(tview), _ptr(res_buf), L, _ptr(out), out.stride(0), st))
+            if mode == _capi.MODE_TILES:
+                _capi.check(lib.sgp_slice_tiles(C.byref(tv_out), _ptr(res_buf), L, _ptr(out), out.stride(0), fast, st))
             else:
-                _capi.check(lib.sgp_slice(C.byref(view), _ptr(res_buf), L, _ptr(out), out.stride(0), st))
+                _capi.check(lib.sgp_slice(C.byref(v_out), _ptr(res_buf), L, _ptr(out), out.stride(0), st))
             ev[3].record()
             torch.cuda.synchronize()
             for k in range(3):
                 acc[k] += ev[k].elapsed_time(ev[k + 1])
         t_splat, t_blur, t_slice = (a / reps for a in acc)
         r = lat.order
+        n_blur = len(lat.groups["list"]) if use_groups else d + 1
         b_splat = 4 * (N * L + 2 * N * (d + 1) + M * L)
-        b_blur_pass = 4 * (2 * M * L + 2 * r * M)
+        b_blur = (d + 1) * 4 * (2 * M * L + 2 * r * M)
         b_slice = 4 * (M * L + 2 * N * (d + 1) + N * L)
+        splat_kernel = {_capi.MODE_ATOMIC: "sgp_splat_atomic_kernel", _capi.MODE_GATHER: "sgp_splat_gather_kernel",
+                        _capi.MODE_TILES: "sgp_splat_tiles_kernel", _capi.MODE_ROWS: "sgp_splat_rows_kernel"}[mode]
         stages = {
-            "splat": {"ms": t_splat, "launches": 1, "alg_bytes": b_splat, "gbs": b_splat / t_splat / 1e6},
-            "blur": {"ms": t_blur, "launches": d + 1, "alg_bytes": b_blur_pass * (d + 1),
-                     "gbs": b_blur_pass * (d + 1) / t_blur / 1e6},
-            "slice": {"ms": t_slice, "launches": 1, "alg_bytes": b_slice, "gbs": b_slice / t_slice / 1e6},
+            "splat": {"ms": t_splat, "launches": 1, "alg_bytes": b_splat, "gbs": b_splat / t_splat / 1e6,
+                      "kernel": splat_kernel},
+            "blur": {"ms": t_blur, "launches": n_blur, "alg_bytes": b_blur, "gbs": b_blur / t_blur / 1e6,
+                     "kernel": "sgp_blur_group_kernel" if use_groups else "sgp_blur_kernel"},
+            "slice": {"ms": t_slice, "launches": 1, "alg_bytes": b_slice, "gbs": b_slice / t_slice / 1e6,
+                      "kernel": "sgp_slice_tiles_kernel" if mode == _capi.MODE_TILES else "sgp_slice_kernel"},
         }
-        dom = max(stages, key=lambda k: stages[k]["ms"])
-        kname = {"splat": {_capi.MODE_ATOMIC: "sgp_splat_atomic_kernel", _capi.MODE_GATHER: "sgp_splat_gather_kernel",
-                           _capi.MODE_TILES: "sgp_splat_tiles_kernel"}[mode],
-                 "blur": "sgp_blur_kernel",
-                 "slice": "sgp_slice_tiles_kernel" if mode == _capi.MODE_TILES else "sgp_slice_kernel"}[dom]
+        dom = max(stages, key=lambda k: stages[k]["ms"] / stages[k]["launches"])
         per_launch_bytes = stages[dom]["alg_bytes"] / stages[dom]["launches"]
         per_launch_ms = stages[dom]["ms"] / stages[dom]["launches"]
         achieved = per_launch_bytes / per_launch_ms / 1e6
-        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "alg_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms}
+        roofline = {"bound": "hbm", "kernel": stages[dom]["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": TRAFFIC_NCU.get(stages[dom]["kernel"]), "peak_source": peak_src,
+                    "alg_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
+                    "share_of_step": stages[dom]["ms"] / ms_per_step}
+        n_launches = 1 + n_blur + 1
 
     # --- end-to-end through the reference-facing call, host buffers ----------------------------------
     e2e = None
@@ -368,11 +393,13 @@ def run_ours(args, w):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(w), "M": M,
-                       "path": {1: "atomic", 2: "gather", 3: "tiles"}[mode],
+                       "path": {"splat": {1: "atomic scatter", 2: "ordered gather", 3: "tiles", 4: "row-sorted segmented gather"}[mode],
+                                "blur": "groups through shared memory" if use_groups else "one launch per axis",
+                                "arithmetic": "reference order (exact)" if lat.exact else "fused multiply-add"},
                        "sharding": "lattice built on rank 0 + NCCL broadcast; one 16-column RHS block per rank",
                        "l2": f"working set {(alg_bytes / (d + 1)) / 1e6:.0f}+ MB per step exceeds the 126 MB L2; "
                              f"V/out rotate over {n_rot} buffer pairs"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": steps * (d + 3),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": steps * n_launches,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "mvm_roofline": {"alg_bytes": alg_bytes, "achieved": alg_bytes / ms_per_step / 1e6, "peak": peak,
                              "unit": "GB/s", "frac": alg_bytes / ms_per_step / 1e6 / peak},
@@ -392,8 +419,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
-    ap.add_argument("--splat", default="auto", choices=["auto", "tiles", "atomic", "gather"],
-                    help="MVM path: locality tiles (default when built), plain atomic scatter, or reference-order gather")
+    ap.add_argument("--splat", default="auto", choices=["auto", "rows", "tiles", "atomic", "gather"],
+                    help="splat form: row-sorted segmented gather (default), locality tiles, atomic scatter, ordered gather")
+    ap.add_argument("--blur", default="groups", choices=["groups", "axis"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -576,12 +576,35 @@ def lattice_filter(src: torch.Tensor, ref: torch.Tensor, coeffs, *, device=None)
     if not torch.cuda.is_available():
         raise RuntimeError("filter: no CUDA device; this package has no CPU path")
     dev = torch.device(device if device is not None else "cuda")
-    ref_d = ref.contiguous().pin_memory().to(dev, non_blocking=True)
-    src_d = src.contiguous().pin_memory().to(dev, non_blocking=True)
-    lat = Lattice(ref_d, coeffs, build_csr=False, build_tiles=False, build_groups=False, sort_points=False, build_rows=False,
-                      keep_structure=False)
-    out_d = lat.mvm(src_d)
-    out = torch.empty(out_d.shape, dtype=out_d.dtype, pin_memory=True)
-    out.copy_(out_d, non_blocking=True)
-    torch.cuda.current_stream(dev).synchronize()
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        ref_h, src_h = ref.contiguous(), src.contiguous()
+        # positions first (the lattice build needs them); the RHS block travels on a second stream while the lattice
+        # is being built.  Pinned host tensors are copied asynchronously, pageable ones through the driver's staging.
+        ref_d = ref_h.to(dev, non_blocking=ref_h.is_pinned())
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            src_d = src_h.to(dev, non_blocking=src_h.is_pinned())
+        lat = Lattice(ref_d, coeffs, build_csr=False, build_tiles=False, build_groups=False, sort_points=False,
+                      build_rows=False, keep_structure=False)
+        main.wait_stream(side)
+        src_d.record_stream(main)
+        out_d = lat.mvm(src_d)
+        out = torch.empty(out_d.shape, dtype=out_d.dtype, pin_memory=True)
+        out.copy_(out_d, non_blocking=True)
+        main.synchronize()
     return out
+
+
+_side_streams = {}
+
+
+def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    s = _side_streams.get(dev.index)
+    if s is None:
+        s = torch.cuda.Stream(device=dev)
+        _side_streams[dev.index] = s
+    return s
