@@ -291,9 +291,9 @@ def run_ours(args, w):
         reps = max(5, min(steps, 20))
         where = C.c_int(0)
         fast = 0 if lat.exact else 1
-        v_in = lat._view(lat._table(False, False), None, lat.exact, True)
+        v_in = lat._view(lat._table(False, False), None, lat.exact)
         v_axis = lat._view(exact=lat.exact)
-        v_out = lat._view(lat._table(False, use_groups), None, lat.exact, True)
+        v_out = lat._view(lat._table(False, use_groups), None, lat.exact)
         tv_in = lat._tiles_view(False) if mode == _capi.MODE_TILES else None
         tv_out = lat._tiles_view(use_groups) if mode == _capi.MODE_TILES else None
         garr = lat.groups["array"] if use_groups else None

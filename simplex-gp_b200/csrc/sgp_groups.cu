@@ -311,7 +311,7 @@ struct GroupCoeffs {
     float c[2 * SGP_MAX_ORDER + 1];
 };
 
-#define STAGE_UNROLL 4
+#define PASS_UNROLL 4
 
 // Shared memory: A[rows_cap][CBT] | B[rows_cap][CBT] | nbs[rows_cap][nax][2r] (uint16), CBT = CHUNKS*VEC channels.
 // A thread owns one channel chunk (c) and the rows lr0, lr0+RSTEP, ... of the batch for the whole kernel, so the
@@ -328,7 +328,7 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
     const int r = R > 0 ? R : order_rt;
     const int w2 = 2 * r;
     extern __shared__ __align__(16) float smem[];
-    const int buf_floats = (rows_cap * CBT + 3) & ~3;   // every array starts 16-byte aligned
+    const int buf_floats = ((rows_cap + 1) * CBT + 3) & ~3;   // +1: the all-zero row; every array starts 16-byte aligned
     float *A = smem, *B = smem + buf_floats;
     uint16_t *nbs = (uint16_t *)(smem + 2 * buf_floats);
     const uint32_t p0 = batch_begin[blockIdx.x];
@@ -339,6 +339,10 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
     const int cg = blockIdx.y * CBT + c;          // first global channel of this thread
     const bool live = cg < L;                      // the last channel block may be partial (L % CBT != 0)
 
+    if (threadIdx.x < CBT) {
+        A[rows_cap * CBT + threadIdx.x] = 0.0f;
+        B[rows_cap * CBT + threadIdx.x] = 0.0f;
+    }
     // stage the batch's neighbour table and its slice of the gather list (plain range copies, asynchronous) ...
     int32_t *SRC = (int32_t *)(nbs + (((size_t)rows_cap * nax * w2 + 7) & ~(size_t)7));
     cta_copy_async(nbs, lnb + (int64_t)p0 * nax * w2, rows * nax * w2 * 2, threadIdx.x, THREADS);   // w2 even: whole words
@@ -352,66 +356,112 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
     cp_async_wait_all();
     __syncthreads();
 
+    // An absent neighbour reads the all-zero row `rows_cap`, exactly what the reference does (permutohedral.h:545
+    // substitutes a zero vector and still adds c*0), so the passes are branch-free.
+    //
+    // A thread owns the same rows (lr0 + i*RSTEP, i < MAXI) in every pass, so a row's own value never has to be read
+    // back from shared memory: it stays in registers from the pass that produced it (shared memory is only for the
+    // neighbours' reads).  PASS_UNROLL rows are processed together -- their neighbour indices, then all their
+    // neighbour rows, are read before any arithmetic -- so that several shared-memory round trips overlap.
+    constexpr int U = PASS_UNROLL;
+    constexpr int ROWS_MAX = THREADS * 2;                    // 512 rows at 256 threads, 1024 at 512 (host-checked)
+    constexpr int MAXI = (ROWS_MAX + RSTEP - 1) / RSTEP;
+    static_assert(MAXI % U == 0 || MAXI < U, "row slots must split into whole unroll groups");
+    const uint32_t zero_row = (uint32_t)rows_cap;
+    Vec<VEC> self[MAXI];
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+        const int lr = lr0 + i * RSTEP;
+        self[i].load_plain(A + ((live && lr < rows) ? lr : (int)zero_row) * CBT + c);
+    }
     for (int a = 0; a < nax; ++a) {
+        const bool last = (a == nax - 1);
         if (live) {
-            for (int lr = lr0; lr < rows; lr += RSTEP) {
-                const uint16_t *nb = nbs + (lr * nax + a) * w2;
-                uint32_t ni[2 * RR];
-                if (R == 1) {
-                    const uint32_t both = *(const uint32_t *)nb;
-                    ni[0] = both & 0xFFFFu;
-                    ni[1] = both >> 16;
-                } else {
 #pragma unroll
-                    for (int t = 0; t < 2 * RR; ++t) ni[t] = (t < w2) ? (uint32_t)nb[t] : LNB_ABSENT;
-                }
-                Vec<VEC> acc;
+            for (int i0 = 0; i0 < MAXI; i0 += U) {
+                if (lr0 + i0 * RSTEP < rows) {
+                    uint32_t ni[U][2 * RR];
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
-                // reference order: o = -r..-1, 0, 1..r
+                    for (int u = 0; u < U; ++u) {
+                        if (i0 + u < MAXI) {
+                            const int lr = lr0 + (i0 + u) * RSTEP;
+                            const uint16_t *nb = nbs + ((lr < rows ? lr : 0) * nax + a) * w2;
+                            if (R == 1) {
+                                const uint32_t both = (lr < rows) ? *(const uint32_t *)nb : 0xFFFFFFFFu;
+                                ni[u][0] = min(both & 0xFFFFu, zero_row);
+                                ni[u][1] = min(both >> 16, zero_row);
+                            } else {
 #pragma unroll
-                for (int t = 0; t < RR; ++t) {
-                    if (t < r && ni[t] != LNB_ABSENT) {
-                        Vec<VEC> v;
-                        v.load_plain(A + ni[t] * CBT + c);
+                                for (int t = 0; t < 2 * RR; ++t)
+                                    ni[u][t] = (t < w2 && lr < rows) ? min((uint32_t)nb[t], zero_row) : zero_row;
+                            }
+                        }
+                    }
+                    Vec<VEC> acc[U];
 #pragma unroll
-                        for (int k = 0; k < VEC; ++k) acc.v[k] = madd<FAST>(cf.c[t], v.v[k], acc.v[k]);
+                    for (int u = 0; u < U; ++u) {
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) acc[u].v[k] = 0.0f;
+                    }
+                    // reference order: o = -r..-1, 0, 1..r
+#pragma unroll
+                    for (int t = 0; t < RR; ++t) {
+                        if (t < r) {
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                if (i0 + u < MAXI) {
+                                    Vec<VEC> v;
+                                    v.load_plain(A + ni[u][t] * CBT + c);
+#pragma unroll
+                                    for (int k = 0; k < VEC; ++k) acc[u].v[k] = madd<FAST>(cf.c[t], v.v[k], acc[u].v[k]);
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (i0 + u < MAXI) {
+#pragma unroll
+                            for (int k = 0; k < VEC; ++k) acc[u].v[k] = madd<FAST>(cf.c[r], self[i0 + u].v[k], acc[u].v[k]);
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < RR; ++t) {
+                        if (t < r) {
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                if (i0 + u < MAXI) {
+                                    Vec<VEC> v;
+                                    v.load_plain(A + ni[u][r + t] * CBT + c);
+#pragma unroll
+                                    for (int k = 0; k < VEC; ++k)
+                                        acc[u].v[k] = madd<FAST>(cf.c[r + 1 + t], v.v[k], acc[u].v[k]);
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (i0 + u < MAXI) {
+                            const int lr = lr0 + (i0 + u) * RSTEP;
+                            self[i0 + u] = acc[u];
+                            if (lr < rows) {
+                                if (last) acc[u].store(out + (int64_t)(p0 + lr) * L + cg);   // the group's result
+                                else acc[u].store(B + lr * CBT + c);
+                            }
+                        }
                     }
                 }
-                {
-                    Vec<VEC> v;
-                    v.load_plain(A + lr * CBT + c);
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) acc.v[k] = madd<FAST>(cf.c[r], v.v[k], acc.v[k]);
-                }
-#pragma unroll
-                for (int t = 0; t < RR; ++t) {
-                    if (t < r && ni[r + t] != LNB_ABSENT) {
-                        Vec<VEC> v;
-                        v.load_plain(A + ni[r + t] * CBT + c);
-#pragma unroll
-                        for (int k = 0; k < VEC; ++k) acc.v[k] = madd<FAST>(cf.c[r + 1 + t], v.v[k], acc.v[k]);
-                    }
-                }
-                acc.store(B + lr * CBT + c);
             }
         }
-        __syncthreads();
+        if (!last) __syncthreads();
         float *t = A; A = B; B = t;
-    }
-
-    if (live) {
-        for (int lr = lr0; lr < rows; lr += RSTEP) {
-            Vec<VEC> v;
-            v.load_plain(A + lr * CBT + c);
-            v.store(out + (int64_t)(p0 + lr) * L + cg);
-        }
     }
 }
 
 static size_t group_smem_bytes(int rows_cap, int cbt, int nax, int order)
 {
-    return (size_t)2 * (((size_t)rows_cap * cbt + 3) & ~(size_t)3) * sizeof(float) +
+    return (size_t)2 * (((size_t)(rows_cap + 1) * cbt + 3) & ~(size_t)3) * sizeof(float) +
            (((size_t)rows_cap * nax * 2 * order * sizeof(uint16_t) + 15) & ~(size_t)15) + (size_t)rows_cap * sizeof(int32_t);
 }
 
@@ -489,13 +539,15 @@ extern "C" int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64
         const sgp_blur_group *g = groups + gi;
         if (!g->batch_begin || !g->src || !g->lnb || g->rows_cap < 1 || g->n_batches < 1 || g->j1 <= g->j0)
             return fail(SGP_EINVAL, "sgp_blur_groups: group %d is not built", gi);
+        if (g->rows_cap > 1024) return fail(SGP_EUNSUPPORTED, "blur group %d: %d rows per CTA (limit 1024)", gi, g->rows_cap);
+        const bool big = threads_env == 512 || g->rows_cap > 512;   // 256 threads hold up to 512 rows, 512 up to 1024
         int rc = SGP_EUNSUPPORTED;
 #define SGP_GROUP_CASE(VV, CC)                                                                          \
     if (vec == VV && chunks == CC)                                                                      \
-        rc = fast ? ((threads_env == 512) ? launch_group<VV, CC, 512, true>(g, order, cf, L, in, out, st)   \
-                                          : launch_group<VV, CC, 256, true>(g, order, cf, L, in, out, st))  \
-                  : ((threads_env == 512) ? launch_group<VV, CC, 512, false>(g, order, cf, L, in, out, st)  \
-                                          : launch_group<VV, CC, 256, false>(g, order, cf, L, in, out, st))
+        rc = fast ? (big ? launch_group<VV, CC, 512, true>(g, order, cf, L, in, out, st)   \
+                         : launch_group<VV, CC, 256, true>(g, order, cf, L, in, out, st))  \
+                  : (big ? launch_group<VV, CC, 512, false>(g, order, cf, L, in, out, st)  \
+                         : launch_group<VV, CC, 256, false>(g, order, cf, L, in, out, st))
         SGP_GROUP_CASE(4, 4);
         else SGP_GROUP_CASE(4, 2);
         else SGP_GROUP_CASE(4, 1);

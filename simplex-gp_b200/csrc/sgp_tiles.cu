@@ -362,7 +362,7 @@ extern "C" int sgp_permute_replay(const int32_t *replay, const uint32_t *perm, c
 // one per point-vertex to one per (row, thread) run; and the gather side moves through L2 as plain loads, which the
 // scatter form's same-address reductions do not.
 // ------------------------------------------------------------------------------------
-#define ROWSEG 8
+#define ROWSEG 16   /* padding granularity of the row-sorted arrays; the kernel takes SEG = 4, 8 or 16 entries per thread */
 
 __global__ void __launch_bounds__(256)
 sgp_rowsort_keys_kernel(const int2 *__restrict__ replay, int64_t total, uint32_t *__restrict__ keys,
@@ -433,8 +433,8 @@ extern "C" int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int6
     return launch_ok("sgp_rowsort_fill_kernel");
 }
 
-// thread = (segment of ROWSEG entries, channel chunk)
-template <int VEC>
+// thread = (segment of SEG entries, channel chunk)
+template <int VEC, int SEG>
 __global__ void __launch_bounds__(256)
 sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ ent_row, int64_t n_seg,
                       const float *__restrict__ src, int64_t lds, int L, int chunks, float *__restrict__ values)
@@ -443,38 +443,38 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     const int64_t seg = tid / chunks;
     if (seg >= n_seg) return;
     const int c0 = (int)(tid - seg * chunks) * VEC;
-    int2 e[ROWSEG];
-    int row[ROWSEG];
-    Vec<VEC> v[ROWSEG];
-    const int4 *ep = (const int4 *)(ent + seg * ROWSEG);     // ROWSEG entries = ROWSEG/2 16-byte loads
-    const int4 *rp = (const int4 *)(ent_row + seg * ROWSEG);
+    int2 e[SEG];
+    int row[SEG];
+    Vec<VEC> v[SEG];
+    const int4 *ep = (const int4 *)(ent + seg * SEG);     // SEG entries = SEG/2 16-byte loads
+    const int4 *rp = (const int4 *)(ent_row + seg * SEG);
 #pragma unroll
-    for (int i = 0; i < ROWSEG / 2; ++i) {
+    for (int i = 0; i < SEG / 2; ++i) {
         const int4 t = __ldg(ep + i);
         e[2 * i] = make_int2(t.x, t.y);
         e[2 * i + 1] = make_int2(t.z, t.w);
     }
 #pragma unroll
-    for (int i = 0; i < ROWSEG / 4; ++i) {
+    for (int i = 0; i < SEG / 4; ++i) {
         const int4 t = __ldg(rp + i);
         row[4 * i] = t.x; row[4 * i + 1] = t.y; row[4 * i + 2] = t.z; row[4 * i + 3] = t.w;
     }
     // point indices are never negative: the branch keeps every entry load ahead of every row load (in-order issue)
     int lowest = e[0].x;
 #pragma unroll
-    for (int i = 1; i < ROWSEG; ++i) lowest = min(lowest, e[i].x);
+    for (int i = 1; i < SEG; ++i) lowest = min(lowest, e[i].x);
     if (lowest < 0) return;
 #pragma unroll
-    for (int i = 0; i < ROWSEG; ++i) v[i].load_ordered(src + (int64_t)e[i].x * lds + c0);
+    for (int i = 0; i < SEG; ++i) v[i].load_ordered(src + (int64_t)e[i].x * lds + c0);
     Vec<VEC> acc;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
 #pragma unroll
-    for (int i = 0; i < ROWSEG; ++i) {
+    for (int i = 0; i < SEG; ++i) {
         const float w = __int_as_float(e[i].y);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc.v[k] = __fmaf_rn(w, v[i].v[k], acc.v[k]);
-        if (i == ROWSEG - 1 || row[i + 1] != row[i]) {
+        if (i == SEG - 1 || row[i + 1] != row[i]) {
             acc.red(values + (int64_t)row[i] * L + c0);
 #pragma unroll
             for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
@@ -489,7 +489,13 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *ent_row, int64_
     if (!ent || !ent_row || !src || !values || N < 0 || M < 0 || d < 1 || L < 1 || lds < L)
         return fail(SGP_EINVAL, "sgp_splat_rows: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t n_seg = sgp_rowsort_padded(N, d) / ROWSEG;
+    static int seg_env = 0;   // tuning hook: SGP_ROWSEG=4|8|16 entries per thread
+    if (seg_env == 0) {
+        const char *e = getenv("SGP_ROWSEG");
+        seg_env = e ? atoi(e) : 8;
+        if (seg_env != 4 && seg_env != 16) seg_env = 8;
+    }
+    const int64_t n_seg = sgp_rowsort_padded(N, d) / seg_env;
     auto al = [](const void *p, int bytes) { return ((uintptr_t)p % bytes) == 0; };
     int vec = 1;
     if (L % 4 == 0 && lds % 4 == 0 && al(src, 16) && al(values, 16)) vec = 4;
@@ -497,9 +503,20 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *ent_row, int64_
     const int chunks = L / vec;
     CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)M * (size_t)L, st));
     const int64_t work = n_seg * chunks;
-    if (vec == 4) sgp_splat_rows_kernel<4><<<grid_for(work, 256), 256, 0, st>>>((const int2 *)ent, ent_row, n_seg, src, lds, L, chunks, values);
-    else if (vec == 2) sgp_splat_rows_kernel<2><<<grid_for(work, 256), 256, 0, st>>>((const int2 *)ent, ent_row, n_seg, src, lds, L, chunks, values);
-    else sgp_splat_rows_kernel<1><<<grid_for(work, 256), 256, 0, st>>>((const int2 *)ent, ent_row, n_seg, src, lds, L, chunks, values);
+#define SGP_ROWS_LAUNCH(VV, SS)                                                                                        \
+    sgp_splat_rows_kernel<VV, SS><<<grid_for(work, 256), 256, 0, st>>>((const int2 *)ent, ent_row, n_seg, src, lds, L, \
+                                                                        chunks, values)
+#define SGP_ROWS_SEG(VV)                                                                                               \
+    do {                                                                                                               \
+        if (seg_env == 4) SGP_ROWS_LAUNCH(VV, 4);                                                                      \
+        else if (seg_env == 16) SGP_ROWS_LAUNCH(VV, 16);                                                               \
+        else SGP_ROWS_LAUNCH(VV, 8);                                                                                   \
+    } while (0)
+    if (vec == 4) SGP_ROWS_SEG(4);
+    else if (vec == 2) SGP_ROWS_SEG(2);
+    else SGP_ROWS_SEG(1);
+#undef SGP_ROWS_SEG
+#undef SGP_ROWS_LAUNCH
     return launch_ok("sgp_splat_rows_kernel");
 }
 

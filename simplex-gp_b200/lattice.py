@@ -202,7 +202,7 @@ class Lattice:
         single axis does not fit (a long 1-D line), no groups are built and the per-axis blur is used."""
         lib = _capi.lib()
         dev, d, M, r = self.device, self.d, self.M, self.order
-        rows_limit = min(int(group_rows), (160 * 1024) // (2 * 16 * 4), 0xFFFF - 1)
+        rows_limit = max(1, min(int(group_rows), 1024))   # a CTA of 256 threads holds 512 rows, of 512 threads 1024
         st = _stream_ptr(dev)
         ws_bytes = int(lib.sgp_group_workspace_bytes(M))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -364,17 +364,19 @@ class Lattice:
         return self.replay[..., 1].view(torch.float32)
 
     def _table(self, sorted: bool, final: bool) -> torch.Tensor:
-        """Internal replay table ``[d+1, N, 2]`` (transposed: the points of a warp read one contiguous run per
-        vertex), built on first use: rows in the locality order when ``sorted``; lattice indices mapped to the order
-        the last blur-group stage leaves the lattice values in when ``final``."""
+        """Internal replay table ``[N, d+1, 2]``, built on first use: rows in the locality order when ``sorted``;
+        lattice indices mapped to the order the last blur-group stage leaves the lattice values in when ``final``.
+        (The transposed layout ``[d+1, N, 2]`` that ``sgp_permute_replay`` can also produce measured slower.)"""
         key = (bool(sorted), bool(final))
+        if key == (False, False):
+            return self.replay
         t = self._tables.get(key)
         if t is None:
-            t = torch.empty((self.d + 1, self.N, 2), dtype=torch.int32, device=self.device)
+            t = torch.empty((self.N, self.d + 1, 2), dtype=torch.int32, device=self.device)
             perm = self.sorted["perm"] if sorted else None
             pos = self.groups["final_pos"] if final else None
             with torch.cuda.device(self.device):
-                check(_capi.lib().sgp_permute_replay(_ptr(self.replay), _ptr(perm), _ptr(pos), self.N, self.d, 1, _ptr(t),
+                check(_capi.lib().sgp_permute_replay(_ptr(self.replay), _ptr(perm), _ptr(pos), self.N, self.d, 0, _ptr(t),
                                                      _stream_ptr(self.device)))
             self._tables[key] = t
         return t
@@ -431,7 +433,7 @@ class Lattice:
                     mode = _capi.MODE_GATHER if self.csr_ptr is not None else _capi.MODE_ATOMIC
                 v = self._view()
                 if sorted and mode == _capi.MODE_ATOMIC:
-                    v = self._view(self._table(True, False), self.sorted["perm"], transposed=True)
+                    v = self._view(self._table(True, False), self.sorted["perm"])
                 check(_capi.lib().sgp_splat(C.byref(v), _ptr(src), src.stride(0), L, _ptr(values), mode,
                                             _stream_ptr(self.device)))
         return values
@@ -474,7 +476,7 @@ class Lattice:
                 check(_capi.lib().sgp_slice_tiles(C.byref(tv), _ptr(values), L, _ptr(out), out.stride(0),
                                                   0 if exact else 1, _stream_ptr(self.device)))
             else:
-                v = self._view(self._table(True, False), self.sorted["perm"], exact, True) if sorted \
+                v = self._view(self._table(True, False), self.sorted["perm"], exact) if sorted \
                     else self._view(exact=exact)
                 check(_capi.lib().sgp_slice(C.byref(v), _ptr(values), L, _ptr(out), out.stride(0),
                                             _stream_ptr(self.device)))
@@ -534,7 +536,7 @@ class Lattice:
                 if mode == _capi.MODE_GATHER:
                     v_in = self._view(exact=exact)
                 else:
-                    v_in = self._view(self._table(use_sorted, False), perm, exact, True)
+                    v_in = self._view(self._table(use_sorted, False), perm, exact)
                 check(lib.sgp_splat(C.byref(v_in), _ptr(src), src.stride(0), L, _ptr(buf0), mode, st))
             if use_groups:
                 arr = self.groups["array"]
@@ -548,7 +550,7 @@ class Lattice:
                 tv = self._tiles_view(use_groups)
                 check(lib.sgp_slice_tiles(C.byref(tv), _ptr(res), L, _ptr(out), out.stride(0), 0 if exact else 1, st))
             else:
-                v_out = self._view(self._table(use_sorted, use_groups), perm, exact, True)
+                v_out = self._view(self._table(use_sorted, use_groups), perm, exact)
                 check(lib.sgp_slice(C.byref(v_out), _ptr(res), L, _ptr(out), out.stride(0), st))
         return out
 
