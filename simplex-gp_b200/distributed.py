@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_columns", "shard_points", "broadcast_lattice_arrays", "broadcast_lattice", "lattice_arrays",
-           "all_gather_columns", "allreduce_lattice_values"]
+           "all_gather_columns", "allreduce_lattice_values", "ColumnShardedOperator", "PointShardedLattice"]
 
 
 def shard_columns(L: int, world: int, rank: int) -> Tuple[int, int]:
@@ -117,3 +117,74 @@ def allreduce_lattice_values(values: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(values, op=dist.ReduceOp.SUM, group=group)
     return values
+
+
+class ColumnShardedOperator:
+    """``K @ V`` with the RHS columns of ``V[N, L]`` split over the ranks (the default multi-GPU form of the north
+    star).  Every rank holds the same lattice (built on ``src`` and broadcast, or built locally from the same ``x``)
+    and filters its own columns; there is no communication inside an MVM.  ``matmul`` returns this rank's column block;
+    ``matmul_full`` all-gathers the blocks (only needed when the caller wants the whole product everywhere -- a CG
+    solver keeps its vectors column-sharded and all-reduces its dot products instead, see ``dots``)."""
+
+    def __init__(self, lat, group=None):
+        self.lat = lat
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def columns(self, L: int) -> Tuple[int, int]:
+        return shard_columns(L, self.world, self.rank)
+
+    def matmul(self, V_local: torch.Tensor) -> torch.Tensor:
+        if V_local.shape[1] == 0:
+            return V_local.new_empty(V_local.shape)
+        return self.lat.mvm(V_local.contiguous())
+
+    def matmul_full(self, V: torch.Tensor) -> torch.Tensor:
+        lo, hi = self.columns(V.shape[1])
+        mine = self.matmul(V[:, lo:hi])
+        if self.world == 1:
+            return mine
+        return all_gather_columns(mine, V.shape[1], group=self.group)
+
+    def dots(self, A_local: torch.Tensor, B_local: torch.Tensor, L: int) -> torch.Tensor:
+        """Column-wise dot products ``[L]`` of two column-sharded blocks, available on every rank (one all-reduce of
+        ``L`` floats: the only collective a column-sharded CG iteration needs)."""
+        lo, hi = self.columns(L)
+        out = A_local.new_zeros(L)
+        out[lo:hi] = (A_local * B_local).sum(0)
+        if self.world > 1:
+            dist.all_reduce(out, group=self.group)
+        return out
+
+
+class PointShardedLattice:
+    """Point sharding for very large N: rank ``k`` owns the points ``[lo_k, hi_k)``.
+
+    The lattice numbering has to be global, so every rank runs the (deterministic) lattice build on all ``N`` points
+    -- positions are ``N*d*4`` bytes, small next to the value traffic -- and then keeps the per-point tables (replay,
+    row-sorted entries) of its own points only.  One MVM is: local splat of the rank's rows of ``V`` into the full
+    ``[M, L]`` lattice, **one all-reduce (sum) of ``M*L*4`` bytes**, blur (replicated), local slice of the rank's rows.
+    ``mvm`` takes and returns this rank's row block ``[hi-lo, L]``."""
+
+    def __init__(self, x_full: torch.Tensor, coeffs, group=None, **lattice_kwargs):
+        from .lattice import Lattice
+
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        N = int(x_full.shape[0])
+        self.lo, self.hi = shard_points(N, self.world, self.rank)
+        full = Lattice(x_full, coeffs, build_groups=False, build_rows=False, sort_points=False, build_tiles=False)
+        self.N, self.M, self.d = full.N, full.M, full.d
+        # the same lattice restricted to this rank's points: shares keys and the neighbour table, rebuilds the
+        # per-point tables for hi-lo points
+        self.local = Lattice.from_arrays(full.coeffs, full.replay[self.lo:self.hi].contiguous(), full.keys, full.nbr,
+                                         **lattice_kwargs)
+        del full
+
+    def mvm(self, V_local: torch.Tensor, **kw) -> torch.Tensor:
+        if V_local.shape[0] != self.hi - self.lo:
+            raise ValueError(f"rank {self.rank} owns {self.hi - self.lo} points, got {V_local.shape[0]} rows")
+        hook = (lambda vals: allreduce_lattice_values(vals, group=self.group)) if self.world > 1 else None
+        return self.local.mvm(V_local, after_splat=hook, **kw)

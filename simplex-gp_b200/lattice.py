@@ -485,7 +485,7 @@ class Lattice:
     # ---- the MVM ------------------------------------------------------------------------------------
     def mvm(self, src: torch.Tensor, out: Optional[torch.Tensor] = None, coeffs=None,
             mode: int = _capi.SGP_SPLAT_AUTO, blur: str = "auto", sorted: Optional[bool] = None,
-            exact: Optional[bool] = None) -> torch.Tensor:
+            exact: Optional[bool] = None, after_splat=None) -> torch.Tensor:
         """``out[N, L] = slice(blur(splat(src[N, L])))`` on the built lattice.
 
         ``mode``   splat form: 0 auto (row-sorted segmented gather when built, else atomic scatter), 1 atomic scatter
@@ -497,7 +497,9 @@ class Lattice:
         ``sorted`` walk the points in the locality order in splat and slice (default: when it was built).
         ``exact``  the reference's arithmetic (one rounding per product and sum, one division per slice term) instead
                    of fused multiply-adds; with ``mode=2`` the result is then bit-identical to the reference's.
-                   Default: the lattice's ``exact`` attribute (False)."""
+                   Default: the lattice's ``exact`` attribute (False).
+        ``after_splat`` optional callable invoked with the splatted lattice values ``[M, L]`` (in place) before the
+                   blur: the exchange step of point sharding (an all-reduce over the ranks' partial splats)."""
         src = self._check_src(src)
         L = int(src.shape[1])
         c = self.coeffs if coeffs is None else _coeffs_np(coeffs)
@@ -538,6 +540,8 @@ class Lattice:
                 else:
                     v_in = self._view(self._table(use_sorted, False), perm, exact)
                 check(lib.sgp_splat(C.byref(v_in), _ptr(src), src.stride(0), L, _ptr(buf0), mode, st))
+            if after_splat is not None:
+                after_splat(buf0[: self.M])
             if use_groups:
                 arr = self.groups["array"]
                 check(lib.sgp_blur_groups(arr, len(arr), self.M, self.order, _fp(c), c.shape[0], L, _ptr(buf0),
