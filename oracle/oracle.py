@@ -32,6 +32,8 @@ def lib():
         L.sgpo_slice_divisor.argtypes = [C.c_int]
         L.sgpo_lattice_build.restype = C.c_void_p
         L.sgpo_lattice_build.argtypes = [fp, C.c_int64, C.c_int, C.c_int64, fp, C.c_int, C.POINTER(C.c_int)]
+        L.sgpo_lattice_build_reftable.restype = C.c_void_p
+        L.sgpo_lattice_build_reftable.argtypes = [fp, C.c_int64, C.c_int, C.c_int64, fp, C.c_int, C.POINTER(C.c_int)]
         L.sgpo_lattice_free.restype = None
         L.sgpo_lattice_free.argtypes = [C.c_void_p]
         L.sgpo_build_neighbours.restype = C.c_int
@@ -79,15 +81,18 @@ def slice_divisor(d: int) -> np.float32:
 class OracleLattice:
     """Lattice structure of ``x[N,d]`` under stencil ``coeffs[2r+1]`` in the reference's numbering."""
 
-    def __init__(self, x, coeffs):
+    def __init__(self, x, coeffs, reference_table: bool = False):
+        """``reference_table=True`` restates the reference's own hash table, growth defect included, and so reproduces
+        the UNMODIFIED reference at any size (orphaned duplicate lattice points and all); the default is a correct
+        table, which is what the product implements (see the header of lattice_oracle.c)."""
         x = _f32(x)
         assert x.ndim == 2
         self.coeffs = _f32(coeffs)
         self.N, self.d = x.shape
         self.order = self.coeffs.shape[0] // 2
         st = C.c_int(0)
-        self._h = lib().sgpo_lattice_build(_fp(x), self.N, self.d, self.d, _fp(self.coeffs), self.coeffs.shape[0],
-                                           C.byref(st))
+        build = lib().sgpo_lattice_build_reftable if reference_table else lib().sgpo_lattice_build
+        self._h = build(_fp(x), self.N, self.d, self.d, _fp(self.coeffs), self.coeffs.shape[0], C.byref(st))
         self.status = st.value
         if not self._h:
             raise RuntimeError(f"oracle build failed with status {st.value}")

@@ -19,9 +19,10 @@ Files written next to this script (small, committed):
   kat.npz            the two known-answer cases of SURVEY.md section 8c (d=2 toy, Snelson-1D)
   structure.npz      full lattice intermediates of a few seeded cases
   autograd.npz       forward / grad_source / grad_reference of LatticeFilterGeneral
-  large.json         sha256 of every intermediate for cases with M > 16383 (reference with its
-                     hash-growth statement re-ordered, see oracle/build_oracle.py) and the
-                     deviation of the unmodified reference from it
+  large.json         sha256 of every intermediate for cases with M > 16383, twice: of the reference with its
+                     hash-growth statement re-ordered (see oracle/build_oracle.py) -- what the product
+                     matches -- and of the UNMODIFIED reference -- what the oracle's reference-table mode
+                     matches --, plus the deviation between the two
 """
 from __future__ import annotations
 
@@ -183,6 +184,7 @@ def main():
         of, ou = fx[7].numpy().astype(np.float64), un[7].numpy().astype(np.float64)
         rec["unmodified_reference"] = {
             "M": int(un[4].shape[0]),
+            "sha256": {fname: sha(val.numpy()) for fname, val in zip(FIELDS, un)},
             "out_rel_l2_vs_fixed": float(np.linalg.norm(of - ou) / np.linalg.norm(of)),
             "out_rows_differing": int((np.abs(of - ou).max(axis=1) > 0).sum()),
             "greedy_equal": bool(torch.equal(fx[0], un[0])), "rank_equal": bool(torch.equal(fx[1], un[1])),

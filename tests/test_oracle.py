@@ -92,6 +92,48 @@ def test_large_golden_hashes(oracle, case):
     assert un["greedy_equal"] and un["rank_equal"] and un["weights_equal"]
 
 
+@pytest.mark.parametrize("case", ["d8_n20000", "d11_r2_n6000", "d18_n3000"])
+def test_reference_table_mode_matches_unmodified_reference_hashes(oracle, case):
+    """The oracle with the reference's own table semantics restated (growth defect included) reproduces the
+    UNMODIFIED reference bit for bit past the table's first doubling -- so the only difference between the reference
+    and what the product matches is that one defect."""
+    rec = json.load(open(os.path.join(GOLDEN_DIR, "large.json")))[case]
+    x, v = make_inputs(rec["N"], rec["d"], rec["L"], seed=rec["seed"])
+    c = np.asarray(rec["coeffs"], dtype=np.float32)
+    O = oracle.OracleLattice(x.numpy(), c, reference_table=True)
+    un = rec["unmodified_reference"]
+    assert O.M == un["M"]
+    out, sp, bl = O.mvm(v.numpy(), return_intermediates=True)
+    got = {"greedy": O.greedy, "rank": O.rank, "offsets": O.offsets, "weights": O.weights, "keys": O.keys,
+           "splatted": sp, "blurred": bl, "out": out, "scale": O.scale}
+    for name in FIELDS:
+        assert _sha(got[name]) == un["sha256"][name], name
+
+
+def test_reference_table_mode_equals_default_below_first_doubling(oracle):
+    x, v = make_inputs(2000, 6, 3, seed=55)
+    a = oracle.OracleLattice(x.numpy(), RBF1)
+    b = oracle.OracleLattice(x.numpy(), RBF1, reference_table=True)
+    assert a.M == b.M < 16383 and np.array_equal(a.keys, b.keys) and np.array_equal(a.offsets, b.offsets)
+    assert np.array_equal(bits(a.mvm(v.numpy())), bits(b.mvm(v.numpy())))
+
+
+def test_reference_table_mode_against_compiled_reference_three_doublings(oracle):
+    ref, _ = _ref_modules()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    x, v = make_inputs(150_000, 8, 2, seed=66)
+    c = torch.tensor(RBF1)
+    want = ref.filter(v, x, c).numpy()
+    O = oracle.OracleLattice(x.numpy(), c.numpy(), reference_table=True)
+    assert O.M > 4 * 16383
+    assert np.array_equal(bits(O.mvm(v.numpy())), bits(want))
+    # and the correct table differs from it only slightly, on a minority of rows
+    good = oracle.OracleLattice(x.numpy(), c.numpy()).mvm(v.numpy())
+    rel = np.linalg.norm(good.astype(np.float64) - want) / np.linalg.norm(want)
+    assert 0 < rel < 2e-2
+
+
 def test_neighbour_table_is_key_lookup(oracle):
     """nbr[j, i, t] must be the index of key[i] - o (all stored coords) with key[j] += o*(d+1) (permutohedral.h:541-542)."""
     x, _ = make_inputs(300, 4, 1, seed=3)
