@@ -1,20 +1,32 @@
-import sys, time, torch, numpy as np, os
+import sys, time, torch, numpy as np, ctypes as C, os
 sys.path.insert(0, '/root/repo')
 import simplex_gp_b200 as sg
+from simplex_gp_b200 import _capi
+from simplex_gp_b200.lattice import _fp, _ptr, _stream_ptr
 torch.manual_seed(0)
 N,d,L=1_000_000,8,16
-x=torch.randn(N,d).pin_memory(); v=torch.randn(N,L).pin_memory()
-c=torch.tensor([0.34608543,1,0.34608543])
-ts=[]
-r=None
-for i in range(12):
-    torch.cuda.synchronize(); t0=time.perf_counter(); r=sg.filter(v,x,c); ts.append((time.perf_counter()-t0)*1e3)
-print('filter per-call ms', [round(t,2) for t in ts])
-ts=[]
-for i in range(8):
-    t0=time.perf_counter(); o=torch.empty((N,L),pin_memory=True); ts.append((time.perf_counter()-t0)*1e3)
-print('alloc pinned (rebinding o) ms', [round(t,2) for t in ts])
-ts=[]
-for i in range(8):
-    t0=time.perf_counter(); o=None; o=torch.empty((N,L),pin_memory=True); ts.append((time.perf_counter()-t0)*1e3)
-print('alloc pinned (free first) ms', [round(t,2) for t in ts])
+x=torch.randn(N,d,device='cuda'); vs=[torch.randn(N,L,device='cuda') for _ in range(4)]
+c=[0.34608543,1,0.34608543]
+def timeit(fn, reps=20, warm=3):
+    for i in range(warm): fn(i)
+    torch.cuda.synchronize()
+    e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps): fn(i)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1)/reps*1000
+lat=sg.Lattice(x,c); torch.cuda.synchronize()
+lib=_capi.lib(); buf0,buf1=lat._scratch(L); st=_stream_ptr(lat.device); where=C.c_int(0); arr=lat.groups['array']; cnp=lat.coeffs
+outs=[torch.empty(N,L,device='cuda') for _ in range(4)]
+r=lat.rows
+big=torch.empty(64*1024*1024, device='cuda')
+def splat_cold(i):
+    big.fill_(1.0)   # evict L2
+    _capi.check(lib.sgp_splat_rows(_ptr(r['ent']),_ptr(r['ent_row']),N,d,lat.M,_ptr(vs[i%4]),L,L,_ptr(buf0),st))
+def flush_only(i): big.fill_(1.0)
+t_f=timeit(flush_only)
+t_c=timeit(splat_cold)
+t_sr=timeit(lambda i: _capi.check(lib.sgp_splat_rows(_ptr(r['ent']),_ptr(r['ent_row']),N,d,lat.M,_ptr(vs[i%4]),L,L,_ptr(buf0),st)))
+t_sr1=timeit(lambda i: _capi.check(lib.sgp_splat_rows(_ptr(r['ent']),_ptr(r['ent_row']),N,d,lat.M,_ptr(vs[0]),L,L,_ptr(buf0),st)))
+t_m=timeit(lambda i: lat.mvm(vs[i%4],out=outs[i%4]))
+print(f'PREFETCH={os.environ.get("SGP_SPLAT_PREFETCH")}: splat rows cold-L2 {t_c-t_f:.1f} rotating {t_sr:.1f} same-V {t_sr1:.1f} | mvm {t_m:.1f} us -> {1e6/t_m:.0f} MVM/s')

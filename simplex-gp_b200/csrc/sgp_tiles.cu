@@ -437,9 +437,16 @@ extern "C" int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int6
 template <int VEC, int SEG>
 __global__ void __launch_bounds__(256)
 sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ ent_row, int64_t n_seg,
-                      const float *__restrict__ src, int64_t lds, int L, int chunks, float *__restrict__ values)
+                      const float *__restrict__ src, int64_t lds, int L, int chunks, int64_t prefetch_bytes,
+                      float *__restrict__ values)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // Optional (off by default, measured without effect on B200): the first blocks ask L2 for the whole of src with
+    // sequential 128-byte prefetches before the random row gathers of the later blocks need it.
+    if (prefetch_bytes > 0) {
+        const int64_t line = tid * 128;
+        if (line < prefetch_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)src + line));
+    }
     const int64_t seg = tid / chunks;
     if (seg >= n_seg) return;
     const int c0 = (int)(tid - seg * chunks) * VEC;
@@ -503,9 +510,15 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *ent_row, int64_
     const int chunks = L / vec;
     CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)M * (size_t)L, st));
     const int64_t work = n_seg * chunks;
+    static int pref_env = -1;   // tuning hook: SGP_SPLAT_PREFETCH=1 enables an L2 prefetch of src (measured: no gain)
+    if (pref_env < 0) {
+        const char *e = getenv("SGP_SPLAT_PREFETCH");
+        pref_env = e ? atoi(e) : 0;
+    }
+    const int64_t prefetch_bytes = pref_env ? (int64_t)N * lds * (int64_t)sizeof(float) : 0;
 #define SGP_ROWS_LAUNCH(VV, SS)                                                                                        \
     sgp_splat_rows_kernel<VV, SS><<<grid_for(work, 256), 256, 0, st>>>((const int2 *)ent, ent_row, n_seg, src, lds, L, \
-                                                                        chunks, values)
+                                                                        chunks, prefetch_bytes, values)
 #define SGP_ROWS_SEG(VV)                                                                                               \
     do {                                                                                                               \
         if (seg_env == 4) SGP_ROWS_LAUNCH(VV, 4);                                                                      \
