@@ -82,7 +82,7 @@ class Lattice:
     """
 
     def __init__(self, x: torch.Tensor, coeffs, *, build_csr: bool = False, build_tiles: bool = False,
-                 build_groups: bool = True, group_axes: int = 3, group_rows: int = 512,
+                 build_groups: bool = True, group_axes: Optional[int] = None, group_rows: int = 512,
                  sort_points: bool = False, build_rows: bool = True, exact: bool = False,
                  tile_points: int = 256, keep_structure: bool = True, hash_capacity: Optional[int] = None):
         if x.dim() != 2:
@@ -163,7 +163,7 @@ class Lattice:
     @classmethod
     def from_arrays(cls, coeffs, replay: torch.Tensor, keys: torch.Tensor, nbr: torch.Tensor,
                     build_csr: bool = False, build_tiles: bool = False, tile_points: int = 256,
-                    build_groups: bool = True, group_axes: int = 3, group_rows: int = 512,
+                    build_groups: bool = True, group_axes: Optional[int] = None, group_rows: int = 512,
                     exact: bool = False) -> "Lattice":
         """Wrap lattice arrays that were built elsewhere (e.g. received by ``distributed.broadcast_lattice``)."""
         self = object.__new__(cls)
@@ -196,10 +196,12 @@ class Lattice:
                 self._build_rows()
         return self
 
-    def _build_groups(self, group_axes: int = 3, group_rows: int = 512) -> None:
-        """Blur groups (csrc/sgp_groups.cu): cover axes 0..d with ranges of up to ``group_axes`` consecutive axes whose
-        classes fit ``group_rows`` rows of one CTA.  A range is shortened until its largest class fits; if even a
-        single axis does not fit (a long 1-D line), no groups are built and the per-axis blur is used."""
+    def _build_groups(self, group_axes: Optional[int] = None, group_rows: int = 512) -> None:
+        """Blur groups (csrc/sgp_groups.cu): cover axes 0..d with ranges of consecutive axes whose classes fit
+        ``group_rows`` rows of one CTA.  ``group_axes=None``: every range is made as long as it can be (3 axes at the
+        metric configuration, 10 on the sparse d = 18 lattice); an integer fixes the length.  A range is shortened until
+        its largest class fits; if even a single axis does not fit (a long 1-D line), no groups are built and the
+        per-axis blur is used."""
         lib = _capi.lib()
         dev, d, M, r = self.device, self.d, self.M, self.order
         rows_limit = max(1, min(int(group_rows), 1024))   # a CTA of 256 threads holds 512 rows, of 512 threads 1024
@@ -209,18 +211,32 @@ class Lattice:
         groups, keep = [], []
         prev_pos = None
         j0 = 0
+        def prepare(j0, j1):
+            order_of = torch.empty(M, dtype=torch.int32, device=dev)
+            pos = torch.empty(M, dtype=torch.int32, device=dev)
+            cstart = torch.empty(M, dtype=torch.int32, device=dev)
+            mx = C.c_int64(0)
+            check(lib.sgp_group_prepare(_ptr(self.keys), M, d, j0, j1, _ptr(order_of), _ptr(pos), _ptr(cstart),
+                                        _ptr(ws), ws_bytes, C.byref(mx), st))
+            return order_of, pos, cstart, mx
+
+        adaptive = group_axes is None or int(group_axes) <= 0
         while j0 <= d:
-            j1 = min(j0 + max(1, int(group_axes)), d + 1)
-            while True:
-                order_of = torch.empty(M, dtype=torch.int32, device=dev)
-                pos = torch.empty(M, dtype=torch.int32, device=dev)
-                cstart = torch.empty(M, dtype=torch.int32, device=dev)
-                mx = C.c_int64(0)
-                check(lib.sgp_group_prepare(_ptr(self.keys), M, d, j0, j1, _ptr(order_of), _ptr(pos), _ptr(cstart),
-                                            _ptr(ws), ws_bytes, C.byref(mx), st))
-                if mx.value <= rows_limit or j1 - j0 == 1:
-                    break
+            j1 = min(j0 + (3 if adaptive else max(1, int(group_axes))), d + 1)
+            order_of, pos, cstart, mx = prepare(j0, j1)
+            while mx.value > rows_limit and j1 - j0 > 1:      # shorten the range until its largest class fits
                 j1 -= 1
+                order_of, pos, cstart, mx = prepare(j0, j1)
+            if adaptive:
+                # ... or lengthen it while it still does and the batch-local neighbour table stays at most 48 bytes a
+                # row (it shares the CTA's shared memory with the values: longer tables cost occupancy)
+                max_axes = max(3, 48 // (4 * r))
+                while mx.value <= rows_limit and j1 <= d and j1 - j0 < max_axes:
+                    trial = prepare(j0, j1 + 1)
+                    if trial[3].value > rows_limit:
+                        break
+                    order_of, pos, cstart, mx = trial
+                    j1 += 1
             if mx.value > rows_limit:
                 self.groups = None
                 return
