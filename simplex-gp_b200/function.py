@@ -100,9 +100,9 @@ def lattice_filter_grad(lat: Lattice, g: torch.Tensor, v: torch.Tensor, x: torch
         return grad_x.zero_(), wg
     per = 2 * (d + 1)
     if chunk is None:
-        # columns per pass: as many as keep the packed block near 64 channels (>= 1), rounded so that the channel
-        # count is a multiple of 4 whenever possible (vectorised kernels)
-        chunk = max(1, 64 // per)
+        # columns per pass: as many as keep the packed block near 144 channels (measured best on B200: 5.8 ms vs 7.4 ms
+        # at 54 channels for N=1M, d=8, L=16), rounded so that the channel count is a multiple of 4 whenever possible
+        chunk = max(1, 144 // per)
         if (per * chunk) % 4 and (per * chunk * 2) % 4 == 0 and chunk * 2 <= max(L, 2):
             chunk *= 2
     chunk = max(1, min(int(chunk), L))
