@@ -100,35 +100,57 @@ sgp_group_pos_kernel(const uint32_t *__restrict__ order, const uint32_t *__restr
 }
 
 // Greedy packing of whole classes into CTA batches of at most `cap` rows: a batch starts where the previous one ended
-// and extends to the last class boundary within cap rows.  Sequential over batches (one thread; a binary search
-// over the monotone class_start array per batch), which is a few thousand steps at the metric configuration.
-// out[0] = n_batches, out[1] = rows of the largest batch.
-__global__ void sgp_group_pack_kernel(const uint32_t *__restrict__ class_start, int64_t M, int64_t cap,
-                                      int64_t max_batches, uint32_t *__restrict__ batch_begin,
-                                      uint32_t *__restrict__ out)
+// and extends to the last class boundary within cap rows, i.e. next = class_start[begin + cap].  The chain is
+// sequential (each hop needs the previous one), so it is walked by one thread -- but out of shared memory: the block
+// streams class_start through a window of PACK_WINDOW entries (coalesced loads by all threads), and the walker hops
+// inside the window at shared-memory latency (~30 cycles a hop instead of a ~500 ns global round trip).
+// out[0] = n_batches, out[1] = rows of the largest batch, out[2] = error flag.
+#define PACK_WINDOW 10240
+#define PACK_THREADS 1024
+__global__ void __launch_bounds__(PACK_THREADS)
+sgp_group_pack_kernel(const uint32_t *__restrict__ class_start, int64_t M, int64_t cap, int64_t max_batches,
+                      uint32_t *__restrict__ batch_begin, uint32_t *__restrict__ out)
 {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    int64_t begin = 0, nb = 0;
-    uint32_t max_rows = 0;
-    while (begin < M && nb < max_batches) {
-        batch_begin[nb++] = (uint32_t)begin;
-        int64_t end = begin + cap;
-        if (end >= M) {
-            end = M;
-        } else {
-            end = class_start[end];          // start of the class that position begin+cap falls into
-            if (end <= begin) {              // a class larger than cap: cannot happen (checked by the caller)
-                out[2] = 1;
-                end = begin + cap;
+    __shared__ uint32_t win[PACK_WINDOW];
+    __shared__ long long s_begin, s_nb, s_w0;
+    __shared__ uint32_t s_max, s_err;
+    if (threadIdx.x == 0) { s_begin = 0; s_nb = 0; s_max = 0; s_err = 0; s_w0 = 0; }
+    __syncthreads();
+    while (true) {
+        const int64_t begin = s_begin;
+        if (begin >= M || s_nb >= max_batches || s_err) break;
+        // window = class_start[w0, w0 + PACK_WINDOW), starting at the first position the walker will read
+        const int64_t w0 = begin + cap < M ? begin + cap : M;
+        const int64_t wn = (M - w0 < PACK_WINDOW) ? M - w0 : PACK_WINDOW;
+        for (int64_t i = threadIdx.x; i < wn; i += PACK_THREADS) win[i] = class_start[w0 + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int64_t b = begin, nb = s_nb;
+            uint32_t mx = s_max;
+            while (b < M && nb < max_batches) {
+                int64_t end = b + cap;
+                if (end >= M) {
+                    end = M;
+                } else {
+                    if (end - w0 >= wn) break;            // next read is beyond the window: reload
+                    end = win[end - w0];                   // start of the class that position b + cap falls into
+                    if (end <= b) { s_err = 1; break; }    // a class larger than cap (the caller checks max_class)
+                }
+                batch_begin[nb++] = (uint32_t)b;
+                if ((uint32_t)(end - b) > mx) mx = (uint32_t)(end - b);
+                b = end;
             }
+            s_begin = b; s_nb = nb; s_max = mx;
         }
-        if ((uint32_t)(end - begin) > max_rows) max_rows = (uint32_t)(end - begin);
-        begin = end;
+        __syncthreads();
     }
-    if (begin < M) out[2] = 1;
-    batch_begin[nb] = (uint32_t)M;
-    out[0] = (uint32_t)nb;
-    out[1] = max_rows;
+    if (threadIdx.x == 0) {
+        if (s_begin < M) s_err = 1;
+        batch_begin[s_nb] = (uint32_t)M;
+        out[0] = (uint32_t)s_nb;
+        out[1] = s_max;
+        out[2] = s_err;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -273,7 +295,7 @@ extern "C" int sgp_group_finalize(const int32_t *nbr, int64_t M, int order_r, in
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t *small = (uint32_t *)((char *)workspace + w.small);
     CUDA_TRY(cudaMemsetAsync(small, 0, 32, st));
-    sgp_group_pack_kernel<<<1, 32, 0, st>>>(class_start, M, cap, max_batches, batch_begin, small);
+    sgp_group_pack_kernel<<<1, PACK_THREADS, 0, st>>>(class_start, M, cap, max_batches, batch_begin, small);
     rc = launch_ok("sgp_group_pack_kernel");
     if (rc) return rc;
     uint32_t host[4] = {0, 0, 0, 0};
