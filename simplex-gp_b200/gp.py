@@ -22,7 +22,7 @@ from typing import Callable, Optional
 
 import torch
 
-__all__ = ["mll_dense", "mll_cg", "batched_cg", "ExactGPModel"]
+__all__ = ["mll_dense", "mll_cg", "mll_cg_sharded", "batched_cg", "ExactGPModel"]
 
 
 def mll_dense(matmul: Callable, y: torch.Tensor, mean: torch.Tensor, outputscale: torch.Tensor,
@@ -110,6 +110,86 @@ def mll_cg(matmul: Callable, y: torch.Tensor, mean: torch.Tensor, outputscale: t
     KV = outputscale * matmul(V) + noise * V
     s = 0.5 * (alpha[:, 0] * KV[:, 0]).sum() - 0.5 * (U * KV[:, 1:]).sum() / n_probes
     s = s + (alpha[:, 0] * (mean - mean.detach())).sum() if mean.requires_grad else s
+    return value, s / n
+
+
+def mll_cg_sharded(matmul: Callable, y: torch.Tensor, mean: torch.Tensor, outputscale: torch.Tensor,
+                   noise: torch.Tensor, probes: torch.Tensor, tol: float = 1e-4, max_iter: int = 500, group=None):
+    """``mll_cg`` with the RHS columns ``[y - mu | probes]`` sharded over the ranks of ``group`` (north star: "the
+    CG/Lanczos probe and RHS columns are sharded across GPUs").  Every rank holds the same lattice and runs CG on its own
+    columns -- columns are independent, so the solve needs no communication at all --, the per-column Lanczos
+    coefficients and solutions are all-gathered once at the end, and each rank back-propagates the surrogate of its own
+    columns; the caller all-reduces (sums) the hyper-parameter gradients, as data-parallel training does.  ``probes``
+    must be identical on every rank.  Returns ``(mll_value, local_surrogate)``."""
+    import torch.distributed as dist
+
+    from .distributed import shard_columns
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = y.shape[0]
+    r = y - mean
+    Z = probes.to(device=y.device, dtype=y.dtype)
+    n_probes = Z.shape[1]
+    B = torch.cat([r.detach().unsqueeze(-1), Z], dim=1)
+    Lt = B.shape[1]
+    lo, hi = shard_columns(Lt, world, rank)
+
+    def A(V):
+        with torch.no_grad():
+            return outputscale.detach() * matmul(V) + noise.detach() * V
+
+    if hi > lo:
+        X_loc, al, be = batched_cg(A, B[:, lo:hi].contiguous(), tol=tol, max_iter=max_iter)
+    else:
+        X_loc, al, be = B.new_zeros(n, 0), B.new_zeros(0, 0), B.new_zeros(0, 0)
+    # gather: pad the coefficient histories to the longest one (alpha = inf, beta = 0 leave the tridiagonal's leading
+    # block untouched -- handled below by truncating each column at its own length)
+    iters = torch.tensor([al.shape[0]], device=y.device)
+    if world > 1:
+        dist.all_reduce(iters, op=dist.ReduceOp.MAX, group=group)
+    kmax = int(iters.item())
+    wmax = max(h - l for l, h in (shard_columns(Lt, world, q) for q in range(world)))
+    pack = B.new_zeros(n + 2 * kmax + 1, wmax)
+    w = hi - lo
+    if w > 0:
+        pack[:n, :w] = X_loc
+        pack[n:n + al.shape[0], :w] = al
+        pack[n + kmax:n + kmax + be.shape[0], :w] = be
+        pack[n + 2 * kmax, :w] = float(al.shape[0])
+    parts = [pack]
+    if world > 1:
+        parts = [torch.empty_like(pack) for _ in range(world)]
+        dist.all_gather(parts, pack, group=group)
+    X = torch.cat([p[:n, : (shard_columns(Lt, world, q)[1] - shard_columns(Lt, world, q)[0])] for q, p in enumerate(parts)], 1)
+    alpha = X[:, :1]
+    quad = float((r.detach().unsqueeze(-1) * alpha).sum())
+    # log-determinant from the probe columns' tridiagonals (every rank computes the same number)
+    total, cnt = 0.0, 0
+    for q, p in enumerate(parts):
+        l_q, h_q = shard_columns(Lt, world, q)
+        for j in range(h_q - l_q):
+            if l_q + j == 0:
+                continue   # column 0 is y - mu, not a probe
+            k_j = int(p[n + 2 * kmax, j].item())
+            total += float(_lanczos_logdet(p[n:n + k_j, j:j + 1], p[n + kmax:n + kmax + k_j, j:j + 1], n))
+            cnt += 1
+    logdet = total / max(cnt, 1)
+    value = (-0.5 * (quad + logdet + n * math.log(2 * math.pi))) / n
+    # surrogate over this rank's columns
+    s = y.new_zeros(())
+    if hi > lo:
+        V_loc = torch.cat([alpha, Z], dim=1)[:, lo:hi].contiguous()
+        KV = outputscale * matmul(V_loc) + noise * V_loc
+        U_loc = X[:, lo:hi]
+        for j in range(hi - lo):
+            col = lo + j
+            if col == 0:
+                s = s + 0.5 * (alpha[:, 0] * KV[:, j]).sum()
+                if mean.requires_grad:
+                    s = s + (alpha[:, 0] * (mean - mean.detach())).sum()
+            else:
+                s = s - 0.5 * (U_loc[:, j] * KV[:, j]).sum() / n_probes
     return value, s / n
 
 

@@ -51,6 +51,31 @@ def _worker(rank, world, port, q):
         lo, hi = shard_points(N, world, rank)
         mine = ps.mvm(vd[lo:hi].contiguous())
         e_pt = float((mine - want[lo:hi]).norm() / want[lo:hi].norm())
+        # 3. a CG training step with the probe / RHS columns sharded: value and lengthscale gradient equal the
+        #    single-GPU ones (gradients summed over ranks)
+        from simplex_gp_b200 import gp
+        n2 = 4000
+        x2, v2 = make_inputs(n2, 4, 1, seed=77)
+        y2 = (torch.sin(x2.sum(1)) + 0.1 * v2[:, 0]).to(dev)
+        probes = torch.randn(n2, 5, generator=torch.Generator().manual_seed(5)).sign().to(dev)
+        res = []
+        for sharded in (False, True):
+            torch.manual_seed(0)
+            k = sg.RBFLattice(ard_num_dims=4, order=1).to(dev)
+            s_, nz, mu = torch.tensor(0.9, device=dev), torch.tensor(0.2, device=dev), torch.tensor(0.0, device=dev)
+            opr = k(x2.to(dev))
+            if sharded:
+                val, sur = gp.mll_cg_sharded(opr.matmul, y2, mu, s_, nz, probes, tol=1e-5)
+            else:
+                val, sur = gp.mll_cg(opr.matmul, y2, mu, s_, nz, probes=probes, tol=1e-5)
+            sur.backward()
+            g = k.raw_lengthscale.grad.clone()
+            if sharded and world > 1:
+                dist.all_reduce(g)
+            res.append((val, g))
+        e_val = abs(res[0][0] - res[1][0]) / abs(res[0][0])
+        e_grad = float((res[0][1] - res[1][1]).norm() / res[0][1].norm())
+        assert e_val < 1e-5 and e_grad < 1e-3, (e_val, e_grad)
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok", (e_col, e_dot, e_pt)))
