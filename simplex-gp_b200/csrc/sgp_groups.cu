@@ -335,11 +335,11 @@ struct GroupCoeffs {
 
 #define PASS_UNROLL 4
 
-// Shared memory: A[rows_cap][CBT] | B[rows_cap][CBT] | nbs[rows_cap][nax][2r] (uint16), CBT = CHUNKS*VEC channels.
+// Shared memory: A[rows_cap+1][CBT] | nbs[rows_cap][nax][2r] (uint16) | SRC[rows_cap], CBT = CHUNKS*VEC channels.
 // A thread owns one channel chunk (c) and the rows lr0, lr0+RSTEP, ... of the batch for the whole kernel, so the
 // index arithmetic is hoisted out of every loop.
 template <int VEC, int R, int CHUNKS, int THREADS, bool FAST>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS)   // (capping registers for a fourth CTA per SM measured slower: 62 vs 56 us)
 sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *__restrict__ src,
                       const uint16_t *__restrict__ lnb, const float *__restrict__ in, float *__restrict__ out, int L,
                       int rows_cap, int nax, int order_rt, GroupCoeffs cf)
@@ -351,8 +351,8 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
     const int w2 = 2 * r;
     extern __shared__ __align__(16) float smem[];
     const int buf_floats = ((rows_cap + 1) * CBT + 3) & ~3;   // +1: the all-zero row; every array starts 16-byte aligned
-    float *A = smem, *B = smem + buf_floats;
-    uint16_t *nbs = (uint16_t *)(smem + 2 * buf_floats);
+    float *A = smem;   // ONE value buffer: a pass reads its neighbours, a barrier, then every thread writes its rows back
+    uint16_t *nbs = (uint16_t *)(smem + buf_floats);
     const uint32_t p0 = batch_begin[blockIdx.x];
     const int rows = (int)(batch_begin[blockIdx.x + 1] - p0);
     if (rows == 0) return;
@@ -361,10 +361,7 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
     const int cg = blockIdx.y * CBT + c;          // first global channel of this thread
     const bool live = cg < L;                      // the last channel block may be partial (L % CBT != 0)
 
-    if (threadIdx.x < CBT) {
-        A[rows_cap * CBT + threadIdx.x] = 0.0f;
-        B[rows_cap * CBT + threadIdx.x] = 0.0f;
-    }
+    if (threadIdx.x < CBT) A[rows_cap * CBT + threadIdx.x] = 0.0f;
     // stage the batch's neighbour table and its slice of the gather list (plain range copies, asynchronous) ...
     int32_t *SRC = (int32_t *)(nbs + (((size_t)rows_cap * nax * w2 + 7) & ~(size_t)7));
     cta_copy_async(nbs, lnb + (int64_t)p0 * nax * w2, rows * nax * w2 * 2, threadIdx.x, THREADS);   // w2 even: whole words
@@ -467,23 +464,29 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
                         if (i0 + u < MAXI) {
                             const int lr = lr0 + (i0 + u) * RSTEP;
                             self[i0 + u] = acc[u];
-                            if (lr < rows) {
-                                if (last) acc[u].store(out + (int64_t)(p0 + lr) * L + cg);   // the group's result
-                                else acc[u].store(B + lr * CBT + c);
-                            }
+                            if (last && lr < rows) acc[u].store(out + (int64_t)(p0 + lr) * L + cg);   // the group's result
                         }
                     }
                 }
             }
         }
-        if (!last) __syncthreads();
-        float *t = A; A = B; B = t;
+        if (!last) {
+            __syncthreads();   // every neighbour read of this pass is done: the rows can be overwritten in place
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < MAXI; ++i) {
+                    const int lr = lr0 + i * RSTEP;
+                    if (lr < rows) self[i].store(A + lr * CBT + c);
+                }
+            }
+            __syncthreads();
+        }
     }
 }
 
 static size_t group_smem_bytes(int rows_cap, int cbt, int nax, int order)
 {
-    return (size_t)2 * (((size_t)(rows_cap + 1) * cbt + 3) & ~(size_t)3) * sizeof(float) +
+    return (size_t)(((size_t)(rows_cap + 1) * cbt + 3) & ~(size_t)3) * sizeof(float) +
            (((size_t)rows_cap * nax * 2 * order * sizeof(uint16_t) + 15) & ~(size_t)15) + (size_t)rows_cap * sizeof(int32_t);
 }
 
