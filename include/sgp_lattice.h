@@ -122,15 +122,6 @@ int sgp_build_neighbours(const int16_t *keys, int64_t M, int d, int order,
                          const uint64_t *table, int64_t capacity, int32_t *nbr,
                          sgp_stream_t stream);
 
-/* Transposed replay table for the gather-form splat: for every lattice point the list of
- * (point, weight) that touch it, in point-vertex order (= the reference's accumulation
- * order).  row_ptr: device [M+1] uint32; entries: device [N*(d+1), 2] int32 {n, weight bits};
- * pv_scratch: device [N*(d+1)] uint32; workspace: device, sgp_csr_workspace_bytes(M). */
-size_t sgp_csr_workspace_bytes(int64_t M);
-int sgp_build_csr(const int32_t *replay, int64_t N, int d, int64_t M, uint32_t *row_ptr,
-                  int32_t *entries, uint32_t *pv_scratch, void *workspace, size_t workspace_bytes,
-                  sgp_stream_t stream);
-
 /* ---- stages 2-4: the MVM on a built lattice -------------------------------------- */
 
 typedef struct sgp_lattice_view {
@@ -140,8 +131,9 @@ typedef struct sgp_lattice_view {
     int32_t order;           /* stencil half-width r */
     const int32_t *replay;   /* device [N, d+1, 2] {lattice index, weight bits} */
     const int32_t *nbr;      /* device [(d+1), M, 2r] */
-    const uint32_t *csr_ptr; /* device [M+1] or NULL */
-    const int32_t *csr_ent;  /* device [N*(d+1), 2] or NULL */
+    const uint32_t *csr_ptr; /* device [M+1] or NULL: row starts into csr_ent (ordered-gather splat) */
+    const int32_t *csr_ent;  /* device [N*(d+1), 2] or NULL: {point, weight bits} sorted by lattice row, point-vertex
+                                order inside a row -- the first N*(d+1) entries of sgp_build_rowsorted's `ent` */
     const uint32_t *perm;    /* device [N] or NULL.  When set, row p of replay describes point perm[p]: splat and
                                 slice walk the points in that (locality) order and address src / out rows through it */
     int32_t fast;            /* 0: the reference's arithmetic, one rounding per product and per sum (bit-exact on the

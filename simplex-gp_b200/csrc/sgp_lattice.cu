@@ -546,46 +546,6 @@ sgp_neighbours_kernel(const int16_t *__restrict__ keys, int64_t M, int d_rt, int
 }
 
 // ------------------------------------------------------------------------------------
-// CSR (lattice point -> touching points) for the gather-form splat
-// ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-sgp_csr_count_kernel(const int32_t *__restrict__ replay, int64_t total, uint32_t *__restrict__ counts)
-{
-    const int64_t pv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pv >= total) return;
-    atomicAdd(counts + replay[pv * 2], 1u);
-}
-
-// unordered fill: tmp[row_ptr[idx] + cursor++] = pv
-__global__ void __launch_bounds__(256)
-sgp_csr_fill_kernel(const int32_t *__restrict__ replay, int64_t total, const uint32_t *__restrict__ row_ptr,
-                    uint32_t *__restrict__ cursor, uint32_t *__restrict__ tmp)
-{
-    const int64_t pv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pv >= total) return;
-    const int32_t idx = replay[pv * 2];
-    const uint32_t p = atomicAdd(cursor + idx, 1u);
-    tmp[row_ptr[idx] + p] = (uint32_t)pv;
-}
-
-// rank sort inside each row: entry position = number of smaller pv in the same row
-__global__ void __launch_bounds__(256)
-sgp_csr_order_kernel(const int32_t *__restrict__ replay, int64_t total, int dp1,
-                     const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ tmp,
-                     int32_t *__restrict__ entries)
-{
-    const int64_t pv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pv >= total) return;
-    const int32_t idx = replay[pv * 2];
-    const uint32_t a = row_ptr[idx], b = row_ptr[idx + 1];
-    uint32_t smaller = 0;
-    for (uint32_t q = a; q < b; ++q) smaller += (tmp[q] < (uint32_t)pv) ? 1u : 0u;
-    const int64_t dst = (int64_t)(a + smaller);
-    entries[dst * 2] = (int32_t)(pv / dp1);
-    entries[dst * 2 + 1] = replay[pv * 2 + 1];
-}
-
-// ------------------------------------------------------------------------------------
 // stages 2-4: splat / blur / slice.  Thread = (row, chunk of VEC channels); a row's
 // channels are adjacent so one row of L=16 fp32 is 4 lanes x float4 = 64 contiguous bytes.
 // ------------------------------------------------------------------------------------
@@ -975,49 +935,6 @@ extern "C" int sgp_build_neighbours(const int16_t *keys, int64_t M, int d, int o
     SGP_DISPATCH_D(d, (sgp_neighbours_kernel<DD><<<grid_for(work, 256), 256, 0, st>>>(
                           keys, M, d, order, (const unsigned long long *)table, (uint64_t)(capacity - 1), nbr)));
     return launch_ok("sgp_neighbours_kernel");
-}
-
-// CSR workspace: [counts->cursor: M uint32][tmp pv list: total uint32 -- sized by caller via N,d][tiles][total]
-// To keep the signature small the pv list lives in `entries` (second half) during the fill.
-extern "C" size_t sgp_csr_workspace_bytes(int64_t M)
-{
-    const int64_t n_tiles = (M + 1 + SCAN_TILE - 1) / SCAN_TILE;
-    size_t o = (size_t)(M + 1) * 4;          // cursor
-    o += (size_t)(n_tiles > 0 ? n_tiles : 1) * 4;
-    o = (o + 15) & ~(size_t)15;
-    o += 16;
-    return o;
-}
-
-extern "C" int sgp_build_csr(const int32_t *replay, int64_t N, int d, int64_t M, uint32_t *row_ptr,
-                             int32_t *entries, uint32_t *pv_scratch, void *workspace, size_t workspace_bytes,
-                             sgp_stream_t stream)
-{
-    int rc = check_dims(N, d);
-    if (rc) return rc;
-    if (N == 0 || M == 0) return SGP_OK;
-    if (!replay || !row_ptr || !entries || !pv_scratch || !workspace || workspace_bytes < sgp_csr_workspace_bytes(M))
-        return fail(SGP_EINVAL, "sgp_build_csr: null pointer or workspace too small");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t total = N * (d + 1);
-    const int64_t n_tiles = (M + 1 + SCAN_TILE - 1) / SCAN_TILE;
-    uint32_t *cursor = (uint32_t *)workspace;
-    uint32_t *tiles = cursor + (M + 1);
-    size_t o = ((size_t)(M + 1) * 4 + (size_t)n_tiles * 4 + 15) & ~(size_t)15;
-    unsigned long long *total_dev = (unsigned long long *)((char *)workspace + o);
-    // counts into row_ptr, scan in place -> row starts
-    CUDA_TRY(cudaMemsetAsync(row_ptr, 0, sizeof(uint32_t) * (size_t)(M + 1), st));
-    sgp_csr_count_kernel<<<grid_for(total, 256), 256, 0, st>>>(replay, total, row_ptr);
-    rc = launch_ok("sgp_csr_count_kernel");
-    if (rc) return rc;
-    rc = sgp_exclusive_scan_u32(row_ptr, M + 1, tiles, total_dev, st);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(uint32_t) * (size_t)(M + 1), st));
-    sgp_csr_fill_kernel<<<grid_for(total, 256), 256, 0, st>>>(replay, total, row_ptr, cursor, pv_scratch);
-    rc = launch_ok("sgp_csr_fill_kernel");
-    if (rc) return rc;
-    sgp_csr_order_kernel<<<grid_for(total, 256), 256, 0, st>>>(replay, total, d + 1, row_ptr, pv_scratch, entries);
-    return launch_ok("sgp_csr_order_kernel");
 }
 
 // ---- MVM ---------------------------------------------------------------------------

@@ -152,7 +152,7 @@ class Lattice:
                     self._sort_points()
                 if build_tiles and self.M > 0:
                     self._build_tiles(tile_points)
-                if build_rows and self.M > 0:
+                if build_rows and self.M > 0 and self.rows is None:
                     self._build_rows()
             if not keep_structure:
                 self.greedy = None
@@ -193,7 +193,8 @@ class Lattice:
                     self._build_csr()
                 if build_groups and self.order >= 1:
                     self._build_groups(group_axes, group_rows)
-                self._build_rows()
+                if self.rows is None:
+                    self._build_rows()
         return self
 
     def _build_groups(self, group_axes: Optional[int] = None, group_rows: int = 512) -> None:
@@ -357,16 +358,15 @@ class Lattice:
                          t["tile_piece_ptr"].data_ptr(), t["piece_ptr"].data_ptr(), t["piece_row"].data_ptr())
 
     def _build_csr(self) -> None:
-        lib = _capi.lib()
-        dev, N, d, M = self.device, self.N, self.d, self.M
-        total = N * (d + 1)
-        self.csr_ptr = torch.empty(M + 1, dtype=torch.int32, device=dev)
-        self.csr_ent = torch.empty((total, 2), dtype=torch.int32, device=dev)
-        scratch = torch.empty(total, dtype=torch.int32, device=dev)
-        ws_bytes = int(lib.sgp_csr_workspace_bytes(M))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        check(lib.sgp_build_csr(_ptr(self.replay), N, d, M, _ptr(self.csr_ptr), _ptr(self.csr_ent), _ptr(scratch),
-                                _ptr(ws), ws_bytes, _stream_ptr(dev)))
+        """Row starts for the ordered-gather splat (``mode=2``): the row-sorted entries are already in the reference's
+        accumulation order (stable sort), so the CSR form is those entries plus a pointer array."""
+        if self.rows is None:
+            self._build_rows()
+        total = self.N * (self.d + 1)
+        rows = self.rows["ent_row"][:total]
+        bounds = torch.arange(self.M + 1, device=self.device, dtype=torch.int32)
+        self.csr_ptr = torch.searchsorted(rows, bounds).to(torch.int32).contiguous()
+        self.csr_ent = self.rows["ent"]
 
     # ---- structure accessors (reference numbering) -------------------------------------------
     @property
