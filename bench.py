@@ -79,7 +79,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -156,10 +156,12 @@ def run_reference_arm(args, w):
         return 0
     import torch
     torch.set_num_threads(1)
-    steps, warm = args.steps, args.warmup
-    # bound the whole run to a few minutes: the -O3 reference needs ~5.7 us per point at this shape
-    budget_s = 150.0 / max(1, steps + warm)
-    n_sample = int(min(w["N"], max(20_000, budget_s / 6.0e-6)))
+    # One full-size reference call costs 2-7 s of one core, so a step is a BOUNDED SAMPLE: the first 100 000 of the N
+    # points (per-point cost at 100k is within 1 % of the per-point cost at 1M -- 7.18 vs 7.16 us here -- whereas at
+    # 20k it is 27 % higher, because M/N differs), scaled linearly to N; and at most 150 steps are executed however
+    # many were asked for (the reference is deterministic CPU code: more repetitions add nothing but minutes).
+    n_sample = int(min(w["N"], 100_000))
+    steps, warm = max(1, min(args.steps, 150)), max(0, min(args.warmup, 2))
     fn, kind = cpu_reference_filter()
     g = torch.Generator().manual_seed(0)
     x = torch.randn(n_sample, w["d"], generator=g)
@@ -174,8 +176,9 @@ def run_reference_arm(args, w):
     per_step = dt / steps
     # scale the sample linearly to the full N: one full-size MVM costs (N / n_sample) sample filters
     value = 1.0 / (per_step * (w["N"] / n_sample))
-    sample = (f"{steps} reference filter() calls (lattice rebuilt inside each call, as the reference does) on the first "
-              f"{n_sample} of {w['N']} points, scaled linearly to N")
+    sample = (f"{steps} reference filter() calls executed ({args.steps} requested), lattice rebuilt inside each call as the "
+              f"reference does, on the first {n_sample} of {w['N']} points, scaled linearly to N; single-threaded code, "
+              f"{os.cpu_count()} host cores present")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": per_step * 1e3 * (w["N"] / n_sample), "higher_is_better": True,
@@ -262,14 +265,14 @@ def run_ours(args, w):
     def step(i):
         lat.mvm(Vs[i % n_rot], out=outs[i % n_rot], mode=mode, blur="groups" if use_groups else "axis")
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()   # sampled over warm-up + timed region (a 50-step timed region alone lasts only ~11 ms)
     for i in range(warm):
         step(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
@@ -426,8 +429,8 @@ def run_ours(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="A", choices=sorted(WORKLOADS))
     ap.add_argument("--splat", default="auto", choices=["auto", "rows", "tiles", "atomic", "gather"],
