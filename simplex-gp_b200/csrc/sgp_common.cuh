@@ -35,6 +35,14 @@ __device__ __forceinline__ int2 ldg_ordered_int2(const int2 *p)
     asm volatile("ld.global.nc.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
 }
+// same, for data that is read exactly once (replay tables): streaming policy, so that it does not displace the
+// lattice values, which the gathers re-read from L2
+__device__ __forceinline__ int2 ldg_ordered_int2_streaming(const int2 *p)
+{
+    int2 v;
+    asm volatile("ld.global.cs.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ float4 ldg_ordered_f4(const float *p)
 {
     float4 v;
@@ -63,6 +71,7 @@ template <> struct Vec<1> {
     __device__ __forceinline__ void load_ordered(const float *p) { v[0] = ldg_ordered_f1(p); }
     __device__ __forceinline__ void load_plain(const float *p) { v[0] = *p; }
     __device__ __forceinline__ void store(float *p) const { *p = v[0]; }
+    __device__ __forceinline__ void store_streaming(float *p) const { __stcs(p, v[0]); }
     __device__ __forceinline__ void red(float *p) const { atomicAdd(p, v[0]); }
 };
 template <> struct Vec<2> {
@@ -72,6 +81,7 @@ template <> struct Vec<2> {
     __device__ __forceinline__ void load_ordered(const float *p) { float2 t = ldg_ordered_f2(p); v[0] = t.x; v[1] = t.y; }
     __device__ __forceinline__ void load_plain(const float *p) { float2 t = *(const float2 *)p; v[0] = t.x; v[1] = t.y; }
     __device__ __forceinline__ void store(float *p) const { *(float2 *)p = make_float2(v[0], v[1]); }
+    __device__ __forceinline__ void store_streaming(float *p) const { __stcs((float2 *)p, make_float2(v[0], v[1])); }
     __device__ __forceinline__ void red(float *p) const
     {
         asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
@@ -84,6 +94,7 @@ template <> struct Vec<4> {
     __device__ __forceinline__ void load_ordered(const float *p) { float4 t = ldg_ordered_f4(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     __device__ __forceinline__ void load_plain(const float *p) { float4 t = *(const float4 *)p; v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
     __device__ __forceinline__ void store(float *p) const { *(float4 *)p = make_float4(v[0], v[1], v[2], v[3]); }
+    __device__ __forceinline__ void store_streaming(float *p) const { __stcs((float4 *)p, make_float4(v[0], v[1], v[2], v[3])); }
     __device__ __forceinline__ void red(float *p) const
     {
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");

@@ -698,7 +698,7 @@ sgp_exact_div_check_kernel(float b, float rb, uint32_t lo, uint32_t count, unsig
 // slice: thread = (point n, chunk).  Vertices are processed in batches of BATCH with all
 // replay entries, then all lattice rows, in flight together (two dependent latencies per batch
 // instead of two per vertex); the sum itself stays in vertex order.
-template <int VEC, int BATCH, bool FAST>
+template <int VEC, int BATCH, bool FAST, bool STREAM>
 __global__ void __launch_bounds__(256)
 sgp_slice_kernel(const int2 *__restrict__ replay, int64_t pstride, int64_t rstride,
                  const uint32_t *__restrict__ perm, const float *__restrict__ values, int64_t N, int dp1, int L,
@@ -717,7 +717,7 @@ sgp_slice_kernel(const int2 *__restrict__ replay, int64_t pstride, int64_t rstri
         int2 e[BATCH];
         Vec<VEC> v[BATCH];
 #pragma unroll
-        for (int b = 0; b < BATCH; ++b) e[b] = ldg_ordered_int2(rp + (r0 + b) * rstride);
+        for (int b = 0; b < BATCH; ++b) e[b] = STREAM ? ldg_ordered_int2_streaming(rp + (r0 + b) * rstride) : ldg_ordered_int2(rp + (r0 + b) * rstride);
         // A warp issues in order, so a row load placed before a later index load would make the warp wait a full
         // memory round trip with that index load not yet issued.  Lattice indices are never negative: branching on
         // all of them keeps every index load ahead of every row load (two round trips per batch, not up to BATCH).
@@ -751,7 +751,8 @@ sgp_slice_kernel(const int2 *__restrict__ replay, int64_t pstride, int64_t rstri
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc.v[k] = exact_div(acc.v[k], divisor, rdivisor);
     }
-    acc.store(out + (perm ? (int64_t)__ldg(perm + n) : n) * ldo + c0);
+    if (STREAM) acc.store_streaming(out + (perm ? (int64_t)__ldg(perm + n) : n) * ldo + c0);
+    else acc.store(out + (perm ? (int64_t)__ldg(perm + n) : n) * ldo + c0);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1076,15 +1077,22 @@ extern "C" int sgp_slice(const sgp_lattice_view *lat, const float *values, int L
         const char *e = getenv("SGP_SLICE_BATCH");
         batch = (e && atoi(e) == 3) ? 3 : 9;
     }
-#define SGP_SLICE_LAUNCH(BB, FF)                                                                                       \
-    SGP_DISPATCH_VEC(vec, (sgp_slice_kernel<VV, BB, FF><<<grid_for(work, 256), 256, 0, st>>>(                          \
+#define SGP_SLICE_LAUNCH(BB, FF, SS)                                                                                     \
+    SGP_DISPATCH_VEC(vec, (sgp_slice_kernel<VV, BB, FF, SS><<<grid_for(work, 256), 256, 0, st>>>(                          \
                               (const int2 *)lat->replay, lat->replay_transposed ? 1 : lat->d + 1,                      \
                               lat->replay_transposed ? lat->N : 1, lat->perm, values, lat->N, lat->d + 1, L, chunks,    \
                               divisor, rdivisor, out, ldo)))
+    static int stream_env = -1;   // SGP_SLICE_STREAM=0 turns off the streaming cache policy of the replay reads / out writes (69 -> 66 us with it)
+    if (stream_env < 0) {
+        const char *e = getenv("SGP_SLICE_STREAM");
+        stream_env = e ? atoi(e) : 1;
+    }
     if (batch == 3) {
-        if (lat->fast) { SGP_SLICE_LAUNCH(3, true); } else { SGP_SLICE_LAUNCH(3, false); }
+        if (lat->fast) { SGP_SLICE_LAUNCH(3, true, false); } else { SGP_SLICE_LAUNCH(3, false, false); }
+    } else if (stream_env) {
+        if (lat->fast) { SGP_SLICE_LAUNCH(9, true, true); } else { SGP_SLICE_LAUNCH(9, false, true); }
     } else {
-        if (lat->fast) { SGP_SLICE_LAUNCH(9, true); } else { SGP_SLICE_LAUNCH(9, false); }
+        if (lat->fast) { SGP_SLICE_LAUNCH(9, true, false); } else { SGP_SLICE_LAUNCH(9, false, false); }
     }
 #undef SGP_SLICE_LAUNCH
     return launch_ok("sgp_slice_kernel");

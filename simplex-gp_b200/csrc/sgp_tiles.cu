@@ -362,6 +362,9 @@ extern "C" int sgp_permute_replay(const int32_t *replay, const uint32_t *perm, c
 // one per point-vertex to one per (row, thread) run; and the gather side moves through L2 as plain loads, which the
 // scatter form's same-address reductions do not.
 // ------------------------------------------------------------------------------------
+#ifndef SGP_LDCS
+#define SGP_LDCS 1
+#endif
 #define ROWSEG 16   /* padding granularity of the row-sorted arrays; the kernel takes SEG = 4, 8 or 16 entries per thread */
 
 __global__ void __launch_bounds__(256)
@@ -457,13 +460,13 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     const int4 *rp = (const int4 *)(ent_row + seg * SEG);
 #pragma unroll
     for (int i = 0; i < SEG / 2; ++i) {
-        const int4 t = __ldg(ep + i);
+        const int4 t = SGP_LDCS ? __ldcs(ep + i) : __ldg(ep + i);   // read once: streaming, keeps src and the lattice in L2
         e[2 * i] = make_int2(t.x, t.y);
         e[2 * i + 1] = make_int2(t.z, t.w);
     }
 #pragma unroll
     for (int i = 0; i < SEG / 4; ++i) {
-        const int4 t = __ldg(rp + i);
+        const int4 t = SGP_LDCS ? __ldcs(rp + i) : __ldg(rp + i);
         row[4 * i] = t.x; row[4 * i + 1] = t.y; row[4 * i + 2] = t.z; row[4 * i + 3] = t.w;
     }
     // point indices are never negative: the branch keeps every entry load ahead of every row load (in-order issue)
