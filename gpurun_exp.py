@@ -1,8 +1,6 @@
 import sys, time, torch, numpy as np, ctypes as C, os
 sys.path.insert(0, '/root/repo')
 import simplex_gp_b200 as sg
-from simplex_gp_b200 import _capi
-from simplex_gp_b200.lattice import _fp, _ptr, _stream_ptr
 torch.manual_seed(0)
 N,d,L=1_000_000,8,16
 x=torch.randn(N,d,device='cuda'); vs=[torch.randn(N,L,device='cuda') for _ in range(4)]
@@ -16,11 +14,15 @@ def timeit(fn, reps=50, warm=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1)/reps*1000
 lat=sg.Lattice(x,c); torch.cuda.synchronize()
-lib=_capi.lib(); buf0,buf1=lat._scratch(L); st=_stream_ptr(lat.device)
 outs=[torch.empty(N,L,device='cuda') for _ in range(4)]
-vo=lat._view(lat._table(False,True),None,False)
-r=lat.rows
-t_sr=timeit(lambda i: _capi.check(lib.sgp_splat_rows(_ptr(r['ent']),_ptr(r['ent_row']),N,d,lat.M,_ptr(vs[i%4]),L,L,_ptr(buf0),st)))
-t_sl=timeit(lambda i: _capi.check(lib.sgp_slice(C.byref(vo),_ptr(buf1),L,_ptr(outs[i%4]),L,st)))
-t_m=timeit(lambda i: lat.mvm(vs[i%4],out=outs[i%4]))
-print(f'splat {t_sr:.1f} slice {t_sl:.1f} | mvm {t_m:.1f} us -> {1e6/t_m:.0f} MVM/s')
+print('eager us/mvm', timeit(lambda i: lat.mvm(vs[i%4],out=outs[i%4])))
+g=torch.cuda.CUDAGraph()
+s=torch.cuda.Stream()
+s.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(s):
+    for i in range(4): lat.mvm(vs[i],out=outs[i])
+torch.cuda.current_stream().wait_stream(s)
+with torch.cuda.graph(g):
+    for i in range(4): lat.mvm(vs[i],out=outs[i])
+print('graph (4 mvm) us/mvm', timeit(lambda i: g.replay(), reps=20)/4)
+ref=outs[0].clone(); lat.mvm(vs[0],out=outs[0]); torch.cuda.synchronize(); print('rel', float((ref-outs[0]).norm()/ref.norm()))

@@ -220,12 +220,14 @@ int sgp_slice_tiles(const sgp_tiles_view *tiles, const float *values, int L, flo
  * after the last stage reads through a replay table remapped to that stage's order (sgp_remap_replay). */
 typedef struct sgp_blur_group {
     int32_t j0, j1;              /* axis range [j0, j1) */
-    int32_t rows_cap;            /* largest number of rows of one CTA batch (sizes the shared memory) */
-    int32_t reserved;
+    int32_t rows_cap;            /* largest number of rows of one CTA batch */
+    int32_t zero_row;            /* 512 or 1024: the `cap` class the group was finalised with (cap <= 512 -> 512); it is
+                                    the index absent neighbours carry in lnb and selects the kernel variant */
     int64_t n_batches;
     const uint32_t *batch_begin; /* device [n_batches+1] positions */
     const int32_t *src;          /* device [M] input row of every position */
-    const uint16_t *lnb;         /* device [M, j1-j0, 2r] batch-local neighbour positions, 0xFFFF = absent */
+    const uint16_t *lnb;         /* device [M*(j1-j0)*2r]: per batch [axis][row][t] batch-local neighbour positions;
+                                    absent = 512 (batches of up to 512 rows) or 1024, the kernel's all-zero row */
 } sgp_blur_group;
 
 size_t sgp_group_workspace_bytes(int64_t M);

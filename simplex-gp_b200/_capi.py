@@ -81,7 +81,7 @@ class BlurGroup(C.Structure):
         ("j0", C.c_int32),
         ("j1", C.c_int32),
         ("rows_cap", C.c_int32),
-        ("reserved", C.c_int32),
+        ("zero_row", C.c_int32),
         ("n_batches", C.c_int64),
         ("batch_begin", C.c_void_p),
         ("src", C.c_void_p),

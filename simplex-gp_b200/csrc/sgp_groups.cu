@@ -15,8 +15,8 @@
 //   order[p]        lattice point (first-touch index) stored at position p: points sorted by class
 //   batch_begin[b]  CTA b owns positions [batch_begin[b], batch_begin[b+1]) -- whole classes, at most rows_cap rows
 //   src[p]          where position p's input row lives in the PREVIOUS stage's output order (gather on load)
-//   lnb[p][a][t]    position, relative to batch_begin[b], of the neighbour along the group's a-th axis, offset
-//                   t over o = -r..-1, 1..r; 0xFFFF = absent
+//   lnb             per batch [axis a][row][t]: position, relative to batch_begin[b], of the neighbour along the group's
+//                   a-th axis, offset t over o = -r..-1, 1..r; absent = index of the kernel's all-zero row (512 or 1024)
 // The arithmetic of a pass is that of sgp_blur_kernel (same products, same order, no FMA), so results are
 // bit-identical to the per-axis path.
 //
@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(256)
 sgp_group_tables_kernel(const int32_t *__restrict__ nbr, int64_t M, int order_r, int j0, int j1,
                         const uint32_t *__restrict__ order, const uint32_t *__restrict__ pos,
                         const uint32_t *__restrict__ prev_pos, int64_t n_batches,
-                        const uint32_t *__restrict__ batch_begin, int32_t *__restrict__ src, uint16_t *__restrict__ lnb,
-                        int32_t *__restrict__ flags)
+                        const uint32_t *__restrict__ batch_begin, uint32_t absent, int32_t *__restrict__ src,
+                        uint16_t *__restrict__ lnb, int32_t *__restrict__ flags)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= M) return;
@@ -176,16 +176,17 @@ sgp_group_tables_kernel(const int32_t *__restrict__ nbr, int64_t M, int order_r,
         const int32_t *np = nbr + ((int64_t)(j0 + a) * M + row) * w;
         for (int t = 0; t < w; ++t) {
             const int32_t nb = np[t];
-            uint32_t local = LNB_ABSENT;
+            uint32_t local = absent;                   // index of the kernel's all-zero row
             if (nb >= 0) {
                 const uint32_t q = pos[nb];
                 local = q - base;
-                if (q < base || q >= limit || local >= LNB_ABSENT) {   // neighbour outside the CTA's rows: must not happen
+                if (q < base || q >= limit || local >= absent) {   // neighbour outside the CTA's rows: must not happen
                     atomicOr(flags, 4);
-                    local = LNB_ABSENT;
+                    local = absent;
                 }
             }
-            lnb[(p * nax + a) * w + t] = (uint16_t)local;
+            // per batch: [axis][row][t], so that a thread's rows of one pass are a fixed stride apart
+            lnb[(int64_t)base * nax * w + ((int64_t)a * (limit - base) + (p - base)) * w + t] = (uint16_t)local;
         }
     }
 }
@@ -285,7 +286,7 @@ extern "C" int sgp_group_finalize(const int32_t *nbr, int64_t M, int order_r, in
                                   sgp_stream_t stream)
 {
     if (!nbr || !order || !pos || !class_start || !batch_begin || !src || !lnb || !workspace || !max_rows_out ||
-        !n_batches_out || M <= 0 || order_r < 1 || order_r > SGP_MAX_ORDER || j1 <= j0 || cap < 1 || cap >= LNB_ABSENT ||
+        !n_batches_out || M <= 0 || order_r < 1 || order_r > SGP_MAX_ORDER || j1 <= j0 || cap < 1 || cap > 1024 ||
         max_batches < 1)
         return fail(SGP_EINVAL, "sgp_group_finalize: bad argument");
     GroupWs w;
@@ -303,8 +304,9 @@ extern "C" int sgp_group_finalize(const int32_t *nbr, int64_t M, int order_r, in
     CUDA_TRY(cudaStreamSynchronize(st));
     if (host[2] != 0) return fail(SGP_EINVAL, "blur group [%d,%d): classes do not fit %lld rows", j0, j1, (long long)cap);
     const int64_t n_batches = host[0];
+    const uint32_t absent = cap > 512 ? 1024u : 512u;   // ROWS_MAX of the kernel variant that takes this group
     sgp_group_tables_kernel<<<grid_for(M, 256), 256, 0, st>>>(nbr, M, order_r, j0, j1, order, pos, prev_pos, n_batches,
-                                                               batch_begin, src, lnb, (int32_t *)(small + 4));
+                                                               batch_begin, absent, src, lnb, (int32_t *)(small + 4));
     rc = launch_ok("sgp_group_tables_kernel");
     if (rc) return rc;
     uint32_t flag = 0;
@@ -335,9 +337,18 @@ struct GroupCoeffs {
 
 #define PASS_UNROLL 4
 
-// Shared memory: A[rows_cap+1][CBT] | nbs[rows_cap][nax][2r] (uint16) | SRC[rows_cap], CBT = CHUNKS*VEC channels.
-// A thread owns one channel chunk (c) and the rows lr0, lr0+RSTEP, ... of the batch for the whole kernel, so the
-// index arithmetic is hoisted out of every loop.
+// Shared memory: A[ROWS_MAX+1][CBT] | nbs[nax][rows][2r] (uint16) | SRC[rows]; CBT = CHUNKS*VEC channels,
+// ROWS_MAX = 2*THREADS rows (the most a CTA of this variant takes), row ROWS_MAX is all zeros.
+//
+// A thread owns one channel chunk (c) and the rows lr0 + i*RSTEP (i < MAXI) of the batch for the whole kernel:
+//   * the index arithmetic is hoisted out of every loop (row slots are compile-time offsets);
+//   * a row's own value never has to be read back from shared memory -- it stays in registers from the pass that
+//     produced it; shared memory holds ONE value buffer that a pass reads (neighbours), then, after a barrier, every
+//     thread overwrites its rows in place;
+//   * an absent neighbour is the index ROWS_MAX of the zero row (written by the builder), exactly what the reference
+//     does (permutohedral.h:545 substitutes a zero vector and still adds c*0): the passes are branch-free;
+//   * PASS_UNROLL rows are processed together -- their neighbour indices, then all their neighbour rows, are read
+//     before any arithmetic -- so that several shared-memory round trips overlap (warps issue in order).
 template <int VEC, int R, int CHUNKS, int THREADS, bool FAST>
 __global__ void __launch_bounds__(THREADS)   // (capping registers for a fourth CTA per SM measured slower: 62 vs 56 us)
 sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *__restrict__ src,
@@ -347,12 +358,16 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
     constexpr int RR = R > 0 ? R : SGP_MAX_ORDER;
     constexpr int CBT = CHUNKS * VEC;
     constexpr int RSTEP = THREADS / CHUNKS;
+    constexpr int U = PASS_UNROLL;
+    constexpr int ROWS_MAX = THREADS * 2;                    // 512 rows at 256 threads, 1024 at 512 (host-checked)
+    constexpr int MAXI = ROWS_MAX / RSTEP;                   // row slots per thread: 2 * CHUNKS
+    constexpr int UU = MAXI < U ? MAXI : U;
+    static_assert(MAXI % UU == 0, "row slots must split into whole unroll groups");
     const int r = R > 0 ? R : order_rt;
     const int w2 = 2 * r;
     extern __shared__ __align__(16) float smem[];
-    const int buf_floats = ((rows_cap + 1) * CBT + 3) & ~3;   // +1: the all-zero row; every array starts 16-byte aligned
-    float *A = smem;   // ONE value buffer: a pass reads its neighbours, a barrier, then every thread writes its rows back
-    uint16_t *nbs = (uint16_t *)(smem + buf_floats);
+    float *A = smem;
+    uint16_t *nbs = (uint16_t *)(smem + (((ROWS_MAX + 1) * CBT + 3) & ~3));   // 16-byte aligned (cp.async)
     const uint32_t p0 = batch_begin[blockIdx.x];
     const int rows = (int)(batch_begin[blockIdx.x + 1] - p0);
     if (rows == 0) return;
@@ -361,7 +376,7 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
     const int cg = blockIdx.y * CBT + c;          // first global channel of this thread
     const bool live = cg < L;                      // the last channel block may be partial (L % CBT != 0)
 
-    if (threadIdx.x < CBT) A[rows_cap * CBT + threadIdx.x] = 0.0f;
+    if (threadIdx.x < CBT) A[ROWS_MAX * CBT + threadIdx.x] = 0.0f;
     // stage the batch's neighbour table and its slice of the gather list (plain range copies, asynchronous) ...
     int32_t *SRC = (int32_t *)(nbs + (((size_t)rows_cap * nax * w2 + 7) & ~(size_t)7));
     cta_copy_async(nbs, lnb + (int64_t)p0 * nax * w2, rows * nax * w2 * 2, threadIdx.x, THREADS);   // w2 even: whole words
@@ -374,119 +389,91 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
     }
     cp_async_wait_all();
     __syncthreads();
+    // (threads of a partial last channel block carry on with scratch values: they keep the barriers uniform and never store)
 
-    // An absent neighbour reads the all-zero row `rows_cap`, exactly what the reference does (permutohedral.h:545
-    // substitutes a zero vector and still adds c*0), so the passes are branch-free.
-    //
-    // A thread owns the same rows (lr0 + i*RSTEP, i < MAXI) in every pass, so a row's own value never has to be read
-    // back from shared memory: it stays in registers from the pass that produced it (shared memory is only for the
-    // neighbours' reads).  PASS_UNROLL rows are processed together -- their neighbour indices, then all their
-    // neighbour rows, are read before any arithmetic -- so that several shared-memory round trips overlap.
-    constexpr int U = PASS_UNROLL;
-    constexpr int ROWS_MAX = THREADS * 2;                    // 512 rows at 256 threads, 1024 at 512 (host-checked)
-    constexpr int MAXI = (ROWS_MAX + RSTEP - 1) / RSTEP;
-    static_assert(MAXI % U == 0 || MAXI < U, "row slots must split into whole unroll groups");
-    const uint32_t zero_row = (uint32_t)rows_cap;
+    float *const Ac = A + c;                                 // this thread's channel chunk of row 0
     Vec<VEC> self[MAXI];
 #pragma unroll
     for (int i = 0; i < MAXI; ++i) {
         const int lr = lr0 + i * RSTEP;
-        self[i].load_plain(A + ((live && lr < rows) ? lr : (int)zero_row) * CBT + c);
+        self[i].load_plain(Ac + (lr < rows ? lr : ROWS_MAX) * CBT);
     }
     for (int a = 0; a < nax; ++a) {
         const bool last = (a == nax - 1);
-        if (live) {
+        const uint16_t *nb_a = nbs + (size_t)a * rows * w2 + lr0 * w2;   // [a][lr][w2], this thread's first row
 #pragma unroll
-            for (int i0 = 0; i0 < MAXI; i0 += U) {
-                if (lr0 + i0 * RSTEP < rows) {
-                    uint32_t ni[U][2 * RR];
+        for (int i0 = 0; i0 < MAXI; i0 += UU) {
+            if (lr0 + i0 * RSTEP < rows) {
+                uint32_t ni[UU][2 * RR];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (i0 + u < MAXI) {
-                            const int lr = lr0 + (i0 + u) * RSTEP;
-                            const uint16_t *nb = nbs + ((lr < rows ? lr : 0) * nax + a) * w2;
-                            if (R == 1) {
-                                const uint32_t both = (lr < rows) ? *(const uint32_t *)nb : 0xFFFFFFFFu;
-                                ni[u][0] = min(both & 0xFFFFu, zero_row);
-                                ni[u][1] = min(both >> 16, zero_row);
-                            } else {
+                for (int u = 0; u < UU; ++u) {
+                    const int lr = lr0 + (i0 + u) * RSTEP;
+                    const uint16_t *nb = nb_a + (i0 + u) * RSTEP * w2;
+                    if (R == 1) {
+                        const uint32_t both = (lr < rows) ? *(const uint32_t *)nb : (uint32_t)(ROWS_MAX | (ROWS_MAX << 16));
+                        ni[u][0] = both & 0xFFFFu;
+                        ni[u][1] = both >> 16;
+                    } else {
 #pragma unroll
-                                for (int t = 0; t < 2 * RR; ++t)
-                                    ni[u][t] = (t < w2 && lr < rows) ? min((uint32_t)nb[t], zero_row) : zero_row;
-                            }
+                        for (int t = 0; t < 2 * RR; ++t) ni[u][t] = (t < w2 && lr < rows) ? (uint32_t)nb[t] : (uint32_t)ROWS_MAX;
+                    }
+                }
+                Vec<VEC> acc[UU];
+#pragma unroll
+                for (int u = 0; u < UU; ++u) {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) acc[u].v[k] = 0.0f;
+                }
+                // reference order: o = -r..-1, 0, 1..r
+#pragma unroll
+                for (int t = 0; t < RR; ++t) {
+                    if (t < r) {
+#pragma unroll
+                        for (int u = 0; u < UU; ++u) {
+                            Vec<VEC> v;
+                            v.load_plain(Ac + ni[u][t] * CBT);
+#pragma unroll
+                            for (int k = 0; k < VEC; ++k) acc[u].v[k] = madd<FAST>(cf.c[t], v.v[k], acc[u].v[k]);
                         }
                     }
-                    Vec<VEC> acc[U];
+                }
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
+                for (int u = 0; u < UU; ++u) {
 #pragma unroll
-                        for (int k = 0; k < VEC; ++k) acc[u].v[k] = 0.0f;
-                    }
-                    // reference order: o = -r..-1, 0, 1..r
+                    for (int k = 0; k < VEC; ++k) acc[u].v[k] = madd<FAST>(cf.c[r], self[i0 + u].v[k], acc[u].v[k]);
+                }
 #pragma unroll
-                    for (int t = 0; t < RR; ++t) {
-                        if (t < r) {
+                for (int t = 0; t < RR; ++t) {
+                    if (t < r) {
 #pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                if (i0 + u < MAXI) {
-                                    Vec<VEC> v;
-                                    v.load_plain(A + ni[u][t] * CBT + c);
+                        for (int u = 0; u < UU; ++u) {
+                            Vec<VEC> v;
+                            v.load_plain(Ac + ni[u][r + t] * CBT);
 #pragma unroll
-                                    for (int k = 0; k < VEC; ++k) acc[u].v[k] = madd<FAST>(cf.c[t], v.v[k], acc[u].v[k]);
-                                }
-                            }
+                            for (int k = 0; k < VEC; ++k) acc[u].v[k] = madd<FAST>(cf.c[r + 1 + t], v.v[k], acc[u].v[k]);
                         }
                     }
+                }
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (i0 + u < MAXI) {
-#pragma unroll
-                            for (int k = 0; k < VEC; ++k) acc[u].v[k] = madd<FAST>(cf.c[r], self[i0 + u].v[k], acc[u].v[k]);
-                        }
-                    }
-#pragma unroll
-                    for (int t = 0; t < RR; ++t) {
-                        if (t < r) {
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                if (i0 + u < MAXI) {
-                                    Vec<VEC> v;
-                                    v.load_plain(A + ni[u][r + t] * CBT + c);
-#pragma unroll
-                                    for (int k = 0; k < VEC; ++k)
-                                        acc[u].v[k] = madd<FAST>(cf.c[r + 1 + t], v.v[k], acc[u].v[k]);
-                                }
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (i0 + u < MAXI) {
-                            const int lr = lr0 + (i0 + u) * RSTEP;
-                            self[i0 + u] = acc[u];
-                            if (last && lr < rows) acc[u].store(out + (int64_t)(p0 + lr) * L + cg);   // the group's result
-                        }
-                    }
+                for (int u = 0; u < UU; ++u) {
+                    const int lr = lr0 + (i0 + u) * RSTEP;
+                    self[i0 + u] = acc[u];
+                    if (last && live && lr < rows) acc[u].store(out + (int64_t)(p0 + lr) * L + cg);   // the group's result
                 }
             }
         }
         if (!last) {
             __syncthreads();   // every neighbour read of this pass is done: the rows can be overwritten in place
-            if (live) {
 #pragma unroll
-                for (int i = 0; i < MAXI; ++i) {
-                    const int lr = lr0 + i * RSTEP;
-                    if (lr < rows) self[i].store(A + lr * CBT + c);
-                }
-            }
+            for (int i = 0; i < MAXI; ++i) self[i].store(Ac + (lr0 + i * RSTEP) * CBT);   // rows >= `rows`: scratch
             __syncthreads();
         }
     }
 }
 
-static size_t group_smem_bytes(int rows_cap, int cbt, int nax, int order)
+static size_t group_smem_bytes(int rows_cap, int rows_max, int cbt, int nax, int order)
 {
-    return (size_t)(((size_t)(rows_cap + 1) * cbt + 3) & ~(size_t)3) * sizeof(float) +
+    return ((((size_t)rows_max + 1) * (size_t)cbt + 3) & ~(size_t)3) * sizeof(float) +
            (((size_t)rows_cap * nax * 2 * order * sizeof(uint16_t) + 15) & ~(size_t)15) + (size_t)rows_cap * sizeof(int32_t);
 }
 
@@ -496,7 +483,7 @@ static int launch_group(const sgp_blur_group *g, int order, const GroupCoeffs &c
 {
     constexpr int CBT = VEC * CHUNKS;
     const int nax = g->j1 - g->j0;
-    const size_t smem = group_smem_bytes(g->rows_cap, CBT, nax, order);
+    const size_t smem = group_smem_bytes(g->rows_cap, THREADS * 2, CBT, nax, order);
     if (smem > 227 * 1024)
         return fail(SGP_EUNSUPPORTED, "blur group needs %zu bytes of shared memory (%d rows x %d channels)", smem,
                     g->rows_cap, CBT);
@@ -554,18 +541,15 @@ extern "C" int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64
     if (L % 4 == 0 && al(buf0, 16) && al(buf1, 16)) vec = 4;
     else if (L % 2 == 0 && al(buf0, 8) && al(buf1, 8)) vec = 2;
     const int chunks = CB / vec;   // 1, 2 or 4 by construction of CB
-    static int threads_env = 0;    // tuning hook: SGP_GROUP_THREADS=256|512
-    if (threads_env == 0) {
-        const char *e = getenv("SGP_GROUP_THREADS");
-        threads_env = (e && atoi(e) == 512) ? 512 : 256;
-    }
     float *in = buf0, *out = buf1;
     for (int gi = 0; gi < n_groups; ++gi) {
         const sgp_blur_group *g = groups + gi;
         if (!g->batch_begin || !g->src || !g->lnb || g->rows_cap < 1 || g->n_batches < 1 || g->j1 <= g->j0)
             return fail(SGP_EINVAL, "sgp_blur_groups: group %d is not built", gi);
         if (g->rows_cap > 1024) return fail(SGP_EUNSUPPORTED, "blur group %d: %d rows per CTA (limit 1024)", gi, g->rows_cap);
-        const bool big = threads_env == 512 || g->rows_cap > 512;   // 256 threads hold up to 512 rows, 512 up to 1024
+        if (g->zero_row != 512 && g->zero_row != 1024) return fail(SGP_EINVAL, "blur group %d: zero_row must be 512 or 1024", gi);
+        if (g->rows_cap > g->zero_row) return fail(SGP_EINVAL, "blur group %d: %d rows exceed its variant's %d", gi, g->rows_cap, g->zero_row);
+        const bool big = g->zero_row == 1024;   // 256 threads hold up to 512 rows, 512 threads up to 1024
         int rc = SGP_EUNSUPPORTED;
 #define SGP_GROUP_CASE(VV, CC)                                                                          \
     if (vec == VV && chunks == CC)                                                                      \

@@ -260,7 +260,8 @@ class Lattice:
             j0 = j1
         arr = (_capi.BlurGroup * len(groups))()
         for k, g in enumerate(groups):
-            arr[k] = _capi.BlurGroup(g["j0"], g["j1"], g["rows_cap"], 0, g["n_batches"], g["batch_begin"].data_ptr(),
+            arr[k] = _capi.BlurGroup(g["j0"], g["j1"], g["rows_cap"], 1024 if rows_limit > 512 else 512, g["n_batches"],
+                                     g["batch_begin"].data_ptr(),
                                      g["src"].data_ptr(), g["lnb"].data_ptr())
         self.groups = {"list": groups, "array": arr, "final_pos": prev_pos}
 
