@@ -262,8 +262,16 @@ def run_ours(args, w):
         lat._build_tiles()
     use_groups = lat.groups is not None and args.blur != "axis"
 
+    blur_arg = "groups" if use_groups else "axis"
+    graphs = None
+    if not args.no_graph:   # one CUDA graph per buffer pair: a step is one replay (memset + 5 kernel nodes)
+        graphs = [lat.capture(Vs[k], outs[k], mode=mode, blur=blur_arg) for k in range(n_rot)]
+
     def step(i):
-        lat.mvm(Vs[i % n_rot], out=outs[i % n_rot], mode=mode, blur="groups" if use_groups else "axis")
+        if graphs is not None:
+            graphs[i % n_rot].replay()
+        else:
+            lat.mvm(Vs[i % n_rot], out=outs[i % n_rot], mode=mode, blur=blur_arg)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -409,7 +417,8 @@ def run_ours(args, w):
             "config": {"workload": workload_name(w), "M": M,
                        "path": {"splat": {1: "atomic scatter", 2: "ordered gather", 3: "tiles", 4: "row-sorted segmented gather"}[mode],
                                 "blur": "groups through shared memory" if use_groups else "one launch per axis",
-                                "arithmetic": "reference order (exact)" if lat.exact else "fused multiply-add"},
+                                "arithmetic": "reference order (exact)" if lat.exact else "fused multiply-add",
+                                "launch": "eager" if graphs is None else "CUDA graph replay (one graph per MVM)"},
                        "sharding": "lattice built on rank 0 + NCCL broadcast; one 16-column RHS block per rank",
                        "l2": f"working set {(alg_bytes / (d + 1)) / 1e6:.0f}+ MB per step exceeds the 126 MB L2; "
                              f"V/out rotate over {n_rot} buffer pairs"},
@@ -436,6 +445,7 @@ def main():
     ap.add_argument("--splat", default="auto", choices=["auto", "rows", "tiles", "atomic", "gather"],
                     help="splat form: row-sorted segmented gather (default), locality tiles, atomic scatter, ordered gather")
     ap.add_argument("--blur", default="groups", choices=["groups", "axis"])
+    ap.add_argument("--no-graph", action="store_true", help="launch the MVM kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

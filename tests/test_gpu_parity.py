@@ -126,6 +126,20 @@ def test_long_line_falls_back_to_axis_blur(sg, oracle):
     assert np.array_equal(bits(lat.mvm(v.cuda(), mode=2, exact=True).cpu().numpy()), bits(O.mvm(v.numpy())))
 
 
+def test_cuda_graph_replay(sg, oracle):
+    x, v = make_inputs(5000, 6, 8, seed=51)
+    O = oracle.OracleLattice(x.numpy(), RBF1)
+    lat = sg.Lattice(x.cuda(), RBF1)
+    src = torch.zeros(5000, 8, device="cuda")
+    out = torch.empty(5000, 8, device="cuda")
+    graph = lat.capture(src, out)
+    for seed in (1, 2):
+        w = torch.randn(5000, 8, generator=torch.Generator().manual_seed(seed))
+        src.copy_(w)
+        graph.replay()
+        assert _rel(out.cpu().numpy(), O.mvm(w.numpy())) < REL_TOL
+
+
 def test_filter_dropin_cpu_and_cuda_inputs(sg, oracle):
     x, v = make_inputs(3000, 4, 3, seed=5)
     c = torch.tensor(RBF1)
