@@ -5,7 +5,7 @@ torch.manual_seed(0)
 N,d,L=1_000_000,8,16
 x=torch.randn(N,d,device='cuda'); vs=[torch.randn(N,L,device='cuda') for _ in range(4)]
 c=[0.34608543,1,0.34608543]
-def timeit(fn, reps=50, warm=5):
+def timeit(fn, reps=100, warm=10):
     for i in range(warm): fn(i)
     torch.cuda.synchronize()
     e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
@@ -15,14 +15,9 @@ def timeit(fn, reps=50, warm=5):
     return e0.elapsed_time(e1)/reps*1000
 lat=sg.Lattice(x,c); torch.cuda.synchronize()
 outs=[torch.empty(N,L,device='cuda') for _ in range(4)]
-print('eager us/mvm', timeit(lambda i: lat.mvm(vs[i%4],out=outs[i%4])))
-g=torch.cuda.CUDAGraph()
-s=torch.cuda.Stream()
-s.wait_stream(torch.cuda.current_stream())
-with torch.cuda.stream(s):
-    for i in range(4): lat.mvm(vs[i],out=outs[i])
-torch.cuda.current_stream().wait_stream(s)
-with torch.cuda.graph(g):
-    for i in range(4): lat.mvm(vs[i],out=outs[i])
-print('graph (4 mvm) us/mvm', timeit(lambda i: g.replay(), reps=20)/4)
-ref=outs[0].clone(); lat.mvm(vs[0],out=outs[0]); torch.cuda.synchronize(); print('rel', float((ref-outs[0]).norm()/ref.norm()))
+ref=lat.mvm(vs[0], mode=1, blur='axis', exact=True).clone()
+t_e=timeit(lambda i: lat.mvm(vs[i%4],out=outs[i%4]))
+graphs=[lat.capture(vs[k],outs[k]) for k in range(4)]
+t_g=timeit(lambda i: graphs[i%4].replay())
+torch.cuda.synchronize()
+print(f'PDL={os.environ.get("SGP_PDL")}: eager {t_e:.1f} graph {t_g:.1f} us/mvm -> {1e6/t_g:.0f} MVM/s; rel err', float((outs[0]-ref).norm()/ref.norm()))

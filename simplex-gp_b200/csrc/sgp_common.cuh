@@ -8,6 +8,7 @@
 #include "sgp_lattice.h"
 
 int sgp_fail(int code, const char *fmt, ...);
+int sgp_pdl_enabled(void);   // SGP_PDL=0 turns programmatic dependent launch off (default on)
 int sgp_launch_ok(const char *what);
 
 #define CUDA_TRY(expr)                                                                        \
@@ -60,6 +61,33 @@ __device__ __forceinline__ float ldg_ordered_f1(const float *p)
     float v;
     asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
+}
+
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// The MVM is a chain of short kernels (splat -> blur stages -> slice, 20-90 us each).  Each of them starts with work
+// that does not depend on its predecessor's output (index-table loads, shared-memory staging of neighbour tables),
+// so they are launched with the programmatic-stream-serialization attribute: a kernel calls pdl_launch_dependents()
+// at once (its successor's CTAs may then be scheduled as SMs drain) and pdl_wait() just before it first touches data
+// its predecessor wrote (that returns only when the predecessor has completed and flushed).  Launched without the
+// attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t sgp_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = sgp_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ---- vector of VEC channels of one row ------------------------------------------------------

@@ -376,6 +376,7 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
     const int cg = blockIdx.y * CBT + c;          // first global channel of this thread
     const bool live = cg < L;                      // the last channel block may be partial (L % CBT != 0)
 
+    pdl_launch_dependents();
     if (threadIdx.x < CBT) A[ROWS_MAX * CBT + threadIdx.x] = 0.0f;
     // stage the batch's neighbour table and its slice of the gather list (plain range copies, asynchronous) ...
     int32_t *SRC = (int32_t *)(nbs + (((size_t)rows_cap * nax * w2 + 7) & ~(size_t)7));
@@ -383,7 +384,9 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
     cta_copy_async(SRC, src + p0, rows * 4, threadIdx.x, THREADS);
     cp_async_wait_all();
     __syncthreads();
-    // ... and the rows themselves, gathered from the previous stage's order, all in flight at once (cp.async)
+    // ... and the rows themselves, gathered from the previous stage's order, all in flight at once (cp.async).
+    // Everything above read build-time tables only; the rows are the previous kernel's output: wait for it here.
+    pdl_wait();
     if (live) {
         for (int lr = lr0; lr < rows; lr += RSTEP) cp_async_vec<VEC>(A + lr * CBT + c, in + (int64_t)SRC[lr] * L + cg);
     }
@@ -496,8 +499,9 @@ static int launch_group(const sgp_blur_group *g, int order, const GroupCoeffs &c
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
             granted = smem;                                                                                           \
         }                                                                                                             \
-        sgp_blur_group_kernel<VEC, RR, CHUNKS, THREADS, FAST><<<grid, THREADS, smem, st>>>(                                  \
-            g->batch_begin, g->src, g->lnb, in, out, L, g->rows_cap, nax, order, cf);                                 \
+        cudaError_t le = sgp_launch_pdl(sgp_blur_group_kernel<VEC, RR, CHUNKS, THREADS, FAST>, grid, dim3(THREADS), smem, st, \
+                                        g->batch_begin, g->src, g->lnb, in, out, L, g->rows_cap, nax, order, cf);     \
+        if (le != cudaSuccess) return fail(SGP_ECUDA, "launch of sgp_blur_group_kernel failed: %s", cudaGetErrorString(le)); \
     } while (0)
     if (order == 1) SGP_LAUNCH_GROUP(1);
     else if (order == 2) SGP_LAUNCH_GROUP(2);

@@ -47,6 +47,16 @@ int sgp_launch_ok(const char *what)
     return SGP_OK;
 }
 
+int sgp_pdl_enabled(void)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SGP_PDL");
+        v = e ? (atoi(e) != 0) : 1;
+    }
+    return v;
+}
+
 #define fail sgp_fail
 #define launch_ok sgp_launch_ok
 
@@ -709,6 +719,8 @@ sgp_slice_kernel(const int2 *__restrict__ replay, int64_t pstride, int64_t rstri
     if (n >= N) return;
     const int c0 = (int)(tid - n * chunks) * VEC;
     const int2 *rp = replay + n * pstride;
+    pdl_launch_dependents();
+    bool waited = false;    // the replay entries do not depend on the blur: they are loaded before the wait
     Vec<VEC> acc;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
@@ -724,6 +736,7 @@ sgp_slice_kernel(const int2 *__restrict__ replay, int64_t pstride, int64_t rstri
         int lowest = e[0].x;
 #pragma unroll
         for (int b = 1; b < BATCH; ++b) lowest = min(lowest, e[b].x);
+        if (!waited) { pdl_wait(); waited = true; }
         if (lowest >= 0) {
 #pragma unroll
             for (int b = 0; b < BATCH; ++b) v[b].load_ordered(values + (int64_t)e[b].x * L + c0);
@@ -737,6 +750,7 @@ sgp_slice_kernel(const int2 *__restrict__ replay, int64_t pstride, int64_t rstri
             }
         }
     }
+    if (!waited) pdl_wait();
     for (; r0 < dp1; ++r0) {
         const int2 e = __ldg(rp + r0 * rstride);
         const float w = __int_as_float(e.y);
@@ -1078,10 +1092,11 @@ extern "C" int sgp_slice(const sgp_lattice_view *lat, const float *values, int L
         batch = (e && atoi(e) == 3) ? 3 : 9;
     }
 #define SGP_SLICE_LAUNCH(BB, FF, SS)                                                                                     \
-    SGP_DISPATCH_VEC(vec, (sgp_slice_kernel<VV, BB, FF, SS><<<grid_for(work, 256), 256, 0, st>>>(                          \
-                              (const int2 *)lat->replay, lat->replay_transposed ? 1 : lat->d + 1,                      \
-                              lat->replay_transposed ? lat->N : 1, lat->perm, values, lat->N, lat->d + 1, L, chunks,    \
-                              divisor, rdivisor, out, ldo)))
+    SGP_DISPATCH_VEC(vec, (launch_err = sgp_launch_pdl(sgp_slice_kernel<VV, BB, FF, SS>, dim3(grid_for(work, 256)), dim3(256), 0, st, \
+                              (const int2 *)lat->replay, (int64_t)(lat->replay_transposed ? 1 : lat->d + 1),             \
+                              (int64_t)(lat->replay_transposed ? lat->N : 1), lat->perm, values, lat->N, lat->d + 1, L, chunks, \
+                              divisor, (float)rdivisor, out, ldo)))
+    cudaError_t launch_err = cudaSuccess;
     static int stream_env = -1;   // SGP_SLICE_STREAM=0 turns off the streaming cache policy of the replay reads / out writes (69 -> 66 us with it)
     if (stream_env < 0) {
         const char *e = getenv("SGP_SLICE_STREAM");
@@ -1095,6 +1110,7 @@ extern "C" int sgp_slice(const sgp_lattice_view *lat, const float *values, int L
         if (lat->fast) { SGP_SLICE_LAUNCH(9, true, false); } else { SGP_SLICE_LAUNCH(9, false, false); }
     }
 #undef SGP_SLICE_LAUNCH
+    if (launch_err != cudaSuccess) return fail(SGP_ECUDA, "launch of sgp_slice_kernel failed: %s", cudaGetErrorString(launch_err));
     return launch_ok("sgp_slice_kernel");
 }
 

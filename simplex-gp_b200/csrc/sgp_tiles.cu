@@ -450,6 +450,7 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
         const int64_t line = tid * 128;
         if (line < prefetch_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)src + line));
     }
+    pdl_launch_dependents();
     const int64_t seg = tid / chunks;
     if (seg >= n_seg) return;
     const int c0 = (int)(tid - seg * chunks) * VEC;
@@ -479,6 +480,7 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     Vec<VEC> acc;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
+    pdl_wait();   // the lattice values are zeroed (and last read) by the stream's previous work
 #pragma unroll
     for (int i = 0; i < SEG; ++i) {
         const float w = __int_as_float(e[i].y);
@@ -519,9 +521,10 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *ent_row, int64_
         pref_env = e ? atoi(e) : 0;
     }
     const int64_t prefetch_bytes = pref_env ? (int64_t)N * lds * (int64_t)sizeof(float) : 0;
+    cudaError_t launch_err = cudaSuccess;
 #define SGP_ROWS_LAUNCH(VV, SS)                                                                                        \
-    sgp_splat_rows_kernel<VV, SS><<<grid_for(work, 256), 256, 0, st>>>((const int2 *)ent, ent_row, n_seg, src, lds, L, \
-                                                                        chunks, prefetch_bytes, values)
+    launch_err = sgp_launch_pdl(sgp_splat_rows_kernel<VV, SS>, dim3(grid_for(work, 256)), dim3(256), 0, st,           \
+                                (const int2 *)ent, ent_row, n_seg, src, lds, L, chunks, prefetch_bytes, values)
 #define SGP_ROWS_SEG(VV)                                                                                               \
     do {                                                                                                               \
         if (seg_env == 4) SGP_ROWS_LAUNCH(VV, 4);                                                                      \
@@ -533,6 +536,7 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *ent_row, int64_
     else SGP_ROWS_SEG(1);
 #undef SGP_ROWS_SEG
 #undef SGP_ROWS_LAUNCH
+    if (launch_err != cudaSuccess) return fail(SGP_ECUDA, "launch of sgp_splat_rows_kernel failed: %s", cudaGetErrorString(launch_err));
     return launch_ok("sgp_splat_rows_kernel");
 }
 
