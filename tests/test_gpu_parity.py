@@ -152,6 +152,48 @@ def test_filter_dropin_cpu_and_cuda_inputs(sg, oracle):
     assert _rel(got_gpu.cpu().numpy(), want) < REL_TOL
 
 
+def test_edge_cases(sg, oracle):
+    # no points
+    lat = sg.Lattice(torch.empty(0, 3, device="cuda"), RBF1)
+    assert lat.M == 0 and lat.mvm(torch.empty(0, 2, device="cuda")).shape == (0, 2)
+    # one point; many copies of one point (a lattice of d+1 points, every row touched N times)
+    for x in (torch.tensor([[0.3, -1.2, 0.7]]), torch.tensor([[0.3, -1.2, 0.7]]).repeat(3000, 1)):
+        v = torch.randn(x.shape[0], 3, generator=torch.Generator().manual_seed(1))
+        O = oracle.OracleLattice(x.numpy(), RBF2)
+        lat = sg.Lattice(x.cuda(), RBF2)
+        assert lat.M == O.M == 4
+        assert _rel(lat.mvm(v.cuda()).cpu().numpy(), O.mvm(v.numpy())) < REL_TOL
+    # RHS and output that are column slices of wider tensors (row stride > L), odd channel counts
+    x, _ = make_inputs(4000, 5, 1, seed=61)
+    O = oracle.OracleLattice(x.numpy(), RBF1)
+    lat = sg.Lattice(x.cuda(), RBF1)
+    wide = torch.randn(4000, 12, generator=torch.Generator().manual_seed(2)).cuda()
+    for lo, hi in ((0, 12), (2, 7), (1, 2), (4, 12)):
+        src = wide[:, lo:hi]
+        outw = torch.full((4000, 16), float("nan"), device="cuda")
+        res = lat.mvm(src, out=outw[:, 3:3 + hi - lo])
+        want = O.mvm(wide[:, lo:hi].contiguous().cpu().numpy())
+        assert _rel(res.cpu().numpy(), want) < REL_TOL
+        assert torch.isnan(outw[:, :3]).all() and torch.isnan(outw[:, 3 + hi - lo:]).all()
+    # a column-major RHS is made contiguous by the host
+    assert _rel(lat.mvm(wide.t().contiguous().t()).cpu().numpy(), O.mvm(wide.cpu().numpy())) < REL_TOL
+    # wrong shapes / devices / dtypes fail loudly
+    with pytest.raises(ValueError):
+        lat.mvm(torch.zeros(3999, 2, device="cuda"))
+    with pytest.raises(TypeError):
+        lat.mvm(torch.zeros(4000, 2))
+    with pytest.raises(TypeError):
+        sg.Lattice(x.double().cuda(), RBF1)
+    with pytest.raises(ValueError):
+        lat.mvm(wide, coeffs=RBF2)
+
+
+def test_hash_table_overflow_is_an_error(sg):
+    x, _ = make_inputs(5000, 6, 1, seed=62)
+    with pytest.raises(RuntimeError):
+        sg.Lattice(x.cuda(), RBF1, hash_capacity=1024)
+
+
 def test_key_range_error(sg):
     x = torch.full((10, 3), 1e6)
     with pytest.raises(RuntimeError):
