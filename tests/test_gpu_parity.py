@@ -188,6 +188,28 @@ def test_edge_cases(sg, oracle):
         lat.mvm(wide, coeffs=RBF2)
 
 
+def test_against_reference_cuda_extension(sg):
+    """The reference's own CUDA path (compiled unmodified into oracle/_ref/cuda_build by
+    profiles/run_reference_cuda.py --build; shipped prebuilt) on the same GPU: allclose-level agreement, M well past the
+    size where the reference's CPU table mis-files keys."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    so = os.path.join(ROOT, "oracle", "_ref", "cuda_build", "sgp_ref_gpu_lattice.so")
+    if not os.path.exists(so):
+        pytest.skip("reference CUDA extension not built")
+    spec = importlib.util.spec_from_file_location("sgp_ref_gpu_lattice", so)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    x, v = make_inputs(60_000, 8, 4, seed=71)
+    c = torch.tensor(RBF1).cuda()
+    theirs = ref.filter(v.cuda(), x.cuda(), c)
+    lat = sg.Lattice(x.cuda(), RBF1)
+    assert lat.M > 3 * 16383
+    assert _rel(lat.mvm(v.cuda()).cpu().numpy(), theirs.cpu().numpy()) < REL_TOL
+    assert _rel(sg.filter(v.cuda(), x.cuda(), c).cpu().numpy(), theirs.cpu().numpy()) < REL_TOL
+
+
 def test_hash_table_overflow_is_an_error(sg):
     x, _ = make_inputs(5000, 6, 1, seed=62)
     with pytest.raises(RuntimeError):
