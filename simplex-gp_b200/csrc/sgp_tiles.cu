@@ -1,25 +1,24 @@
-// sgp_tiles.cu -- locality tiles for splat and slice (B200, sm_100a).
+// sgp_tiles.cu -- sorted forms of the point-vertex table for splat and slice (B200, sm_100a).
 //
-// Why: at the metric configuration (N=1M, d=8, 16 RHS, M=0.4M) a lattice point is touched by 22
-// point-vertices on average and by ~9000 at the centre of the data.  The plain scatter splat
-// therefore sends 9M x 64 B vector reductions to L2 (L1TEX and the L2 atomic units are the
-// limiter, and same-address reductions serialise), and the plain slice gathers 9M x 64 B rows
-// from L2.  Both are bounded by L2 traffic, not HBM.
+// Three things live here, all built on a radix sort of the N(d+1) point-vertices (CUB, toolkit header library --
+// plumbing of the build phase; every kernel on the MVM path is hand-written):
 //
-// What: points are sorted once per lattice so that points sharing lattice vertices are adjacent
-// (sgp_sort_points: lexicographic order of their remainder-0 lattice point), and cut into tiles of T points.  For every
-// tile the distinct lattice rows its T*(d+1) point-vertices touch form the tile's DICTIONARY
-// (`seg_row`), and the point-vertices are grouped by dictionary entry into SEGMENTS (`seg_ptr`,
-// `seg_ent`).  Then
-//   splat: one CTA per tile stages the tile's T RHS rows in shared memory, sums every segment
-//          in registers (deterministic order) and issues ONE vector reduction per segment;
-//   slice: one CTA per tile stages the tile's dictionary rows in shared memory once and every
-//          point combines its d+1 vertices from shared memory.
-// L2 traffic per stage drops from N(d+1) rows to S rows (S = number of segments, ~3.3x fewer at
-// the metric configuration).
+// 1. ROW-SORTED SPLAT (production; sgp_build_rowsorted / sgp_splat_rows).  At the metric configuration (N=1M, d=8,
+//    16 RHS, M=0.4M) a lattice point is touched by 22 point-vertices on average and by ~9000 at the centre of the data.
+//    The scatter splat sends 9M x 64 B vector reductions to L2, where same-address reductions serialise (125 us).  With
+//    the point-vertices sorted by lattice row, a thread owns 8 consecutive entries, gathers their RHS rows as plain
+//    loads and issues one reduction per run of equal rows: balanced, 6x fewer reductions, 88 us.
 //
-// Sorting uses cub::DeviceRadixSort (CUDA toolkit header library) -- plumbing of the build
-// phase; every kernel on the MVM path is hand-written below.
+// 2. LOCALITY ORDER OF THE POINTS (sgp_sort_points, sgp_permute_replay): optional; measured slower than the input
+//    order with the plain kernels (adjacent threads then hit the same L2 lines at the same time).
+//
+// 3. LOCALITY TILES (sgp_tiles_*, sgp_splat_tiles, sgp_slice_tiles): optional.  Points in locality order are cut into
+//    tiles of T points; the distinct lattice rows a tile touches form its DICTIONARY (`seg_row`) and its
+//    point-vertices are grouped by dictionary entry into SEGMENTS, cut into PIECES of <= 8 entries.  splat: a CTA
+//    stages its tile's RHS rows in shared memory and issues one reduction per piece; slice: a CTA stages its tile's
+//    dictionary rows once and every point combines its d+1 vertices from shared memory.  L2 row traffic drops 3.3x,
+//    but the 9M x 64 B row reads then go through shared memory, whose LSU cost is no lower than the L2 path's at this
+//    reuse factor: 101 / 97 us against 88 / 66 us for the production kernels.
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 #include <stdint.h>

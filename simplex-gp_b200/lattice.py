@@ -76,9 +76,21 @@ class Lattice:
     replay    int32 ``[N, d+1, 2]`` ``{lattice index, fp32 weight bits}`` per simplex vertex (:482-483)
     keys      int16 ``[M, d]``     lattice keys in first-touch order (:73-79, :470-471)
     nbr       int32 ``[d+1, M, 2r]`` blur neighbours, ``t`` over ``o = -r..-1, 1..r``; -1 = absent (:541-545)
-    csr_ptr   uint32 ``[M+1]``     rows of the transposed replay table (gather-form splat), optional
-    csr_ent   int32 ``[N(d+1), 2]`` ``{point, weight bits}`` in point-vertex order within each row
     ========  ==================  =========================================================================
+
+    Derived tables for the MVM kernels (internal orderings; none of them changes the numbering above):
+
+    * ``rows``    point-vertices sorted by lattice row, ``ent[9M', 2] {point, weight}`` / ``ent_row[9M']``: the
+                  segmented-gather splat (``build_rows``, default on); ``csr_ptr`` adds row starts for the ordered gather
+                  of ``mode=2`` (``build_csr``).
+    * ``groups``  blur groups: for each range of consecutive axes, lattice points sorted by class, CTA batches, gather
+                  list and batch-local neighbour table (``build_groups``, default on; ``group_axes=None`` sizes the
+                  ranges adaptively, ``group_rows`` is the CTA capacity).
+    * ``sorted`` / ``tiles``  locality order of the points and shared-memory tiles (``sort_points`` / ``build_tiles``,
+                  default off: measured slower on B200, kept for comparison).
+
+    ``exact=True`` makes ``mvm`` default to the reference's arithmetic (see ``mvm``); ``keep_structure=False`` drops
+    ``greedy`` / ``rank`` after the build; ``hash_capacity`` overrides the table size (tests).
     """
 
     def __init__(self, x: torch.Tensor, coeffs, *, build_csr: bool = False, build_tiles: bool = False,
