@@ -1,0 +1,39 @@
+"""Small end-to-end exercise of every kernel family for compute-sanitizer (memcheck / racecheck), one tool per run:
+
+    compute-sanitizer --tool memcheck python profiles/sanitize_small.py
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import simplex_gp_b200 as sg  # noqa: E402
+
+torch.manual_seed(0)
+for (N, d, L, c) in ((3000, 8, 16, [0.34608543, 1.0, 0.34608543]), (1500, 5, 3, [0.1, 0.5, 1.0, 0.5, 0.1]),
+                     (800, 18, 11, [0.34608543, 1.0, 0.34608543]), (64, 1, 2, [0.5, 1.0, 0.5])):
+    x = torch.randn(N, d, device="cuda")
+    v = torch.randn(N, L, device="cuda")
+    lat = sg.Lattice(x, c, build_csr=True, build_tiles=True, sort_points=True)
+    ref = lat.mvm(v, mode=2, blur="axis", exact=True)
+    for kw in (dict(), dict(mode=1), dict(mode=3), dict(mode=4, blur="axis"), dict(sorted=True, mode=1), dict(exact=True)):
+        out = lat.mvm(v, **kw)
+        err = float((out - ref).norm() / ref.norm())
+        assert err < 1e-5, (N, d, kw, err)
+    g = lat.capture(v, torch.empty_like(v))
+    g.replay()
+
+    class KF:
+        def get_coeffs(self):
+            return torch.tensor(c)
+
+        def get_deriv_coeffs(self):
+            return torch.tensor(c)
+
+    xr = x.clone().requires_grad_(True)
+    vr = v.clone().requires_grad_(True)
+    sg.LatticeFilterGeneral.apply(vr, xr, KF()).sum().backward()
+    assert torch.isfinite(xr.grad).all() and torch.isfinite(vr.grad).all()
+torch.cuda.synchronize()
+print("sanitize_small ok")
