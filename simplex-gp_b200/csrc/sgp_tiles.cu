@@ -18,7 +18,7 @@
 //    stages its tile's RHS rows in shared memory and issues one reduction per piece; slice: a CTA stages its tile's
 //    dictionary rows once and every point combines its d+1 vertices from shared memory.  L2 row traffic drops 3.3x,
 //    but the 9M x 64 B row reads then go through shared memory, whose LSU cost is no lower than the L2 path's at this
-//    reuse factor: 101 / 97 us against 88 / 66 us for the production kernels (DESIGN.md section 3.7).
+//    reuse factor: 101 / 97 us against 88 / 66 us for the production kernels (DESIGN.md section 3.8).
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 #include <stdint.h>
