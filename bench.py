@@ -324,7 +324,7 @@ def run_ours(args, w):
                 _capi.check(lib.sgp_splat_tiles(C.byref(tv_in), _ptr(V), V.stride(0), L, _ptr(buf0), st))
             elif mode == _capi.MODE_ROWS:
                 _capi.check(lib.sgp_splat_rows(_ptr(lat.rows["ent"]), _ptr(lat.rows["ent_row"]), N, d, M, _ptr(V),
-                                               V.stride(0), L, _ptr(buf0), st))
+                                               V.stride(0), L, _ptr(buf0), L, st))
             else:
                 _capi.check(lib.sgp_splat(C.byref(v_in if mode == _capi.MODE_ATOMIC else v_axis), _ptr(V), V.stride(0), L,
                                           _ptr(buf0), mode, st))
@@ -340,7 +340,7 @@ def run_ours(args, w):
             if mode == _capi.MODE_TILES:
                 _capi.check(lib.sgp_slice_tiles(C.byref(tv_out), _ptr(res_buf), L, _ptr(out), out.stride(0), fast, st))
             else:
-                _capi.check(lib.sgp_slice(C.byref(v_out), _ptr(res_buf), L, _ptr(out), out.stride(0), st))
+                _capi.check(lib.sgp_slice(C.byref(v_out), _ptr(res_buf), L, _ptr(out), out.stride(0), L, st))
             ev[3].record()
             torch.cuda.synchronize()
             for k in range(3):

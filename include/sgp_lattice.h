@@ -154,9 +154,11 @@ int sgp_splat(const sgp_lattice_view *lat, const float *src, int64_t lds, int L,
  * coeffs: HOST [2r+1].  *result_in_buf1 tells where the blurred values ended. */
 int sgp_blur(const sgp_lattice_view *lat, const float *coeffs, int k, int L,
              float *buf0, float *buf1, int *result_in_buf1, sgp_stream_t stream);
-/* out[n, :] = sum_rem (w * values[idx, :]) / (1 + 2^-d)   (permutohedral.h:497-510) */
+/* out[n, :L_out] = sum_rem (w * values[idx, :L_out]) / (1 + 2^-d)   (permutohedral.h:497-510).  values: [M, L];
+ * L_out <= L lets the lattice rows be padded to a multiple of 4 channels (16-byte vectors) while out keeps the
+ * caller's width and alignment (then written one channel at a time). */
 int sgp_slice(const sgp_lattice_view *lat, const float *values, int L, float *out,
-              int64_t ldo, sgp_stream_t stream);
+              int64_t ldo, int L_out, sgp_stream_t stream);
 /* splat -> blur -> slice; buf0/buf1: device [M, L] fp32 scratch each */
 int sgp_mvm(const sgp_lattice_view *lat, const float *src, int64_t lds, int L,
             const float *coeffs, int k, float *out, int64_t ldo,
@@ -284,8 +286,10 @@ size_t sgp_rowsort_workspace_bytes(int64_t N, int d);
 int64_t sgp_rowsort_padded(int64_t N, int d);
 int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int64_t M, int32_t *ent, int32_t *ent_row,
                         void *workspace, size_t workspace_bytes, sgp_stream_t stream);
+/* src: [N, lds] with L_src columns; values: [M, L], L >= L_src (columns L_src..L-1 receive zeros): as for sgp_slice,
+ * the lattice rows may be padded to a multiple of 4 channels */
 int sgp_splat_rows(const int32_t *ent, const int32_t *ent_row, int64_t N, int d, int64_t M, const float *src,
-                   int64_t lds, int L, float *values, sgp_stream_t stream);
+                   int64_t lds, int L_src, float *values, int L, sgp_stream_t stream);
 
 /* ---- locality order of the points --------------------------------------------------------
  * perm (device [N]): the points in lexicographic order of their remainder-0 lattice point, so that points sharing

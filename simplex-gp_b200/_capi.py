@@ -141,7 +141,7 @@ def lib() -> C.CDLL:
     L.sgp_blur.restype = i32
     L.sgp_blur.argtypes = [pv, fp, i32, i32, vp, vp, C.POINTER(C.c_int), vp]
     L.sgp_slice.restype = i32
-    L.sgp_slice.argtypes = [pv, vp, i32, vp, i64, vp]
+    L.sgp_slice.argtypes = [pv, vp, i32, vp, i64, i32, vp]
     L.sgp_mvm.restype = i32
     L.sgp_mvm.argtypes = [pv, vp, i64, i32, fp, i32, vp, i64, vp, vp, i32, vp]
     pt = C.POINTER(TilesView)
@@ -189,7 +189,7 @@ def lib() -> C.CDLL:
     L.sgp_build_rowsorted.restype = i32
     L.sgp_build_rowsorted.argtypes = [vp, i64, i32, i64, vp, vp, vp, sz, vp]
     L.sgp_splat_rows.restype = i32
-    L.sgp_splat_rows.argtypes = [vp, vp, i64, i32, i64, vp, i64, i32, vp, vp]
+    L.sgp_splat_rows.argtypes = [vp, vp, i64, i32, i64, vp, i64, i32, vp, i32, vp]
     L.sgp_debug_division_mismatches.restype = i32
     L.sgp_debug_division_mismatches.argtypes = [i32, C.c_uint32, C.c_uint32, vp, vp]
     if L.sgp_abi_version() != 2:

@@ -521,7 +521,7 @@ extern "C" int sgp_blur_groups_channel_block(int L)
     }
     if (L % 4 == 0) {
         if (cb_env == 8 && L >= 8) return 8;
-        return L >= 16 ? 16 : (L >= 8 ? 8 : 4);
+        return L >= 12 ? 16 : (L >= 8 ? 8 : 4);   // L = 12: one block of 16 with an idle quarter beats 8 + 4
     }
     if (L % 2 == 0) return L >= 8 ? 8 : (L >= 4 ? 4 : 2);
     return L >= 4 ? 4 : (L >= 2 ? 2 : 1);

@@ -708,11 +708,13 @@ sgp_exact_div_check_kernel(float b, float rb, uint32_t lo, uint32_t count, unsig
 // slice: thread = (point n, chunk).  Vertices are processed in batches of BATCH with all
 // replay entries, then all lattice rows, in flight together (two dependent latencies per batch
 // instead of two per vertex); the sum itself stays in vertex order.
-template <int VEC, int BATCH, bool FAST, bool STREAM>
+// RAGGED (only instantiated with STREAM): out has L_out <= L columns and arbitrary row alignment; it is written one
+// channel at a time (the lattice rows stay 16-byte vectors).
+template <int VEC, int BATCH, bool FAST, bool STREAM, bool RAGGED>
 __global__ void __launch_bounds__(256)
 sgp_slice_kernel(const int2 *__restrict__ replay, int64_t pstride, int64_t rstride,
                  const uint32_t *__restrict__ perm, const float *__restrict__ values, int64_t N, int dp1, int L,
-                 int chunks, float divisor, float rdivisor, float *__restrict__ out, int64_t ldo)
+                 int chunks, float divisor, float rdivisor, float *__restrict__ out, int64_t ldo, int L_out)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n = tid / chunks;
@@ -765,8 +767,16 @@ sgp_slice_kernel(const int2 *__restrict__ replay, int64_t pstride, int64_t rstri
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc.v[k] = exact_div(acc.v[k], divisor, rdivisor);
     }
-    if (STREAM) acc.store_streaming(out + (perm ? (int64_t)__ldg(perm + n) : n) * ldo + c0);
-    else acc.store(out + (perm ? (int64_t)__ldg(perm + n) : n) * ldo + c0);
+    float *orow = out + (perm ? (int64_t)__ldg(perm + n) : n) * ldo + c0;
+    if (RAGGED) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+            if (c0 + k < L_out) __stcs(orow + k, acc.v[k]);
+    } else if (STREAM) {
+        acc.store_streaming(orow);
+    } else {
+        acc.store(orow);
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -1074,14 +1084,18 @@ extern "C" int sgp_blur(const sgp_lattice_view *lat, const float *coeffs, int k,
 }
 
 extern "C" int sgp_slice(const sgp_lattice_view *lat, const float *values, int L, float *out,
-                         int64_t ldo, sgp_stream_t stream)
+                         int64_t ldo, int L_out, sgp_stream_t stream)
 {
     int rc = check_view(lat, L);
     if (rc) return rc;
     if (lat->N == 0) return SGP_OK;
-    if (!values || !out || !lat->replay || ldo < L) return fail(SGP_EINVAL, "sgp_slice: null pointer or ldo < L");
+    if (!values || !out || !lat->replay || L_out < 1 || L_out > L || ldo < L_out)
+        return fail(SGP_EINVAL, "sgp_slice: null pointer, L_out outside [1, L] or ldo < L_out");
     cudaStream_t st = (cudaStream_t)stream;
-    const int vec = pick_vec(L, ldo, L, values, out, out);
+    // the lattice side decides the vector width; out is written channel by channel when it does not match it
+    int vec = pick_vec(L, L, L, values, values, values);
+    const bool ragged = vec > 1 && !(L_out == L && ldo % vec == 0 && ((uintptr_t)out % (4 * vec)) == 0);
+    if (vec == 1 && L_out != L) return fail(SGP_EUNSUPPORTED, "sgp_slice: L_out < L needs vectorisable lattice rows");
     const int chunks = L / vec;
     const int64_t work = lat->N * chunks;
     const float divisor = sgp_slice_divisor(lat->d);
@@ -1091,23 +1105,25 @@ extern "C" int sgp_slice(const sgp_lattice_view *lat, const float *values, int L
         const char *e = getenv("SGP_SLICE_BATCH");
         batch = (e && atoi(e) == 3) ? 3 : 9;
     }
-#define SGP_SLICE_LAUNCH(BB, FF, SS)                                                                                     \
-    SGP_DISPATCH_VEC(vec, (launch_err = sgp_launch_pdl(sgp_slice_kernel<VV, BB, FF, SS>, dim3(grid_for(work, 256)), dim3(256), 0, st, \
+#define SGP_SLICE_LAUNCH(BB, FF, SS, RG)                                                                                     \
+    SGP_DISPATCH_VEC(vec, (launch_err = sgp_launch_pdl(sgp_slice_kernel<VV, BB, FF, SS, RG>, dim3(grid_for(work, 256)), dim3(256), 0, st, \
                               (const int2 *)lat->replay, (int64_t)(lat->replay_transposed ? 1 : lat->d + 1),             \
                               (int64_t)(lat->replay_transposed ? lat->N : 1), lat->perm, values, lat->N, lat->d + 1, L, chunks, \
-                              divisor, (float)rdivisor, out, ldo)))
+                              divisor, (float)rdivisor, out, ldo, L_out)))
     cudaError_t launch_err = cudaSuccess;
     static int stream_env = -1;   // SGP_SLICE_STREAM=0 turns off the streaming cache policy of the replay reads / out writes (69 -> 66 us with it)
     if (stream_env < 0) {
         const char *e = getenv("SGP_SLICE_STREAM");
         stream_env = e ? atoi(e) : 1;
     }
-    if (batch == 3) {
-        if (lat->fast) { SGP_SLICE_LAUNCH(3, true, false); } else { SGP_SLICE_LAUNCH(3, false, false); }
+    if (ragged) {
+        if (lat->fast) { SGP_SLICE_LAUNCH(9, true, true, true); } else { SGP_SLICE_LAUNCH(9, false, true, true); }
+    } else if (batch == 3) {
+        if (lat->fast) { SGP_SLICE_LAUNCH(3, true, false, false); } else { SGP_SLICE_LAUNCH(3, false, false, false); }
     } else if (stream_env) {
-        if (lat->fast) { SGP_SLICE_LAUNCH(9, true, true); } else { SGP_SLICE_LAUNCH(9, false, true); }
+        if (lat->fast) { SGP_SLICE_LAUNCH(9, true, true, false); } else { SGP_SLICE_LAUNCH(9, false, true, false); }
     } else {
-        if (lat->fast) { SGP_SLICE_LAUNCH(9, true, false); } else { SGP_SLICE_LAUNCH(9, false, false); }
+        if (lat->fast) { SGP_SLICE_LAUNCH(9, true, false, false); } else { SGP_SLICE_LAUNCH(9, false, false, false); }
     }
 #undef SGP_SLICE_LAUNCH
     if (launch_err != cudaSuccess) return fail(SGP_ECUDA, "launch of sgp_slice_kernel failed: %s", cudaGetErrorString(launch_err));
@@ -1136,5 +1152,5 @@ extern "C" int sgp_mvm(const sgp_lattice_view *lat, const float *src, int64_t ld
     int in1 = 0;
     rc = sgp_blur(lat, coeffs, k, L, buf0, buf1, &in1, stream);
     if (rc) return rc;
-    return sgp_slice(lat, in1 ? buf1 : buf0, L, out, ldo, stream);
+    return sgp_slice(lat, in1 ? buf1 : buf0, L, out, ldo, L, stream);
 }

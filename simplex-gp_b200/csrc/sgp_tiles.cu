@@ -436,10 +436,13 @@ extern "C" int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int6
 }
 
 // thread = (segment of SEG entries, channel chunk)
-template <int VEC, int SEG>
+// RAGGED: the lattice rows are L (a multiple of VEC) channels wide but src has only L_src < L columns and arbitrary
+// row alignment (e.g. the 11-column CG block of a training step, padded to 12 on the lattice): src is read one
+// channel at a time, the missing channels as zeros; everything downstream moves 16-byte vectors.
+template <int VEC, int SEG, bool RAGGED>
 __global__ void __launch_bounds__(256)
 sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ ent_row, int64_t n_seg,
-                      const float *__restrict__ src, int64_t lds, int L, int chunks, int64_t prefetch_bytes,
+                      const float *__restrict__ src, int64_t lds, int L, int L_src, int chunks, int64_t prefetch_bytes,
                       float *__restrict__ values)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -475,7 +478,14 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     for (int i = 1; i < SEG; ++i) lowest = min(lowest, e[i].x);
     if (lowest < 0) return;
 #pragma unroll
-    for (int i = 0; i < SEG; ++i) v[i].load_ordered(src + (int64_t)e[i].x * lds + c0);
+    for (int i = 0; i < SEG; ++i) {
+        if (RAGGED) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) v[i].v[k] = (c0 + k < L_src) ? ldg_ordered_f1(src + (int64_t)e[i].x * lds + c0 + k) : 0.0f;
+        } else {
+            v[i].load_ordered(src + (int64_t)e[i].x * lds + c0);
+        }
+    }
     Vec<VEC> acc;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
@@ -494,10 +504,10 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
 }
 
 extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *ent_row, int64_t N, int d, int64_t M, const float *src,
-                              int64_t lds, int L, float *values, sgp_stream_t stream)
+                              int64_t lds, int L_src, float *values, int L, sgp_stream_t stream)
 {
     if (N == 0 || M == 0) return SGP_OK;
-    if (!ent || !ent_row || !src || !values || N < 0 || M < 0 || d < 1 || L < 1 || lds < L)
+    if (!ent || !ent_row || !src || !values || N < 0 || M < 0 || d < 1 || L_src < 1 || lds < L_src || L < L_src)
         return fail(SGP_EINVAL, "sgp_splat_rows: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     static int seg_env = 0;   // tuning hook: SGP_ROWSEG=4|8|16 entries per thread
@@ -508,9 +518,11 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *ent_row, int64_
     }
     const int64_t n_seg = sgp_rowsort_padded(N, d) / seg_env;
     auto al = [](const void *p, int bytes) { return ((uintptr_t)p % bytes) == 0; };
+    // the lattice side decides the vector width; src is read channel by channel when it does not match it
     int vec = 1;
-    if (L % 4 == 0 && lds % 4 == 0 && al(src, 16) && al(values, 16)) vec = 4;
-    else if (L % 2 == 0 && lds % 2 == 0 && al(src, 8) && al(values, 8)) vec = 2;
+    if (L % 4 == 0 && al(values, 16)) vec = 4;
+    else if (L % 2 == 0 && al(values, 8)) vec = 2;
+    const bool ragged = vec > 1 && !(L_src == L && lds % vec == 0 && al(src, 4 * vec));
     const int chunks = L / vec;
     CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)M * (size_t)L, st));
     const int64_t work = n_seg * chunks;
@@ -522,8 +534,12 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *ent_row, int64_
     const int64_t prefetch_bytes = pref_env ? (int64_t)N * lds * (int64_t)sizeof(float) : 0;
     cudaError_t launch_err = cudaSuccess;
 #define SGP_ROWS_LAUNCH(VV, SS)                                                                                        \
-    launch_err = sgp_launch_pdl(sgp_splat_rows_kernel<VV, SS>, dim3(grid_for(work, 256)), dim3(256), 0, st,           \
-                                (const int2 *)ent, ent_row, n_seg, src, lds, L, chunks, prefetch_bytes, values)
+    launch_err = ragged ? sgp_launch_pdl(sgp_splat_rows_kernel<VV, SS, true>, dim3(grid_for(work, 256)), dim3(256), 0,  \
+                                         st, (const int2 *)ent, ent_row, n_seg, src, lds, L, L_src, chunks,            \
+                                         prefetch_bytes, values)                                                      \
+                        : sgp_launch_pdl(sgp_splat_rows_kernel<VV, SS, false>, dim3(grid_for(work, 256)), dim3(256), 0, \
+                                         st, (const int2 *)ent, ent_row, n_seg, src, lds, L, L_src, chunks,            \
+                                         prefetch_bytes, values)
 #define SGP_ROWS_SEG(VV)                                                                                               \
     do {                                                                                                               \
         if (seg_env == 4) SGP_ROWS_LAUNCH(VV, 4);                                                                      \
