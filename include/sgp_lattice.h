@@ -243,7 +243,10 @@ int sgp_group_prepare(const int16_t *keys, int64_t M, int d, int j0, int j1, uin
  * (NULL for the first stage, whose input is in lattice-index order).  Synchronises; *n_batches_out = batches
  * used, *max_rows_out = rows of the largest batch. */
 int64_t sgp_group_max_batches(int64_t M, int64_t cap, int64_t max_class);
-int sgp_group_finalize(const int32_t *nbr, int64_t M, int order, int j0, int j1, const uint32_t *order_of,
+/* Neighbours: from nbr (sgp_build_neighbours) when non-NULL, else looked up in the key hash table as left by
+ * sgp_number_points (keys, d, table, capacity) -- the whole-lattice neighbour table then need not exist. */
+int sgp_group_finalize(const int32_t *nbr, const int16_t *keys, int d, const uint64_t *table, int64_t capacity,
+                       int64_t M, int order, int j0, int j1, const uint32_t *order_of,
                        const uint32_t *pos, const uint32_t *class_start, const uint32_t *prev_pos,
                        int64_t cap, int64_t max_batches, uint32_t *batch_begin, int32_t *src, uint16_t *lnb,
                        void *workspace, size_t workspace_bytes, int64_t *n_batches_out, int32_t *max_rows_out,

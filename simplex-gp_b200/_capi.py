@@ -166,7 +166,7 @@ def lib() -> C.CDLL:
     L.sgp_group_prepare.restype = i32
     L.sgp_group_prepare.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, sz, C.POINTER(i64), vp]
     L.sgp_group_finalize.restype = i32
-    L.sgp_group_finalize.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, sz,
+    L.sgp_group_finalize.argtypes = [vp, vp, i32, vp, i64, i64, i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, sz,
                                      C.POINTER(i64), C.POINTER(C.c_int32), vp]
     L.sgp_group_max_batches.restype = i64
     L.sgp_group_max_batches.argtypes = [i64, i64, i64]

@@ -63,6 +63,78 @@ __device__ __forceinline__ float ldg_ordered_f1(const float *p)
     return v;
 }
 
+// ---- key hash table (shared by the lattice build and the blur-group build) ------------------------------
+// A slot is {fingerprint:32 | value:32}; after sgp_number_points the value is the lattice index of the key.
+#define SGP_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+__device__ __forceinline__ uint64_t mix64(uint64_t h)
+{
+    h ^= h >> 33;
+    h *= 0xFF51AFD7ED558CCDull;
+    h ^= h >> 33;
+    h *= 0xC4CEB9FE1A85EC53ull;
+    h ^= h >> 33;
+    return h;
+}
+
+// hash of a d-vector of int16 (table layout and hash are not observable: permutohedral.h:114-121
+// only has to be *a* hash).  Two coordinates per round.
+template <int D, typename KeyArr>
+__device__ __forceinline__ uint64_t hash_key(const KeyArr &key, int d)
+{
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    if (D > 0) {
+#pragma unroll
+        for (int i = 0; i + 1 < (D > 0 ? D : 1); i += 2) {
+            uint32_t w = (uint32_t)(uint16_t)key[i] | ((uint32_t)(uint16_t)key[i + 1] << 16);
+            h = (h ^ w) * 0x9FB21C651E98DF25ull;
+            h ^= h >> 29;
+        }
+        if (D & 1) {
+            uint32_t w = (uint32_t)(uint16_t)key[(D > 0 ? D : 1) - 1];
+            h = (h ^ w) * 0x9FB21C651E98DF25ull;
+            h ^= h >> 29;
+        }
+    } else {
+        int i = 0;
+        for (; i + 1 < d; i += 2) {
+            uint32_t w = (uint32_t)(uint16_t)key[i] | ((uint32_t)(uint16_t)key[i + 1] << 16);
+            h = (h ^ w) * 0x9FB21C651E98DF25ull;
+            h ^= h >> 29;
+        }
+        if (i < d) {
+            uint32_t w = (uint32_t)(uint16_t)key[i];
+            h = (h ^ w) * 0x9FB21C651E98DF25ull;
+            h ^= h >> 29;
+        }
+    }
+    return mix64(h);
+}
+
+
+// find the lattice index of key nk[0..d) in a table built by sgp_hash_insert + sgp_number_points; -1 if absent
+__device__ __forceinline__ int32_t sgp_table_find(const int16_t *__restrict__ keys,
+                                                  const unsigned long long *__restrict__ table, uint64_t mask,
+                                                  const int16_t *nk, int d)
+{
+    const uint64_t h = hash_key<0>(nk, d);
+    const uint32_t fp = (uint32_t)(h >> 32);
+    uint64_t slot = h & mask;
+    for (uint64_t probe = 0; probe <= mask; ++probe) {
+        const unsigned long long cur = table[slot];
+        if (cur == SGP_EMPTY) return -1;
+        if ((uint32_t)(cur >> 32) == fp) {
+            const uint32_t idx = (uint32_t)cur;
+            const int16_t *op = keys + (int64_t)idx * d;
+            bool same = true;
+            for (int c = 0; c < d; ++c) same = same && (op[c] == nk[c]);
+            if (same) return (int32_t)idx;
+        }
+        slot = (slot + 1) & mask;
+    }
+    return -1;
+}
+
 // ---- programmatic dependent launch ---------------------------------------------------------------
 // The MVM is a chain of short kernels (splat -> blur stages -> slice, 20-90 us each).  Each of them starts with work
 // that does not depend on its predecessor's output (index-table loads, shared-memory staging of neighbour tables),

@@ -153,8 +153,11 @@ sgp_group_pack_kernel(const uint32_t *__restrict__ class_start, int64_t M, int64
     }
 }
 
+// Neighbours come from the whole-lattice table nbr when it exists, else straight from the key hash table (the lattice
+// build then never materialises the (d+1) x M x 2r neighbour table: 150 GB at the stress configuration).
 __global__ void __launch_bounds__(256)
-sgp_group_tables_kernel(const int32_t *__restrict__ nbr, int64_t M, int order_r, int j0, int j1,
+sgp_group_tables_kernel(const int32_t *__restrict__ nbr, const int16_t *__restrict__ keys, int d,
+                        const unsigned long long *__restrict__ table, uint64_t mask, int64_t M, int order_r, int j0, int j1,
                         const uint32_t *__restrict__ order, const uint32_t *__restrict__ pos,
                         const uint32_t *__restrict__ prev_pos, int64_t n_batches,
                         const uint32_t *__restrict__ batch_begin, uint32_t absent, int32_t *__restrict__ src,
@@ -173,9 +176,19 @@ sgp_group_tables_kernel(const int32_t *__restrict__ nbr, int64_t M, int order_r,
     const uint32_t base = batch_begin[lo], limit = batch_begin[lo + 1];
     const int nax = j1 - j0, w = 2 * order_r;
     for (int a = 0; a < nax; ++a) {
-        const int32_t *np = nbr + ((int64_t)(j0 + a) * M + row) * w;
+        const int j = j0 + a;
         for (int t = 0; t < w; ++t) {
-            const int32_t nb = np[t];
+            int32_t nb;
+            if (nbr) {
+                nb = nbr[((int64_t)j * M + row) * w + t];
+            } else {   // key - o on every stored coordinate, key[j] + o*d on coordinate j (permutohedral.h:541-542)
+                const int o = (t < order_r) ? t - order_r : t - order_r + 1;
+                const int16_t *kp = keys + (int64_t)row * d;
+                int16_t nk[SGP_MAX_DIM];
+                for (int c = 0; c < d; ++c) nk[c] = (int16_t)((int)kp[c] - o);
+                if (j < d) nk[j] = (int16_t)((int)kp[j] + o * d);
+                nb = sgp_table_find(keys, table, mask, nk, d);
+            }
             uint32_t local = absent;                   // index of the kernel's all-zero row
             if (nb >= 0) {
                 const uint32_t q = pos[nb];
@@ -279,13 +292,16 @@ extern "C" int64_t sgp_group_max_batches(int64_t M, int64_t cap, int64_t max_cla
     return M / (cap - max_class + 1) + 2;   // every batch but the last holds more than cap - max_class rows
 }
 
-extern "C" int sgp_group_finalize(const int32_t *nbr, int64_t M, int order_r, int j0, int j1, const uint32_t *order,
+extern "C" int sgp_group_finalize(const int32_t *nbr, const int16_t *keys, int d, const uint64_t *table, int64_t capacity,
+                                  int64_t M, int order_r, int j0, int j1, const uint32_t *order,
                                   const uint32_t *pos, const uint32_t *class_start, const uint32_t *prev_pos,
                                   int64_t cap, int64_t max_batches, uint32_t *batch_begin, int32_t *src, uint16_t *lnb,
                                   void *workspace, size_t workspace_bytes, int64_t *n_batches_out, int32_t *max_rows_out,
                                   sgp_stream_t stream)
 {
-    if (!nbr || !order || !pos || !class_start || !batch_begin || !src || !lnb || !workspace || !max_rows_out ||
+    if (!nbr && (!keys || !table || capacity < 2 || (capacity & (capacity - 1)) != 0 || d < 1 || d > SGP_MAX_DIM))
+        return fail(SGP_EINVAL, "sgp_group_finalize: needs either nbr or keys + hash table");
+    if (!order || !pos || !class_start || !batch_begin || !src || !lnb || !workspace || !max_rows_out ||
         !n_batches_out || M <= 0 || order_r < 1 || order_r > SGP_MAX_ORDER || j1 <= j0 || cap < 1 || cap > 1024 ||
         max_batches < 1)
         return fail(SGP_EINVAL, "sgp_group_finalize: bad argument");
@@ -305,7 +321,8 @@ extern "C" int sgp_group_finalize(const int32_t *nbr, int64_t M, int order_r, in
     if (host[2] != 0) return fail(SGP_EINVAL, "blur group [%d,%d): classes do not fit %lld rows", j0, j1, (long long)cap);
     const int64_t n_batches = host[0];
     const uint32_t absent = cap > 512 ? 1024u : 512u;   // ROWS_MAX of the kernel variant that takes this group
-    sgp_group_tables_kernel<<<grid_for(M, 256), 256, 0, st>>>(nbr, M, order_r, j0, j1, order, pos, prev_pos, n_batches,
+    sgp_group_tables_kernel<<<grid_for(M, 256), 256, 0, st>>>(nbr, keys, d, (const unsigned long long *)table,
+                                                               (uint64_t)(capacity - 1), M, order_r, j0, j1, order, pos, prev_pos, n_batches,
                                                                batch_begin, absent, src, lnb, (int32_t *)(small + 4));
     rc = launch_ok("sgp_group_tables_kernel");
     if (rc) return rc;

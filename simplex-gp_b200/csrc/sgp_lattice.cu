@@ -107,52 +107,6 @@ struct ScaleParam {
     float s[SGP_MAX_DIM];
 };
 
-#define SGP_EMPTY 0xFFFFFFFFFFFFFFFFull
-
-__device__ __forceinline__ uint64_t mix64(uint64_t h)
-{
-    h ^= h >> 33;
-    h *= 0xFF51AFD7ED558CCDull;
-    h ^= h >> 33;
-    h *= 0xC4CEB9FE1A85EC53ull;
-    h ^= h >> 33;
-    return h;
-}
-
-// hash of a d-vector of int16 (table layout and hash are not observable: permutohedral.h:114-121
-// only has to be *a* hash).  Two coordinates per round.
-template <int D, typename KeyArr>
-__device__ __forceinline__ uint64_t hash_key(const KeyArr &key, int d)
-{
-    uint64_t h = 0x9E3779B97F4A7C15ull;
-    if (D > 0) {
-#pragma unroll
-        for (int i = 0; i + 1 < (D > 0 ? D : 1); i += 2) {
-            uint32_t w = (uint32_t)(uint16_t)key[i] | ((uint32_t)(uint16_t)key[i + 1] << 16);
-            h = (h ^ w) * 0x9FB21C651E98DF25ull;
-            h ^= h >> 29;
-        }
-        if (D & 1) {
-            uint32_t w = (uint32_t)(uint16_t)key[(D > 0 ? D : 1) - 1];
-            h = (h ^ w) * 0x9FB21C651E98DF25ull;
-            h ^= h >> 29;
-        }
-    } else {
-        int i = 0;
-        for (; i + 1 < d; i += 2) {
-            uint32_t w = (uint32_t)(uint16_t)key[i] | ((uint32_t)(uint16_t)key[i + 1] << 16);
-            h = (h ^ w) * 0x9FB21C651E98DF25ull;
-            h ^= h >> 29;
-        }
-        if (i < d) {
-            uint32_t w = (uint32_t)(uint16_t)key[i];
-            h = (h ^ w) * 0x9FB21C651E98DF25ull;
-            h ^= h >> 29;
-        }
-    }
-    return mix64(h);
-}
-
 // canonical simplex coordinate of vertex `rem` for an axis whose rank is rk (permutohedral.h:364-369)
 __device__ __forceinline__ int canon(int rk, int rem, int d) { return (rk <= d - rem) ? rem : rem - (d + 1); }
 

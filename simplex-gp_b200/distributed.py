@@ -50,6 +50,9 @@ _ARRAY_SPECS = (
 
 def lattice_arrays(lat) -> dict:
     """The arrays that define a built lattice for the MVM (what has to travel to the other ranks)."""
+    if lat.nbr is None:
+        raise RuntimeError("a lattice built with build_nbr=False cannot be broadcast: the receiving ranks rebuild "
+                           "their blur groups from the neighbour table")
     return {"replay": lat.replay, "keys": lat.keys, "nbr": lat.nbr}
 
 

@@ -95,7 +95,7 @@ class Lattice:
 
     def __init__(self, x: torch.Tensor, coeffs, *, build_csr: bool = False, build_tiles: bool = False,
                  build_groups: bool = True, group_axes: Optional[int] = None, group_rows: int = 512,
-                 sort_points: bool = False, build_rows: bool = True, exact: bool = False,
+                 sort_points: bool = False, build_rows: bool = True, build_nbr: bool = True, exact: bool = False,
                  tile_points: int = 256, keep_structure: bool = True, hash_capacity: Optional[int] = None):
         if x.dim() != 2:
             raise ValueError(f"x must be [N, d], got {tuple(x.shape)}")
@@ -153,13 +153,19 @@ class Lattice:
                 check(lib.sgp_number_points(_ptr(table), cap, _ptr(slot_of), _ptr(self.greedy), _ptr(self.rank), N, d,
                                             _ptr(ws), self.M, _ptr(self.replay), _ptr(self.keys), st))
                 del slot_of, ws
-                self.nbr = torch.empty((d + 1, self.M, 2 * r), dtype=torch.int32, device=dev)
-                check(lib.sgp_build_neighbours(_ptr(self.keys), self.M, d, r, _ptr(table), cap, _ptr(self.nbr), st))
-                del table
+                if build_nbr:
+                    self.nbr = torch.empty((d + 1, self.M, 2 * r), dtype=torch.int32, device=dev)
+                    check(lib.sgp_build_neighbours(_ptr(self.keys), self.M, d, r, _ptr(table), cap, _ptr(self.nbr), st))
+                else:
+                    self.nbr = None    # the blur groups are built straight from the hash table
                 if build_csr:
                     self._build_csr()
                 if build_groups and r >= 1 and self.M > 0:
-                    self._build_groups(group_axes, group_rows)
+                    self._build_groups(group_axes, group_rows, table=None if build_nbr else table)
+                if not build_nbr and r >= 1 and self.groups is None:   # no groups (long 1-D lines): the per-axis blur needs nbr
+                    self.nbr = torch.empty((d + 1, self.M, 2 * r), dtype=torch.int32, device=dev)
+                    check(lib.sgp_build_neighbours(_ptr(self.keys), self.M, d, r, _ptr(table), cap, _ptr(self.nbr), st))
+                del table
                 if (sort_points or build_tiles) and self.M > 0:
                     self._sort_points()
                 if build_tiles and self.M > 0:
@@ -209,7 +215,7 @@ class Lattice:
                     self._build_rows()
         return self
 
-    def _build_groups(self, group_axes: Optional[int] = None, group_rows: int = 512) -> None:
+    def _build_groups(self, group_axes: Optional[int] = None, group_rows: int = 512, table=None) -> None:
         """Blur groups (csrc/sgp_groups.cu): cover axes 0..d with ranges of consecutive axes whose classes fit
         ``group_rows`` rows of one CTA.  ``group_axes=None``: every range is made as long as it can be (3 axes at the
         metric configuration, 10 on the sparse d = 18 lattice); an integer fixes the length.  A range is shortened until
@@ -261,7 +267,9 @@ class Lattice:
                 "lnb": torch.empty((M, j1 - j0, 2 * r), dtype=torch.int16, device=dev),
             }
             rows, nb = C.c_int32(0), C.c_int64(0)
-            check(lib.sgp_group_finalize(_ptr(self.nbr), M, r, j0, j1, _ptr(order_of), _ptr(pos), _ptr(cstart),
+            check(lib.sgp_group_finalize(_ptr(self.nbr if table is None else None), _ptr(self.keys), d, _ptr(table),
+                                         0 if table is None else int(table.numel()), M, r, j0, j1, _ptr(order_of),
+                                         _ptr(pos), _ptr(cstart),
                                          _ptr(prev_pos), rows_limit, max_batches, _ptr(g["batch_begin"]), _ptr(g["src"]),
                                          _ptr(g["lnb"]), _ptr(ws), ws_bytes, C.byref(nb), C.byref(rows), st))
             g["n_batches"] = int(nb.value)
@@ -414,7 +422,7 @@ class Lattice:
               exact: Optional[bool] = None, transposed: bool = False) -> LatticeView:
         exact = self.exact if exact is None else exact
         return LatticeView(self.N, self.M, self.d, self.order, (self.replay if replay is None else replay).data_ptr(),
-                           self.nbr.data_ptr() if self.nbr.numel() else 0,
+                           self.nbr.data_ptr() if (self.nbr is not None and self.nbr.numel()) else 0,
                            self.csr_ptr.data_ptr() if self.csr_ptr is not None else 0,
                            self.csr_ent.data_ptr() if self.csr_ent is not None else 0,
                            0 if perm is None else perm.data_ptr(), 0 if exact else 1, 1 if transposed else 0)
@@ -558,6 +566,8 @@ class Lattice:
         use_groups = (self.groups is not None) if blur == "auto" else (blur == "groups")
         if use_groups and self.groups is None:
             raise RuntimeError("blur groups were not built for this lattice")
+        if not use_groups and self.order > 0 and self.nbr is None:
+            raise RuntimeError("the per-axis blur needs the neighbour table (build_nbr=True)")
         where = C.c_int(0)
         with torch.cuda.device(self.device):
             perm = self.sorted["perm"] if use_sorted else None

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import MAT15_2, MAT15_3, RBF1
+from conftest import MAT15_2, MAT15_3, RBF1, bits
 
 pytestmark = pytest.mark.gpu
 
@@ -75,3 +75,41 @@ def test_full_size_properties(sg, oracle, name):
     assert _rel(Ku, plain) < 1e-5
     ones = lat.mvm(torch.ones(N, 1, device="cuda"))
     assert float(ones.min()) > 0
+
+
+def test_full_stress_configuration_on_one_gpu(sg, oracle):
+    """BASELINE.json configs[4] at FULL size on one B200: N = 10M, d = 24, Matern-1.5 order 3 (M = 250M lattice points,
+    ~122 GB).  The blur groups are built straight from the hash table (build_nbr=False): the whole-lattice neighbour
+    table would be 150 GB.  The reference cannot run this size at all (its `int keyIdx = filled*kd` overflows,
+    permutohedral.h:75,166)."""
+    free, total = torch.cuda.mem_get_info()
+    if total < 160e9:
+        pytest.skip("needs a 180 GB GPU")
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    N, d, L = 10_000_000, 24, 1
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(N, d, generator=g)
+    try:
+        lat = sg.Lattice(x.cuda(), MAT15_3, build_nbr=False)
+    except torch.OutOfMemoryError:
+        pytest.skip("not enough free GPU memory in this process")
+    M = lat.M
+    assert 0.99 * N * (d + 1) < M <= N * (d + 1) and lat.nbr is None and lat.groups is not None
+    w = lat.weights
+    assert float((w.sum(1) - 1).abs().max()) < 1e-5
+    assert int(lat.offsets.min()) >= 0 and int(lat.offsets.max()) == M - 1
+    n = 2000
+    O = oracle.OracleLattice(x[:n].numpy(), MAT15_3)
+    assert np.array_equal(lat.greedy[:n].cpu().numpy(), O.greedy) and np.array_equal(lat.rank[:n].cpu().numpy(), O.rank)
+    assert np.array_equal(bits(lat.weights[:n].cpu().numpy()), bits(O.weights))
+    u = torch.randn(N, L, generator=g).cuda()
+    v = torch.randn(N, L, generator=g).cuda()
+    Ku, Kv = lat.mvm(u).clone(), lat.mvm(v).clone()
+    assert torch.isfinite(Ku).all()
+    assert _rel(lat.mvm(0.5 * u - 2.0 * v), 0.5 * Ku - 2.0 * Kv) < 2e-5
+    assert float(lat.mvm(torch.ones(N, 1, device="cuda")).min()) > 0
+    del lat
+    gc.collect()
+    torch.cuda.empty_cache()

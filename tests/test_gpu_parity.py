@@ -118,6 +118,29 @@ def test_blur_group_partitions(sg, oracle, group_axes, group_rows):
     assert np.array_equal(bits(lat.mvm(v.cuda(), mode=2, blur="groups", exact=True).cpu().numpy()), bits(out_o))
 
 
+def test_groups_from_hash_table_without_neighbour_table(sg, oracle):
+    """build_nbr=False: the blur groups are built straight from the key hash table, the (d+1) x M x 2r neighbour table
+    never exists; the MVM is bit-identical to the one of the lattice that has it."""
+    x, v = make_inputs(8000, 11, 8, seed=43)
+    a = sg.Lattice(x.cuda(), MAT15_2, build_csr=True)
+    b = sg.Lattice(x.cuda(), MAT15_2, build_csr=True, build_nbr=False)
+    assert b.nbr is None and b.groups is not None
+    for ga, gb in zip(a.groups["list"], b.groups["list"]):
+        assert (ga["j0"], ga["j1"], ga["n_batches"]) == (gb["j0"], gb["j1"], gb["n_batches"])
+        assert torch.equal(ga["lnb"], gb["lnb"]) and torch.equal(ga["src"], gb["src"])
+    out_a = a.mvm(v.cuda(), mode=2, exact=True)
+    out_b = b.mvm(v.cuda(), mode=2, exact=True)
+    assert torch.equal(out_a, out_b)
+    assert np.array_equal(bits(out_b.cpu().numpy()), bits(oracle.OracleLattice(x.numpy(), MAT15_2).mvm(v.numpy())))
+    with pytest.raises(RuntimeError):
+        b.mvm(v.cuda(), blur="axis")
+    # a lattice whose lines do not fit a CTA falls back to the per-axis blur and builds the table after all
+    x1, v1 = make_inputs(20000, 1, 2, seed=42, scale=2000.0)
+    c = sg.Lattice(x1.cuda(), RBF1, build_nbr=False)
+    assert c.groups is None and c.nbr is not None
+    assert _rel(c.mvm(v1.cuda()).cpu().numpy(), oracle.OracleLattice(x1.numpy(), RBF1).mvm(v1.numpy())) < REL_TOL
+
+
 def test_long_line_falls_back_to_axis_blur(sg, oracle):
     x, v = make_inputs(20000, 1, 2, seed=42, scale=2000.0)   # d = 1: one lattice line holds every point
     lat = sg.Lattice(x.cuda(), RBF1, build_csr=True)
