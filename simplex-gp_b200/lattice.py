@@ -522,7 +522,7 @@ class Lattice:
     # ---- the MVM ------------------------------------------------------------------------------------
     def mvm(self, src: torch.Tensor, out: Optional[torch.Tensor] = None, coeffs=None,
             mode: int = _capi.SGP_SPLAT_AUTO, blur: str = "auto", sorted: Optional[bool] = None,
-            exact: Optional[bool] = None, after_splat=None) -> torch.Tensor:
+            exact: Optional[bool] = None, after_splat=None, scratch=None) -> torch.Tensor:
         """``out[N, L] = slice(blur(splat(src[N, L])))`` on the built lattice.
 
         ``mode``   splat form: 0 auto (row-sorted segmented gather when built, else atomic scatter), 1 atomic scatter
@@ -531,12 +531,15 @@ class Lattice:
                    tile slice), 4 row-sorted segmented gather (``build_rows=True``).
         ``blur``   "groups" (several axes per launch through shared memory), "axis" (one launch per axis) or "auto"
                    (groups when they were built).
-        ``sorted`` walk the points in the locality order in splat and slice (default: when it was built).
+        ``sorted`` walk the points in the locality order in splat and slice (needs ``sort_points=True``; default off:
+                   measured slower than the input order on B200).
         ``exact``  the reference's arithmetic (one rounding per product and sum, one division per slice term) instead
                    of fused multiply-adds; with ``mode=2`` the result is then bit-identical to the reference's.
                    Default: the lattice's ``exact`` attribute (False).
         ``after_splat`` optional callable invoked with the splatted lattice values ``[M, L]`` (in place) before the
-                   blur: the exchange step of point sharding (an all-reduce over the ranks' partial splats)."""
+                   blur: the exchange step of point sharding (an all-reduce over the ranks' partial splats).
+        ``scratch`` a private pair of ``[M, ceil4(L)]`` work buffers instead of the lattice's shared ones (a captured CUDA
+                   graph owns its pair: its nodes must not point into buffers the lattice may free or reuse)."""
         src = self._check_src(src)
         L = int(src.shape[1])
         c = self.coeffs if coeffs is None else _coeffs_np(coeffs)
@@ -544,6 +547,9 @@ class Lattice:
             raise ValueError("stencil length does not match the order this lattice was built for")
         if out is None:
             out = torch.empty((self.N, L), dtype=torch.float32, device=self.device)
+        elif (tuple(out.shape) != (self.N, L) or out.dtype != torch.float32 or out.device != self.device
+              or (L > 1 and out.stride(1) != 1)):
+            raise ValueError(f"out must be a float32 [{self.N}, {L}] tensor on {self.device} with unit column stride")
         if self.N == 0 or L == 0:
             return out
         exact = self.exact if exact is None else bool(exact)
@@ -559,7 +565,9 @@ class Lattice:
         # 16-byte vectors (L = 11, the CG block of a training step: 301 us on the scalar path at the metric shape);
         # the row-sorted splat and the slice read / write the caller's ragged rows channel by channel.
         Lv = (L + 3) // 4 * 4 if (mode == _capi.MODE_ROWS and L > 4) else L
-        buf0, buf1 = self._scratch(Lv)
+        buf0, buf1 = self._scratch(Lv) if scratch is None else scratch
+        if tuple(buf0.shape) != (max(self.M, 1), Lv) or tuple(buf1.shape) != (max(self.M, 1), Lv):
+            raise ValueError(f"scratch buffers must be [{max(self.M, 1)}, {Lv}]")
         use_sorted = False if sorted is None else bool(sorted)   # measured slower than the input order on B200
         if use_sorted and self.sorted is None:
             raise RuntimeError("the locality order was not built for this lattice (sort_points=True)")
@@ -609,14 +617,21 @@ class Lattice:
         src = self._check_src(src)
         if out.shape != src.shape or out.dtype != torch.float32 or out.device != self.device or out.stride(1) != 1:
             raise ValueError("out must be a float32 [N, L] tensor on the lattice's device with unit column stride")
+        L = int(src.shape[1])
+        Lv = (L + 3) // 4 * 4 if L > 4 else L
+        if mvm_kwargs.get("mode", _capi.MODE_AUTO) not in (_capi.MODE_AUTO, _capi.MODE_ROWS) or self.rows is None:
+            Lv = L
+        scratch = (torch.empty((max(self.M, 1), Lv), dtype=torch.float32, device=self.device),
+                   torch.empty((max(self.M, 1), Lv), dtype=torch.float32, device=self.device))
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):     # warm-up outside the capture: lazy tables, scratch buffers, function attributes
-            self.mvm(src, out=out, **mvm_kwargs)
+        with torch.cuda.stream(side):     # warm-up outside the capture: lazy tables, function attributes
+            self.mvm(src, out=out, scratch=scratch, **mvm_kwargs)
         torch.cuda.current_stream(self.device).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.mvm(src, out=out, **mvm_kwargs)
+            self.mvm(src, out=out, scratch=scratch, **mvm_kwargs)
+        graph._sgp_keepalive = (scratch, src, out, self)   # the graph's nodes point into these: keep them alive with it
         return graph
 
     def algorithmic_bytes(self, L: int) -> int:
