@@ -220,6 +220,11 @@ def run_ours(args, w):
             print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
 
     N, d, L = w["N"], w["d"], w["L"]
+    L_job = L
+    if args.scaling == "strong":   # the job is ONE L-column block; every rank filters L/world of its columns
+        from simplex_gp_b200.distributed import shard_columns
+        lo_c, hi_c = shard_columns(L, world, rank)
+        L = max(1, hi_c - lo_c)
     coeffs = COEFFS[(w["kernel"], w["order"])]
     steps, warm = args.steps, max(args.warmup, 3)
     n_rot = 4   # V/out buffer pairs rotated so consecutive steps never re-read the same RHS from L2
@@ -299,7 +304,7 @@ def run_ours(args, w):
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
     elapsed_ms = float(elapsed_ms.item())
     ms_per_step = elapsed_ms / steps
-    value = world * steps / (elapsed_ms * 1e-3)
+    value = (1 if args.scaling == "strong" else world) * steps / (elapsed_ms * 1e-3)
 
     # --- per-stage device times (CUDA events on the launching stream), same buffers, rank 0 -----------
     peak, peak_src = load_peaks()
@@ -415,9 +420,9 @@ def run_ours(args, w):
         line = {
             "metric": METRIC if args.workload == "A" else f"lattice MVM/s ({workload_name(w)})", "value": value,
             "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(w), "M": M,
+            "config": {"workload": workload_name(w), "M": M, "columns_per_rank": L, "columns_per_job": L_job * (1 if args.scaling == "strong" else world),
                        "path": {"splat": {1: "atomic scatter", 2: "ordered gather", 3: "tiles", 4: "row-sorted segmented gather"}[mode],
                                 "blur": "groups through shared memory" if use_groups else "one launch per axis",
                                 "arithmetic": "reference order (exact)" if lat.exact else "fused multiply-add",
@@ -450,6 +455,8 @@ def main():
     ap.add_argument("--splat", default="auto", choices=["auto", "rows", "tiles", "atomic", "gather"],
                     help="splat form: row-sorted segmented gather (default), locality tiles, atomic scatter, ordered gather")
     ap.add_argument("--blur", default="groups", choices=["groups", "axis"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: one L-column RHS block per rank (default); strong: ONE L-column block split over the ranks")
     ap.add_argument("--no-graph", action="store_true", help="launch the MVM kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
