@@ -157,12 +157,13 @@ def run_reference_arm(args, w):
         return 0
     import torch
     torch.set_num_threads(1)
-    # One full-size reference call costs 2-7 s of one core, so a step is a BOUNDED SAMPLE: the first 100 000 of the N
-    # points (per-point cost at 100k is within 1 % of the per-point cost at 1M -- 7.18 vs 7.16 us here -- whereas at
-    # 20k it is 27 % higher, because M/N differs), scaled linearly to N; and at most 150 steps are executed however
-    # many were asked for (the reference is deterministic CPU code: more repetitions add nothing but minutes).
-    n_sample = int(min(w["N"], 100_000))
-    steps, warm = max(1, min(args.steps, 150)), max(0, min(args.warmup, 2))
+    # One reference call at the full workload costs 2-7 s of one core (the code is single-threaded), so the run is
+    # bounded in STEPS, not in points: every executed step is a full-size filter() call (a 100k-point sample scaled
+    # linearly was tried and is 57 % pessimistic on the GPU box's CPU: per-point cost depends on M/N and cache size),
+    # and at most 40 steps / 1 warm-up are executed however many were asked for -- the reference is deterministic CPU
+    # code, more repetitions add nothing but minutes.
+    n_sample = int(w["N"])
+    steps, warm = max(1, min(args.steps, 40)), max(0, min(args.warmup, 1))
     fn, kind = cpu_reference_filter()
     g = torch.Generator().manual_seed(0)
     x = torch.randn(n_sample, w["d"], generator=g)
@@ -178,7 +179,7 @@ def run_reference_arm(args, w):
     # scale the sample linearly to the full N: one full-size MVM costs (N / n_sample) sample filters
     value = 1.0 / (per_step * (w["N"] / n_sample))
     sample = (f"{steps} reference filter() calls executed ({args.steps} requested), lattice rebuilt inside each call as the "
-              f"reference does, on the first {n_sample} of {w['N']} points, scaled linearly to N; single-threaded code, "
+              f"reference does, on all {n_sample} points (the full workload in every step); single-threaded code, "
               f"{os.cpu_count()} host cores present")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
