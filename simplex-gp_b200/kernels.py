@@ -61,12 +61,14 @@ class RectangularLazyLattice(LazyTensor):
         self.dkernel = dkernel
 
     def _matmul(self, V):
-        n = V.shape[-2]
-        assert n == self.xout.shape[-2], f"mismatched shapes? {V.shape, self.xout.shape}"
-        x_large = torch.cat([self.xout, self.xin], dim=-2)
-        V_large = torch.zeros(*V.shape[:-2], x_large.shape[-2], V.shape[-1], device=V.device, dtype=V.dtype)
-        V_large[..., :n, :] += V
-        return LatticeFilterGeneral.apply(V_large, x_large, self.dkernel)[..., n:, :]
+        n_out = self.xout.shape[-2]
+        assert V.shape[-2] == n_out, f"mismatched shapes? {V.shape, self.xout.shape}"
+        # one square filter on the union of both point sets: the rows of V sit on xout, the xin rows carry zeros and
+        # receive the product
+        union = torch.cat([self.xout, self.xin], dim=-2)
+        padding = V.new_zeros(*V.shape[:-2], self.xin.shape[-2], V.shape[-1])
+        filtered = LatticeFilterGeneral.apply(torch.cat([V, padding], dim=-2), union, self.dkernel)
+        return filtered[..., n_out:, :]
 
     def _size(self):
         return torch.Size((*self.xin.shape[:-1], self.xout.shape[-2]))
