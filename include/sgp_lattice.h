@@ -261,6 +261,14 @@ int sgp_blur_groups_channel_block(int L);
 int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64_t M, int order, const float *coeffs,
                     int k, int L, float *buf0, float *buf1, int *result_in_buf1, int fast, sgp_stream_t stream);
 
+/* The production chain in one call: sgp_splat_rows -> sgp_blur_groups -> sgp_slice.  slice_view->replay addresses
+ * the lattice values in the order the last group stage leaves them (sgp_permute_replay with that stage's pos);
+ * buf0 / buf1: device [M, Lv] scratch, Lv = L or L rounded up to a multiple of 4 (see sgp_slice). */
+int sgp_mvm_rows_groups(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *ent_row,
+                        const sgp_blur_group *groups, int n_groups, const float *src, int64_t lds, int L,
+                        const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1, int Lv,
+                        sgp_stream_t stream);
+
 /* ---- stage 5: lengthscale-gradient pass (bilateral_kernel.py:97-124) -------------------
  *
  * The reference filters one N x 2L(1+d) block [g | g(x)x | v | v(x)x] with the derivative stencil and

@@ -26,7 +26,7 @@ SYMBOLS = [
     "sgp_grad_channels", "sgp_grad_pack", "sgp_grad_contract",
     "sgp_group_workspace_bytes", "sgp_group_prepare", "sgp_group_max_batches", "sgp_group_finalize",
     "sgp_remap_replay",
-    "sgp_blur_groups_channel_block", "sgp_blur_groups", "sgp_sort_points_workspace_bytes", "sgp_sort_points",
+    "sgp_blur_groups_channel_block", "sgp_blur_groups", "sgp_mvm_rows_groups", "sgp_sort_points_workspace_bytes", "sgp_sort_points",
     "sgp_permute_replay", "sgp_rowsort_workspace_bytes", "sgp_rowsort_padded", "sgp_build_rowsorted",
     "sgp_splat_rows",
 ]
@@ -176,6 +176,8 @@ def lib() -> C.CDLL:
     L.sgp_blur_groups_channel_block.argtypes = [i32]
     L.sgp_blur_groups.restype = i32
     L.sgp_blur_groups.argtypes = [C.POINTER(BlurGroup), i32, i64, i32, fp, i32, i32, vp, vp, C.POINTER(C.c_int), i32, vp]
+    L.sgp_mvm_rows_groups.restype = i32
+    L.sgp_mvm_rows_groups.argtypes = [pv, vp, vp, C.POINTER(BlurGroup), i32, vp, i64, i32, fp, i32, vp, i64, vp, vp, i32, vp]
     L.sgp_sort_points_workspace_bytes.restype = sz
     L.sgp_sort_points_workspace_bytes.argtypes = [i64]
     L.sgp_sort_points.restype = i32

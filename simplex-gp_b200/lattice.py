@@ -577,6 +577,15 @@ class Lattice:
         if not use_groups and self.order > 0 and self.nbr is None:
             raise RuntimeError("the per-axis blur needs the neighbour table (build_nbr=True)")
         where = C.c_int(0)
+        if mode == _capi.MODE_ROWS and use_groups and not use_tiles and not use_sorted and after_splat is None:
+            # the production chain, one call across the C ABI
+            arr = self.groups["array"]
+            v_out = self._view(self._table(False, True), None, exact)
+            with torch.cuda.device(self.device):
+                check(lib.sgp_mvm_rows_groups(C.byref(v_out), _ptr(self.rows["ent"]), _ptr(self.rows["ent_row"]), arr,
+                                              len(arr), _ptr(src), src.stride(0), L, _fp(c), c.shape[0], _ptr(out),
+                                              out.stride(0), _ptr(buf0), _ptr(buf1), Lv, st))
+            return out
         with torch.cuda.device(self.device):
             perm = self.sorted["perm"] if use_sorted else None
             if use_tiles:
