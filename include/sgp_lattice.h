@@ -114,6 +114,35 @@ int sgp_number_points(uint64_t *table, int64_t capacity, const uint32_t *slot_of
                       const void *workspace, int64_t M, int32_t *replay, int16_t *keys,
                       sgp_stream_t stream);
 
+/* ---- Extending a built lattice with more points ------------------------------------
+ * The rectangular operator K(Xin, Xout) of the reference filters on the lattice of cat([Xout, Xin])
+ * (gpytorch_lattice_kernel/bilateral_kernel.py:142-160) and rebuilds that lattice in every product.  First-touch
+ * numbering is sequential over the points (permutohedral.h:73-79, 467-485), so the union lattice numbers the keys of
+ * Xout exactly as the lattice of Xout alone and appends the keys only Xin touches: these calls add the new points to
+ * an existing lattice without revisiting the old ones.
+ *
+ * sgp_hash_seed      fills an empty table (all 0xFF) with key -> index for keys[M_old]  (cost ~ M_old).
+ * sgp_hash_extend    inserts the N_new*(d+1) new point-vertices (greedy_new / rank_new from sgp_build_points on the
+ *                    new points) against it; slot_of_new: device [N_new*(d+1)].
+ * sgp_count_extension  marks + scans the new point-vertices; *M_add_out = lattice points they create.  Synchronises.
+ *                    Workspace: sgp_number_workspace_bytes(N_new, d).
+ * sgp_number_extension  writes replay_new[..., 0] (indices into the union lattice), keys rows [M_old, M_old + M_add)
+ *                    (keys: device [M_old + M_add, d] whose first M_old rows the caller has filled), and leaves the
+ *                    table mapping every key of the union to its index (for sgp_build_neighbours / sgp_group_finalize).
+ * Limits: N_new*(d+1) and M_old + N_new*(d+1) below 2^31. */
+int sgp_hash_seed(const int16_t *keys, int64_t M_old, int d, uint64_t *table, int64_t capacity,
+                  int32_t *status_flags, sgp_stream_t stream);
+int sgp_hash_extend(const int16_t *greedy_new, const int8_t *rank_new, int64_t N_new, int d,
+                    const int16_t *keys, int64_t M_old, uint64_t *table, int64_t capacity,
+                    uint32_t *slot_of_new, int32_t *status_flags, sgp_stream_t stream);
+int sgp_count_extension(const uint64_t *table, int64_t capacity, const uint32_t *slot_of_new, int64_t N_new,
+                        int d, void *workspace, size_t workspace_bytes, const int32_t *status_flags,
+                        int64_t *M_add_out, int32_t *flags_out, sgp_stream_t stream);
+int sgp_number_extension(uint64_t *table, int64_t capacity, const uint32_t *slot_of_new,
+                         const int16_t *greedy_new, const int8_t *rank_new, int64_t N_new, int d,
+                         const void *workspace, int64_t M_old, int64_t M_add, int32_t *replay_new,
+                         int16_t *keys, sgp_stream_t stream);
+
 /* Neighbour table of the blur (permutohedral.h:539-545): nbr[j, i, t] = lattice index of
  * the key "key[i] - o on every stored coordinate, then key[i][j] + o*d on coordinate j when
  * j < d" (axis j = d only shifts), t enumerating o = -r..-1, 1..r; -1 if absent.

@@ -21,7 +21,8 @@ SGP_MAX_ORDER = 7
 SYMBOLS = [
     "sgp_abi_version", "sgp_last_error", "sgp_stencil_variance", "sgp_scale_factors", "sgp_slice_divisor",
     "sgp_build_points", "sgp_hash_capacity", "sgp_hash_insert", "sgp_number_workspace_bytes",
-    "sgp_count_points", "sgp_number_points", "sgp_build_neighbours", "sgp_splat", "sgp_blur", "sgp_slice", "sgp_mvm", "sgp_debug_division_mismatches",
+    "sgp_count_points", "sgp_number_points", "sgp_hash_seed", "sgp_hash_extend", "sgp_count_extension",
+    "sgp_number_extension", "sgp_build_neighbours", "sgp_splat", "sgp_blur", "sgp_slice", "sgp_mvm", "sgp_debug_division_mismatches",
     "sgp_tiles_workspace_bytes", "sgp_tiles_prepare", "sgp_tiles_finalize", "sgp_splat_tiles", "sgp_slice_tiles",
     "sgp_grad_channels", "sgp_grad_pack", "sgp_grad_contract",
     "sgp_group_workspace_bytes", "sgp_group_prepare", "sgp_group_max_batches", "sgp_group_finalize",
@@ -133,6 +134,14 @@ def lib() -> C.CDLL:
     L.sgp_count_points.argtypes = [vp, i64, vp, i64, i32, vp, sz, vp, C.POINTER(i64), C.POINTER(C.c_int32), vp]
     L.sgp_number_points.restype = i32
     L.sgp_number_points.argtypes = [vp, i64, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp]
+    L.sgp_hash_seed.restype = i32
+    L.sgp_hash_seed.argtypes = [vp, i64, i32, vp, i64, vp, vp]
+    L.sgp_hash_extend.restype = i32
+    L.sgp_hash_extend.argtypes = [vp, vp, i64, i32, vp, i64, vp, i64, vp, vp, vp]
+    L.sgp_count_extension.restype = i32
+    L.sgp_count_extension.argtypes = [vp, i64, vp, i64, i32, vp, sz, vp, C.POINTER(i64), C.POINTER(C.c_int32), vp]
+    L.sgp_number_extension.restype = i32
+    L.sgp_number_extension.argtypes = [vp, i64, vp, vp, vp, i64, i32, vp, i64, i64, vp, vp, vp]
     L.sgp_build_neighbours.restype = i32
     L.sgp_build_neighbours.argtypes = [vp, i64, i32, i32, vp, i64, vp, vp]
     pv = C.POINTER(LatticeView)

@@ -455,6 +455,147 @@ sgp_retarget_kernel(unsigned long long *__restrict__ table, int64_t capacity, co
 }
 
 // ------------------------------------------------------------------------------------
+// Extension of a built lattice by more points (the union lattice of the rectangular operator,
+// bilateral_kernel.py:142-160).  First-touch numbering is sequential over the points, so the lattice of
+// cat([x_old, x_new]) numbers the old keys exactly as the lattice of x_old alone and appends the keys only the new
+// points touch, in their own first-touch order.  The table is therefore seeded from keys[M_old] ({fp | index}), the new
+// point-vertices are inserted against it, and only they are marked, scanned and numbered.  A slot claimed by a new
+// point-vertex carries SGP_NEW_OWNER in its low word until it is numbered.
+// ------------------------------------------------------------------------------------
+#define SGP_NEW_OWNER 0x80000000u
+
+template <int D>
+__global__ void __launch_bounds__(256)
+sgp_seed_kernel(const int16_t *__restrict__ keys, int64_t M, int d_rt, unsigned long long *table, uint64_t mask,
+                int32_t *__restrict__ flags)
+{
+    constexpr int DK = D > 0 ? D : SGP_MAX_DIM;
+    const int d = D > 0 ? D : d_rt;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    int16_t key[DK];
+#pragma unroll
+    for (int c = 0; c < (D > 0 ? D : d); ++c) key[c] = keys[i * d + c];
+    const uint64_t h = hash_key<D>(key, d);
+    const unsigned long long mine = ((unsigned long long)(uint32_t)(h >> 32) << 32) | (uint32_t)i;
+    uint64_t slot = h & mask;
+    for (uint64_t probe = 0; probe <= mask; ++probe) {   // the keys are distinct: any empty slot on the probe path will do
+        if (atomicCAS(table + slot, SGP_EMPTY, mine) == SGP_EMPTY) return;
+        slot = (slot + 1) & mask;
+    }
+    atomicOr(flags, SGP_FLAG_TABLE_FULL);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+sgp_extend_insert_kernel(const int16_t *__restrict__ greedy, const int8_t *__restrict__ rank, int64_t N, int d_rt,
+                         const int16_t *__restrict__ keys, unsigned long long *table, uint64_t mask,
+                         uint32_t *__restrict__ slot_of, int32_t *__restrict__ flags)
+{
+    constexpr int DK = D > 0 ? D : SGP_MAX_DIM;
+    const int d = D > 0 ? D : d_rt;
+    const int64_t pv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pv >= N * (d + 1)) return;
+    const int64_t n = pv / (d + 1);
+    const int rem = (int)(pv - n * (d + 1));
+    int16_t key[DK];
+    {
+        const int16_t *gp = greedy + n * (d + 1);
+        const int8_t *rp = rank + n * (d + 1);
+#pragma unroll
+        for (int i = 0; i < (D > 0 ? D : d); ++i) key[i] = (int16_t)(gp[i] + canon(rp[i], rem, d));
+    }
+    const uint64_t h = hash_key<D>(key, d);
+    const uint32_t fp = (uint32_t)(h >> 32);
+    uint64_t slot = h & mask;
+    const unsigned long long mine = ((unsigned long long)fp << 32) | SGP_NEW_OWNER | (uint32_t)pv;
+
+    for (uint64_t probe = 0; probe <= mask; ++probe) {
+        unsigned long long cur = *((volatile unsigned long long *)(table + slot));
+        if (cur == SGP_EMPTY) {
+            unsigned long long prev = atomicCAS(table + slot, SGP_EMPTY, mine);
+            if (prev == SGP_EMPTY) {
+                slot_of[pv] = (uint32_t)slot;
+                return;
+            }
+            cur = prev;
+        }
+        if ((uint32_t)(cur >> 32) == fp) {
+            const uint32_t low = (uint32_t)cur;
+            bool same = true;
+            if (low & SGP_NEW_OWNER) {     // claimed by another new point-vertex: its key comes from greedy/rank
+                const uint32_t opv = low & ~SGP_NEW_OWNER;
+                const int64_t on = opv / (uint32_t)(d + 1);
+                const int orem = (int)(opv - on * (d + 1));
+                const int16_t *gp = greedy + on * (d + 1);
+                const int8_t *rp = rank + on * (d + 1);
+#pragma unroll
+                for (int i = 0; i < (D > 0 ? D : d); ++i)
+                    same = same && ((int16_t)(gp[i] + canon(rp[i], orem, d)) == key[i]);
+                if (same && (uint32_t)pv < opv) atomicMin(table + slot, mine);
+            } else {                       // a lattice point of the lattice being extended
+                const int16_t *kp = keys + (int64_t)low * d;
+#pragma unroll
+                for (int i = 0; i < (D > 0 ? D : d); ++i) same = same && (kp[i] == key[i]);
+            }
+            if (same) {
+                slot_of[pv] = (uint32_t)slot;
+                return;
+            }
+        }
+        slot = (slot + 1) & mask;
+    }
+    atomicOr(flags, SGP_FLAG_TABLE_FULL);
+    slot_of[pv] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+sgp_extend_mark_kernel(const unsigned long long *__restrict__ table, const uint32_t *__restrict__ slot_of,
+                       int64_t total, uint32_t *__restrict__ marks)
+{
+    const int64_t pv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pv >= total) return;
+    marks[pv] = ((uint32_t)table[slot_of[pv]] == (SGP_NEW_OWNER | (uint32_t)pv)) ? 1u : 0u;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+sgp_extend_renumber_kernel(const unsigned long long *__restrict__ table, const uint32_t *__restrict__ slot_of,
+                           const uint32_t *__restrict__ pos, const int16_t *__restrict__ greedy,
+                           const int8_t *__restrict__ rank, int64_t N, int d_rt, uint32_t M_old,
+                           int32_t *__restrict__ replay, int16_t *__restrict__ keys)
+{
+    const int d = D > 0 ? D : d_rt;
+    const int64_t pv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pv >= N * (d + 1)) return;
+    const uint32_t low = (uint32_t)table[slot_of[pv]];
+    const uint32_t idx = (low & SGP_NEW_OWNER) ? M_old + pos[low & ~SGP_NEW_OWNER] : low;
+    replay[pv * 2] = (int32_t)idx;
+    if (low == (SGP_NEW_OWNER | (uint32_t)pv)) {
+        const int64_t n = pv / (d + 1);
+        const int rem = (int)(pv - n * (d + 1));
+        const int16_t *gp = greedy + n * (d + 1);
+        const int8_t *rp = rank + n * (d + 1);
+        int16_t *kp = keys + (int64_t)idx * d;
+#pragma unroll
+        for (int i = 0; i < (D > 0 ? D : d); ++i) kp[i] = (int16_t)(gp[i] + canon(rp[i], rem, d));
+    }
+}
+
+// slots owned by new point-vertices: {fp | NEW | pv} -> {fp | lattice index}.  Only the owner writes its slot; a
+// reader that sees the rewritten word no longer matches NEW | pv and leaves it alone.
+__global__ void __launch_bounds__(256)
+sgp_extend_retarget_kernel(unsigned long long *__restrict__ table, const uint32_t *__restrict__ slot_of, int64_t total,
+                           const uint32_t *__restrict__ pos, uint32_t M_old)
+{
+    const int64_t pv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pv >= total) return;
+    const uint32_t slot = slot_of[pv];
+    const unsigned long long e = table[slot];
+    if ((uint32_t)e == (SGP_NEW_OWNER | (uint32_t)pv)) table[slot] = (e & 0xFFFFFFFF00000000ull) | (M_old + pos[pv]);
+}
+
+// ------------------------------------------------------------------------------------
 // stage 1d: neighbour table.  One thread per (axis j, lattice point i).
 // ------------------------------------------------------------------------------------
 template <int D>
@@ -898,6 +1039,123 @@ extern "C" int sgp_number_points(uint64_t *table, int64_t capacity, const uint32
     if (rc) return rc;
     sgp_retarget_kernel<<<grid_for(capacity, 256), 256, 0, st>>>((unsigned long long *)table, capacity, pos);
     return launch_ok("sgp_retarget_kernel");
+}
+
+// ---- extension ---------------------------------------------------------------------
+static int check_capacity(int64_t capacity)
+{
+    if (capacity < 2 || (capacity & (capacity - 1)) != 0 || capacity > (1ll << 32))
+        return fail(SGP_EINVAL, "hash capacity must be a power of two <= 2^32");
+    return SGP_OK;
+}
+
+extern "C" int sgp_hash_seed(const int16_t *keys, int64_t M, int d, uint64_t *table, int64_t capacity,
+                             int32_t *status_flags, sgp_stream_t stream)
+{
+    if (d < 1 || d > SGP_MAX_DIM) return fail(SGP_EUNSUPPORTED, "d=%d outside [1, %d]", d, SGP_MAX_DIM);
+    if (M < 0 || M >= (1ll << 31)) return fail(SGP_EINVAL, "M=%lld out of range", (long long)M);
+    int rc = check_capacity(capacity);
+    if (rc) return rc;
+    if (M == 0) return SGP_OK;
+    if (!keys || !table || !status_flags) return fail(SGP_EINVAL, "sgp_hash_seed: null pointer");
+    if (capacity < M) return fail(SGP_EINVAL, "hash capacity %lld below M=%lld", (long long)capacity, (long long)M);
+    cudaStream_t st = (cudaStream_t)stream;
+    SGP_DISPATCH_D(d, (sgp_seed_kernel<DD><<<grid_for(M, 256), 256, 0, st>>>(keys, M, d, (unsigned long long *)table,
+                                                                             (uint64_t)(capacity - 1), status_flags)));
+    return launch_ok("sgp_seed_kernel");
+}
+
+static int check_extension(int64_t N_new, int d, int64_t M_old)
+{
+    int rc = check_dims(N_new, d);
+    if (rc) return rc;
+    if (N_new * (int64_t)(d + 1) >= (1ll << 31))
+        return fail(SGP_EOVERFLOW, "N_new*(d+1) = %lld does not fit 31-bit point-vertex ids", (long long)(N_new * (d + 1)));
+    if (M_old < 0 || M_old + N_new * (int64_t)(d + 1) >= (1ll << 31))
+        return fail(SGP_EOVERFLOW, "M_old + N_new*(d+1) does not fit 31-bit lattice indices");
+    return SGP_OK;
+}
+
+extern "C" int sgp_hash_extend(const int16_t *greedy_new, const int8_t *rank_new, int64_t N_new, int d,
+                               const int16_t *keys, int64_t M_old, uint64_t *table, int64_t capacity,
+                               uint32_t *slot_of, int32_t *status_flags, sgp_stream_t stream)
+{
+    int rc = check_extension(N_new, d, M_old);
+    if (rc) return rc;
+    rc = check_capacity(capacity);
+    if (rc) return rc;
+    if (N_new == 0) return SGP_OK;
+    if (!greedy_new || !rank_new || !table || !slot_of || !status_flags || (M_old > 0 && !keys))
+        return fail(SGP_EINVAL, "sgp_hash_extend: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = N_new * (d + 1);
+    SGP_DISPATCH_D(d, (sgp_extend_insert_kernel<DD><<<grid_for(total, 256), 256, 0, st>>>(
+                          greedy_new, rank_new, N_new, d, keys, (unsigned long long *)table, (uint64_t)(capacity - 1),
+                          slot_of, status_flags)));
+    return launch_ok("sgp_extend_insert_kernel");
+}
+
+extern "C" int sgp_count_extension(const uint64_t *table, int64_t capacity, const uint32_t *slot_of, int64_t N_new,
+                                   int d, void *workspace, size_t workspace_bytes, const int32_t *status_flags,
+                                   int64_t *M_add_out, int32_t *flags_out, sgp_stream_t stream)
+{
+    int rc = check_extension(N_new, d, 0);
+    if (rc) return rc;
+    if (!M_add_out || !flags_out) return fail(SGP_EINVAL, "sgp_count_extension: null output");
+    *M_add_out = 0;
+    *flags_out = 0;
+    if (N_new == 0) return SGP_OK;
+    const int64_t total = N_new * (d + 1);
+    size_t off_tiles, off_total, need;
+    number_ws_layout(total, &off_tiles, &off_total, &need);
+    if (!table || !slot_of || !workspace || !status_flags || workspace_bytes < need)
+        return fail(SGP_EINVAL, "sgp_count_extension: null pointer or workspace too small (%zu < %zu)", workspace_bytes,
+                    need);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *marks = (uint32_t *)workspace;
+    uint32_t *tiles = (uint32_t *)((char *)workspace + off_tiles);
+    unsigned long long *total_dev = (unsigned long long *)((char *)workspace + off_total);
+    sgp_extend_mark_kernel<<<grid_for(total, 256), 256, 0, st>>>((const unsigned long long *)table, slot_of, total, marks);
+    rc = launch_ok("sgp_extend_mark_kernel");
+    if (rc) return rc;
+    rc = sgp_exclusive_scan_u32(marks, total, tiles, total_dev, st);
+    if (rc) return rc;
+    unsigned long long m_host = 0;
+    int32_t f_host = 0;
+    CUDA_TRY(cudaMemcpyAsync(&m_host, total_dev, sizeof(m_host), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&f_host, status_flags, sizeof(f_host), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *M_add_out = (int64_t)m_host;
+    *flags_out = f_host;
+    if (f_host & SGP_FLAG_TABLE_FULL) return fail(SGP_EOVERFLOW, "hash table full (capacity %lld)", (long long)capacity);
+    if (f_host & SGP_FLAG_KEY_RANGE)
+        return fail(SGP_ERANGE, "a lattice coordinate does not fit int16: inputs too large for the lengthscale");
+    return SGP_OK;
+}
+
+extern "C" int sgp_number_extension(uint64_t *table, int64_t capacity, const uint32_t *slot_of,
+                                    const int16_t *greedy_new, const int8_t *rank_new, int64_t N_new, int d,
+                                    const void *workspace, int64_t M_old, int64_t M_add, int32_t *replay_new,
+                                    int16_t *keys, sgp_stream_t stream)
+{
+    int rc = check_extension(N_new, d, M_old);
+    if (rc) return rc;
+    if (N_new == 0) return SGP_OK;
+    if (!table || !slot_of || !greedy_new || !rank_new || !workspace || !replay_new || !keys)
+        return fail(SGP_EINVAL, "sgp_number_extension: null pointer");
+    if (M_add < 0 || M_add > N_new * (int64_t)(d + 1)) return fail(SGP_EINVAL, "M_add=%lld out of range", (long long)M_add);
+    (void)capacity;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = N_new * (d + 1);
+    const uint32_t *pos = (const uint32_t *)workspace;
+    SGP_DISPATCH_D(d, (sgp_extend_renumber_kernel<DD><<<grid_for(total, 256), 256, 0, st>>>(
+                          (const unsigned long long *)table, slot_of, pos, greedy_new, rank_new, N_new, d,
+                          (uint32_t)M_old, replay_new, keys)));
+    rc = launch_ok("sgp_extend_renumber_kernel");
+    if (rc) return rc;
+    sgp_extend_retarget_kernel<<<grid_for(total, 256), 256, 0, st>>>((unsigned long long *)table, slot_of, total, pos,
+                                                                     (uint32_t)M_old);
+    return launch_ok("sgp_extend_retarget_kernel");
 }
 
 extern "C" int sgp_build_neighbours(const int16_t *keys, int64_t M, int d, int order,

@@ -59,13 +59,29 @@ class RectangularLazyLattice(LazyTensor):
         self.xin = xin
         self.xout = xout
         self.dkernel = dkernel
+        self._union = None
+
+    def _union_reference(self):
+        """``cat([xout, xin])`` with its lattice made by extending the cached lattice of ``xout`` (the training inputs
+        in a prediction) by the rows of ``xin`` -- the reference builds the union lattice from nothing in every product
+        (bilateral_kernel.py:150-156).  The tensor is kept so that later products of this operator hit the lattice
+        cache by identity; with gradients attached it is rebuilt per call and found by value."""
+        if self._union is not None:
+            return self._union
+        union = torch.cat([self.xout, self.xin], dim=-2)
+        if union.is_cuda and union.dtype == torch.float32 and union.dim() == 2 and self.dkernel is not None:
+            LatticeFilterGeneral.cache.get_union(union, self.xout.shape[-2], self.dkernel.get_coeffs(),
+                                                 base=self.xout)
+        if not union.requires_grad:
+            self._union = union
+        return union
 
     def _matmul(self, V):
         n_out = self.xout.shape[-2]
         assert V.shape[-2] == n_out, f"mismatched shapes? {V.shape, self.xout.shape}"
         # one square filter on the union of both point sets: the rows of V sit on xout, the xin rows carry zeros and
         # receive the product
-        union = torch.cat([self.xout, self.xin], dim=-2)
+        union = self._union_reference()
         padding = V.new_zeros(*V.shape[:-2], self.xin.shape[-2], V.shape[-1])
         filtered = LatticeFilterGeneral.apply(torch.cat([V, padding], dim=-2), union, self.dkernel)
         return filtered[..., n_out:, :]

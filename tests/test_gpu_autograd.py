@@ -85,10 +85,20 @@ def test_lattice_cache(sg):
     c = sg.LatticeFilterGeneral.apply(vd, xd, kf)
     assert cache.builds == b0 + 2
     assert not torch.allclose(a, c)
-    y = xd.clone()  # a different tensor object, even with equal content, is a different key
-    sg.LatticeFilterGeneral.apply(vd, y, kf)
+    y = xd.clone()  # a different tensor object with equal content: found by value, no rebuild
+    ch0 = cache.content_hits
+    e = sg.LatticeFilterGeneral.apply(vd, y, kf)
+    assert cache.builds == b0 + 2 and cache.content_hits == ch0 + 1
+    assert _rel(e.cpu().numpy(), c.cpu().numpy()) < 2e-6
+    y2 = xd.clone()
+    y2[5, 1] += 1e-3   # one value differs: a different lattice
+    sg.LatticeFilterGeneral.apply(vd, y2, kf)
     assert cache.builds == b0 + 3
-    del y
+    xd.add_(1.0)       # the cached tensor changed in place after the build: its entry must not answer for y's content
+    z = y.clone()
+    sg.LatticeFilterGeneral.apply(vd, z, kf)
+    assert cache.builds == b0 + 3 and cache.content_hits == ch0 + 2   # served by y's entry
+    del y, y2, z
     torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
 
 
@@ -133,6 +143,34 @@ def test_rectangular_operator(sg, oracle):
     assert _rel(got.detach().cpu().numpy(), want) < REL_TOL
     t = op.transpose(-1, -2)
     assert tuple(t.shape) == (220, 150)
+
+
+def test_rectangular_operator_extends_the_cached_training_lattice(sg, oracle):
+    """Prediction-shaped use: the square operator on the training inputs first, then K(test, train) products.  The
+    union lattice must come from extending the cached training lattice (no second build of the training points), be
+    reused across products and across fresh `x / lengthscale` tensors, and give the reference's numbers."""
+    cache = sg.lattice_cache
+    cache.clear()
+    xtr, v = make_inputs(3000, 4, 3, seed=21)
+    xte, _ = make_inputs(400, 4, 1, seed=22)
+    k = sg.RBFLattice(ard_num_dims=4, order=1).cuda()
+    xtr_d, xte_d, vd = xtr.cuda(), xte.cuda(), v.cuda()
+    with torch.no_grad():
+        k(xtr_d).matmul(vd)                              # builds the training lattice
+        b0, e0 = cache.builds, cache.extensions
+        op = k(xte_d, xtr_d)                             # fresh xtr / lengthscale tensor: found by value
+        got = op.matmul(vd)
+        got2 = op.matmul(vd * 2)
+        assert cache.builds == b0 and cache.extensions == e0 + 1
+        got3 = k(xte_d, xtr_d).matmul(vd)               # a new operator object: union found by value
+        assert cache.builds == b0 and cache.extensions == e0 + 1
+    ls = k.lengthscale.detach().cpu()
+    big_x = torch.cat([xtr, xte]) / ls
+    big_v = torch.cat([v, torch.zeros(400, 3)])
+    want = oracle.filter(big_v.numpy(), big_x.numpy(), k.dkernel_fn.get_coeffs().numpy())[3000:]
+    assert _rel(got.cpu().numpy(), want) < REL_TOL
+    assert _rel(got3.cpu().numpy(), got.cpu().numpy()) < 2e-6
+    assert _rel(got2.cpu().numpy(), 2 * want) < REL_TOL
 
 
 def test_matern_nu_validation(sg):

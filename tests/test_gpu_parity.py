@@ -259,3 +259,70 @@ def test_exact_division(sg, d):
     for k in range(4):
         _capi.check(lib.sgp_debug_division_mismatches(d, k * chunk, chunk, C.c_void_p(bad.data_ptr()), st))
     assert bad.tolist() == [0, 0]
+
+
+@pytest.mark.parametrize("N,Nn,d,coeffs", [(4000, 700, 5, RBF1), (900, 2500, 3, MAT15_2), (20000, 1, 8, RBF1),
+                                            (1, 300, 2, RBF1), (500, 0, 4, RBF1)])
+def test_extend_equals_union_build(sg, oracle, N, Nn, d, coeffs):
+    """Lattice.extend (sgp_hash_seed / sgp_hash_extend / sgp_count_extension / sgp_number_extension): the lattice of
+    cat([x, x_new]) made without revisiting x is bit for bit the one built from the concatenation -- and therefore
+    the oracle's (first-touch numbering is sequential over the points, permutohedral.h:467-485)."""
+    x, v = make_inputs(N + Nn, d, 4, seed=300 + N)
+    xd = x.cuda()
+    base = sg.Lattice(xd[:N], coeffs)
+    ext = base.extend(xd[N:])
+    full = sg.Lattice(xd, coeffs)
+    assert (ext.N, ext.M) == (full.N, full.M)
+    assert torch.equal(ext.keys, full.keys)
+    assert torch.equal(ext.replay, full.replay)
+    assert torch.equal(ext.nbr, full.nbr)
+    assert torch.equal(ext.greedy, full.greedy) and torch.equal(ext.rank, full.rank)
+    O = oracle.OracleLattice(x.numpy(), np.asarray(coeffs, dtype=np.float32))
+    assert O.M == ext.M and np.array_equal(O.keys, ext.keys.cpu().numpy())
+    assert np.array_equal(O.offsets, ext.offsets.cpu().numpy())
+    vd = v.cuda()
+    a, b = ext.mvm(vd, exact=True), full.mvm(vd, exact=True)
+    assert float((a - b).norm()) <= 2e-6 * float(b.norm())      # same tables; splat atomics may reorder sums
+    want = O.mvm(v.numpy())
+    assert np.linalg.norm(a.cpu().numpy().astype(np.float64) - want) <= 1e-5 * np.linalg.norm(want)
+    # the lattice that was extended is untouched
+    again = sg.Lattice(xd[:N], coeffs)
+    assert torch.equal(base.keys, again.keys) and torch.equal(base.replay, again.replay)
+    assert float((base.mvm(vd[:N], exact=True) - again.mvm(vd[:N], exact=True)).norm()) <= 2e-6 * float(vd.norm())
+
+
+def test_extend_twice_and_from_arrays(sg):
+    x, v = make_inputs(6000, 6, 2, seed=909)
+    xd = x.cuda()
+    a = sg.Lattice(xd[:2000], RBF1, keep_structure=False).extend(xd[2000:3500]).extend(xd[3500:])
+    full = sg.Lattice(xd, RBF1)
+    assert torch.equal(a.keys, full.keys) and torch.equal(a.replay, full.replay) and torch.equal(a.nbr, full.nbr)
+    assert a.greedy is None
+    base = sg.Lattice(xd[:2000], RBF1)
+    wrapped = sg.Lattice.from_arrays(RBF1, base.replay, base.keys, base.nbr)
+    b = wrapped.extend(xd[2000:])
+    assert torch.equal(b.keys, full.keys) and torch.equal(b.replay, full.replay)
+    assert float((b.mvm(v.cuda(), exact=True) - full.mvm(v.cuda(), exact=True)).norm()) <= 2e-6 * float(v.norm())
+    with pytest.raises(ValueError):
+        base.extend(xd[:10, :3])
+
+
+def test_extend_lazy_tables(sg, oracle):
+    """lazy_tables=k: the first k products run on the neighbour table alone, the k+1-th builds the blur groups and the
+    row-sorted entries; every product gives the oracle's numbers."""
+    x, v = make_inputs(5000, 5, 8, seed=911)
+    xd, vd = x.cuda(), v.cuda()
+    lat = sg.Lattice(xd[:4000], RBF1).extend(xd[4000:], lazy_tables=2)
+    assert lat.groups is None and lat.rows is None and lat.nbr is not None
+    want = oracle.OracleLattice(x.numpy(), np.asarray(RBF1, dtype=np.float32)).mvm(v.numpy())
+    for k in range(4):
+        got = lat.mvm(vd).cpu().numpy()
+        assert np.linalg.norm(got.astype(np.float64) - want) <= 1e-5 * np.linalg.norm(want)
+        assert (lat.groups is not None and lat.rows is not None) == (k >= 2)
+    lat2 = sg.Lattice(xd[:4000], RBF1).extend(xd[4000:], lazy_tables=5)
+    out = torch.empty_like(vd)
+    g = lat2.capture(vd, out)        # a graph wants the production chain: tables are built before the capture
+    assert lat2.groups is not None and lat2.rows is not None
+    g.replay()
+    torch.cuda.synchronize()
+    assert np.linalg.norm(out.cpu().numpy().astype(np.float64) - want) <= 1e-5 * np.linalg.norm(want)
