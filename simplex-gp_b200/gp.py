@@ -226,3 +226,44 @@ class ExactGPModel(torch.nn.Module):
         if self.train_x.shape[0] <= self.max_cholesky_size:
             return mll_dense(matmul, self.train_y, self.raw_mean, self.outputscale, self.noise)
         return mll_cg(matmul, self.train_y, self.raw_mean, self.outputscale, self.noise, **cg_kwargs)
+
+    @torch.no_grad()
+    def predict(self, test_x, tol: float = 1e-2, max_iter: int = 1000, variance: bool = False, var_block: int = 16):
+        """Posterior mean (and, on request, the latent variance) at ``test_x`` -- what ``model(test_x)`` of
+        experiments/train_simplexgp.py:60-84 returns in evaluation mode.
+
+        ``alpha = (s K + noise I)^-1 (y - mu)`` by a dense factorisation (N <= ``max_cholesky_size``) or CG at relative residual
+        ``tol`` (the reference's ``eval_cg_tolerance``); ``mean = mu + s K(test, train) alpha`` is ONE rectangular
+        product on the training lattice extended by the test points.  The variance
+        ``s - s^2 k_i^T (s K + noise I)^-1 k_i`` is exact up to ``tol`` and costs a solve with ``var_block`` columns per
+        ``var_block`` test points (the reference uses GPyTorch's LOVE approximation, ``fast_pred_var``, instead)."""
+        op = self.operator()
+        n = self.train_x.shape[0]
+        s, noise, mu = self.outputscale, self.noise, self.raw_mean
+        r = (self.train_y - mu).unsqueeze(-1)
+        dense = None
+        if n <= self.max_cholesky_size:
+            # LU of the operator as it is: on a finite lattice the blur passes do not commute exactly, so the filter is
+            # symmetric only approximately, and CG (below) solves the unsymmetrised system too
+            eye = torch.eye(n, dtype=r.dtype, device=r.device)
+            dense = torch.linalg.lu_factor(s * op.matmul(eye) + noise * eye)
+
+        def solve(B):
+            if dense is not None:
+                return torch.linalg.lu_solve(*dense, B)
+            return batched_cg(lambda V: s * op.matmul(V) + noise * V, B, tol=tol, max_iter=max_iter)[0]
+
+        cross = self.kernel(test_x, self.train_x)              # K(test, train)
+        mean = mu + s * cross.matmul(solve(r))[:, 0]
+        if not variance:
+            return mean
+        n_test = test_x.shape[0]
+        back = cross.transpose(-1, -2)                         # K(train, test)
+        var = torch.empty(n_test, dtype=mean.dtype, device=mean.device)
+        for lo in range(0, n_test, var_block):
+            hi = min(lo + var_block, n_test)
+            E = torch.zeros(n_test, hi - lo, dtype=mean.dtype, device=mean.device)
+            E[torch.arange(lo, hi), torch.arange(hi - lo)] = 1.0
+            Kb = s * back.matmul(E)                            # s k_i as columns [n, block]
+            var[lo:hi] = s - (Kb * solve(Kb)).sum(0)
+        return mean, var.clamp_min(0.0)

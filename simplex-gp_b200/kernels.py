@@ -60,6 +60,7 @@ class RectangularLazyLattice(LazyTensor):
         self.xout = xout
         self.dkernel = dkernel
         self._union = None
+        self._partner = None    # set on a transposed view: the operator whose union lattice it shares
 
     def _union_reference(self):
         """``cat([xout, xin])`` with its lattice made by extending the cached lattice of ``xout`` (the training inputs
@@ -79,6 +80,14 @@ class RectangularLazyLattice(LazyTensor):
     def _matmul(self, V):
         n_out = self.xout.shape[-2]
         assert V.shape[-2] == n_out, f"mismatched shapes? {V.shape, self.xout.shape}"
+        if self._partner is not None:
+            # transposed view: the union filter is symmetric, so K(xin, xout) is the other off-diagonal block of the
+            # partner's union operator -- same lattice, V on the last rows, the product read from the first
+            union = self._partner._union_reference()
+            n_in = self.xin.shape[-2]
+            padding = V.new_zeros(*V.shape[:-2], n_in, V.shape[-1])
+            filtered = LatticeFilterGeneral.apply(torch.cat([padding, V], dim=-2), union, self.dkernel)
+            return filtered[..., :n_in, :]
         # one square filter on the union of both point sets: the rows of V sit on xout, the xin rows carry zeros and
         # receive the product
         union = self._union_reference()
@@ -90,7 +99,11 @@ class RectangularLazyLattice(LazyTensor):
         return torch.Size((*self.xin.shape[:-1], self.xout.shape[-2]))
 
     def _transpose_nonbatch(self):
-        return RectangularLazyLattice(self.xout, self.xin, self.dkernel)
+        if self._partner is not None:
+            return self._partner
+        t = RectangularLazyLattice(self.xout, self.xin, self.dkernel)
+        t._partner = self       # shares this operator's union lattice instead of building cat([xin, xout])'s
+        return t
 
 
 class LatticeAccelerated(Kernel):

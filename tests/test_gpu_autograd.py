@@ -143,6 +143,20 @@ def test_rectangular_operator(sg, oracle):
     assert _rel(got.detach().cpu().numpy(), want) < REL_TOL
     t = op.transpose(-1, -2)
     assert tuple(t.shape) == (220, 150)
+    # the transpose shares the union lattice: it is the other off-diagonal block of the same union filter, which is
+    # what the reference computes on cat([xin, xout]) (the same key set numbered differently)
+    u = torch.randn(150, 2, generator=torch.Generator().manual_seed(3))
+    b0 = sg.lattice_cache.builds + sg.lattice_cache.extensions
+    tu = t.matmul(u.cuda())
+    assert sg.lattice_cache.builds + sg.lattice_cache.extensions == b0
+    assert tuple(tu.shape) == (220, 2)
+    want_t = oracle.filter(torch.cat([torch.zeros(220, 2), u]).numpy(), big_x.numpy(),
+                           k.dkernel_fn.get_coeffs().numpy())[:220]
+    assert _rel(tu.detach().cpu().numpy(), want_t) < REL_TOL
+    other = oracle.filter(torch.cat([u, torch.zeros(220, 2)]).numpy(), (torch.cat([xin, xout]) / ls).numpy(),
+                          k.dkernel_fn.get_coeffs().numpy())[150:]
+    assert _rel(tu.detach().cpu().numpy(), other) < REL_TOL
+    assert t.transpose(-1, -2) is op
 
 
 def test_rectangular_operator_extends_the_cached_training_lattice(sg, oracle):

@@ -97,3 +97,45 @@ def test_cg_training_step_gradients(sg, oracle):
     g = k.raw_lengthscale.grad
     assert np.isfinite(value) and torch.isfinite(g).all() and g.abs().sum() > 0
     assert torch.isfinite(model.raw_noise.grad) and torch.isfinite(model.raw_outputscale.grad)
+
+
+def test_predict_mean_and_variance_against_dense_algebra(sg):
+    """ExactGPModel.predict (CG path) against the same posterior written with dense matrices made from the operator:
+    mean = mu + s K(test, train) A^-1 (y - mu), var = s - s^2 k^T A^-1 k, A = s K + noise I."""
+    from simplex_gp_b200 import gp
+    torch.manual_seed(5)
+    n, nt, d = 1200, 40, 2
+    x = torch.rand(n, d, device="cuda") * 4 - 2
+    y = torch.sin(2 * x[:, 0]) * torch.cos(x[:, 1]) + 0.05 * torch.randn(n, device="cuda")
+    xt = torch.rand(nt, d, device="cuda") * 4 - 2
+    kernel = sg.RBFLattice(ard_num_dims=d, order=2).cuda()
+    with torch.no_grad():
+        kernel.raw_lengthscale.fill_(-0.5)
+    model = gp.ExactGPModel(x, y, kernel, max_cholesky_size=0).cuda()
+    with torch.no_grad():
+        model.raw_noise.fill_(-1.0)    # noise 0.31: keeps s K + noise I well conditioned (the lattice operator is not
+                                       # exactly positive semi-definite), so CG and the dense solve agree
+    mean, var = model.predict(xt, tol=1e-6, max_iter=2000, variance=True, var_block=16)
+    with torch.no_grad():
+        s, noise, mu = model.outputscale.double(), model.noise.double(), model.raw_mean.double()
+        ls = kernel.lengthscale.detach()
+        union = torch.cat([x, xt]) / ls
+        W = sg.Lattice(union, kernel.dkernel_fn.get_coeffs()).mvm(torch.eye(n + nt, device="cuda"), exact=True).double()
+        Kst, Kts = W[n:, :n], W[:n, n:]
+        # the training block of the union filter differs from the filter on the training lattice alone (the test points
+        # add lattice points that the blur passes through), so alpha comes from the model's own operator
+        Ktr = kernel(x).matmul(torch.eye(n, device="cuda")).double()
+        asym = float((Ktr - Ktr.T).norm() / Ktr.norm())
+        A = s * Ktr + noise * torch.eye(n, device="cuda", dtype=torch.float64)
+        alpha = torch.linalg.solve(A, (y.double() - mu))
+        want_mean = mu + s * (Kst @ alpha)
+        want_var = s - (s * Kts * torch.linalg.solve(A, s * Kts)).sum(0)
+    assert float((mean.double() - want_mean).norm() / want_mean.norm()) < 1e-3, asym
+    assert float((var.double() - want_var.clamp_min(0)).abs().max()) < 2e-3
+    # and it predicts: far better than the constant predictor
+    yt = torch.sin(2 * xt[:, 0]) * torch.cos(xt[:, 1])
+    assert float((mean - yt).pow(2).mean().sqrt()) < 0.5 * float(yt.std())
+    # the small-N (Cholesky) path gives the same mean
+    model.max_cholesky_size = 5000
+    mean_dense = model.predict(xt)
+    assert float((mean_dense - mean).norm() / mean.norm()) < 1e-3
