@@ -139,3 +139,18 @@ def test_predict_mean_and_variance_against_dense_algebra(sg):
     model.max_cholesky_size = 5000
     mean_dense = model.predict(xt)
     assert float((mean_dense - mean).norm() / mean.norm()) < 1e-3
+
+
+def test_experiment_harness_learns_on_toy_shape(sg):
+    """experiments/train_simplexgp.py end to end (train steps by CG + SLQ, prediction through the extended lattice,
+    early-stopping bookkeeping) on the small synthetic problem."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("train_simplexgp", os.path.join(root, "experiments", "train_simplexgp.py"))
+    h = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(h)
+    summary = h.main(dataset="toy", epochs=8, seed=0, nu=1.5, order=1, min_noise=0.1, quiet=True, variance_points=32)
+    assert summary["val/best_step"] >= 1
+    assert summary["test/best_rmse"] < 0.75          # targets are standardised: the constant predictor scores 1.0
+    assert np.isfinite(summary["test/best_nll"])
+    assert len(summary["lengthscale"]) == 3
