@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SGP_ABI_VERSION 2
+#define SGP_ABI_VERSION 3
 
 #define SGP_OK 0
 #define SGP_EINVAL (-1)       /* bad argument */
@@ -162,7 +162,8 @@ typedef struct sgp_lattice_view {
     const int32_t *nbr;      /* device [(d+1), M, 2r] */
     const uint32_t *csr_ptr; /* device [M+1] or NULL: row starts into csr_ent (ordered-gather splat) */
     const int32_t *csr_ent;  /* device [N*(d+1), 2] or NULL: {point, weight bits} sorted by lattice row, point-vertex
-                                order inside a row -- the first N*(d+1) entries of sgp_build_rowsorted's `ent` */
+                                order inside a row -- the first N*(d+1) entries of sgp_build_rowsorted's `ent` (bit 31 of
+                                the point word is ignored) */
     const uint32_t *perm;    /* device [N] or NULL.  When set, row p of replay describes point perm[p]: splat and
                                 slice walk the points in that (locality) order and address src / out rows through it */
     int32_t fast;            /* 0: the reference's arithmetic, one rounding per product and per sum (bit-exact on the
@@ -293,7 +294,7 @@ int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64_t M, int o
 /* The production chain in one call: sgp_splat_rows -> sgp_blur_groups -> sgp_slice.  slice_view->replay addresses
  * the lattice values in the order the last group stage leaves them (sgp_permute_replay with that stage's pos);
  * buf0 / buf1: device [M, Lv] scratch, Lv = L or L rounded up to a multiple of 4 (see sgp_slice). */
-int sgp_mvm_rows_groups(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *ent_row,
+int sgp_mvm_rows_groups(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
                         const sgp_blur_group *groups, int n_groups, const float *src, int64_t lds, int L,
                         const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1, int Lv,
                         sgp_stream_t stream);
@@ -318,17 +319,22 @@ int sgp_grad_contract(const float *filtered, int64_t ldp, const float *g, int64_
                       sgp_stream_t stream);
 
 /* ---- row-sorted splat ("segmented gather") -------------------------------------------------
- * ent (device [sgp_rowsort_padded(N,d), 2] int32 {point, weight bits}) and ent_row (device [same] int32 lattice
- * row): the point-vertices sorted by lattice row, point-vertex order within a row (the reference's accumulation
- * order), padded with zero-weight entries to a multiple of 8.  sgp_splat_rows gives every thread 8 consecutive
- * entries: balanced whatever the row lengths, one vector reduction per run of equal rows (values is zeroed inside). */
+ * The point-vertices sorted by lattice row, point-vertex order within a row (the reference's accumulation order),
+ * padded with zero-weight entries to a multiple of 16:
+ *   ent      device [sgp_rowsort_padded(N,d), 2] int32 {point | row-start flag in bit 31, weight bits}; the flag marks
+ *            the first entry of a lattice row (every row has at least one entry and rows are consecutive integers);
+ *   seg_row  device [sgp_rowsort_padded(N,d) / 4] int32: lattice row of every fourth entry;
+ *   ent_row  optional (may be NULL) device [sgp_rowsort_padded(N,d)] int32: lattice row of every entry, for callers
+ *            that want row starts (the CSR of the ordered gather).
+ * sgp_splat_rows gives every thread 8 consecutive entries -- 8.5 bytes of index stream per point-vertex: balanced
+ * whatever the row lengths, one vector reduction per run of equal rows (values is zeroed inside). */
 size_t sgp_rowsort_workspace_bytes(int64_t N, int d);
 int64_t sgp_rowsort_padded(int64_t N, int d);
 int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int64_t M, int32_t *ent, int32_t *ent_row,
-                        void *workspace, size_t workspace_bytes, sgp_stream_t stream);
+                        int32_t *seg_row, void *workspace, size_t workspace_bytes, sgp_stream_t stream);
 /* src: [N, lds] with L_src columns; values: [M, L], L >= L_src (columns L_src..L-1 receive zeros): as for sgp_slice,
  * the lattice rows may be padded to a multiple of 4 channels */
-int sgp_splat_rows(const int32_t *ent, const int32_t *ent_row, int64_t N, int d, int64_t M, const float *src,
+int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_t N, int d, int64_t M, const float *src,
                    int64_t lds, int L_src, float *values, int L, sgp_stream_t stream);
 
 /* ---- locality order of the points --------------------------------------------------------

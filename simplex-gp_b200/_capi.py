@@ -198,13 +198,13 @@ def lib() -> C.CDLL:
     L.sgp_rowsort_padded.restype = i64
     L.sgp_rowsort_padded.argtypes = [i64, i32]
     L.sgp_build_rowsorted.restype = i32
-    L.sgp_build_rowsorted.argtypes = [vp, i64, i32, i64, vp, vp, vp, sz, vp]
+    L.sgp_build_rowsorted.argtypes = [vp, i64, i32, i64, vp, vp, vp, vp, sz, vp]
     L.sgp_splat_rows.restype = i32
     L.sgp_splat_rows.argtypes = [vp, vp, i64, i32, i64, vp, i64, i32, vp, i32, vp]
     L.sgp_debug_division_mismatches.restype = i32
     L.sgp_debug_division_mismatches.argtypes = [i32, C.c_uint32, C.c_uint32, vp, vp]
-    if L.sgp_abi_version() != 2:
-        raise RuntimeError(f"{LIB_PATH}: ABI version {L.sgp_abi_version()} != 2, rebuild the library")
+    if L.sgp_abi_version() != 3:
+        raise RuntimeError(f"{LIB_PATH}: ABI version {L.sgp_abi_version()} != 3, rebuild the library")
     _lib = L
     return L
 

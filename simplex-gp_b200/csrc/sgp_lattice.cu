@@ -709,7 +709,7 @@ sgp_splat_gather_kernel(const uint32_t *__restrict__ row_ptr, const int2 *__rest
         const int2 e = __ldg(entries + q);
         const float w = __int_as_float(e.y);
         Vec<VEC> v;
-        v.load(src + (int64_t)e.x * lds + c0);
+        v.load(src + (int64_t)(e.x & 0x7fffffff) * lds + c0);   // bit 31 is the row-start flag of the row-sorted entries
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc.v[k] = __fadd_rn(acc.v[k], __fmul_rn(w, v.v[k]));
     }

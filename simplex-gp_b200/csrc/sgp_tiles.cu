@@ -376,21 +376,31 @@ sgp_rowsort_keys_kernel(const int2 *__restrict__ replay, int64_t total, uint32_t
     vals[q] = (uint32_t)q;
 }
 
+// ent[k] = {point | SGP_ROW_START, weight}: the flag marks the first entry of a lattice row.  Every lattice row has at
+// least one entry and the rows are consecutive integers, so a thread that knows the row of its first entry
+// (seg_row, one int per 4 entries) finds the others by counting flags: 8.5 bytes per entry instead of 12.
+#define SGP_ROW_START 0x80000000u
+#define SGP_ROW_GRAIN 4
+
 __global__ void __launch_bounds__(256)
 sgp_rowsort_fill_kernel(const int2 *__restrict__ replay, const uint32_t *__restrict__ sorted_row,
                         const uint32_t *__restrict__ sorted_pv, int64_t total, int64_t padded, int dp1,
-                        int2 *__restrict__ ent, int32_t *__restrict__ ent_row)
+                        int2 *__restrict__ ent, int32_t *__restrict__ ent_row, int32_t *__restrict__ seg_row)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= padded) return;
+    uint32_t row;
     if (k < total) {
         const uint32_t q = sorted_pv[k];
-        ent[k] = make_int2((int)(q / (uint32_t)dp1), replay[q].y);
-        ent_row[k] = (int32_t)sorted_row[k];
+        row = sorted_row[k];
+        const uint32_t start = (k > 0 && sorted_row[k - 1] != row) ? SGP_ROW_START : 0u;
+        ent[k] = make_int2((int)((q / (uint32_t)dp1) | start), replay[q].y);
     } else {   // padding: weight 0 on the last row
+        row = sorted_row[total - 1];
         ent[k] = make_int2(0, 0);
-        ent_row[k] = (int32_t)sorted_row[total - 1];
     }
+    if (ent_row) ent_row[k] = (int32_t)row;
+    if (k % SGP_ROW_GRAIN == 0) seg_row[k / SGP_ROW_GRAIN] = (int32_t)row;
 }
 
 extern "C" size_t sgp_rowsort_workspace_bytes(int64_t N, int d)
@@ -412,9 +422,10 @@ extern "C" int64_t sgp_rowsort_padded(int64_t N, int d)
 }
 
 extern "C" int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int64_t M, int32_t *ent, int32_t *ent_row,
-                                   void *workspace, size_t workspace_bytes, sgp_stream_t stream)
+                                   int32_t *seg_row, void *workspace, size_t workspace_bytes, sgp_stream_t stream)
 {
-    if (!replay || !ent || !ent_row || !workspace || N <= 0 || M <= 0 || d < 1) return fail(SGP_EINVAL, "sgp_build_rowsorted: bad argument");
+    if (!replay || !ent || !seg_row || !workspace || N <= 0 || M <= 0 || d < 1) return fail(SGP_EINVAL, "sgp_build_rowsorted: bad argument");
+    if (N >= (1ll << 31)) return fail(SGP_EOVERFLOW, "sgp_build_rowsorted: N does not fit 31 bits");
     if (workspace_bytes < sgp_rowsort_workspace_bytes(N, d)) return fail(SGP_EINVAL, "sgp_build_rowsorted: workspace too small");
     const int64_t total = N * (int64_t)(d + 1);
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -431,7 +442,7 @@ extern "C" int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int6
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ka, kb, va, vb, (int64_t)total, 0, bits_for((uint64_t)M), st));
     const int64_t padded = sgp_rowsort_padded(N, d);
     sgp_rowsort_fill_kernel<<<grid_for(padded, 256), 256, 0, st>>>((const int2 *)replay, kb, vb, total, padded, d + 1,
-                                                                  (int2 *)ent, ent_row);
+                                                                  (int2 *)ent, ent_row, seg_row);
     return launch_ok("sgp_rowsort_fill_kernel");
 }
 
@@ -441,7 +452,7 @@ extern "C" int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int6
 // channel at a time, the missing channels as zeros; everything downstream moves 16-byte vectors.
 template <int VEC, int SEG, bool RAGGED>
 __global__ void __launch_bounds__(256)
-sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ ent_row, int64_t n_seg,
+sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ seg_row, int64_t n_seg,
                       const float *__restrict__ src, int64_t lds, int L, int L_src, int chunks, int64_t prefetch_bytes,
                       float *__restrict__ values)
 {
@@ -457,33 +468,28 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     if (seg >= n_seg) return;
     const int c0 = (int)(tid - seg * chunks) * VEC;
     int2 e[SEG];
-    int row[SEG];
     Vec<VEC> v[SEG];
     const int4 *ep = (const int4 *)(ent + seg * SEG);     // SEG entries = SEG/2 16-byte loads
-    const int4 *rp = (const int4 *)(ent_row + seg * SEG);
+    int row = __ldg(seg_row + seg * (SEG / SGP_ROW_GRAIN));   // lattice row of the first entry
 #pragma unroll
     for (int i = 0; i < SEG / 2; ++i) {
         const int4 t = SGP_LDCS ? __ldcs(ep + i) : __ldg(ep + i);   // read once: streaming, keeps src and the lattice in L2
         e[2 * i] = make_int2(t.x, t.y);
         e[2 * i + 1] = make_int2(t.z, t.w);
     }
+    // no weight has all bits set: the branch keeps every entry load ahead of every row load (in-order issue)
+    int all = e[0].y;
 #pragma unroll
-    for (int i = 0; i < SEG / 4; ++i) {
-        const int4 t = SGP_LDCS ? __ldcs(rp + i) : __ldg(rp + i);
-        row[4 * i] = t.x; row[4 * i + 1] = t.y; row[4 * i + 2] = t.z; row[4 * i + 3] = t.w;
-    }
-    // point indices are never negative: the branch keeps every entry load ahead of every row load (in-order issue)
-    int lowest = e[0].x;
-#pragma unroll
-    for (int i = 1; i < SEG; ++i) lowest = min(lowest, e[i].x);
-    if (lowest < 0) return;
+    for (int i = 1; i < SEG; ++i) all &= e[i].y;
+    if (all == -1 || row < 0) return;
 #pragma unroll
     for (int i = 0; i < SEG; ++i) {
         if (RAGGED) {
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) v[i].v[k] = (c0 + k < L_src) ? ldg_ordered_f1(src + (int64_t)e[i].x * lds + c0 + k) : 0.0f;
+            for (int k = 0; k < VEC; ++k)
+                v[i].v[k] = (c0 + k < L_src) ? ldg_ordered_f1(src + (int64_t)(e[i].x & 0x7fffffff) * lds + c0 + k) : 0.0f;
         } else {
-            v[i].load_ordered(src + (int64_t)e[i].x * lds + c0);
+            v[i].load_ordered(src + (int64_t)(e[i].x & 0x7fffffff) * lds + c0);
         }
     }
     Vec<VEC> acc;
@@ -495,19 +501,20 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
         const float w = __int_as_float(e[i].y);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc.v[k] = __fmaf_rn(w, v[i].v[k], acc.v[k]);
-        if (i == SEG - 1 || row[i + 1] != row[i]) {
-            acc.red(values + (int64_t)row[i] * L + c0);
+        if (i == SEG - 1 || e[i + 1].x < 0) {      // the next entry starts the next lattice row
+            acc.red(values + (int64_t)row * L + c0);
+            ++row;
 #pragma unroll
             for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
         }
     }
 }
 
-extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *ent_row, int64_t N, int d, int64_t M, const float *src,
+extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_t N, int d, int64_t M, const float *src,
                               int64_t lds, int L_src, float *values, int L, sgp_stream_t stream)
 {
     if (N == 0 || M == 0) return SGP_OK;
-    if (!ent || !ent_row || !src || !values || N < 0 || M < 0 || d < 1 || L_src < 1 || lds < L_src || L < L_src)
+    if (!ent || !seg_row || !src || !values || N < 0 || M < 0 || d < 1 || L_src < 1 || lds < L_src || L < L_src)
         return fail(SGP_EINVAL, "sgp_splat_rows: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     static int seg_env = 0;   // tuning hook: SGP_ROWSEG=4|8|16 entries per thread
@@ -535,10 +542,10 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *ent_row, int64_
     cudaError_t launch_err = cudaSuccess;
 #define SGP_ROWS_LAUNCH(VV, SS)                                                                                        \
     launch_err = ragged ? sgp_launch_pdl(sgp_splat_rows_kernel<VV, SS, true>, dim3(grid_for(work, 256)), dim3(256), 0,  \
-                                         st, (const int2 *)ent, ent_row, n_seg, src, lds, L, L_src, chunks,            \
+                                         st, (const int2 *)ent, seg_row, n_seg, src, lds, L, L_src, chunks,            \
                                          prefetch_bytes, values)                                                      \
                         : sgp_launch_pdl(sgp_splat_rows_kernel<VV, SS, false>, dim3(grid_for(work, 256)), dim3(256), 0, \
-                                         st, (const int2 *)ent, ent_row, n_seg, src, lds, L, L_src, chunks,            \
+                                         st, (const int2 *)ent, seg_row, n_seg, src, lds, L, L_src, chunks,            \
                                          prefetch_bytes, values)
 #define SGP_ROWS_SEG(VV)                                                                                               \
     do {                                                                                                               \

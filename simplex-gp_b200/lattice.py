@@ -80,7 +80,7 @@ class Lattice:
 
     Derived tables for the MVM kernels (internal orderings; none of them changes the numbering above):
 
-    * ``rows``    point-vertices sorted by lattice row, ``ent[9M', 2] {point, weight}`` / ``ent_row[9M']``: the
+    * ``rows``    point-vertices sorted by lattice row, ``ent[9M', 2] {point | row-start flag, weight}`` / ``seg_row[9M'/4]``: the
                   segmented-gather splat (``build_rows``, default on); ``csr_ptr`` adds row starts for the ordered gather
                   of ``mode=2`` (``build_csr``).
     * ``groups``  blur groups: for each range of consecutive axes, lattice points sorted by class, CTA batches, gather
@@ -393,7 +393,8 @@ class Lattice:
         self.groups = {"list": groups, "array": arr, "final_pos": prev_pos}
 
     def _build_rows(self) -> None:
-        """Point-vertices sorted by lattice row for the segmented-gather splat (csrc/sgp_tiles.cu, sgp_build_rowsorted)."""
+        """Point-vertices sorted by lattice row for the segmented-gather splat (csrc/sgp_tiles.cu, sgp_build_rowsorted):
+        ``ent {point | row-start flag, weight}`` and ``seg_row`` (lattice row of every fourth entry)."""
         lib = _capi.lib()
         dev, N, d, M = self.device, self.N, self.d, self.M
         st = _stream_ptr(dev)
@@ -401,9 +402,9 @@ class Lattice:
         ws_bytes = int(lib.sgp_rowsort_workspace_bytes(N, d))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         ent = torch.empty((padded, 2), dtype=torch.int32, device=dev)
-        ent_row = torch.empty(padded, dtype=torch.int32, device=dev)
-        check(lib.sgp_build_rowsorted(_ptr(self.replay), N, d, M, _ptr(ent), _ptr(ent_row), _ptr(ws), ws_bytes, st))
-        self.rows = {"ent": ent, "ent_row": ent_row}
+        seg_row = torch.empty(padded // 4, dtype=torch.int32, device=dev)
+        check(lib.sgp_build_rowsorted(_ptr(self.replay), N, d, M, _ptr(ent), None, _ptr(seg_row), _ptr(ws), ws_bytes, st))
+        self.rows = {"ent": ent, "seg_row": seg_row}
 
     def _sort_points(self) -> None:
         """Locality order of the points (csrc/sgp_tiles.cu, sgp_sort_points); the replay tables re-ordered with it are
@@ -491,9 +492,11 @@ class Lattice:
         if self.rows is None:
             self._build_rows()
         total = self.N * (self.d + 1)
-        rows = self.rows["ent_row"][:total]
-        bounds = torch.arange(self.M + 1, device=self.device, dtype=torch.int32)
-        self.csr_ptr = torch.searchsorted(rows, bounds).to(torch.int32).contiguous()
+        starts = torch.nonzero(self.rows["ent"][:total, 0] < 0).flatten().to(torch.int32)   # row-start flags
+        ends = torch.tensor([total], dtype=torch.int32, device=self.device)
+        self.csr_ptr = torch.cat([torch.zeros(1, dtype=torch.int32, device=self.device), starts, ends]).contiguous()
+        if self.csr_ptr.numel() != self.M + 1:
+            raise RuntimeError("row-sorted entries do not cover every lattice row")
         self.csr_ent = self.rows["ent"]
 
     # ---- structure accessors (reference numbering) -------------------------------------------
@@ -569,7 +572,7 @@ class Lattice:
                 check(_capi.lib().sgp_splat_tiles(C.byref(tv), _ptr(src), src.stride(0), L, _ptr(values),
                                                   _stream_ptr(self.device)))
             elif mode == _capi.MODE_ROWS:
-                check(_capi.lib().sgp_splat_rows(_ptr(self.rows["ent"]), _ptr(self.rows["ent_row"]), self.N, self.d,
+                check(_capi.lib().sgp_splat_rows(_ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]), self.N, self.d,
                                                  self.M, _ptr(src), src.stride(0), L, _ptr(values), L,
                                                  _stream_ptr(self.device)))
             else:
@@ -690,7 +693,7 @@ class Lattice:
             arr = self.groups["array"]
             v_out = self._view(self._table(False, True), None, exact)
             with torch.cuda.device(self.device):
-                check(lib.sgp_mvm_rows_groups(C.byref(v_out), _ptr(self.rows["ent"]), _ptr(self.rows["ent_row"]), arr,
+                check(lib.sgp_mvm_rows_groups(C.byref(v_out), _ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]), arr,
                                               len(arr), _ptr(src), src.stride(0), L, _fp(c), c.shape[0], _ptr(out),
                                               out.stride(0), _ptr(buf0), _ptr(buf1), Lv, st))
             return out
@@ -700,7 +703,7 @@ class Lattice:
                 tv = self._tiles_view(False)
                 check(lib.sgp_splat_tiles(C.byref(tv), _ptr(src), src.stride(0), L, _ptr(buf0), st))
             elif mode == _capi.MODE_ROWS:
-                check(lib.sgp_splat_rows(_ptr(self.rows["ent"]), _ptr(self.rows["ent_row"]), self.N, self.d, self.M,
+                check(lib.sgp_splat_rows(_ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]), self.N, self.d, self.M,
                                          _ptr(src), src.stride(0), L, _ptr(buf0), Lv, st))
             else:
                 if mode == _capi.MODE_GATHER:
