@@ -47,7 +47,7 @@ RBF1 = [0.34608543, 1.0, 0.34608543]   # get_coeffs(rbf, 1), tests/golden/coeffs
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/),
 # cold-cache replays of the same command; None until a capture exists for the kernel
 TRAFFIC_NCU = {   # profiles/r1_mvm_full.txt
-    "sgp_splat_rows_kernel": 224.7e6, "sgp_blur_group_kernel": 32.7e6, "sgp_slice_kernel": 119.3e6,
+    "sgp_splat_rows_kernel": 200.8e6, "sgp_blur_group_kernel": 32.4e6, "sgp_slice_kernel": 120.2e6,
 }
 
 
