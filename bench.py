@@ -332,7 +332,7 @@ def run_ours(args, w):
             if mode == _capi.MODE_TILES:
                 _capi.check(lib.sgp_splat_tiles(C.byref(tv_in), _ptr(V), V.stride(0), L, _ptr(buf0), st))
             elif mode == _capi.MODE_ROWS:
-                _capi.check(lib.sgp_splat_rows(_ptr(lat.rows["ent"]), _ptr(lat.rows["seg_row"]), N, d, M, _ptr(V),
+                _capi.check(lib.sgp_splat_rows(_ptr(lat.rows["ent"]), _ptr(lat.rows["seg_row"]), lat.rows["n"], N, M, _ptr(V),
                                                V.stride(0), L, _ptr(buf0), L, st))
             else:
                 _capi.check(lib.sgp_splat(C.byref(v_in if mode == _capi.MODE_ATOMIC else v_axis), _ptr(V), V.stride(0), L,

@@ -295,7 +295,7 @@ int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64_t M, int o
  * the lattice values in the order the last group stage leaves them (sgp_permute_replay with that stage's pos);
  * buf0 / buf1: device [M, Lv] scratch, Lv = L or L rounded up to a multiple of 4 (see sgp_slice). */
 int sgp_mvm_rows_groups(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
-                        const sgp_blur_group *groups, int n_groups, const float *src, int64_t lds, int L,
+                        int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src, int64_t lds, int L,
                         const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1, int Lv,
                         sgp_stream_t stream);
 
@@ -320,22 +320,25 @@ int sgp_grad_contract(const float *filtered, int64_t ldp, const float *g, int64_
 
 /* ---- row-sorted splat ("segmented gather") -------------------------------------------------
  * The point-vertices sorted by lattice row, point-vertex order within a row (the reference's accumulation order),
- * padded with zero-weight entries to a multiple of 16:
- *   ent      device [sgp_rowsort_padded(N,d), 2] int32 {point | row-start flag in bit 31, weight bits}; the flag marks
- *            the first entry of a lattice row (every row has at least one entry and rows are consecutive integers);
- *   seg_row  device [sgp_rowsort_padded(N,d) / 4] int32: lattice row of every fourth entry;
- *   ent_row  optional (may be NULL) device [sgp_rowsort_padded(N,d)] int32: lattice row of every entry, for callers
- *            that want row starts (the CSR of the ordered gather).
+ * padded with zero-weight entries to n_entries = sgp_rowsort_padded(N, d, fill_rows), a multiple of 16:
+ *   ent      device [n_entries, 2] int32 {point | row-start flag in bit 31, weight bits}; the flag marks the first
+ *            entry of a lattice row;
+ *   seg_row  device [n_entries / 4] int32: lattice row of every fourth entry;
+ *   ent_row  optional (may be NULL) device [n_entries] int32: lattice row of every entry.
+ * The encoding needs every lattice row 0..M-1 to own an entry.  That holds for the lattice of the points themselves
+ * (fill_rows = 0); for a subset of the points on the full key set (a rank's share under point sharding) pass
+ * fill_rows = M: one weightless filler entry per row is sorted in.
  * sgp_splat_rows gives every thread 8 consecutive entries -- 8.5 bytes of index stream per point-vertex: balanced
  * whatever the row lengths, one vector reduction per run of equal rows (values is zeroed inside). */
-size_t sgp_rowsort_workspace_bytes(int64_t N, int d);
-int64_t sgp_rowsort_padded(int64_t N, int d);
-int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int64_t M, int32_t *ent, int32_t *ent_row,
-                        int32_t *seg_row, void *workspace, size_t workspace_bytes, sgp_stream_t stream);
+size_t sgp_rowsort_workspace_bytes(int64_t N, int d, int64_t fill_rows);
+int64_t sgp_rowsort_padded(int64_t N, int d, int64_t fill_rows);
+int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int64_t M, int64_t fill_rows, int32_t *ent,
+                        int32_t *ent_row, int32_t *seg_row, void *workspace, size_t workspace_bytes,
+                        sgp_stream_t stream);
 /* src: [N, lds] with L_src columns; values: [M, L], L >= L_src (columns L_src..L-1 receive zeros): as for sgp_slice,
  * the lattice rows may be padded to a multiple of 4 channels */
-int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_t N, int d, int64_t M, const float *src,
-                   int64_t lds, int L_src, float *values, int L, sgp_stream_t stream);
+int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
+                   const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream);
 
 /* ---- locality order of the points --------------------------------------------------------
  * perm (device [N]): the points in lexicographic order of their remainder-0 lattice point, so that points sharing

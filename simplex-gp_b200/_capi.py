@@ -186,7 +186,7 @@ def lib() -> C.CDLL:
     L.sgp_blur_groups.restype = i32
     L.sgp_blur_groups.argtypes = [C.POINTER(BlurGroup), i32, i64, i32, fp, i32, i32, vp, vp, C.POINTER(C.c_int), i32, vp]
     L.sgp_mvm_rows_groups.restype = i32
-    L.sgp_mvm_rows_groups.argtypes = [pv, vp, vp, C.POINTER(BlurGroup), i32, vp, i64, i32, fp, i32, vp, i64, vp, vp, i32, vp]
+    L.sgp_mvm_rows_groups.argtypes = [pv, vp, vp, i64, C.POINTER(BlurGroup), i32, vp, i64, i32, fp, i32, vp, i64, vp, vp, i32, vp]
     L.sgp_sort_points_workspace_bytes.restype = sz
     L.sgp_sort_points_workspace_bytes.argtypes = [i64]
     L.sgp_sort_points.restype = i32
@@ -194,13 +194,13 @@ def lib() -> C.CDLL:
     L.sgp_permute_replay.restype = i32
     L.sgp_permute_replay.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
     L.sgp_rowsort_workspace_bytes.restype = sz
-    L.sgp_rowsort_workspace_bytes.argtypes = [i64, i32]
+    L.sgp_rowsort_workspace_bytes.argtypes = [i64, i32, i64]
     L.sgp_rowsort_padded.restype = i64
-    L.sgp_rowsort_padded.argtypes = [i64, i32]
+    L.sgp_rowsort_padded.argtypes = [i64, i32, i64]
     L.sgp_build_rowsorted.restype = i32
-    L.sgp_build_rowsorted.argtypes = [vp, i64, i32, i64, vp, vp, vp, vp, sz, vp]
+    L.sgp_build_rowsorted.argtypes = [vp, i64, i32, i64, i64, vp, vp, vp, vp, sz, vp]
     L.sgp_splat_rows.restype = i32
-    L.sgp_splat_rows.argtypes = [vp, vp, i64, i32, i64, vp, i64, i32, vp, i32, vp]
+    L.sgp_splat_rows.argtypes = [vp, vp, i64, i64, i64, vp, i64, i32, vp, i32, vp]
     L.sgp_debug_division_mismatches.restype = i32
     L.sgp_debug_division_mismatches.argtypes = [i32, C.c_uint32, C.c_uint32, vp, vp]
     if L.sgp_abi_version() != 3:

@@ -599,13 +599,13 @@ extern "C" int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64
 // The production chain in one call: row-sorted splat -> blur-group stages -> slice.  `slice_view->replay` must address
 // the lattice values in the order the last stage leaves them (sgp_permute_replay with that stage's pos).
 extern "C" int sgp_mvm_rows_groups(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
-                                   const sgp_blur_group *groups, int n_groups, const float *src, int64_t lds, int L,
+                                   int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src, int64_t lds, int L,
                                    const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1, int Lv,
                                    sgp_stream_t stream)
 {
     if (!slice_view) return fail(SGP_EINVAL, "sgp_mvm_rows_groups: null view");
     if (Lv < L || (Lv != L && Lv % 4 != 0)) return fail(SGP_EINVAL, "sgp_mvm_rows_groups: Lv must be L or L rounded up to a multiple of 4");
-    int rc = sgp_splat_rows(ent, seg_row, slice_view->N, slice_view->d, slice_view->M, src, lds, L, buf0, Lv, stream);
+    int rc = sgp_splat_rows(ent, seg_row, n_entries, slice_view->N, slice_view->M, src, lds, L, buf0, Lv, stream);
     if (rc) return rc;
     int in1 = 0;
     rc = sgp_blur_groups(groups, n_groups, slice_view->M, slice_view->order, coeffs, k, Lv, buf0, buf1, &in1,

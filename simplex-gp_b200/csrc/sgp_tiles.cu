@@ -366,14 +366,19 @@ extern "C" int sgp_permute_replay(const int32_t *replay, const uint32_t *perm, c
 #endif
 #define ROWSEG 16   /* padding granularity of the row-sorted arrays; the kernel takes SEG = 4, 8 or 16 entries per thread */
 
+// q < total: a point-vertex, keyed by its lattice row.  total <= q < total + fill: one weightless filler per lattice
+// row 0..fill-1 (value 0xFFFFFFFF), for lattices whose points do not touch every row (a rank's share of the points
+// on the full key set): the row-start encoding below needs every row to own at least one entry.
+#define SGP_ROW_FILLER 0xFFFFFFFFu
+
 __global__ void __launch_bounds__(256)
-sgp_rowsort_keys_kernel(const int2 *__restrict__ replay, int64_t total, uint32_t *__restrict__ keys,
+sgp_rowsort_keys_kernel(const int2 *__restrict__ replay, int64_t total, int64_t fill, uint32_t *__restrict__ keys,
                         uint32_t *__restrict__ vals)
 {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= total) return;
-    keys[q] = (uint32_t)replay[q].x;
-    vals[q] = (uint32_t)q;
+    if (q >= total + fill) return;
+    keys[q] = q < total ? (uint32_t)replay[q].x : (uint32_t)(q - total);
+    vals[q] = q < total ? (uint32_t)q : SGP_ROW_FILLER;
 }
 
 // ent[k] = {point | SGP_ROW_START, weight}: the flag marks the first entry of a lattice row.  Every lattice row has at
@@ -394,7 +399,7 @@ sgp_rowsort_fill_kernel(const int2 *__restrict__ replay, const uint32_t *__restr
         const uint32_t q = sorted_pv[k];
         row = sorted_row[k];
         const uint32_t start = (k > 0 && sorted_row[k - 1] != row) ? SGP_ROW_START : 0u;
-        ent[k] = make_int2((int)((q / (uint32_t)dp1) | start), replay[q].y);
+        ent[k] = q == SGP_ROW_FILLER ? make_int2((int)start, 0) : make_int2((int)((q / (uint32_t)dp1) | start), replay[q].y);
     } else {   // padding: weight 0 on the last row
         row = sorted_row[total - 1];
         ent[k] = make_int2(0, 0);
@@ -403,9 +408,9 @@ sgp_rowsort_fill_kernel(const int2 *__restrict__ replay, const uint32_t *__restr
     if (k % SGP_ROW_GRAIN == 0) seg_row[k / SGP_ROW_GRAIN] = (int32_t)row;
 }
 
-extern "C" size_t sgp_rowsort_workspace_bytes(int64_t N, int d)
+extern "C" size_t sgp_rowsort_workspace_bytes(int64_t N, int d, int64_t fill_rows)
 {
-    const int64_t total = N * (int64_t)(d + 1);
+    const int64_t total = N * (int64_t)(d + 1) + (fill_rows > 0 ? fill_rows : 0);
     if (total <= 0) return 0;
     size_t t = 0;
     if (cub::DeviceRadixSort::SortPairs(nullptr, t, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
@@ -415,19 +420,22 @@ extern "C" size_t sgp_rowsort_workspace_bytes(int64_t N, int d)
     return al((size_t)total * 4) * 4 + al(t);
 }
 
-extern "C" int64_t sgp_rowsort_padded(int64_t N, int d)
+extern "C" int64_t sgp_rowsort_padded(int64_t N, int d, int64_t fill_rows)
 {
-    const int64_t total = N * (int64_t)(d + 1);
+    const int64_t total = N * (int64_t)(d + 1) + (fill_rows > 0 ? fill_rows : 0);
     return (total + ROWSEG - 1) / ROWSEG * ROWSEG;
 }
 
-extern "C" int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int64_t M, int32_t *ent, int32_t *ent_row,
-                                   int32_t *seg_row, void *workspace, size_t workspace_bytes, sgp_stream_t stream)
+extern "C" int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int64_t M, int64_t fill_rows, int32_t *ent,
+                                   int32_t *ent_row, int32_t *seg_row, void *workspace, size_t workspace_bytes,
+                                   sgp_stream_t stream)
 {
     if (!replay || !ent || !seg_row || !workspace || N <= 0 || M <= 0 || d < 1) return fail(SGP_EINVAL, "sgp_build_rowsorted: bad argument");
+    if (fill_rows != 0 && fill_rows != M) return fail(SGP_EINVAL, "sgp_build_rowsorted: fill_rows must be 0 or M");
     if (N >= (1ll << 31)) return fail(SGP_EOVERFLOW, "sgp_build_rowsorted: N does not fit 31 bits");
-    if (workspace_bytes < sgp_rowsort_workspace_bytes(N, d)) return fail(SGP_EINVAL, "sgp_build_rowsorted: workspace too small");
-    const int64_t total = N * (int64_t)(d + 1);
+    if (workspace_bytes < sgp_rowsort_workspace_bytes(N, d, fill_rows)) return fail(SGP_EINVAL, "sgp_build_rowsorted: workspace too small");
+    const int64_t total = N * (int64_t)(d + 1) + fill_rows;
+    if (total >= (1ll << 32) - 1) return fail(SGP_EOVERFLOW, "sgp_build_rowsorted: too many entries");
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     char *base = (char *)workspace;
     const size_t blk = al((size_t)total * 4);
@@ -436,11 +444,11 @@ extern "C" int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int6
     void *tmp = base + 4 * blk;
     size_t tmp_bytes = workspace_bytes - 4 * blk;
     cudaStream_t st = (cudaStream_t)stream;
-    sgp_rowsort_keys_kernel<<<grid_for(total, 256), 256, 0, st>>>((const int2 *)replay, total, ka, va);
+    sgp_rowsort_keys_kernel<<<grid_for(total, 256), 256, 0, st>>>((const int2 *)replay, total - fill_rows, fill_rows, ka, va);
     int rc = launch_ok("sgp_rowsort_keys_kernel");
     if (rc) return rc;
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ka, kb, va, vb, (int64_t)total, 0, bits_for((uint64_t)M), st));
-    const int64_t padded = sgp_rowsort_padded(N, d);
+    const int64_t padded = sgp_rowsort_padded(N, d, fill_rows);
     sgp_rowsort_fill_kernel<<<grid_for(padded, 256), 256, 0, st>>>((const int2 *)replay, kb, vb, total, padded, d + 1,
                                                                   (int2 *)ent, ent_row, seg_row);
     return launch_ok("sgp_rowsort_fill_kernel");
@@ -510,11 +518,12 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     }
 }
 
-extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_t N, int d, int64_t M, const float *src,
-                              int64_t lds, int L_src, float *values, int L, sgp_stream_t stream)
+extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
+                              const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream)
 {
     if (N == 0 || M == 0) return SGP_OK;
-    if (!ent || !seg_row || !src || !values || N < 0 || M < 0 || d < 1 || L_src < 1 || lds < L_src || L < L_src)
+    if (!ent || !seg_row || !src || !values || N < 0 || M < 0 || n_entries < 0 || n_entries % ROWSEG != 0 || L_src < 1 ||
+        lds < L_src || L < L_src)
         return fail(SGP_EINVAL, "sgp_splat_rows: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     static int seg_env = 0;   // tuning hook: SGP_ROWSEG=4|8|16 entries per thread
@@ -523,7 +532,7 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_
         seg_env = e ? atoi(e) : 8;
         if (seg_env != 4 && seg_env != 16) seg_env = 8;
     }
-    const int64_t n_seg = sgp_rowsort_padded(N, d) / seg_env;
+    const int64_t n_seg = n_entries / seg_env;
     auto al = [](const void *p, int bytes) { return ((uintptr_t)p % bytes) == 0; };
     // the lattice side decides the vector width; src is read channel by channel when it does not match it
     int vec = 1;

@@ -149,6 +149,7 @@ class Lattice:
                 check(lib.sgp_count_points(_ptr(table), cap, _ptr(slot_of), N, d, _ptr(ws), ws_bytes, _ptr(flags),
                                            C.byref(M), C.byref(fl), st))
                 self.M = int(M.value)
+                self._covers_all_rows = True      # every lattice point was created by one of these points
                 self.keys = torch.empty((self.M, d), dtype=torch.int16, device=dev)
                 check(lib.sgp_number_points(_ptr(table), cap, _ptr(slot_of), _ptr(self.greedy), _ptr(self.rank), N, d,
                                             _ptr(ws), self.M, _ptr(self.replay), _ptr(self.keys), st))
@@ -246,6 +247,7 @@ class Lattice:
                                               C.byref(m_add), C.byref(fl), st))
                 M_add = int(m_add.value)
             new.M = self.M + M_add
+            new._covers_all_rows = getattr(self, "_covers_all_rows", False)
             new.keys = torch.empty((new.M, d), dtype=torch.int16, device=dev)
             new.keys[:self.M].copy_(self.keys)
             if Nn > 0:
@@ -394,17 +396,31 @@ class Lattice:
 
     def _build_rows(self) -> None:
         """Point-vertices sorted by lattice row for the segmented-gather splat (csrc/sgp_tiles.cu, sgp_build_rowsorted):
-        ``ent {point | row-start flag, weight}`` and ``seg_row`` (lattice row of every fourth entry)."""
+        ``ent {point | row-start flag, weight}`` and ``seg_row`` (lattice row of every fourth entry).  The encoding needs
+        an entry in every lattice row: a lattice wrapped around a subset of the points (``from_arrays`` under point
+        sharding) gets one weightless filler entry per row."""
         lib = _capi.lib()
         dev, N, d, M = self.device, self.N, self.d, self.M
         st = _stream_ptr(dev)
-        padded = int(lib.sgp_rowsort_padded(N, d))
-        ws_bytes = int(lib.sgp_rowsort_workspace_bytes(N, d))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        ent = torch.empty((padded, 2), dtype=torch.int32, device=dev)
-        seg_row = torch.empty(padded // 4, dtype=torch.int32, device=dev)
-        check(lib.sgp_build_rowsorted(_ptr(self.replay), N, d, M, _ptr(ent), None, _ptr(seg_row), _ptr(ws), ws_bytes, st))
-        self.rows = {"ent": ent, "seg_row": seg_row}
+        total = N * (d + 1)
+
+        def build(fill):
+            n = int(lib.sgp_rowsort_padded(N, d, fill))
+            ws_bytes = int(lib.sgp_rowsort_workspace_bytes(N, d, fill))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            ent = torch.empty((n, 2), dtype=torch.int32, device=dev)
+            seg_row = torch.empty(n // 4, dtype=torch.int32, device=dev)
+            check(lib.sgp_build_rowsorted(_ptr(self.replay), N, d, M, fill, _ptr(ent), None, _ptr(seg_row), _ptr(ws),
+                                          ws_bytes, st))
+            return {"ent": ent, "seg_row": seg_row, "n": n, "entries": total + fill}
+
+        rows = build(0)
+        if not getattr(self, "_covers_all_rows", False):
+            # wrapped arrays: do the points touch every row?  (row starts = flags + the first entry)
+            starts = int((rows["ent"][:total, 0] < 0).sum()) + 1
+            if starts != M:
+                rows = build(M)
+        self.rows = rows
 
     def _sort_points(self) -> None:
         """Locality order of the points (csrc/sgp_tiles.cu, sgp_sort_points); the replay tables re-ordered with it are
@@ -491,7 +507,7 @@ class Lattice:
         accumulation order (stable sort), so the CSR form is those entries plus a pointer array."""
         if self.rows is None:
             self._build_rows()
-        total = self.N * (self.d + 1)
+        total = self.rows["entries"]
         starts = torch.nonzero(self.rows["ent"][:total, 0] < 0).flatten().to(torch.int32)   # row-start flags
         ends = torch.tensor([total], dtype=torch.int32, device=self.device)
         self.csr_ptr = torch.cat([torch.zeros(1, dtype=torch.int32, device=self.device), starts, ends]).contiguous()
@@ -572,8 +588,8 @@ class Lattice:
                 check(_capi.lib().sgp_splat_tiles(C.byref(tv), _ptr(src), src.stride(0), L, _ptr(values),
                                                   _stream_ptr(self.device)))
             elif mode == _capi.MODE_ROWS:
-                check(_capi.lib().sgp_splat_rows(_ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]), self.N, self.d,
-                                                 self.M, _ptr(src), src.stride(0), L, _ptr(values), L,
+                check(_capi.lib().sgp_splat_rows(_ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]), self.rows["n"],
+                                                 self.N, self.M, _ptr(src), src.stride(0), L, _ptr(values), L,
                                                  _stream_ptr(self.device)))
             else:
                 if mode == _capi.MODE_AUTO:
@@ -693,7 +709,8 @@ class Lattice:
             arr = self.groups["array"]
             v_out = self._view(self._table(False, True), None, exact)
             with torch.cuda.device(self.device):
-                check(lib.sgp_mvm_rows_groups(C.byref(v_out), _ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]), arr,
+                check(lib.sgp_mvm_rows_groups(C.byref(v_out), _ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]),
+                                              self.rows["n"], arr,
                                               len(arr), _ptr(src), src.stride(0), L, _fp(c), c.shape[0], _ptr(out),
                                               out.stride(0), _ptr(buf0), _ptr(buf1), Lv, st))
             return out
@@ -703,7 +720,7 @@ class Lattice:
                 tv = self._tiles_view(False)
                 check(lib.sgp_splat_tiles(C.byref(tv), _ptr(src), src.stride(0), L, _ptr(buf0), st))
             elif mode == _capi.MODE_ROWS:
-                check(lib.sgp_splat_rows(_ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]), self.N, self.d, self.M,
+                check(lib.sgp_splat_rows(_ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]), self.rows["n"], self.N, self.M,
                                          _ptr(src), src.stride(0), L, _ptr(buf0), Lv, st))
             else:
                 if mode == _capi.MODE_GATHER:

@@ -326,3 +326,28 @@ def test_extend_lazy_tables(sg, oracle):
     g.replay()
     torch.cuda.synchronize()
     assert np.linalg.norm(out.cpu().numpy().astype(np.float64) - want) <= 1e-5 * np.linalg.norm(want)
+
+
+def test_row_sorted_splat_on_a_point_subset_with_the_full_key_set(sg, oracle):
+    """A rank's share of the points under point sharding: lattice arrays of the full point set, replay of a subset, so
+    many lattice rows have no entry.  The row-sorted entries then carry one weightless filler per row
+    (sgp_build_rowsorted, fill_rows = M); splat, blur and slice must agree with the oracle's partial splat."""
+    x, v = make_inputs(6000, 6, 8, seed=77)
+    full = sg.Lattice(x.cuda(), RBF1)
+    lo, hi = 1500, 2600
+    part = sg.Lattice.from_arrays(RBF1, full.replay[lo:hi].contiguous(), full.keys, full.nbr, build_csr=True)
+    assert part.rows["entries"] == (hi - lo) * 7 + full.M            # fillers were needed
+    whole = sg.Lattice.from_arrays(RBF1, full.replay, full.keys, full.nbr)
+    assert whole.rows["entries"] == 6000 * 7                           # ... and are not when every row is touched
+    vd = v.cuda()[lo:hi].contiguous()
+    sp_rows = part.splat(vd, mode=4)
+    sp_atomic = part.splat(vd, mode=1)
+    sp_gather = part.splat(vd, mode=2)
+    O = oracle.OracleLattice(x.numpy(), np.asarray(RBF1, dtype=np.float32))
+    vz = np.zeros((6000, 8), dtype=np.float32)
+    vz[lo:hi] = v.numpy()[lo:hi]
+    _, sp_o, _ = O.mvm(vz, return_intermediates=True)
+    for got in (sp_rows, sp_atomic, sp_gather):
+        assert _rel(got.cpu().numpy(), sp_o) < REL_TOL
+    want = O.mvm(vz)[lo:hi]
+    assert _rel(part.mvm(vd).cpu().numpy(), want) < REL_TOL
