@@ -54,7 +54,7 @@ __device__ __forceinline__ uint64_t mix_u64(uint64_t h)
 // k being the first axis outside it.  Points of one class get equal hashes; distinct classes that collide are merely
 // processed together (harmless).
 __global__ void __launch_bounds__(256)
-sgp_group_hash_kernel(const int16_t *__restrict__ keys, int64_t M, int d, int j0, int j1,
+sgp_group_hash_kernel(const int16_t *__restrict__ keys, int64_t M, int d, int j0, int j1, int shift,
                       unsigned long long *__restrict__ hash, uint32_t *__restrict__ ids)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -76,7 +76,7 @@ sgp_group_hash_kernel(const int16_t *__restrict__ keys, int64_t M, int d, int j0
             h = mix_u64(h ^ (uint64_t)(uint32_t)diff);
         }
     }
-    hash[i] = h;
+    hash[i] = h >> shift;     // the top bits only: fewer radix passes (see group_hash_bits)
     ids[i] = (uint32_t)i;
 }
 
@@ -241,6 +241,17 @@ static int group_ws_layout(int64_t M, GroupWs *w)
     return SGP_OK;
 }
 
+// Bits of class hash that are sorted: log2(M) + 20, rounded up to whole 8-bit radix passes.  Two of at most M classes
+// then collide with probability below 2^-20 per class -- about one merged pair per million classes, and a merged
+// pair is merely processed together.  40 bits (5 passes instead of 8) at M = 4e5, 48 at M = 2.5e8.
+static int group_hash_bits(int64_t M)
+{
+    int lg = 0;
+    while ((1ll << lg) < M) ++lg;
+    int bits = (lg + 20 + 7) / 8 * 8;
+    return bits > 64 ? 64 : bits;
+}
+
 extern "C" size_t sgp_group_workspace_bytes(int64_t M)
 {
     GroupWs w;
@@ -266,10 +277,11 @@ extern "C" int sgp_group_prepare(const int16_t *keys, int64_t M, int d, int j0, 
     uint32_t *ids = (uint32_t *)(base + w.ids_a), *head = (uint32_t *)(base + w.head);
     uint32_t *small = (uint32_t *)(base + w.small);
     size_t cub_bytes = w.cub_bytes;
-    sgp_group_hash_kernel<<<grid_for(M, 256), 256, 0, st>>>(keys, M, d, j0, j1, ha, ids);
+    const int bits = group_hash_bits(M);
+    sgp_group_hash_kernel<<<grid_for(M, 256), 256, 0, st>>>(keys, M, d, j0, j1, 64 - bits, ha, ids);
     rc = launch_ok("sgp_group_hash_kernel");
     if (rc) return rc;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(base + w.cub, cub_bytes, ha, hb, ids, order, (int64_t)M, 0, 64, st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(base + w.cub, cub_bytes, ha, hb, ids, order, (int64_t)M, 0, bits, st));
     sgp_group_heads_kernel<<<grid_for(M, 256), 256, 0, st>>>(hb, M, head);
     rc = launch_ok("sgp_group_heads_kernel");
     if (rc) return rc;

@@ -359,7 +359,9 @@ class Lattice:
                 # ... or lengthen it while it still does and the batch-local neighbour table stays at most 48 bytes a
                 # row (it shares the CTA's shared memory with the values: longer tables cost occupancy)
                 max_axes = max(3, 48 // (4 * r))
-                while mx.value <= rows_limit and j1 <= d and j1 - j0 < max_axes:
+                # (one more axis at least doubles the largest class of a lattice this dense: do not pay for a trial that
+                # cannot fit)
+                while mx.value * 2 <= rows_limit and j1 <= d and j1 - j0 < max_axes:
                     trial = prepare(j0, j1 + 1)
                     if trial[3].value > rows_limit:
                         break
