@@ -318,6 +318,24 @@ int sgp_grad_contract(const float *filtered, int64_t ldp, const float *g, int64_
                       int first, int last, float *grad_x, int64_t ldgx, float *grad_src, int64_t ldgs,
                       sgp_stream_t stream);
 
+/* ---- batched conjugate gradients: the vector updates either side of the MVM ------------------------------
+ * The reference leaves the solve of (s K + noise I) X = B to GPyTorch (experiments/train_simplexgp.py:29-48).  One
+ * CG iteration on an [N, L] block of right-hand sides is one lattice MVM (KP = K P) followed by
+ *   sgp_cg_apply      AP = s*KP + noise*P in place on KP;  pAp[l] = sum_n P*AP
+ *   sgp_cg_update     alpha = rs/max(pAp,1e-30);  X += alpha*P;  R -= alpha*AP;  rs_new = sum_n R*R;
+ *                     beta = rs_new/max(rs,1e-30);  rs <- rs_new;  *done = all_l sqrt(rs_new[l])/bnorm[l] < tol
+ *   sgp_cg_direction  P = R + beta*P
+ * alpha_out / beta_out: device [L], this iteration's coefficients (rows of the Lanczos tridiagonals).  Blocks are
+ * device [N, L] fp32, row-major, no row padding; 1 <= L <= 256.  s, noise: device scalars.  scratch: device
+ * [sgp_cg_scratch_floats(L)] floats.  The dot products are summed in a fixed order (deterministic). */
+size_t sgp_cg_scratch_floats(int L);
+int sgp_cg_apply(float *AP, const float *P, const float *s, const float *noise, int64_t N, int L,
+                 float *pAp, float *scratch, sgp_stream_t stream);
+int sgp_cg_update(float *X, float *R, const float *P, const float *AP, float *rs, const float *pAp,
+                  const float *bnorm, float tol, int64_t N, int L, float *alpha_out, float *beta_out,
+                  int32_t *done, float *scratch, sgp_stream_t stream);
+int sgp_cg_direction(float *P, const float *R, const float *beta, int64_t N, int L, sgp_stream_t stream);
+
 /* ---- row-sorted splat ("segmented gather") -------------------------------------------------
  * The point-vertices sorted by lattice row, point-vertex order within a row (the reference's accumulation order),
  * padded with zero-weight entries to n_entries = sgp_rowsort_padded(N, d, fill_rows), a multiple of 16:

@@ -29,7 +29,7 @@ SYMBOLS = [
     "sgp_remap_replay",
     "sgp_blur_groups_channel_block", "sgp_blur_groups", "sgp_mvm_rows_groups", "sgp_sort_points_workspace_bytes", "sgp_sort_points",
     "sgp_permute_replay", "sgp_rowsort_workspace_bytes", "sgp_rowsort_padded", "sgp_build_rowsorted",
-    "sgp_splat_rows",
+    "sgp_splat_rows", "sgp_cg_scratch_floats", "sgp_cg_apply", "sgp_cg_update", "sgp_cg_direction",
 ]
 
 
@@ -199,6 +199,14 @@ def lib() -> C.CDLL:
     L.sgp_rowsort_padded.argtypes = [i64, i32, i64]
     L.sgp_build_rowsorted.restype = i32
     L.sgp_build_rowsorted.argtypes = [vp, i64, i32, i64, i64, vp, vp, vp, vp, sz, vp]
+    L.sgp_cg_scratch_floats.restype = sz
+    L.sgp_cg_scratch_floats.argtypes = [i32]
+    L.sgp_cg_apply.restype = i32
+    L.sgp_cg_apply.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp]
+    L.sgp_cg_update.restype = i32
+    L.sgp_cg_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_float, i64, i32, vp, vp, vp, vp, vp]
+    L.sgp_cg_direction.restype = i32
+    L.sgp_cg_direction.argtypes = [vp, vp, vp, i64, i32, vp]
     L.sgp_splat_rows.restype = i32
     L.sgp_splat_rows.argtypes = [vp, vp, i64, i64, i64, vp, i64, i32, vp, i32, vp]
     L.sgp_debug_division_mismatches.restype = i32

@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 SRC = [os.path.join(HERE, "sgp_lattice.cu"), os.path.join(HERE, "sgp_tiles.cu"),
-       os.path.join(HERE, "sgp_grad.cu"), os.path.join(HERE, "sgp_groups.cu")]
+       os.path.join(HERE, "sgp_grad.cu"), os.path.join(HERE, "sgp_groups.cu"),
+       os.path.join(HERE, "sgp_solver.cu")]
 HDR = [os.path.join(ROOT, "include", "sgp_lattice.h"), os.path.join(HERE, "sgp_common.cuh")]
 OUT = os.path.join(PKG, "libsgp_lattice.so")
 

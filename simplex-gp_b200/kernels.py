@@ -36,6 +36,15 @@ class SquareLazyLattice(LazyTensor):
     def _matmul(self, V):
         return LatticeFilterGeneral.apply(V, self.x, self.dkernel)
 
+    def lattice(self):
+        """The cached ``Lattice`` behind this operator (forward stencil), or ``None`` when ``x`` is not a float32 CUDA
+        matrix.  Solvers that do not need autograd drive it directly (``lattice().mvm(P, out=AP)``, ``capture``)
+        instead of paying for an autograd node per product."""
+        x = self.x
+        if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):
+            return None
+        return LatticeFilterGeneral.cache.get(x, self.dkernel.get_coeffs())
+
     def _size(self):
         return torch.Size((self.x.shape[-2], self.x.shape[-2]))
 

@@ -154,3 +154,57 @@ def test_experiment_harness_learns_on_toy_shape(sg):
     assert summary["test/best_rmse"] < 0.75          # targets are standardised: the constant predictor scores 1.0
     assert np.isfinite(summary["test/best_nll"])
     assert len(summary["lengthscale"]) == 3
+
+
+@pytest.mark.parametrize("n,L", [(5000, 11), (777, 1), (3000, 16), (1200, 37), (40, 256)])
+def test_cuda_cg_sweeps_match_tensor_expressions(sg, n, L):
+    """batched_cg on the sweeps of csrc/sgp_solver.cu against the same iteration written with tensor expressions, on a
+    dense SPD operator (so that only the vector updates differ)."""
+    from simplex_gp_b200 import gp
+    g = torch.Generator().manual_seed(n + L)
+    Q = torch.randn(n, 64, generator=g).cuda()
+    Kmat = Q @ Q.T / 64
+    B = torch.randn(n, L, generator=g).cuda()
+    s, noise = torch.tensor(0.7, device="cuda"), torch.tensor(0.3, device="cuda")
+    matmul = lambda V: Kmat @ V
+    A = lambda V: s * matmul(V) + noise * V
+    X0, a0, b0 = gp.batched_cg(A, B, tol=1e-5, max_iter=200)
+    X1, a1, b1 = gp.batched_cg(A, B, tol=1e-5, max_iter=200, matmul=matmul, scale=s, shift=noise)
+    assert 0 <= a1.shape[0] - a0.shape[0] <= 2 or abs(a0.shape[0] - a1.shape[0]) <= 2   # the flag is read one iteration late
+    k = min(a0.shape[0], a1.shape[0]) - 1
+    assert float((X0 - X1).norm() / X0.norm()) < 1e-4
+    early = min(max(k, 1), 4)      # the coefficient histories of fp32 CG drift apart in the late iterations
+    torch.testing.assert_close(a1[:early], a0[:early], rtol=2e-3, atol=1e-6)
+    torch.testing.assert_close(b1[:early], b0[:early], rtol=2e-3, atol=1e-6)
+    torch.testing.assert_close(a1[: max(k, 1)], a0[: max(k, 1)], rtol=0.1, atol=1e-3)
+    resid = (A(X1) - B).norm(dim=0) / B.norm(dim=0)
+    assert float(resid.max()) < 5e-5
+    # a single iteration (max_iter = 1) and an immediately converged system
+    X2, a2, b2 = gp.batched_cg(A, B, tol=1e-5, max_iter=1, matmul=matmul, scale=s, shift=noise)
+    assert a2.shape == (1, L)
+    X3, a3, _ = gp.batched_cg(A, B, tol=1e9, max_iter=50, matmul=matmul, scale=s, shift=noise)
+    assert a3.shape[0] <= 2
+
+
+def test_cg_on_the_lattice_operator_uses_the_lattice_directly(sg):
+    """mll_cg through the kernel module: the CUDA sweeps drive the cached Lattice directly and agree with the tensor-expression iteration over the autograd operator."""
+    from simplex_gp_b200 import gp
+    x, _ = make_inputs(6000, 3, 1, seed=12)
+    xd = x.cuda()
+    y = torch.sin(xd[:, 0]) + 0.1 * torch.randn(6000, device="cuda")
+    kernel = sg.RBFLattice(ard_num_dims=3, order=1).cuda()
+    op = kernel(xd)
+    assert op.lattice() is not None
+    mu, s, noise = torch.tensor(0.1, device="cuda"), torch.tensor(0.9, device="cuda"), torch.tensor(0.2, device="cuda")
+    probes = torch.randn(6000, 10, generator=torch.Generator().manual_seed(3)).sign().cuda()
+    with torch.no_grad():
+        B = torch.cat([(y - mu).unsqueeze(-1), probes], 1)
+        A = lambda V: s * op.matmul(V) + noise * V
+        X0, a0, _ = gp.batched_cg(A, B, tol=1e-4, max_iter=200)
+        X1, a1, _ = gp.batched_cg(A, B, tol=1e-4, max_iter=200, matmul=op.matmul, scale=s, shift=noise)
+    # ~120 iterations on this system: the count moves by a few with the rounding of the dot products
+    assert a1.shape[0] > 3 and abs(a0.shape[0] - a1.shape[0]) <= max(2, a0.shape[0] // 10)
+    assert float((X0 - X1).norm() / X0.norm()) < 1e-3
+    v0, _ = gp.mll_cg(lambda V: op.matmul(V), y, mu, s, noise, probes=probes, tol=1e-4)   # a plain function: no fast path
+    v1, _ = gp.mll_cg(op.matmul, y, mu, s, noise, probes=probes, tol=1e-4)
+    assert abs(v0 - v1) < 2e-3 * max(abs(v0), 1.0)
