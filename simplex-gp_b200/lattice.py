@@ -64,6 +64,9 @@ def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+_GROUP_HINTS = {}   # (d, order, rows per CTA) -> axis-range lengths of the last blur-group build of that shape
+
+
 class Lattice:
     """Permutohedral lattice of the points ``x[N, d]`` (already divided by the lengthscale).
 
@@ -349,8 +352,14 @@ class Lattice:
             return order_of, pos, cstart, mx
 
         adaptive = group_axes is None or int(group_axes) <= 0
+        # the ranges the last lattice of this shape ended up with: successive hyper-parameter steps build almost the
+        # same lattice, and on sparse high-dimensional lattices finding a 10-axis range one axis at a time costs more
+        # than everything else in the build (16 sorts at d = 18)
+        hint_key = (d, r, rows_limit)
+        hints = _GROUP_HINTS.get(hint_key, []) if adaptive else []
         while j0 <= d:
-            j1 = min(j0 + (3 if adaptive else max(1, int(group_axes))), d + 1)
+            start = hints[len(groups)] if len(groups) < len(hints) else 3
+            j1 = min(j0 + (start if adaptive else max(1, int(group_axes))), d + 1)
             order_of, pos, cstart, mx = prepare(j0, j1)
             while mx.value > rows_limit and j1 - j0 > 1:      # shorten the range until its largest class fits
                 j1 -= 1
@@ -395,6 +404,8 @@ class Lattice:
                                      g["batch_begin"].data_ptr(),
                                      g["src"].data_ptr(), g["lnb"].data_ptr())
         self.groups = {"list": groups, "array": arr, "final_pos": prev_pos}
+        if adaptive:
+            _GROUP_HINTS[hint_key] = [g["j1"] - g["j0"] for g in groups]
 
     def _build_rows(self) -> None:
         """Point-vertices sorted by lattice row for the segmented-gather splat (csrc/sgp_tiles.cu, sgp_build_rowsorted):
