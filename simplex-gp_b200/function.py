@@ -156,18 +156,20 @@ def lattice_filter_grad(lat: Lattice, g: torch.Tensor, v: torch.Tensor, x: torch
     chunk = max(1, min(int(chunk), L))
     width = per * chunk
     ldp = (width + 3) // 4 * 4
-    packed = torch.zeros((N, ldp), dtype=torch.float32, device=dev)
+    packed = torch.empty((N, ldp), dtype=torch.float32, device=dev)
     filtered = torch.empty((N, ldp), dtype=torch.float32, device=dev)
     st = _stream_ptr(dev)
     with torch.cuda.device(dev):
         l0 = 0
         while l0 < L:
             nl = min(chunk, L - l0)
-            if nl < chunk:
-                packed.zero_()
+            # a short last pass filters only its own channels (the first ceil4(per * nl) columns of the buffers, same
+            # row stride); sgp_grad_pack zero-fills up to the multiple of four
+            w = (per * nl + 3) // 4 * 4
+            pk, fl = (packed, filtered) if w == ldp else (packed[:, :w], filtered[:, :w])
             check(lib.sgp_grad_pack(_ptr(g), g.stride(0), _ptr(v), v.stride(0), _ptr(x), x.stride(0), N, d, l0, nl,
                                     _ptr(packed), ldp, st))
-            lat.mvm(packed, out=filtered, coeffs=c)
+            lat.mvm(pk, out=fl, coeffs=c)
             check(lib.sgp_grad_contract(_ptr(filtered), ldp, _ptr(g), g.stride(0), _ptr(v), v.stride(0), _ptr(x),
                                         x.stride(0), N, d, l0, nl, int(l0 == 0), int(l0 + nl >= L), _ptr(grad_x),
                                         grad_x.stride(0), _ptr(wg), wg.stride(0) if wg is not None else 0, st))
