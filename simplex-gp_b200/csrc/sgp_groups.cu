@@ -105,13 +105,13 @@ sgp_group_pos_kernel(const uint32_t *__restrict__ order, const uint32_t *__restr
 // streams class_start through a window of PACK_WINDOW entries (coalesced loads by all threads), and the walker hops
 // inside the window at shared-memory latency (~30 cycles a hop instead of a ~500 ns global round trip).
 // out[0] = n_batches, out[1] = rows of the largest batch, out[2] = error flag.
-#define PACK_WINDOW 10240
+#define PACK_WINDOW 51200      /* 200 KB of dynamic shared memory: 8 window loads at M = 4e5 instead of 40 */
 #define PACK_THREADS 1024
 __global__ void __launch_bounds__(PACK_THREADS)
 sgp_group_pack_kernel(const uint32_t *__restrict__ class_start, int64_t M, int64_t cap, int64_t max_batches,
                       uint32_t *__restrict__ batch_begin, uint32_t *__restrict__ out)
 {
-    __shared__ uint32_t win[PACK_WINDOW];
+    extern __shared__ uint32_t win[];   // PACK_WINDOW entries
     __shared__ long long s_begin, s_nb, s_w0;
     __shared__ uint32_t s_max, s_err;
     if (threadIdx.x == 0) { s_begin = 0; s_nb = 0; s_max = 0; s_err = 0; s_w0 = 0; }
@@ -324,7 +324,14 @@ extern "C" int sgp_group_finalize(const int32_t *nbr, const int16_t *keys, int d
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t *small = (uint32_t *)((char *)workspace + w.small);
     CUDA_TRY(cudaMemsetAsync(small, 0, 32, st));
-    sgp_group_pack_kernel<<<1, PACK_THREADS, 0, st>>>(class_start, M, cap, max_batches, batch_begin, small);
+    static bool pack_attr_set = false;
+    if (!pack_attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(sgp_group_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(PACK_WINDOW * sizeof(uint32_t))));
+        pack_attr_set = true;
+    }
+    sgp_group_pack_kernel<<<1, PACK_THREADS, PACK_WINDOW * sizeof(uint32_t), st>>>(class_start, M, cap, max_batches,
+                                                                                   batch_begin, small);
     rc = launch_ok("sgp_group_pack_kernel");
     if (rc) return rc;
     uint32_t host[4] = {0, 0, 0, 0};
