@@ -31,6 +31,22 @@ for (N, d, L, c) in ((3000, 8, 16, [0.34608543, 1.0, 0.34608543]), (1500, 5, 3, 
         def get_deriv_coeffs(self):
             return torch.tensor(c)
 
+    # lattice extension (sgp_hash_seed / sgp_hash_extend / sgp_*_extension) and the point-subset row tables (fillers)
+    k = N // 2
+    ext = sg.Lattice(x[:k].contiguous(), c).extend(x[k:].contiguous())
+    assert torch.equal(ext.keys, lat.keys) and torch.equal(ext.replay, lat.replay)
+    part = sg.Lattice.from_arrays(c, lat.replay[: k // 2].contiguous(), lat.keys, lat.nbr)
+    part.mvm(v[: k // 2].contiguous())
+    # CG sweeps (csrc/sgp_solver.cu) on the lattice operator
+    from simplex_gp_b200 import gp
+    kern = sg.RBFLattice(ard_num_dims=d, order=1).cuda() if len(c) == 3 else sg.MaternLattice(nu=1.5, order=2).cuda()
+    op = kern(x)
+    s_, n_ = torch.tensor(0.8, device="cuda"), torch.tensor(0.5, device="cuda")
+    with torch.no_grad():
+        X, al, be = gp.batched_cg(lambda V: s_ * op.matmul(V) + n_ * V, v, tol=1e-3, max_iter=50, matmul=op.matmul,
+                                  scale=s_, shift=n_)
+    assert torch.isfinite(X).all() and al.shape[0] >= 1
+
     xr = x.clone().requires_grad_(True)
     vr = v.clone().requires_grad_(True)
     sg.LatticeFilterGeneral.apply(vr, xr, KF()).sum().backward()
