@@ -33,6 +33,7 @@ WORKLOADS = {
     # name: (N, d, L, kernel, order)   -- SURVEY.md section 8: config A is the metric's configuration
     "A": dict(N=1_000_000, d=8, L=16, kernel="rbf", order=1),
     # the other BASELINE.json configurations: parity-test cases, timed for information only (--workload)
+    "A1": dict(N=1_000_000, d=8, L=1, kernel="rbf", order=1),   # configs[1]: the single-RHS MVM
     "B": dict(N=16_600, d=18, L=11, kernel="rbf", order=1),
     "C": dict(N=2_050_000, d=11, L=16, kernel="matern1.5", order=2),
     "D10": dict(N=1_000_000, d=24, L=4, kernel="matern1.5", order=3),

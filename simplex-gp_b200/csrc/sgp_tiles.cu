@@ -462,7 +462,7 @@ template <int VEC, int SEG, bool RAGGED>
 __global__ void __launch_bounds__(256)
 sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ seg_row, int64_t n_seg,
                       const float *__restrict__ src, int64_t lds, int L, int L_src, int chunks, int64_t prefetch_bytes,
-                      float *__restrict__ values)
+                      bool aggregate, float *__restrict__ values)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // Optional (off by default, measured without effect on B200): the first blocks ask L2 for the whole of src with
@@ -473,6 +473,7 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     }
     pdl_launch_dependents();
     const int64_t seg = tid / chunks;
+    const unsigned mask = __ballot_sync(0xffffffffu, seg < n_seg);   // the lanes that take part in the shuffles below
     if (seg >= n_seg) return;
     const int c0 = (int)(tid - seg * chunks) * VEC;
     int2 e[SEG];
@@ -503,19 +504,44 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     Vec<VEC> acc;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
+    // A thread whose SEG entries all belong to one lattice row ("single") does not reduce into memory by itself: the
+    // most-touched rows span hundreds of consecutive segments (1250 at the centre of the metric lattice), and that
+    // many reductions to one address serialise in L2.  Singles of the same row and channel chunk that sit in the same
+    // warp are summed with shuffles first and the first of them issues one reduction.
+    bool single = aggregate;
+#pragma unroll
+    for (int i = 1; i < SEG; ++i) single = single && !(e[i].x < 0);
     pdl_wait();   // the lattice values are zeroed (and last read) by the stream's previous work
 #pragma unroll
     for (int i = 0; i < SEG; ++i) {
         const float w = __int_as_float(e[i].y);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc.v[k] = __fmaf_rn(w, v[i].v[k], acc.v[k]);
-        if (i == SEG - 1 || e[i + 1].x < 0) {      // the next entry starts the next lattice row
+        if ((i == SEG - 1 && !single) || (i < SEG - 1 && e[i + 1].x < 0)) {      // the next entry starts the next lattice row
             acc.red(values + (int64_t)row * L + c0);
             ++row;
 #pragma unroll
             for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
         }
     }
+    if (!aggregate) return;
+    // segmented sum over the lanes lane, lane + chunks, lane + 2 chunks, ... (same channel chunk, consecutive segments)
+    const int lane = threadIdx.x & 31;
+    const int key = single ? row : -1 - lane;      // non-singles never match anybody
+    const int prev_key = __shfl_up_sync(mask, key, chunks);
+    const bool prev_there = lane >= chunks && ((mask >> (lane - chunks)) & 1u);
+    if (__any_sync(mask, single && prev_there && prev_key == key)) {
+        for (int step = chunks; step < 32; step <<= 1) {
+            const int other_key = __shfl_down_sync(mask, key, step);
+            const bool take = single && lane + step < 32 && ((mask >> (lane + step)) & 1u) && other_key == key;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const float y = __shfl_down_sync(mask, acc.v[k], step);
+                if (take) acc.v[k] += y;
+            }
+        }
+    }
+    if (single && !(prev_there && prev_key == key)) acc.red(values + (int64_t)row * L + c0);
 }
 
 extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
@@ -548,14 +574,25 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_
         pref_env = e ? atoi(e) : 0;
     }
     const int64_t prefetch_bytes = pref_env ? (int64_t)N * lds * (int64_t)sizeof(float) : 0;
+    // warp-level aggregation of whole-segment runs: lanes l, l + chunks, l + 2 chunks, ... hold the same channel chunk of
+    // consecutive segments
+    static int agg_env = -1;    // tuning hook: SGP_SPLAT_AGG=0 disables
+    if (agg_env < 0) {
+        const char *e = getenv("SGP_SPLAT_AGG");
+        agg_env = e ? atoi(e) : 1;
+    }
+    // Measured at the metric shape: 1 column 55 -> 43 us, 2 columns 54 -> 46, 4 columns 57 -> 52 (one or two chunks: up to
+    // 32 / 16 segments of a row meet in a warp); neutral at 12 columns, 2 us slower at 16 (8 segments per warp do not pay
+    // for the shuffles), so it is used for one or two chunks only.
+    const bool aggregate = agg_env && chunks <= 2;
     cudaError_t launch_err = cudaSuccess;
 #define SGP_ROWS_LAUNCH(VV, SS)                                                                                        \
     launch_err = ragged ? sgp_launch_pdl(sgp_splat_rows_kernel<VV, SS, true>, dim3(grid_for(work, 256)), dim3(256), 0,  \
                                          st, (const int2 *)ent, seg_row, n_seg, src, lds, L, L_src, chunks,            \
-                                         prefetch_bytes, values)                                                      \
+                                         prefetch_bytes, aggregate, values)                                           \
                         : sgp_launch_pdl(sgp_splat_rows_kernel<VV, SS, false>, dim3(grid_for(work, 256)), dim3(256), 0, \
                                          st, (const int2 *)ent, seg_row, n_seg, src, lds, L, L_src, chunks,            \
-                                         prefetch_bytes, values)
+                                         prefetch_bytes, aggregate, values)
 #define SGP_ROWS_SEG(VV)                                                                                               \
     do {                                                                                                               \
         if (seg_env == 4) SGP_ROWS_LAUNCH(VV, 4);                                                                      \
