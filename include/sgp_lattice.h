@@ -293,6 +293,7 @@ int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64_t M, int o
 
 /* The production chain in one call: sgp_splat_rows -> sgp_blur_groups -> sgp_slice.  slice_view->replay addresses
  * the lattice values in the order the last group stage leaves them (sgp_permute_replay with that stage's pos);
+ * ent / seg_row / n_entries: the row-sorted entries of sgp_build_rowsorted (n_entries = sgp_rowsort_padded(...));
  * buf0 / buf1: device [M, Lv] scratch, Lv = L or L rounded up to a multiple of 4 (see sgp_slice). */
 int sgp_mvm_rows_groups(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
                         int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src, int64_t lds, int L,
