@@ -8,22 +8,27 @@
  * (pybind11 function exported by gpytorch_lattice_kernel/cpp/lattice.cpp:6-16 and
  * gpytorch_lattice_kernel/cuda/permutohedral_cuda.cpp:12-22 of the reference, called
  * from gpytorch_lattice_kernel/bilateral_kernel.py:95,111,119).  The reference rebuilds
- * the lattice inside every call; here the stages are separate entry points so that a
- * lattice is built once per hyper-parameter step and reused by every MVM, and
- * sgp_filter_* keeps the one-call form.
+ * the lattice inside every call.  Two forms are exported:
+ *   - sgp_filter / sgp_filter_host (end of this file): the one-call form, same semantics
+ *     as the reference's filter -- build, one product, nothing kept;
+ *   - the stage entry points, so that a lattice is built once per hyper-parameter step and
+ *     reused by every MVM of a solve (what sgp_filter itself is made of).
  *
  * Conventions
  *   - plain C, no torch types: raw pointers, sizes, and a cudaStream_t passed as void*.
  *   - every pointer documented "device" is device memory owned by the caller (PyTorch's
- *     caching allocator in the Python host); the library never allocates device memory
- *     except inside sgp_filter_host, which owns a private scratch pool.
+ *     caching allocator in the Python host); the library never allocates device memory:
+ *     entry points that need scratch take a caller-provided workspace and have a
+ *     *_workspace_bytes companion.
  *   - every function returns an int status: 0 = OK, negative = error; the message of
  *     the last error on the calling thread is available from sgp_last_error().
  *     Nothing calls exit() or throws across the boundary (the reference's CUDA path
  *     exits the process on a CUDA error, permutohedral_cuda_kernel.cu:24-32).
- *   - all launches go to the given stream and are asynchronous; the only host
- *     synchronisation is inside sgp_count_points (the caller needs M to size the
- *     lattice arrays) and sgp_filter_host.
+ *   - all launches go to the given stream and are asynchronous.  The entry points that
+ *     synchronise it say so: the ones that return a count the host must size arrays with
+ *     (sgp_count_points, sgp_count_extension, sgp_group_prepare, sgp_group_finalize,
+ *     sgp_tiles_prepare, sgp_tiles_finalize), sgp_filter (through sgp_count_points) and
+ *     sgp_filter_host (which returns with the result in host memory).
  *   - fp32 values (the reference CPU path is fp32-only, permutohedral.h:12,17),
  *     int16 keys, int8 ranks, int32 lattice indices.
  */
@@ -37,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SGP_ABI_VERSION 3
+#define SGP_ABI_VERSION 4
 
 #define SGP_OK 0
 #define SGP_EINVAL (-1)       /* bad argument */
@@ -45,7 +50,7 @@ extern "C" {
 #define SGP_EOVERFLOW (-3)    /* hash table full or an index exceeds 32 bits */
 #define SGP_ECUDA (-4)        /* CUDA runtime error */
 #define SGP_EUNSUPPORTED (-5) /* shape outside what the kernels are built for */
-#define SGP_ENOMEM (-6)       /* host or scratch allocation failed (sgp_filter_host only) */
+#define SGP_ENOMEM (-6)       /* the caller's workspace was sized for fewer lattice points than the lattice has */
 
 #define SGP_MAX_DIM 126   /* rank is a signed char in the reference (permutohedral.h:354) */
 #define SGP_MAX_ORDER 7
@@ -359,6 +364,22 @@ int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int64_t M, int6
 int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
                    const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream);
 
+/* ---- splat and slice with TMA-prefetched index streams (the production kernels; simplex-gp_b200/csrc/sgp_ring.cu) ----
+ * Same contracts as sgp_splat_rows / sgp_slice, which forward here unless the environment says SGP_RING=0 or the shape
+ * is outside what a warp covers (more than 32 channel chunks, a permuted or transposed replay table, d > 63).
+ * Persistent warps stream the row-sorted entries / the replay table into shared-memory rings with cp.async.bulk +
+ * mbarrier; sgp_splat_rows_ring writes every lattice row that lies inside one warp tile with a plain store and zeroes
+ * (then reduces into) only the rows that cross a tile boundary -- `values` is NOT memset. */
+int sgp_ring_enabled(void);        /* SGP_RING (default 1) */
+int sgp_ring_splat_enabled(void);  /* ... and SGP_RING_SPLAT (default 0: measured slower) */
+int sgp_ring_slice_enabled(void);  /* ... and SGP_RING_SLICE (default 1) */
+int sgp_splat_ring_supported(const float *values, int L);
+int sgp_slice_ring_supported(const sgp_lattice_view *lat, const float *values, int L);
+int sgp_splat_rows_ring(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
+                        const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream);
+int sgp_slice_ring(const sgp_lattice_view *lat, const float *values, int L, float *out, int64_t ldo, int L_out,
+                   sgp_stream_t stream);
+
 /* ---- locality order of the points --------------------------------------------------------
  * perm (device [N]): the points in lexicographic order of their remainder-0 lattice point, so that points sharing
  * lattice vertices are adjacent.  A replay table re-ordered with sgp_permute_replay plus sgp_lattice_view.perm makes
@@ -370,6 +391,38 @@ int sgp_sort_points(const int16_t *greedy, int64_t N, int d, uint32_t *perm, voi
  * weight bits}; perm and pos may be NULL */
 int sgp_permute_replay(const int32_t *replay, const uint32_t *perm, const uint32_t *pos, int64_t N, int d,
                        int transposed, int32_t *replay_out, sgp_stream_t stream);
+
+/* ---- the reference operator in one call --------------------------------------------------------
+ *
+ *     out[N, L] = filter(src[N, L], ref[N, d], coeffs[2r+1])
+ *
+ * exactly what gpytorch_lattice_kernel/cpp/lattice.cpp:6-16 and cuda/permutohedral_cuda.cpp:12-22 export:
+ * the lattice of `ref` (positions already divided by the lengthscale) is built, `src` is splatted, blurred
+ * along the d+1 axes with the stencil `coeffs` (HOST pointer, k = 2r+1 values) and sliced; nothing is kept
+ * (permutohedral.h:259-340).  Values are those of the stage entry points with the fused-multiply-add
+ * arithmetic (1e-7 relative from the reference's).
+ *
+ *   sgp_filter       src / ref / out are DEVICE pointers with leading dimensions lds / ldx / ldo (elements);
+ *                    asynchronous on `stream` apart from the one synchronisation that fetches the number of
+ *                    lattice points M.
+ *   sgp_filter_host  src / ref / out are HOST pointers (pinned memory is copied asynchronously, pageable memory
+ *                    through the driver's staging); the uploads, the filter and the download run inside and the
+ *                    call returns with `out` complete.  The RHS block is uploaded on a second stream while the
+ *                    lattice is being built.
+ *
+ * workspace: device memory, 256-byte aligned, at least sgp_filter[_host]_workspace_bytes(N, d, L, r, M_max)
+ * bytes.  M_max is the caller's bound on the number of lattice points the workspace must hold (M_max <= 0 or
+ * M_max > N(d+1): the worst case N(d+1), e.g. 9e6 x (72 B neighbour table + 2 x 4L B values) at N = 1M, d = 8).
+ * *M_out (may be NULL) receives the actual M; if it exceeds M_max the call fails with SGP_ENOMEM and may be
+ * repeated with a workspace sized for *M_out. */
+size_t sgp_filter_workspace_bytes(int64_t N, int d, int L, int order, int64_t M_max);
+size_t sgp_filter_host_workspace_bytes(int64_t N, int d, int L, int order, int64_t M_max);
+int sgp_filter(const float *src, int64_t lds, const float *ref, int64_t ldx, const float *coeffs, int k,
+               int64_t N, int L, int d, float *out, int64_t ldo, void *workspace, size_t workspace_bytes,
+               int64_t M_max, int64_t *M_out, sgp_stream_t stream);
+int sgp_filter_host(const float *src_host, int64_t lds, const float *ref_host, int64_t ldx, const float *coeffs,
+                    int k, int64_t N, int L, int d, float *out_host, int64_t ldo, void *workspace,
+                    size_t workspace_bytes, int64_t M_max, int64_t *M_out, sgp_stream_t stream);
 
 /* Test hook: number of fp32 bit patterns a in [lo, lo+count) for which the division-by-constant
  * used inside sgp_slice differs from the IEEE division a / sgp_slice_divisor(d).  Must be 0. */

@@ -12,6 +12,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libsgp_lattice.so")
 
 SGP_OK = 0
+SGP_ENOMEM = -6
 SGP_SPLAT_AUTO, SGP_SPLAT_ATOMIC, SGP_SPLAT_GATHER = 0, 1, 2
 MODE_AUTO, MODE_ATOMIC, MODE_GATHER, MODE_TILES, MODE_ROWS = 0, 1, 2, 3, 4   # Lattice.mvm(mode=...)
 SGP_MAX_DIM = 126
@@ -30,6 +31,8 @@ SYMBOLS = [
     "sgp_blur_groups_channel_block", "sgp_blur_groups", "sgp_mvm_rows_groups", "sgp_sort_points_workspace_bytes", "sgp_sort_points",
     "sgp_permute_replay", "sgp_rowsort_workspace_bytes", "sgp_rowsort_padded", "sgp_build_rowsorted",
     "sgp_splat_rows", "sgp_cg_scratch_floats", "sgp_cg_apply", "sgp_cg_update", "sgp_cg_direction",
+    "sgp_ring_enabled", "sgp_ring_splat_enabled", "sgp_ring_slice_enabled", "sgp_splat_ring_supported", "sgp_slice_ring_supported", "sgp_splat_rows_ring", "sgp_slice_ring",
+    "sgp_filter_workspace_bytes", "sgp_filter_host_workspace_bytes", "sgp_filter", "sgp_filter_host",
 ]
 
 
@@ -209,10 +212,27 @@ def lib() -> C.CDLL:
     L.sgp_cg_direction.argtypes = [vp, vp, vp, i64, i32, vp]
     L.sgp_splat_rows.restype = i32
     L.sgp_splat_rows.argtypes = [vp, vp, i64, i64, i64, vp, i64, i32, vp, i32, vp]
+    for fn in (L.sgp_ring_enabled, L.sgp_ring_splat_enabled, L.sgp_ring_slice_enabled):
+        fn.restype = i32
+        fn.argtypes = []
+    L.sgp_splat_ring_supported.restype = i32
+    L.sgp_splat_ring_supported.argtypes = [vp, i32]
+    L.sgp_slice_ring_supported.restype = i32
+    L.sgp_slice_ring_supported.argtypes = [pv, vp, i32]
+    L.sgp_splat_rows_ring.restype = i32
+    L.sgp_splat_rows_ring.argtypes = [vp, vp, i64, i64, i64, vp, i64, i32, vp, i32, vp]
+    L.sgp_slice_ring.restype = i32
+    L.sgp_slice_ring.argtypes = [pv, vp, i32, vp, i64, i32, vp]
+    for fn in (L.sgp_filter_workspace_bytes, L.sgp_filter_host_workspace_bytes):
+        fn.restype = sz
+        fn.argtypes = [i64, i32, i32, i32, i64]
+    for fn in (L.sgp_filter, L.sgp_filter_host):
+        fn.restype = i32
+        fn.argtypes = [vp, i64, vp, i64, fp, i32, i64, i32, i32, vp, i64, vp, sz, i64, C.POINTER(i64), vp]
     L.sgp_debug_division_mismatches.restype = i32
     L.sgp_debug_division_mismatches.argtypes = [i32, C.c_uint32, C.c_uint32, vp, vp]
-    if L.sgp_abi_version() != 3:
-        raise RuntimeError(f"{LIB_PATH}: ABI version {L.sgp_abi_version()} != 3, rebuild the library")
+    if L.sgp_abi_version() != 4:
+        raise RuntimeError(f"{LIB_PATH}: ABI version {L.sgp_abi_version()} != 4, rebuild the library")
     _lib = L
     return L
 

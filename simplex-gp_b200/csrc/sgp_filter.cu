@@ -1,0 +1,239 @@
+// sgp_filter.cu -- the reference's native operator in ONE call across the C ABI (B200, sm_100a).
+//
+//     filter(src[N,L], ref[N,d], coeffs[2r+1]) -> out[N,L]
+//
+// is what gpytorch_lattice_kernel/cpp/lattice.cpp:6-16 (CPU tensors) and cuda/permutohedral_cuda.cpp:12-22 (CUDA
+// tensors) export and bilateral_kernel.py:95,111,119 calls: the lattice of `ref` is built, `src` is splatted, blurred
+// along the d+1 axes and sliced, and everything is thrown away again (permutohedral.h:259-340).  sgp_filter is that
+// call on device pointers, sgp_filter_host the same on host pointers (the copies ride inside); both run the stage entry
+// points of this library in the order a host would: sgp_build_points -> sgp_hash_insert -> sgp_count_points (the one
+// host synchronisation: M sizes everything after it) -> sgp_number_points -> sgp_build_neighbours -> sgp_splat ->
+// sgp_blur -> sgp_slice.  One product per lattice, so the tables that only pay off over many products (blur groups,
+// row-sorted entries) are not built: atomic scatter splat, one blur launch per axis, TMA-ring slice.
+//
+// The library still allocates no device memory: the caller passes one workspace sized by sgp_filter_workspace_bytes.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "sgp_common.cuh"
+#include "sgp_lattice.h"
+
+#define fail sgp_fail
+
+namespace {
+
+struct FilterWs {
+    // phase 1 only (dead once the neighbour table exists) -- the blur buffers reuse this space
+    size_t greedy, rank, slot_of, number, table;
+    // alive until the product is done
+    size_t replay, flags, keys, nbr;
+    size_t buf0, buf1;
+    // host variant: staged operands
+    size_t ref, src, out;
+    size_t bytes;
+    int64_t cap, M_max;
+    size_t number_bytes;
+    int Lv;
+};
+
+inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int filter_layout(int64_t N, int d, int L, int order, int64_t M_max, bool host, FilterWs *w)
+{
+    if (N < 0 || d < 1 || d > SGP_MAX_DIM || L < 1 || order < 0 || order > SGP_MAX_ORDER)
+        return fail(SGP_EINVAL, "sgp_filter: bad shape (N=%lld d=%d L=%d order=%d)", (long long)N, d, L, order);
+    const int64_t total = N * (int64_t)(d + 1);
+    if ((double)N * (double)(d + 1) >= 4294967295.0) return fail(SGP_EOVERFLOW, "sgp_filter: N*(d+1) does not fit 32 bits");
+    if (M_max <= 0 || M_max > total) M_max = total;
+    w->M_max = M_max;
+    w->cap = sgp_hash_capacity(total);
+    w->number_bytes = sgp_number_workspace_bytes(N, d);
+    w->Lv = L;
+    size_t o = 0;
+    // persistent part
+    w->replay = o; o += al256((size_t)total * 8);
+    w->flags = o; o += 256;
+    w->keys = o; o += al256((size_t)M_max * d * 2);
+    w->nbr = o; o += al256((size_t)(d + 1) * M_max * 2 * order * 4);
+    if (host) {
+        w->ref = o; o += al256((size_t)N * d * 4);
+        w->src = o; o += al256((size_t)N * L * 4);
+        w->out = o; o += al256((size_t)N * L * 4);
+    } else {
+        w->ref = w->src = w->out = 0;
+    }
+    // phase 1 / phase 2 share the rest
+    const size_t base = o;
+    size_t a = base;
+    w->greedy = a; a += al256((size_t)total * 2);
+    w->rank = a; a += al256((size_t)total);
+    w->slot_of = a; a += al256((size_t)total * 4);
+    w->number = a; a += al256(w->number_bytes);
+    w->table = a; a += al256((size_t)w->cap * 8);
+    size_t b = base;
+    w->buf0 = b; b += al256((size_t)M_max * L * 4);
+    w->buf1 = b; b += al256((size_t)M_max * L * 4);
+    w->bytes = a > b ? a : b;
+    return SGP_OK;
+}
+
+// one side stream per device for the host variant's second upload (created on first use, never destroyed)
+cudaStream_t copy_stream(int dev)
+{
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {};
+    if (dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
+    return streams[dev];
+}
+
+int filter_device(const float *src, int64_t lds, const float *ref, int64_t ldx, const float *coeffs, int k, int64_t N,
+                  int L, int d, float *out, int64_t ldo, char *base, const FilterWs &w, int64_t *M_out, cudaStream_t st,
+                  cudaEvent_t src_ready)
+{
+    const int order = k / 2;
+    float var = 0.0f;
+    int rc = sgp_stencil_variance(coeffs, k, &var);
+    if (rc) return rc;
+    float scale[SGP_MAX_DIM];
+    rc = sgp_scale_factors(d, var, scale);
+    if (rc) return rc;
+    int16_t *greedy = (int16_t *)(base + w.greedy);
+    int8_t *rank = (int8_t *)(base + w.rank);
+    int32_t *replay = (int32_t *)(base + w.replay);
+    int32_t *flags = (int32_t *)(base + w.flags);
+    uint64_t *table = (uint64_t *)(base + w.table);
+    uint32_t *slot_of = (uint32_t *)(base + w.slot_of);
+    int16_t *keys = (int16_t *)(base + w.keys);
+    int32_t *nbr = (int32_t *)(base + w.nbr);
+    float *buf0 = (float *)(base + w.buf0), *buf1 = (float *)(base + w.buf1);
+    sgp_stream_t s = (sgp_stream_t)st;
+    CUDA_TRY(cudaMemsetAsync(flags, 0, 16, st));
+    CUDA_TRY(cudaMemsetAsync(table, 0xFF, (size_t)w.cap * 8, st));
+    rc = sgp_build_points(ref, N, d, ldx, scale, greedy, rank, replay, flags, s);
+    if (rc) return rc;
+    rc = sgp_hash_insert(greedy, rank, N, d, table, w.cap, slot_of, flags, s);
+    if (rc) return rc;
+    int64_t M = 0;
+    int32_t fl = 0;
+    rc = sgp_count_points(table, w.cap, slot_of, N, d, base + w.number, w.number_bytes, flags, &M, &fl, s);
+    if (M_out) *M_out = M;
+    if (rc) return rc;
+    if (M > w.M_max)
+        return fail(SGP_ENOMEM, "sgp_filter: the lattice has %lld points but the workspace was sized for %lld", (long long)M,
+                    (long long)w.M_max);
+    rc = sgp_number_points(table, w.cap, slot_of, greedy, rank, N, d, base + w.number, M, replay, keys, s);
+    if (rc) return rc;
+    rc = sgp_build_neighbours(keys, M, d, order, table, w.cap, nbr, s);
+    if (rc) return rc;
+    sgp_lattice_view v;
+    memset(&v, 0, sizeof(v));
+    v.N = N;
+    v.M = M;
+    v.d = d;
+    v.order = order;
+    v.replay = replay;
+    v.nbr = order > 0 ? nbr : nullptr;
+    v.fast = 1;
+    if (src_ready) CUDA_TRY(cudaStreamWaitEvent(st, src_ready, 0));
+    rc = sgp_splat(&v, src, lds, L, buf0, SGP_SPLAT_ATOMIC, s);   // (buf0/buf1 overwrite the build scratch: stream order)
+    if (rc) return rc;
+    int in1 = 0;
+    rc = sgp_blur(&v, coeffs, k, L, buf0, buf1, &in1, s);
+    if (rc) return rc;
+    return sgp_slice(&v, in1 ? buf1 : buf0, L, out, ldo, L, s);
+}
+
+}   // namespace
+
+extern "C" size_t sgp_filter_workspace_bytes(int64_t N, int d, int L, int order, int64_t M_max)
+{
+    FilterWs w;
+    if (filter_layout(N, d, L, order, M_max, false, &w) != SGP_OK) return 0;
+    return w.bytes;
+}
+
+extern "C" size_t sgp_filter_host_workspace_bytes(int64_t N, int d, int L, int order, int64_t M_max)
+{
+    FilterWs w;
+    if (filter_layout(N, d, L, order, M_max, true, &w) != SGP_OK) return 0;
+    return w.bytes;
+}
+
+extern "C" int sgp_filter(const float *src, int64_t lds, const float *ref, int64_t ldx, const float *coeffs, int k,
+                          int64_t N, int L, int d, float *out, int64_t ldo, void *workspace, size_t workspace_bytes,
+                          int64_t M_max, int64_t *M_out, sgp_stream_t stream)
+{
+    if (M_out) *M_out = 0;
+    if (!coeffs || k < 1 || (k & 1) == 0) return fail(SGP_EINVAL, "sgp_filter: the stencil must have odd length >= 1");
+    FilterWs w;
+    int rc = filter_layout(N, d, L, k / 2, M_max, false, &w);
+    if (rc) return rc;
+    if (N == 0) return SGP_OK;
+    if (!src || !ref || !out || !workspace || lds < L || ldo < L || ldx < d)
+        return fail(SGP_EINVAL, "sgp_filter: null pointer or a leading dimension below its width");
+    if (workspace_bytes < w.bytes)
+        return fail(SGP_EINVAL, "sgp_filter: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+    if (((uintptr_t)workspace & 255) != 0) return fail(SGP_EINVAL, "sgp_filter: the workspace must be 256-byte aligned");
+    return filter_device(src, lds, ref, ldx, coeffs, k, N, L, d, out, ldo, (char *)workspace, w, M_out,
+                         (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int sgp_filter_host(const float *src_host, int64_t lds, const float *ref_host, int64_t ldx, const float *coeffs,
+                               int k, int64_t N, int L, int d, float *out_host, int64_t ldo, void *workspace,
+                               size_t workspace_bytes, int64_t M_max, int64_t *M_out, sgp_stream_t stream)
+{
+    if (M_out) *M_out = 0;
+    if (!coeffs || k < 1 || (k & 1) == 0) return fail(SGP_EINVAL, "sgp_filter_host: the stencil must have odd length >= 1");
+    FilterWs w;
+    int rc = filter_layout(N, d, L, k / 2, M_max, true, &w);
+    if (rc) return rc;
+    if (N == 0) return SGP_OK;
+    if (!src_host || !ref_host || !out_host || !workspace || lds < L || ldo < L || ldx < d)
+        return fail(SGP_EINVAL, "sgp_filter_host: null pointer or a leading dimension below its width");
+    if (workspace_bytes < w.bytes)
+        return fail(SGP_EINVAL, "sgp_filter_host: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+    if (((uintptr_t)workspace & 255) != 0) return fail(SGP_EINVAL, "sgp_filter_host: the workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *base = (char *)workspace;
+    float *ref_d = (float *)(base + w.ref), *src_d = (float *)(base + w.src), *out_d = (float *)(base + w.out);
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    // positions first (the lattice build needs them); the RHS block travels on a second stream while the lattice is
+    // being built.  Pinned host memory is copied asynchronously, pageable memory through the driver's staging.
+    CUDA_TRY(cudaMemcpy2DAsync(ref_d, (size_t)d * 4, ref_host, (size_t)ldx * 4, (size_t)d * 4, (size_t)N, cudaMemcpyHostToDevice, st));
+    cudaStream_t side = copy_stream(dev);
+    cudaEvent_t fork = nullptr, ready = nullptr;
+    if (side) {
+        if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ready, cudaEventDisableTiming) != cudaSuccess) {
+            if (fork) cudaEventDestroy(fork);
+            fork = ready = nullptr;
+            side = nullptr;
+        }
+    }
+    cudaStream_t up = side ? side : st;
+    if (side) {   // the workspace may still be in use by earlier work of the caller's stream
+        CUDA_TRY(cudaEventRecord(fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(side, fork, 0));
+    }
+    cudaError_t ce = cudaMemcpy2DAsync(src_d, (size_t)L * 4, src_host, (size_t)lds * 4, (size_t)L * 4, (size_t)N,
+                                       cudaMemcpyHostToDevice, up);
+    if (ce == cudaSuccess && side) ce = cudaEventRecord(ready, side);
+    if (ce == cudaSuccess)
+        rc = filter_device(src_d, L, ref_d, d, coeffs, k, N, L, d, out_d, L, base, w, M_out, st, side ? ready : nullptr);
+    if (ce == cudaSuccess && rc == SGP_OK)
+        ce = cudaMemcpy2DAsync(out_host, (size_t)ldo * 4, out_d, (size_t)L * 4, (size_t)L * 4, (size_t)N, cudaMemcpyDeviceToHost, st);
+    if (side) cudaStreamSynchronize(side);   // also on the error paths: the upload must not outlive the call
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (fork) cudaEventDestroy(fork);
+    if (ready) cudaEventDestroy(ready);
+    if (ce != cudaSuccess) return fail(SGP_ECUDA, "sgp_filter_host: copy failed: %s", cudaGetErrorString(ce));
+    if (rc) return rc;
+    if (se != cudaSuccess) return fail(SGP_ECUDA, "sgp_filter_host: %s", cudaGetErrorString(se));
+    return SGP_OK;
+}

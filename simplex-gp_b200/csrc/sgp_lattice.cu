@@ -1303,6 +1303,9 @@ extern "C" int sgp_slice(const sgp_lattice_view *lat, const float *values, int L
     if (lat->N == 0) return SGP_OK;
     if (!values || !out || !lat->replay || L_out < 1 || L_out > L || ldo < L_out)
         return fail(SGP_EINVAL, "sgp_slice: null pointer, L_out outside [1, L] or ldo < L_out");
+    // production form: replay table through warp-private TMA rings (sgp_ring.cu); SGP_RING=0 selects the one-shot kernel
+    if (sgp_ring_slice_enabled() && sgp_slice_ring_supported(lat, values, L) && !(L_out != L && L % 2 != 0))
+        return sgp_slice_ring(lat, values, L, out, ldo, L_out, stream);
     cudaStream_t st = (cudaStream_t)stream;
     // the lattice side decides the vector width; out is written channel by channel when it does not match it
     int vec = pick_vec(L, L, L, values, values, values);

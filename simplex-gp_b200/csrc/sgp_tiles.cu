@@ -462,8 +462,9 @@ template <int VEC, int SEG, bool RAGGED>
 __global__ void __launch_bounds__(256)
 sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ seg_row, int64_t n_seg,
                       const float *__restrict__ src, int64_t lds, int L, int L_src, int chunks, int64_t prefetch_bytes,
-                      bool aggregate, float *__restrict__ values)
+                      bool aggregate, float *__restrict__ values, int dbg)
 {
+    // dbg (experiments only, SGP_SPLAT_DBG): bit 0 = issue no reductions; bits 8-15 = k > 0: point indices folded to k bits
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // Optional (off by default, measured without effect on B200): the first blocks ask L2 for the whole of src with
     // sequential 128-byte prefetches before the random row gathers of the later blocks need it.
@@ -498,7 +499,7 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
             for (int k = 0; k < VEC; ++k)
                 v[i].v[k] = (c0 + k < L_src) ? ldg_ordered_f1(src + (int64_t)(e[i].x & 0x7fffffff) * lds + c0 + k) : 0.0f;
         } else {
-            v[i].load_ordered(src + (int64_t)(e[i].x & 0x7fffffff) * lds + c0);
+            v[i].load_ordered(src + (int64_t)(e[i].x & 0x7fffffff & (dbg >> 8 ? (1 << (dbg >> 8)) - 1 : 0x7fffffff)) * lds + c0);
         }
     }
     Vec<VEC> acc;
@@ -518,7 +519,7 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc.v[k] = __fmaf_rn(w, v[i].v[k], acc.v[k]);
         if ((i == SEG - 1 && !single) || (i < SEG - 1 && e[i + 1].x < 0)) {      // the next entry starts the next lattice row
-            acc.red(values + (int64_t)row * L + c0);
+            if (!(dbg & 1) || acc.v[0] == 1.2345e-30f) acc.red(values + (int64_t)row * L + c0);
             ++row;
 #pragma unroll
             for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
@@ -551,6 +552,10 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_
     if (!ent || !seg_row || !src || !values || N < 0 || M < 0 || n_entries < 0 || n_entries % ROWSEG != 0 || L_src < 1 ||
         lds < L_src || L < L_src)
         return fail(SGP_EINVAL, "sgp_splat_rows: bad argument");
+    // production form: index stream through warp-private TMA rings, stores instead of reductions (sgp_ring.cu);
+    // SGP_RING=0 selects the one-shot kernel below (kept for comparison)
+    if (sgp_ring_splat_enabled() && n_entries >= 16 && sgp_splat_ring_supported(values, L))
+        return sgp_splat_rows_ring(ent, seg_row, n_entries, N, M, src, lds, L_src, values, L, stream);
     cudaStream_t st = (cudaStream_t)stream;
     static int seg_env = 0;   // tuning hook: SGP_ROWSEG=4|8|16 entries per thread
     if (seg_env == 0) {
@@ -566,7 +571,9 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_
     else if (L % 2 == 0 && al(values, 8)) vec = 2;
     const bool ragged = vec > 1 && !(L_src == L && lds % vec == 0 && al(src, 4 * vec));
     const int chunks = L / vec;
-    CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)M * (size_t)L, st));
+    const char *dbg_e = getenv("SGP_SPLAT_DBG");   // experiments only: bit 0 no reductions, bit 1 no memset, bits 8+ fold
+    const int dbg = dbg_e ? atoi(dbg_e) : 0;
+    if (!(dbg & 2)) CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)M * (size_t)L, st));
     const int64_t work = n_seg * chunks;
     static int pref_env = -1;   // tuning hook: SGP_SPLAT_PREFETCH=1 enables an L2 prefetch of src (measured: no gain)
     if (pref_env < 0) {
@@ -589,10 +596,10 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_
 #define SGP_ROWS_LAUNCH(VV, SS)                                                                                        \
     launch_err = ragged ? sgp_launch_pdl(sgp_splat_rows_kernel<VV, SS, true>, dim3(grid_for(work, 256)), dim3(256), 0,  \
                                          st, (const int2 *)ent, seg_row, n_seg, src, lds, L, L_src, chunks,            \
-                                         prefetch_bytes, aggregate, values)                                           \
+                                         prefetch_bytes, aggregate, values, dbg)                                      \
                         : sgp_launch_pdl(sgp_splat_rows_kernel<VV, SS, false>, dim3(grid_for(work, 256)), dim3(256), 0, \
                                          st, (const int2 *)ent, seg_row, n_seg, src, lds, L, L_src, chunks,            \
-                                         prefetch_bytes, aggregate, values)
+                                         prefetch_bytes, aggregate, values, dbg)
 #define SGP_ROWS_SEG(VV)                                                                                               \
     do {                                                                                                               \
         if (seg_env == 4) SGP_ROWS_LAUNCH(VV, 4);                                                                      \
