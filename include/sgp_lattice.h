@@ -148,6 +148,29 @@ int sgp_number_extension(uint64_t *table, int64_t capacity, const uint32_t *slot
                          const void *workspace, int64_t M_old, int64_t M_add, int32_t *replay_new,
                          int16_t *keys, sgp_stream_t stream);
 
+/* ---- Merging key lists: the numbering step of a point-sharded build ------------------------
+ * Under point sharding rank g builds the lattice of its own points [lo_g, hi_g) and gets its keys in local first-touch
+ * order.  Ranks own contiguous point ranges, so the reference's sequential numbering (permutohedral.h:73-79,467-485) of
+ * the whole point set is: rank 0's keys, then rank 1's keys that rank 0 does not hold, ... each list in its own order.
+ * Every rank replays that merge over the all-gathered lists, with the same result everywhere:
+ *   table seeded with the keys so far (sgp_hash_seed, or empty = all 0xFF for the first list; capacity >=
+ *   sgp_hash_capacity(total keys)), then per list
+ * sgp_hash_append_keys   find-or-insert the m_new DISTINCT keys new_keys[m_new, d]; slot_of_new: device [m_new].
+ * sgp_count_appended     *M_add_out = keys of the list that were not in the table.  Synchronises.  Workspace:
+ *                        sgp_number_workspace_bytes(ceil(m_new / (d+1)), d) bytes or more (4 m_new + scan scratch).
+ * sgp_number_appended    keys rows [M_old, M_old + M_add) <- the new keys in list order; map_out (device [m_new], may be
+ *                        NULL) <- index of every listed key in the merged numbering; the table ends mapping every key of
+ *                        the union to its index (for sgp_build_neighbours / sgp_group_finalize). */
+int sgp_hash_append_keys(const int16_t *new_keys, int64_t m_new, int d, const int16_t *keys, int64_t M_old,
+                         uint64_t *table, int64_t capacity, uint32_t *slot_of_new, int32_t *status_flags,
+                         sgp_stream_t stream);
+int sgp_count_appended(const uint64_t *table, int64_t capacity, const uint32_t *slot_of_new, int64_t m_new,
+                       void *workspace, size_t workspace_bytes, const int32_t *status_flags, int64_t *M_add_out,
+                       int32_t *flags_out, sgp_stream_t stream);
+int sgp_number_appended(uint64_t *table, int64_t capacity, const uint32_t *slot_of_new, const int16_t *new_keys,
+                        int64_t m_new, int d, const void *workspace, int64_t M_old, int64_t M_add, int32_t *map_out,
+                        int16_t *keys, sgp_stream_t stream);
+
 /* Neighbour table of the blur (permutohedral.h:539-545): nbr[j, i, t] = lattice index of
  * the key "key[i] - o on every stored coordinate, then key[i][j] + o*d on coordinate j when
  * j < d" (axis j = d only shifts), t enumerating o = -r..-1, 1..r; -1 if absent.

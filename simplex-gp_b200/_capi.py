@@ -32,6 +32,7 @@ SYMBOLS = [
     "sgp_permute_replay", "sgp_rowsort_workspace_bytes", "sgp_rowsort_padded", "sgp_build_rowsorted",
     "sgp_splat_rows", "sgp_cg_scratch_floats", "sgp_cg_apply", "sgp_cg_update", "sgp_cg_direction",
     "sgp_ring_enabled", "sgp_ring_splat_enabled", "sgp_ring_slice_enabled", "sgp_splat_ring_supported", "sgp_slice_ring_supported", "sgp_splat_rows_ring", "sgp_slice_ring",
+    "sgp_hash_append_keys", "sgp_count_appended", "sgp_number_appended",
     "sgp_filter_workspace_bytes", "sgp_filter_host_workspace_bytes", "sgp_filter", "sgp_filter_host",
 ]
 
@@ -145,6 +146,12 @@ def lib() -> C.CDLL:
     L.sgp_count_extension.argtypes = [vp, i64, vp, i64, i32, vp, sz, vp, C.POINTER(i64), C.POINTER(C.c_int32), vp]
     L.sgp_number_extension.restype = i32
     L.sgp_number_extension.argtypes = [vp, i64, vp, vp, vp, i64, i32, vp, i64, i64, vp, vp, vp]
+    L.sgp_hash_append_keys.restype = i32
+    L.sgp_hash_append_keys.argtypes = [vp, i64, i32, vp, i64, vp, i64, vp, vp, vp]
+    L.sgp_count_appended.restype = i32
+    L.sgp_count_appended.argtypes = [vp, i64, vp, i64, vp, sz, vp, C.POINTER(i64), C.POINTER(C.c_int32), vp]
+    L.sgp_number_appended.restype = i32
+    L.sgp_number_appended.argtypes = [vp, i64, vp, vp, i64, i32, vp, i64, i64, vp, vp, vp]
     L.sgp_build_neighbours.restype = i32
     L.sgp_build_neighbours.argtypes = [vp, i64, i32, i32, vp, i64, vp, vp]
     pv = C.POINTER(LatticeView)

@@ -324,12 +324,9 @@ extern "C" int sgp_group_finalize(const int32_t *nbr, const int16_t *keys, int d
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t *small = (uint32_t *)((char *)workspace + w.small);
     CUDA_TRY(cudaMemsetAsync(small, 0, 32, st));
-    static bool pack_attr_set = false;
-    if (!pack_attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(sgp_group_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(PACK_WINDOW * sizeof(uint32_t))));
-        pack_attr_set = true;
-    }
+    // the opt-in above 48 KB is per device (and cheap): set it on every call rather than caching it per process
+    CUDA_TRY(cudaFuncSetAttribute(sgp_group_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(PACK_WINDOW * sizeof(uint32_t))));
     sgp_group_pack_kernel<<<1, PACK_THREADS, PACK_WINDOW * sizeof(uint32_t), st>>>(class_start, M, cap, max_batches,
                                                                                    batch_begin, small);
     rc = launch_ok("sgp_group_pack_kernel");
@@ -529,12 +526,11 @@ static int launch_group(const sgp_blur_group *g, int order, const GroupCoeffs &c
     dim3 grid((unsigned)g->n_batches, (unsigned)((L + CBT - 1) / CBT));
 #define SGP_LAUNCH_GROUP(RR)                                                                                          \
     do {                                                                                                              \
-        static size_t granted = 48 * 1024;   /* per instantiation: raise the dynamic shared-memory limit once */         \
-        if (smem > granted) {                                                                                         \
+        /* the opt-in above 48 KB is an attribute of (function, device): set it on every launch (a host-side call of  \
+           about a microsecond) instead of caching it per process, so that a second device works too */              \
+        if (smem > 48 * 1024)                                                                                         \
             CUDA_TRY(cudaFuncSetAttribute(sgp_blur_group_kernel<VEC, RR, CHUNKS, THREADS, FAST>,                            \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
-            granted = smem;                                                                                           \
-        }                                                                                                             \
         cudaError_t le = sgp_launch_pdl(sgp_blur_group_kernel<VEC, RR, CHUNKS, THREADS, FAST>, grid, dim3(THREADS), smem, st, \
                                         g->batch_begin, g->src, g->lnb, in, out, L, g->rows_cap, nax, order, cf);     \
         if (le != cudaSuccess) return fail(SGP_ECUDA, "launch of sgp_blur_group_kernel failed: %s", cudaGetErrorString(le)); \

@@ -596,6 +596,69 @@ sgp_extend_retarget_kernel(unsigned long long *__restrict__ table, const uint32_
 }
 
 // ------------------------------------------------------------------------------------
+// Appending an explicit list of DISTINCT keys to a seeded table: the merge step of a point-sharded build.  Rank g
+// builds the lattice of its own points; the global first-touch numbering is then the concatenation, in rank order, of
+// every rank's keys that no earlier rank holds, each list in its own (local first-touch) order -- ranks own contiguous
+// point ranges, so this IS the sequential order of permutohedral.h:73-79,467-485.  Every rank replays that merge on the
+// all-gathered key lists and ends with the same keys[M, d] and, for its own list, the local -> global index map.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sgp_append_insert_kernel(const int16_t *__restrict__ new_keys, int64_t m_new, int d, const int16_t *__restrict__ keys,
+                         unsigned long long *table, uint64_t mask, uint32_t *__restrict__ slot_of,
+                         int32_t *__restrict__ flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m_new) return;
+    const int16_t *key = new_keys + i * d;
+    const uint64_t h = hash_key<0>(key, d);
+    const uint32_t fp = (uint32_t)(h >> 32);
+    uint64_t slot = h & mask;
+    const unsigned long long mine = ((unsigned long long)fp << 32) | SGP_NEW_OWNER | (uint32_t)i;
+    for (uint64_t probe = 0; probe <= mask; ++probe) {
+        unsigned long long cur = *((volatile unsigned long long *)(table + slot));
+        if (cur == SGP_EMPTY) {
+            const unsigned long long prev = atomicCAS(table + slot, SGP_EMPTY, mine);
+            if (prev == SGP_EMPTY) {
+                slot_of[i] = (uint32_t)slot;
+                return;
+            }
+            cur = prev;
+        }
+        if ((uint32_t)(cur >> 32) == fp) {
+            const uint32_t low = (uint32_t)cur;
+            const int16_t *op = (low & SGP_NEW_OWNER) ? new_keys + (int64_t)(low & ~SGP_NEW_OWNER) * d : keys + (int64_t)low * d;
+            bool same = true;
+            for (int c = 0; c < d; ++c) same = same && (op[c] == key[c]);
+            if (same) {
+                if ((low & SGP_NEW_OWNER) && (uint32_t)i < (low & ~SGP_NEW_OWNER)) atomicMin(table + slot, mine);   // duplicate in the list
+                slot_of[i] = (uint32_t)slot;
+                return;
+            }
+        }
+        slot = (slot + 1) & mask;
+    }
+    atomicOr(flags, SGP_FLAG_TABLE_FULL);
+    slot_of[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+sgp_append_number_kernel(const unsigned long long *__restrict__ table, const uint32_t *__restrict__ slot_of,
+                         const uint32_t *__restrict__ pos, const int16_t *__restrict__ new_keys, int64_t m_new, int d,
+                         uint32_t M_old, int32_t *__restrict__ map_out, int16_t *__restrict__ keys)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m_new) return;
+    const uint32_t low = (uint32_t)table[slot_of[i]];
+    const uint32_t idx = (low & SGP_NEW_OWNER) ? M_old + pos[low & ~SGP_NEW_OWNER] : low;
+    if (map_out) map_out[i] = (int32_t)idx;
+    if (low == (SGP_NEW_OWNER | (uint32_t)i)) {
+        const int16_t *key = new_keys + i * d;
+        int16_t *kp = keys + (int64_t)idx * d;
+        for (int c = 0; c < d; ++c) kp[c] = key[c];
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // stage 1d: neighbour table.  One thread per (axis j, lattice point i).
 // ------------------------------------------------------------------------------------
 template <int D>
@@ -1154,6 +1217,79 @@ extern "C" int sgp_number_extension(uint64_t *table, int64_t capacity, const uin
     rc = launch_ok("sgp_extend_renumber_kernel");
     if (rc) return rc;
     sgp_extend_retarget_kernel<<<grid_for(total, 256), 256, 0, st>>>((unsigned long long *)table, slot_of, total, pos,
+                                                                     (uint32_t)M_old);
+    return launch_ok("sgp_extend_retarget_kernel");
+}
+
+// ---- merging key lists (point-sharded build) -------------------------------------------
+extern "C" int sgp_hash_append_keys(const int16_t *new_keys, int64_t m_new, int d, const int16_t *keys, int64_t M_old,
+                                    uint64_t *table, int64_t capacity, uint32_t *slot_of_new, int32_t *status_flags,
+                                    sgp_stream_t stream)
+{
+    if (d < 1 || d > SGP_MAX_DIM) return fail(SGP_EUNSUPPORTED, "d=%d outside [1, %d]", d, SGP_MAX_DIM);
+    if (m_new < 0 || M_old < 0 || M_old + m_new >= (1ll << 31))
+        return fail(SGP_EOVERFLOW, "M_old + m_new does not fit 31-bit lattice indices");
+    int rc = check_capacity(capacity);
+    if (rc) return rc;
+    if (m_new == 0) return SGP_OK;
+    if (!new_keys || !table || !slot_of_new || !status_flags || (M_old > 0 && !keys))
+        return fail(SGP_EINVAL, "sgp_hash_append_keys: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    sgp_append_insert_kernel<<<grid_for(m_new, 256), 256, 0, st>>>(new_keys, m_new, d, keys, (unsigned long long *)table,
+                                                                   (uint64_t)(capacity - 1), slot_of_new, status_flags);
+    return launch_ok("sgp_append_insert_kernel");
+}
+
+extern "C" int sgp_count_appended(const uint64_t *table, int64_t capacity, const uint32_t *slot_of_new, int64_t m_new,
+                                  void *workspace, size_t workspace_bytes, const int32_t *status_flags,
+                                  int64_t *M_add_out, int32_t *flags_out, sgp_stream_t stream)
+{
+    if (!M_add_out || !flags_out) return fail(SGP_EINVAL, "sgp_count_appended: null output");
+    *M_add_out = 0;
+    *flags_out = 0;
+    if (m_new == 0) return SGP_OK;
+    if (m_new < 0 || m_new >= (1ll << 31)) return fail(SGP_EINVAL, "sgp_count_appended: m_new out of range");
+    size_t off_tiles, off_total, need;
+    number_ws_layout(m_new, &off_tiles, &off_total, &need);
+    if (!table || !slot_of_new || !workspace || !status_flags || workspace_bytes < need)
+        return fail(SGP_EINVAL, "sgp_count_appended: null pointer or workspace too small (%zu < %zu)", workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *marks = (uint32_t *)workspace;
+    uint32_t *tiles = (uint32_t *)((char *)workspace + off_tiles);
+    unsigned long long *total_dev = (unsigned long long *)((char *)workspace + off_total);
+    // a listed key is new iff its slot is owned by its own list position: the marks of sgp_extend_mark_kernel
+    sgp_extend_mark_kernel<<<grid_for(m_new, 256), 256, 0, st>>>((const unsigned long long *)table, slot_of_new, m_new, marks);
+    int rc = launch_ok("sgp_extend_mark_kernel");
+    if (rc) return rc;
+    rc = sgp_exclusive_scan_u32(marks, m_new, tiles, total_dev, st);
+    if (rc) return rc;
+    unsigned long long m_host = 0;
+    int32_t f_host = 0;
+    CUDA_TRY(cudaMemcpyAsync(&m_host, total_dev, sizeof(m_host), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&f_host, status_flags, sizeof(f_host), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *M_add_out = (int64_t)m_host;
+    *flags_out = f_host;
+    if (f_host & SGP_FLAG_TABLE_FULL) return fail(SGP_EOVERFLOW, "hash table full (capacity %lld)", (long long)capacity);
+    return SGP_OK;
+}
+
+extern "C" int sgp_number_appended(uint64_t *table, int64_t capacity, const uint32_t *slot_of_new, const int16_t *new_keys,
+                                   int64_t m_new, int d, const void *workspace, int64_t M_old, int64_t M_add,
+                                   int32_t *map_out, int16_t *keys, sgp_stream_t stream)
+{
+    if (m_new == 0) return SGP_OK;
+    if (!table || !slot_of_new || !new_keys || !workspace || !keys || d < 1 || d > SGP_MAX_DIM || m_new < 0 || M_old < 0 ||
+        M_add < 0 || M_add > m_new)
+        return fail(SGP_EINVAL, "sgp_number_appended: bad argument");
+    (void)capacity;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t *pos = (const uint32_t *)workspace;
+    sgp_append_number_kernel<<<grid_for(m_new, 256), 256, 0, st>>>((const unsigned long long *)table, slot_of_new, pos, new_keys,
+                                                                   m_new, d, (uint32_t)M_old, map_out, keys);
+    int rc = launch_ok("sgp_append_number_kernel");
+    if (rc) return rc;
+    sgp_extend_retarget_kernel<<<grid_for(m_new, 256), 256, 0, st>>>((unsigned long long *)table, slot_of_new, m_new, pos,
                                                                      (uint32_t)M_old);
     return launch_ok("sgp_extend_retarget_kernel");
 }

@@ -802,12 +802,9 @@ extern "C" int sgp_splat_tiles(const sgp_tiles_view *t, const float *src, int64_
     dim3 grid((unsigned)n_tiles, ncb);
 #define SGP_LAUNCH_SPLAT_TILES(VV)                                                                                   \
     do {                                                                                                             \
-        static size_t granted = 48 * 1024;                                                                           \
-        if (smem > granted) {                                                                                        \
+        if (smem > 48 * 1024) /* per (function, device): set on every launch, see sgp_groups.cu */                   \
             CUDA_TRY(cudaFuncSetAttribute(sgp_splat_tiles_kernel<VV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                           (int)smem));                                                               \
-            granted = smem;                                                                                          \
-        }                                                                                                            \
         sgp_splat_tiles_kernel<VV><<<grid, TILE_THREADS, smem, st>>>(t->perm, t->tile_piece_ptr, t->piece_ptr,      \
                                                                      t->piece_row, (const int2 *)t->seg_ent, src,    \
                                                                      lds, t->N, T, dp1, L, CB, values);              \
@@ -849,12 +846,9 @@ extern "C" int sgp_slice_tiles(const sgp_tiles_view *t, const float *values, int
     dim3 grid((unsigned)n_tiles, ncb);
 #define SGP_LAUNCH_SLICE_TILES(VV, FF)                                                                               \
     do {                                                                                                             \
-        static size_t granted = 48 * 1024;                                                                           \
-        if (smem > granted) {                                                                                        \
+        if (smem > 48 * 1024)                                                                                        \
             CUDA_TRY(cudaFuncSetAttribute(sgp_slice_tiles_kernel<VV, FF>,                                            \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
-            granted = smem;                                                                                          \
-        }                                                                                                            \
         sgp_slice_tiles_kernel<VV, FF><<<grid, TILE_THREADS, smem, st>>>(t->perm, t->tile_seg_ptr, t->seg_row,      \
                                                                          t->lidx, t->tile_w, values, t->N, T, dp1,   \
                                                                          L, CB, cap, divisor, rdivisor, out, ldo);   \

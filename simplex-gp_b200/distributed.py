@@ -7,8 +7,11 @@ north star:
   hyper-parameter step on one rank and broadcast; every rank then filters its own RHS columns with no
   communication per MVM (columns are independent: splat, blur and slice are linear and per-channel).
 * ``shard_columns`` -- which RHS columns a rank owns.
-* ``PointShardedLattice`` -- for very large N: every rank holds the points ``[lo, hi)`` and the full lattice
-  numbering; splat is local, lattice values are combined with one all-reduce before the blur, slice is local.
+* ``PointShardedLattice`` -- for very large N: every rank holds the points ``[lo, hi)`` only.  The lattice is built
+  SHARDED: each rank builds the lattice of its own points, the ranks' key lists are all-gathered and merged in rank
+  order (``merge_key_lists``: that IS the reference's sequential first-touch numbering, because ranks own contiguous
+  point ranges), and each rank keeps its own points' replay table in the global numbering.  splat is local, lattice
+  values are combined with one all-reduce before the blur, slice is local.
 
 Everything works on the ``gloo`` backend with CPU tensors for the host-logic tests (no GPU kernels are called
 by the helpers that tests exercise on CPU).
@@ -21,7 +24,8 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_columns", "shard_points", "broadcast_lattice_arrays", "broadcast_lattice", "lattice_arrays",
-           "all_gather_columns", "allreduce_lattice_values", "ColumnShardedOperator", "PointShardedLattice"]
+           "all_gather_columns", "allreduce_lattice_values", "ColumnShardedOperator", "PointShardedLattice",
+           "gather_key_lists", "merge_key_lists"]
 
 
 def shard_columns(L: int, world: int, rank: int) -> Tuple[int, int]:
@@ -56,44 +60,94 @@ def lattice_arrays(lat) -> dict:
     return {"replay": lat.replay, "keys": lat.keys, "nbr": lat.nbr}
 
 
-def broadcast_lattice_arrays(arrays: Optional[dict], meta: Optional[dict], src: int = 0, device=None, group=None):
-    """Broadcast ``meta`` (small dict: N, M, d, order, coeffs) and the lattice arrays from ``src``.
+_HEADER_WORDS = 8 + 16   # N, M, d, order, exact, n_coeffs, 2 spare, then up to 16 stencil coefficients as float32 bits
 
-    On ``src`` pass the real ``arrays``/``meta``; elsewhere pass ``None``.  Returns ``(arrays, meta)`` on every
-    rank.  One ``broadcast_object_list`` for the metadata and one ``broadcast`` per array."""
+
+def _pack_header(meta: dict) -> torch.Tensor:
+    import numpy as np
+    c = np.asarray(meta["coeffs"], dtype=np.float32)
+    if c.shape[0] > 16:
+        raise ValueError("stencil too long for the broadcast header")
+    h = torch.zeros(_HEADER_WORDS, dtype=torch.int64)
+    h[:6] = torch.tensor([meta["N"], meta["M"], meta["d"], meta["order"], int(bool(meta.get("exact", False))), c.shape[0]])
+    h[8:8 + c.shape[0]] = torch.from_numpy(c.view(np.int32).astype(np.int64))
+    return h
+
+
+def _unpack_header(h: torch.Tensor) -> dict:
+    import numpy as np
+    v = h.cpu().tolist()
+    k = int(v[5])
+    coeffs = np.asarray(v[8:8 + k], dtype=np.int64).astype(np.int32).view(np.float32).tolist()
+    return {"N": int(v[0]), "M": int(v[1]), "d": int(v[2]), "order": int(v[3]), "exact": bool(v[4]), "coeffs": coeffs}
+
+
+def _al(n: int) -> int:
+    return (n + 255) & ~255
+
+
+def broadcast_lattice_arrays(arrays: Optional[dict], meta: Optional[dict], src: int = 0, device=None, group=None):
+    """Broadcast ``meta`` (N, M, d, order, coeffs, exact) and the lattice arrays from ``src``.
+
+    On ``src`` pass the real ``arrays``/``meta``; elsewhere pass ``None``.  Returns ``(arrays, meta)`` on every rank.
+    Two collectives: a 192-byte header (it sizes the receive buffer) and ONE byte buffer holding replay, keys and the
+    neighbour table back to back -- three broadcasts plus a pickled ``broadcast_object_list`` cost 162 ms at 8 ranks in
+    round 1 for 107 MB that need ~150 us of NVLink time.  As bytes: neither NCCL nor gloo has an int16 type, and a
+    broadcast moves bits anyway."""
     rank = dist.get_rank(group)
-    box = [meta if rank == src else None]
-    dist.broadcast_object_list(box, src=src, group=group)
-    meta = box[0]
+    if rank == src:
+        dev = arrays["replay"].device
+        header = _pack_header(meta).to(dev)
+    else:
+        dev = torch.device(device) if device is not None else torch.device("cpu")
+        header = torch.zeros(_HEADER_WORDS, dtype=torch.int64, device=dev)
+    dist.broadcast(header, src=src, group=group)
+    meta = _unpack_header(header)
     N, M, d, r = meta["N"], meta["M"], meta["d"], meta["order"]
     shapes = {"replay": (N, d + 1, 2), "keys": (M, d), "nbr": (d + 1, M, 2 * r)}
+    sizes, offs, o = {}, {}, 0
+    for name, dtype in _ARRAY_SPECS:
+        n = 1
+        for k in shapes[name]:
+            n *= k
+        sizes[name] = n * torch.empty((), dtype=dtype).element_size()
+        offs[name] = o
+        o += _al(sizes[name])
+    buf = torch.empty(max(o, 1), dtype=torch.uint8, device=dev)
+    if rank == src:
+        for name, _ in _ARRAY_SPECS:
+            if sizes[name]:
+                buf[offs[name]:offs[name] + sizes[name]].copy_(arrays[name].contiguous().view(-1).view(torch.uint8))
+    if o > 0:
+        dist.broadcast(buf, src=src, group=group)
     out = {}
     for name, dtype in _ARRAY_SPECS:
         if rank == src:
-            t = arrays[name].contiguous()
+            out[name] = arrays[name]
+        elif sizes[name]:
+            out[name] = buf[offs[name]:offs[name] + sizes[name]].view(dtype).view(shapes[name])
         else:
-            t = torch.empty(shapes[name], dtype=dtype, device=device)
-        if t.numel() > 0:
-            # as bytes: neither NCCL nor gloo has an int16 type, and a broadcast moves bits anyway
-            dist.broadcast(t.view(-1).view(torch.uint8), src=src, group=group)
-        out[name] = t
+            out[name] = torch.empty(shapes[name], dtype=dtype, device=dev)
     return out, meta
 
 
 def broadcast_lattice(lat, src: int = 0, device=None, group=None, build_csr: bool = False):
-    """Broadcast a built ``Lattice`` from ``src``; other ranks pass ``lat=None`` and get a ``Lattice`` back."""
+    """Broadcast a built ``Lattice`` from ``src``; other ranks pass ``lat=None`` and get a ``Lattice`` back (same
+    structure arrays, same ``exact`` setting; the derived tables -- blur groups, row-sorted entries -- are rebuilt
+    locally, which is cheaper than moving them)."""
     from .lattice import Lattice
 
     rank = dist.get_rank(group)
     if rank == src:
-        meta = {"N": lat.N, "M": lat.M, "d": lat.d, "order": lat.order, "coeffs": lat.coeffs.tolist()}
+        meta = {"N": lat.N, "M": lat.M, "d": lat.d, "order": lat.order, "coeffs": lat.coeffs.tolist(), "exact": lat.exact}
         arrays = lattice_arrays(lat)
     else:
         meta, arrays = None, None
     arrays, meta = broadcast_lattice_arrays(arrays, meta, src=src, device=device, group=group)
     if rank == src:
         return lat
-    return Lattice.from_arrays(meta["coeffs"], arrays["replay"], arrays["keys"], arrays["nbr"], build_csr=build_csr)
+    return Lattice.from_arrays(meta["coeffs"], arrays["replay"], arrays["keys"], arrays["nbr"], build_csr=build_csr,
+                               exact=meta["exact"])
 
 
 def all_gather_columns(mine: torch.Tensor, L: int, group=None) -> torch.Tensor:
@@ -161,30 +215,125 @@ class ColumnShardedOperator:
         return out
 
 
+def gather_key_lists(keys_local: torch.Tensor, group=None):
+    """All-gather the ranks' key lists ``[M_g, d]`` int16 (ragged): returns the list of all ranks' key tensors, in rank
+    order, identical on every rank.  One all-gather of the counts and one of the keys padded to the longest list (as
+    bytes: no int16 collective type)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return [keys_local]
+    d = int(keys_local.shape[1])
+    dev = keys_local.device
+    count = torch.tensor([keys_local.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count, group=group)
+    counts = [int(c.item()) for c in counts]
+    mmax = max(max(counts), 1)
+    pad = torch.zeros((mmax, d), dtype=torch.int16, device=dev)
+    pad[: keys_local.shape[0]] = keys_local
+    parts = [torch.empty_like(pad).view(-1).view(torch.uint8) for _ in range(world)]
+    dist.all_gather(parts, pad.view(-1).view(torch.uint8), group=group)
+    return [p.view(torch.int16).view(mmax, d)[:c] for p, c in zip(parts, counts)]
+
+
+def merge_key_lists(key_lists, want_map_of: Optional[int] = None):
+    """Merge per-rank key lists (each in its rank's local first-touch order) into the global first-touch numbering:
+    list 0, then the keys of list 1 that list 0 does not hold, ... (csrc: sgp_hash_append_keys / sgp_count_appended /
+    sgp_number_appended).  Returns ``(keys[M, d], table, map)``: ``table`` is the key -> index hash table of the union
+    (input of the neighbour / blur-group builders), ``map`` the int32 ``[M_g]`` local -> global index map of list
+    ``want_map_of`` (or None).  CUDA tensors only -- there is no CPU path."""
+    import ctypes as C
+
+    from . import _capi
+    from .lattice import _ptr, _stream_ptr
+    lib = _capi.lib()
+    first = key_lists[0]
+    if not first.is_cuda:
+        raise RuntimeError("merge_key_lists needs CUDA tensors: this package has no CPU path")
+    dev, d = first.device, int(first.shape[1])
+    total = sum(int(k.shape[0]) for k in key_lists)
+    cap = int(lib.sgp_hash_capacity(max(total, 1)))
+    with torch.cuda.device(dev):
+        st = _stream_ptr(dev)
+        table = torch.full((cap,), -1, dtype=torch.int64, device=dev)
+        keys = torch.empty((max(total, 1), d), dtype=torch.int16, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        M, out_map = 0, None
+        for g, kl in enumerate(key_lists):
+            m = int(kl.shape[0])
+            if m == 0:
+                if want_map_of == g:
+                    out_map = torch.empty(0, dtype=torch.int32, device=dev)
+                continue
+            kl = kl.contiguous()
+            slot_of = torch.empty(m, dtype=torch.int32, device=dev)
+            ws_bytes = int(lib.sgp_number_workspace_bytes(m, 0))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _capi.check(lib.sgp_hash_append_keys(_ptr(kl), m, d, _ptr(keys), M, _ptr(table), cap, _ptr(slot_of), _ptr(flags),
+                                                 st))
+            m_add, fl = C.c_int64(0), C.c_int32(0)
+            _capi.check(lib.sgp_count_appended(_ptr(table), cap, _ptr(slot_of), m, _ptr(ws), ws_bytes, _ptr(flags),
+                                               C.byref(m_add), C.byref(fl), st))
+            mp = torch.empty(m, dtype=torch.int32, device=dev) if want_map_of == g else None
+            _capi.check(lib.sgp_number_appended(_ptr(table), cap, _ptr(slot_of), _ptr(kl), m, d, _ptr(ws), M, int(m_add.value),
+                                                _ptr(mp), _ptr(keys), st))
+            if mp is not None:
+                out_map = mp
+            M += int(m_add.value)
+    return keys[:M], table, out_map
+
+
 class PointShardedLattice:
-    """Point sharding for very large N: rank ``k`` owns the points ``[lo_k, hi_k)``.
+    """Point sharding for very large N: rank ``k`` owns the points ``[lo_k, hi_k)`` and builds ONLY their part of the
+    lattice (per-point stage, hash insertion, replay table: everything sized by ``N (d+1)`` is sharded).
 
-    The lattice numbering has to be global, so every rank runs the (deterministic) lattice build on all ``N`` points
-    -- positions are ``N*d*4`` bytes, small next to the value traffic -- and then keeps the per-point tables (replay,
-    row-sorted entries) of its own points only.  One MVM is: local splat of the rank's rows of ``V`` into the full
-    ``[M, L]`` lattice, **one all-reduce (sum) of ``M*L*4`` bytes**, blur (replicated), local slice of the rank's rows.
-    ``mvm`` takes and returns this rank's row block ``[hi-lo, L]``."""
+    Build: (1) the lattice of the rank's own points -> local keys in local first-touch order; (2) all-gather of the key
+    lists (``M_g * d * 2`` bytes each); (3) every rank merges the lists in rank order, which reproduces the reference's
+    sequential first-touch numbering of the whole point set bit for bit (``merge_key_lists``); (4) the rank's replay
+    table is re-indexed to the global numbering and the tables every rank needs whole (blur groups / neighbour table,
+    built from the merged key table) are built locally.  One MVM is: local splat of the rank's rows of ``V`` into the
+    full ``[M, L]`` lattice, **one all-reduce (sum) of ``M*L*4`` bytes**, blur (replicated), local slice of the rank's
+    rows.  ``mvm`` takes and returns this rank's row block ``[hi-lo, L]``.
 
-    def __init__(self, x_full: torch.Tensor, coeffs, group=None, **lattice_kwargs):
+    ``x``: the rank's own points ``[hi-lo, d]`` (``x_is_local=True``) or the whole point set, of which the rank takes
+    its share (contiguous blocks, ``shard_points``)."""
+
+    def __init__(self, x: torch.Tensor, coeffs, group=None, x_is_local: bool = False, **lattice_kwargs):
         from .lattice import Lattice
 
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        N = int(x_full.shape[0])
-        self.lo, self.hi = shard_points(N, self.world, self.rank)
-        full = Lattice(x_full, coeffs, build_groups=False, build_rows=False, sort_points=False, build_tiles=False)
-        self.N, self.M, self.d = full.N, full.M, full.d
-        # the same lattice restricted to this rank's points: shares keys and the neighbour table, rebuilds the
-        # per-point tables for hi-lo points
-        self.local = Lattice.from_arrays(full.coeffs, full.replay[self.lo:self.hi].contiguous(), full.keys, full.nbr,
+        if x_is_local:
+            n_loc = torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device)
+            if self.world > 1:
+                counts = [torch.zeros_like(n_loc) for _ in range(self.world)]
+                dist.all_gather(counts, n_loc, group=group)
+                counts = [int(c.item()) for c in counts]
+            else:
+                counts = [int(x.shape[0])]
+            self.lo = sum(counts[: self.rank])
+            self.hi = self.lo + counts[self.rank]
+            self.N = sum(counts)
+            x_loc = x
+        else:
+            self.N = int(x.shape[0])
+            self.lo, self.hi = shard_points(self.N, self.world, self.rank)
+            x_loc = x[self.lo:self.hi]
+        build_nbr = lattice_kwargs.pop("build_nbr", True)
+        mine = Lattice(x_loc.contiguous(), coeffs, build_groups=False, build_rows=False, build_nbr=False,
+                       keep_structure=False)
+        self.d, self.M_local = mine.d, mine.M
+        lists = gather_key_lists(mine.keys, group=group)
+        keys, table, lmap = merge_key_lists(lists, want_map_of=self.rank)
+        self.M = int(keys.shape[0])
+        replay = mine.replay
+        if replay.numel():
+            replay[..., 0] = lmap[replay[..., 0].long()]      # local -> global lattice indices
+        del lists, lmap
+        self.local = Lattice.from_arrays(mine.coeffs, replay, keys.contiguous(), None, table=table, build_nbr=build_nbr,
                                          **lattice_kwargs)
-        del full
+        del mine, table
 
     def mvm(self, V_local: torch.Tensor, **kw) -> torch.Tensor:
         if V_local.shape[0] != self.hi - self.lo:

@@ -184,7 +184,7 @@ class Lattice:
             self._build_csr()
         if build_groups and r >= 1 and self.M > 0:
             self._build_groups(group_axes, group_rows, table=None if build_nbr else table)
-        if not build_nbr and r >= 1 and self.groups is None:   # no groups (long 1-D lines): the per-axis blur needs nbr
+        if not build_nbr and build_groups and r >= 1 and self.groups is None:   # no groups (long 1-D lines): the per-axis blur needs nbr
             self.nbr = torch.empty((d + 1, self.M, 2 * r), dtype=torch.int32, device=dev)
             check(lib.sgp_build_neighbours(_ptr(self.keys), self.M, d, r, _ptr(table), cap, _ptr(self.nbr), st))
         if (sort_points or build_tiles) and self.M > 0 and self.greedy is not None:
@@ -291,11 +291,14 @@ class Lattice:
         self._tables = {}
 
     @classmethod
-    def from_arrays(cls, coeffs, replay: torch.Tensor, keys: torch.Tensor, nbr: torch.Tensor,
+    def from_arrays(cls, coeffs, replay: torch.Tensor, keys: torch.Tensor, nbr: Optional[torch.Tensor],
                     build_csr: bool = False, build_tiles: bool = False, tile_points: int = 256,
                     build_groups: bool = True, group_axes: Optional[int] = None, group_rows: int = 512,
-                    exact: bool = False) -> "Lattice":
-        """Wrap lattice arrays that were built elsewhere (e.g. received by ``distributed.broadcast_lattice``)."""
+                    exact: bool = False, table: Optional[torch.Tensor] = None, build_nbr: bool = True,
+                    build_rows: bool = True) -> "Lattice":
+        """Wrap lattice arrays that were built elsewhere: received by ``distributed.broadcast_lattice`` (``nbr`` given),
+        or merged from per-rank builds (``nbr=None`` and ``table`` = the key -> index hash table of ``keys``, from which
+        the neighbour table -- or, with ``build_nbr=False``, the blur groups directly -- are made)."""
         self = object.__new__(cls)
         self.device = replay.device
         self.N, self.d = int(replay.shape[0]), int(replay.shape[1]) - 1
@@ -304,9 +307,12 @@ class Lattice:
         self.var = stencil_variance(self.coeffs)
         self.scale = scale_factors(self.d, self.var)
         self.M = int(keys.shape[0])
-        if tuple(nbr.shape) != (self.d + 1, self.M, 2 * self.order):
+        if nbr is None and table is None:
+            raise ValueError("from_arrays needs the neighbour table or the key hash table")
+        if nbr is not None and tuple(nbr.shape) != (self.d + 1, self.M, 2 * self.order):
             raise ValueError(f"nbr shape {tuple(nbr.shape)} does not match (d+1, M, 2r)")
-        self.replay, self.keys, self.nbr = replay.contiguous(), keys.contiguous(), nbr.contiguous()
+        self.replay, self.keys = replay.contiguous(), keys.contiguous()
+        self.nbr = nbr.contiguous() if nbr is not None else None
         self.greedy = self.rank = None
         self.csr_ptr = self.csr_ent = None
         self.tiles = None
@@ -314,17 +320,22 @@ class Lattice:
         self.sorted = None      # the locality order needs greedy, which does not travel with the arrays
         self.rows = None
         self.exact = bool(exact)
-        self.hash_capacity = 0
+        self.hash_capacity = 0 if table is None else int(table.numel())
         self._bufs = {}
         self._tables = {}
-        if self.N > 0 and self.M > 0:
+        if self.M > 0:
             with torch.cuda.device(self.device):
-                if build_csr:
-                    self._build_csr()
-                if build_groups and self.order >= 1:
-                    self._build_groups(group_axes, group_rows)
-                if self.rows is None:
-                    self._build_rows()
+                if nbr is None:
+                    self._build_derived(table, build_nbr=build_nbr, build_csr=build_csr and self.N > 0,
+                                        build_groups=build_groups, group_axes=group_axes, group_rows=group_rows,
+                                        build_rows=build_rows and self.N > 0)
+                elif self.N > 0:
+                    if build_csr:
+                        self._build_csr()
+                    if build_groups and self.order >= 1:
+                        self._build_groups(group_axes, group_rows)
+                    if build_rows and self.rows is None:
+                        self._build_rows()
         return self
 
     def _build_groups(self, group_axes: Optional[int] = None, group_rows: int = 512, table=None) -> None:
@@ -794,53 +805,88 @@ class Lattice:
         return 4 * (2 * N * L + 4 * N * (d + 1) + 2 * M * L + (d + 1) * (2 * M * L + 2 * r * M))
 
 
+_M_HINT = {}   # (N, d, order) -> lattice points of the last filter() call of that shape: sizes the next workspace
+
+
+def _filter_call(fn, ws_fn, dev, N, d, L, order, args_before, args_after):
+    """Run sgp_filter / sgp_filter_host with a workspace from PyTorch's allocator.  The workspace is sized for the
+    number of lattice points the last call of this shape produced (plus a quarter), else for the worst case N(d+1) when
+    that is affordable; if the lattice turns out larger the call reports M and is repeated once with the exact size."""
+    total = N * (d + 1)
+    hint = _M_HINT.get((N, d, order))
+    if hint is not None:
+        m_max = min(total, hint + hint // 4 + 1024)
+    else:
+        m_max = total
+        free, _ = torch.cuda.mem_get_info(dev)
+        while m_max > 1024 and int(ws_fn(N, d, L, order, m_max)) > free // 2:
+            m_max //= 2
+    m_out = C.c_int64(0)
+    for attempt in range(2):
+        nbytes = int(ws_fn(N, d, L, order, m_max))
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+        code = fn(*args_before, _ptr(ws), nbytes, m_max, C.byref(m_out), *args_after)
+        if code == _capi.SGP_ENOMEM and attempt == 0 and m_out.value > m_max:
+            m_max = int(m_out.value)
+            del ws
+            continue
+        check(code)
+        break
+    _M_HINT[(N, d, order)] = int(m_out.value)
+    return ws
+
+
 def lattice_filter(src: torch.Tensor, ref: torch.Tensor, coeffs, *, device=None) -> torch.Tensor:
-    """Drop-in for the reference operator ``filter(src[N,L], ref[N,d], coeffs[2r+1]) -> out[N,L]``.
+    """Drop-in for the reference operator ``filter(src[N,L], ref[N,d], coeffs[2r+1]) -> out[N,L]``
+    (cpp/lattice.cpp:6-16 for CPU tensors, cuda/permutohedral_cuda.cpp:12-22 for CUDA tensors).
 
     Builds the lattice of ``ref`` and applies one MVM, as the reference does on every call
-    (permutohedral.h:259-340).  The result is a fresh tensor with ``src``'s dtype and device.  CPU inputs
-    are staged through pinned memory to the GPU and back: the computation always runs in the CUDA kernels.
+    (permutohedral.h:259-340): ONE call across the C ABI -- ``sgp_filter`` for CUDA tensors, ``sgp_filter_host`` for CPU
+    tensors (the uploads and the download ride inside; pinned tensors are copied asynchronously).  The result is a fresh
+    tensor with ``src``'s dtype and device; the arithmetic is fp32 whatever the input dtype (the reference's CPU filter
+    is fp32-only; its CUDA twin also dispatches double).  There is no CPU path: the computation
+    always runs in the CUDA kernels.
     """
     assert src.shape[0] == ref.shape[0], "Incompatible shapes {}, and {}".format(src.shape, ref.shape)
-    if src.dtype != torch.float32 or ref.dtype != torch.float32:
-        raise TypeError("filter: float32 tensors required (reference CPU filter is fp32-only)")
+    if src.dim() != 2 or ref.dim() != 2:
+        raise ValueError(f"filter: src and ref must be 2-D, got {tuple(src.shape)} and {tuple(ref.shape)}")
+    if not (src.is_floating_point() and ref.is_floating_point()):
+        raise TypeError("filter: floating-point tensors required")
+    lib = _capi.lib()
+    c = _coeffs_np(coeffs)
+    N, L, d, order = int(src.shape[0]), int(src.shape[1]), int(ref.shape[1]), c.shape[0] // 2
+    if not (1 <= d <= _capi.SGP_MAX_DIM):
+        raise ValueError(f"d={d} outside [1, {_capi.SGP_MAX_DIM}]")
+    out_dtype = src.dtype
     if src.is_cuda:
         dev = src.device
-        lat = Lattice(ref.to(dev), coeffs, build_csr=False, build_tiles=False, build_groups=False, sort_points=False, build_rows=False,
-                      keep_structure=False)
-        return lat.mvm(src)
+        src_d = src.detach().to(torch.float32)
+        if L > 1 and src_d.stride(1) != 1:
+            src_d = src_d.contiguous()
+        ref_d = ref.detach().to(device=dev, dtype=torch.float32)
+        if d > 1 and ref_d.stride(1) != 1:
+            ref_d = ref_d.contiguous()
+        out = torch.empty((N, L), dtype=torch.float32, device=dev)
+        if N == 0 or L == 0:
+            return out.to(out_dtype)
+        with torch.cuda.device(dev):
+            _filter_call(lib.sgp_filter, lib.sgp_filter_workspace_bytes, dev, N, d, L, order,
+                         (_ptr(src_d), max(src_d.stride(0), L), _ptr(ref_d), max(ref_d.stride(0), d), _fp(c), c.shape[0], N, L, d,
+                          _ptr(out), L), (_stream_ptr(dev),))
+        return out if out_dtype == torch.float32 else out.to(out_dtype)
     if not torch.cuda.is_available():
         raise RuntimeError("filter: no CUDA device; this package has no CPU path")
     dev = torch.device(device if device is not None else "cuda")
     if dev.index is None:
         dev = torch.device("cuda", torch.cuda.current_device())
+    src_h = src.detach().to(torch.float32).contiguous()
+    ref_h = ref.detach().to(device="cpu", dtype=torch.float32).contiguous()
+    out = torch.empty((N, L), dtype=torch.float32, pin_memory=True)
+    if N == 0 or L == 0:
+        return out.to(out_dtype)
     with torch.cuda.device(dev):
-        main = torch.cuda.current_stream(dev)
-        side = _side_stream(dev)
-        ref_h, src_h = ref.contiguous(), src.contiguous()
-        # positions first (the lattice build needs them); the RHS block travels on a second stream while the lattice
-        # is being built.  Pinned host tensors are copied asynchronously, pageable ones through the driver's staging.
-        ref_d = ref_h.to(dev, non_blocking=ref_h.is_pinned())
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            src_d = src_h.to(dev, non_blocking=src_h.is_pinned())
-        lat = Lattice(ref_d, coeffs, build_csr=False, build_tiles=False, build_groups=False, sort_points=False,
-                      build_rows=False, keep_structure=False)
-        main.wait_stream(side)
-        src_d.record_stream(main)
-        out_d = lat.mvm(src_d)
-        out = torch.empty(out_d.shape, dtype=out_d.dtype, pin_memory=True)
-        out.copy_(out_d, non_blocking=True)
-        main.synchronize()
-    return out
-
-
-_side_streams = {}
-
-
-def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
-    s = _side_streams.get(dev.index)
-    if s is None:
-        s = torch.cuda.Stream(device=dev)
-        _side_streams[dev.index] = s
-    return s
+        ws = _filter_call(lib.sgp_filter_host, lib.sgp_filter_host_workspace_bytes, dev, N, d, L, order,
+                          (C.c_void_p(src_h.data_ptr()), L, C.c_void_p(ref_h.data_ptr()), d, _fp(c), c.shape[0], N, L, d,
+                           C.c_void_p(out.data_ptr()), L), (_stream_ptr(dev),))
+        del ws   # sgp_filter_host has synchronised: nothing is in flight on the workspace
+    return out if out_dtype == torch.float32 else out.to(out_dtype)

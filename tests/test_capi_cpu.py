@@ -63,6 +63,25 @@ def test_status_codes_not_exceptions(sg):
     assert lib.sgp_number_workspace_bytes(1000, 8) >= 9000 * 4
 
 
+def test_one_call_filter_argument_handling(sg):
+    """sgp_filter / sgp_filter_host validate their arguments and size their workspace on the host, before any CUDA call."""
+    from simplex_gp_b200 import _capi
+    lib = _capi.lib()
+    c = (C.c_float * 3)(0.5, 1.0, 0.5)
+    M = C.c_int64(-1)
+    for fn in (lib.sgp_filter, lib.sgp_filter_host):
+        assert fn(None, 4, None, 3, c, 3, 0, 4, 3, None, 4, None, 0, 0, C.byref(M), None) == 0    # N = 0: nothing to do
+        assert M.value == 0
+        assert fn(None, 4, None, 3, c, 2, 10, 4, 3, None, 4, None, 0, 0, None, None) == -1       # even stencil
+        assert fn(None, 4, None, 3, c, 3, 10, 4, 3, None, 4, None, 0, 0, None, None) == -1       # null pointers
+        assert fn(None, 4, None, 3, c, 3, 10, 4, 500, None, 4, None, 0, 0, None, None) == -1     # d out of range
+    worst = lib.sgp_filter_workspace_bytes(1000, 8, 16, 1, 0)
+    assert worst == lib.sgp_filter_workspace_bytes(1000, 8, 16, 1, 9000) == lib.sgp_filter_workspace_bytes(1000, 8, 16, 1, 10**9)
+    assert lib.sgp_filter_workspace_bytes(1000, 8, 16, 1, 500) < worst
+    assert lib.sgp_filter_host_workspace_bytes(1000, 8, 16, 1, 500) >= lib.sgp_filter_workspace_bytes(1000, 8, 16, 1, 500) + 4 * 1000 * (8 + 32)
+    assert lib.sgp_filter_workspace_bytes(1000, 0, 16, 1, 0) == 0 and lib.sgp_filter_workspace_bytes(-1, 8, 16, 1, 0) == 0
+
+
 def test_no_cpu_fallback(sg):
     """The product path must fail loudly without a CUDA device / library, never fall back to the oracle."""
     if torch.cuda.is_available():

@@ -129,3 +129,42 @@ def _pointshard_worker(rank, world):
 def test_point_sharded_splat_allreduce_gloo():
     res = _run(_pointshard_worker, 2)
     assert res[0] < 1e-6 and res[1] < 1e-6
+
+
+def _keylists_worker(rank, world):
+    """The ragged all-gather of the ranks' key lists (point-sharded build): same lists, in rank order, on every rank."""
+    from simplex_gp_b200.distributed import gather_key_lists
+    g = torch.Generator().manual_seed(100 + rank)
+    mine = torch.randint(-300, 300, (5 + 7 * rank, 4), generator=g, dtype=torch.int16)
+    lists = gather_key_lists(mine)
+    return [t.numpy().copy() for t in lists]
+
+
+def test_gather_key_lists_gloo():
+    res = _run(_keylists_worker, 2)
+    assert [a.shape for a in res[0]] == [(5, 4), (12, 4)]
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    g = torch.Generator().manual_seed(101)
+    assert np.array_equal(res[0][1], torch.randint(-300, 300, (12, 4), generator=g, dtype=torch.int16).numpy())
+
+
+def _bcast_lattice_meta_worker(rank, world):
+    from simplex_gp_b200.distributed import broadcast_lattice_arrays
+    if rank == 0:
+        arrays = {"replay": torch.zeros((0, 3, 2), dtype=torch.int32), "keys": torch.zeros((0, 2), dtype=torch.int16),
+                  "nbr": torch.zeros((3, 0, 2), dtype=torch.int32)}
+        meta = {"N": 0, "M": 0, "d": 2, "order": 1, "coeffs": [0.34608543, 1.0, 0.34608543], "exact": True}
+    else:
+        arrays, meta = None, None
+    arrays, meta = broadcast_lattice_arrays(arrays, meta, src=0, device="cpu")
+    return meta, {k: tuple(v.shape) for k, v in arrays.items()}
+
+
+def test_broadcast_header_carries_exact_and_stencil_bits():
+    res = _run(_bcast_lattice_meta_worker, 2)
+    for meta, shapes in (res[0], res[1]):
+        assert meta["exact"] is True and meta["order"] == 1
+        assert np.array_equal(np.asarray(meta["coeffs"], np.float32).view(np.int32),
+                              np.asarray([0.34608543, 1.0, 0.34608543], np.float32).view(np.int32))
+        assert shapes == {"replay": (0, 3, 2), "keys": (0, 2), "nbr": (3, 0, 2)}

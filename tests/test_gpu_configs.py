@@ -113,3 +113,54 @@ def test_full_stress_configuration_on_one_gpu(sg, oracle):
     del lat
     gc.collect()
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("L", [1, 16])
+def test_metric_configuration_against_oracle_at_full_size(sg, oracle, L):
+    """BASELINE.json configs[1] / the metric shape, ALL points: N = 1M, d = 8, RBF order 1 against the oracle's
+    restatement of the reference (permutohedral.h:259-340) -- lattice structure bit-exact (M, keys in first-touch
+    order, vertex indices, neighbour table), the deterministic path (ordered-gather splat, reference arithmetic)
+    bit-exact on every output, the production path within the north star's 1e-5.  Also measures how far the UNMODIFIED
+    reference (stale-bucket defect of its hash-table growth, permutohedral.h:104-106 vs :61-63; oracle
+    ``reference_table=True``) is from the correct table the product implements; the figure goes to DESIGN.md section 2."""
+    import json
+    import os
+    N, d = 1_000_000, 8
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(N, d, generator=g)
+    v = torch.randn(N, L, generator=g)
+    O = oracle.OracleLattice(x.numpy(), RBF1)
+    lat = sg.Lattice(x.cuda(), RBF1, build_csr=True)
+    assert lat.M == O.M
+    assert np.array_equal(lat.keys.cpu().numpy(), O.keys)
+    assert np.array_equal(lat.offsets.cpu().numpy(), O.offsets)
+    assert np.array_equal(bits(lat.weights.cpu().numpy()), bits(O.weights))
+    assert np.array_equal(lat.greedy.cpu().numpy(), O.greedy) and np.array_equal(lat.rank.cpu().numpy(), O.rank)
+    assert np.array_equal(lat.nbr.cpu().numpy(), O.nbr)
+    want = O.mvm(v.numpy())
+    vd = v.cuda()
+    exact = lat.mvm(vd, mode=2, exact=True).cpu().numpy()
+    assert np.array_equal(bits(exact), bits(want))                      # bit-exact on all N x L outputs
+    prod = lat.mvm(vd).cpu().numpy().astype(np.float64)
+    rel = float(np.linalg.norm(prod - want) / np.linalg.norm(want))
+    assert rel < 1e-5
+    one_call = sg.filter(vd, x.cuda(), torch.tensor(RBF1)).cpu().numpy().astype(np.float64)
+    rel_filter = float(np.linalg.norm(one_call - want) / np.linalg.norm(want))
+    assert rel_filter < 1e-5
+    # the unmodified reference: same geometry, a few orphaned / duplicated lattice points per table doubling
+    R = oracle.OracleLattice(x.numpy(), RBF1, reference_table=True)
+    ref = R.mvm(v.numpy()).astype(np.float64)
+    dev = np.abs(ref - want)
+    rel_ref = float(np.linalg.norm(ref - want) / np.linalg.norm(want))
+    rows_off = int((dev.max(axis=1) > 1e-6 * np.abs(want).max()).sum())
+    worst = float(dev.max() / np.abs(want).max())
+    assert 0 < rel_ref < 2e-2 and R.M != O.M
+    rec = {"N": N, "d": d, "L": L, "M": int(O.M), "M_unmodified_reference": int(R.M),
+           "production_rel_l2_vs_oracle": rel, "one_call_filter_rel_l2_vs_oracle": rel_filter,
+           "unmodified_reference_rel_l2_vs_correct_table": rel_ref,
+           "unmodified_reference_rows_differing": rows_off, "unmodified_reference_worst_abs_over_max": worst}
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, f"parity_full_size_L{L}.json"), "w") as f:
+            json.dump(rec, f, indent=1)
+    print(json.dumps(rec))

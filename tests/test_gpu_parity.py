@@ -351,3 +351,49 @@ def test_row_sorted_splat_on_a_point_subset_with_the_full_key_set(sg, oracle):
         assert _rel(got.cpu().numpy(), sp_o) < REL_TOL
     want = O.mvm(vz)[lo:hi]
     assert _rel(part.mvm(vd).cpu().numpy(), want) < REL_TOL
+
+
+@pytest.mark.parametrize("N,d,coeffs,shards", [(6000, 5, RBF1, 3), (2500, 11, MAT15_2, 2), (900, 2, RBF1, 4), (40, 3, RBF1, 5)])
+def test_sharded_build_equals_full_build(sg, N, d, coeffs, shards):
+    """Point-sharded lattice build, its ranks emulated in one process: each share of the points builds its own lattice,
+    the key lists are merged in rank order (sgp_hash_append_keys / count / number) -- keys, vertex indices and the
+    tables derived from the merged hash table are those of the lattice built from all points at once
+    (the reference's sequential first-touch numbering, permutohedral.h:73-79,467-485)."""
+    from simplex_gp_b200.distributed import merge_key_lists, shard_points
+    x, v = make_inputs(N, d, 6, seed=N + shards)
+    xd, vd = x.cuda(), v.cuda()
+    full = sg.Lattice(xd, coeffs)
+    parts = []
+    for g in range(shards):
+        lo, hi = shard_points(N, shards, g)
+        parts.append(sg.Lattice(xd[lo:hi].contiguous(), coeffs, build_groups=False, build_rows=False, build_nbr=False))
+        assert parts[-1].nbr is None and parts[-1].groups is None
+    lists = [p.keys for p in parts]
+    want_out = full.mvm(vd, mode=1, blur="axis", exact=True)
+    total = torch.zeros(full.M, 6, device="cuda")
+    outs = []
+    for g in range(shards):
+        lo, hi = shard_points(N, shards, g)
+        keys, table, lmap = merge_key_lists(lists, want_map_of=g)
+        assert torch.equal(keys, full.keys)
+        replay = parts[g].replay.clone()
+        replay[..., 0] = lmap[replay[..., 0].long()]
+        assert torch.equal(replay, full.replay[lo:hi])
+        loc = sg.Lattice.from_arrays(coeffs, replay, keys.contiguous(), None, table=table)
+        assert torch.equal(loc.nbr, full.nbr)
+        # this share's splat into the full lattice; the sum over the shares is the exchange step of point sharding
+        total += loc.splat(vd[lo:hi].contiguous(), mode=4)
+        outs.append(loc)
+    assert float((total - full.splat(vd, mode=1)).norm() / total.norm()) < 1e-6
+    for g, loc in enumerate(outs):
+        lo, hi = shard_points(N, shards, g)
+        state = {}
+        got = loc.mvm(vd[lo:hi].contiguous(), after_splat=lambda vals: vals[:, :6].copy_(total))
+        assert float((got - want_out[lo:hi]).norm() / want_out[lo:hi].norm()) < 1e-5
+        # without the whole-lattice neighbour table: blur groups straight from the merged hash table
+        keys, table, lmap = merge_key_lists(lists, want_map_of=g)
+        lean = sg.Lattice.from_arrays(coeffs, loc.replay, keys.contiguous(), None, table=table, build_nbr=False)
+        if lean.groups is not None:
+            assert lean.nbr is None
+            got = lean.mvm(vd[lo:hi].contiguous(), after_splat=lambda vals: vals[:, :6].copy_(total))
+            assert float((got - want_out[lo:hi]).norm() / want_out[lo:hi].norm()) < 1e-5
