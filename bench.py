@@ -45,11 +45,36 @@ COEFFS = {   # tests/golden/coeffs.json (the reference's DiscretizedKernelFN)
     ("matern1.5", 3): [0.08435782, 0.24239115, 0.60311586, 1.0, 0.60311586, 0.24239115, 0.08435782],
 }
 RBF1 = [0.34608543, 1.0, 0.34608543]   # get_coeffs(rbf, 1), tests/golden/coeffs.json
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/),
-# cold-cache replays of the same command; None until a capture exists for the kernel
-TRAFFIC_NCU = {   # profiles/r1_mvm_full.txt
-    "sgp_splat_rows_kernel": 200.8e6, "sgp_blur_group_kernel": 32.4e6, "sgp_slice_kernel": 120.2e6,
-}
+
+
+def kernel_source_stamp():
+    """sha256 over the CUDA sources and the public header: profiles/traffic.json is only valid for the kernels it was
+    captured from (profiles/summarize.py --traffic writes the same stamp)."""
+    import hashlib
+    h = hashlib.sha256()
+    files = []
+    for base in (os.path.join(ROOT, "simplex-gp_b200", "csrc"), os.path.join(ROOT, "include")):
+        for f in sorted(os.listdir(base)):
+            if f.endswith((".cu", ".cuh", ".h")):
+                files.append(os.path.join(base, f))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_traffic():
+    """{kernel name: dram__bytes_read.sum + dram__bytes_write.sum per launch} from the committed `ncu --set full` capture
+    (profiles/traffic.json, cold-cache replays of profiles/ncu_mvm.py), or {} when the capture is older than the
+    kernels: a stale figure is reported as null, never as a number."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+    except Exception:
+        return {}, "no profiles/traffic.json"
+    if t.get("source_stamp") != kernel_source_stamp():
+        return {}, f"profiles/traffic.json is stale (captured for sources {t.get('source_stamp')})"
+    return t.get("kernels", {}), f"profiles/traffic.json ({t.get('report')})"
 
 
 def workload_name(w):
@@ -196,8 +221,238 @@ def run_reference_arm(args, w):
 
 
 # ---------------------------------------------------------------------------------------------
+# host placement: one rank per GPU, its threads and pinned buffers on the GPU's NUMA node
+# ---------------------------------------------------------------------------------------------
+def pin_rank_to_gpu_numa(local: int):
+    """Restrict this process to the CPUs local to GPU `local` (sysfs local_cpulist of its PCI device), so that the
+    pinned staging buffers it allocates afterwards are first-touched on that NUMA node: in round 1 all 8 ranks ran on
+    CPUs 0-31 and the end-to-end filter() scaled 3.0x at 8 GPUs.  Returns a short description for the bench line."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return f"gpu {local}: no local cpus within the allowed set"
+        os.sched_setaffinity(0, cpus)
+        node = None
+        try:
+            with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+                node = int(f.read().strip())
+        except Exception:
+            pass
+        return f"gpu {local} ({bus}) numa {node}: {len(cpus)} cpus {spec}"
+    except Exception as exc:
+        return f"not pinned: {exc!r}"
+
+
+def timed_steps(step, steps, warm, world, dev):
+    """`warm` untimed + exactly `steps` timed calls of step(i): barrier + synchronize on both sides, CUDA events on the
+    launching stream, MAX over ranks.  Returns elapsed milliseconds."""
+    import torch
+    import torch.distributed as dist
+    for i in range(warm):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def array_checksum(t):
+    """Order-sensitive 64-bit checksum of a tensor's bytes (for comparing broadcast / merged lattices across ranks)."""
+    import torch
+    b = t.contiguous().view(-1).view(torch.uint8)
+    pad = (-b.numel()) % 8
+    if pad:
+        b = torch.cat([b, torch.zeros(pad, dtype=torch.uint8, device=b.device)])
+    w = b.view(torch.int64)
+    idx = torch.arange(w.numel(), device=w.device, dtype=torch.int64)
+    return int(((w ^ (idx * 0x1E3779B97F4A7C15)).sum()).item())
+
+
+# ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+def strong_and_check(args, w, lat, world, rank, dev, ms_full_block, mode, blur_arg, steps, warm):
+    """N > 1, inside the line the driver records:
+    strong -- ONE L-column job (the block every rank filtered whole in the weak run) with its columns split over the
+              ranks: MVM/s of that job and the speed-up over one GPU filtering all L columns (this run's own weak step);
+    check  -- NCCL correctness against the single-GPU result: the broadcast lattice is rank 0's (checksums of replay /
+              keys / nbr gathered from every rank), the column-sharded product gathered with all_gather equals the
+              unsharded one, and the point-sharded product (sharded build + all-reduce of the lattice values) equals it
+              too, with the sharded build's keys equal to rank 0's."""
+    import torch
+    import torch.distributed as dist
+
+    from simplex_gp_b200.distributed import ColumnShardedOperator, PointShardedLattice, shard_columns, shard_points
+    N, d, L = w["N"], w["d"], w["L"]
+    coeffs = COEFFS[(w["kernel"], w["order"])]
+    lo, hi = shard_columns(L, world, rank)
+    Lr = hi - lo
+    strong = None
+    if Lr >= 1 and L >= world:
+        gv = torch.Generator(device=dev).manual_seed(4321)      # the same job on every rank
+        n_rot = 4
+        Vfull = [torch.randn(N, L, generator=gv, device=dev) for _ in range(n_rot)]
+        Vs = [v[:, lo:hi].contiguous() for v in Vfull]
+        del Vfull
+        outs = [torch.empty(N, Lr, device=dev) for _ in range(n_rot)]
+        graphs = None if args.no_graph else [lat.capture(Vs[k], outs[k], mode=mode, blur=blur_arg) for k in range(n_rot)]
+
+        def step(i):
+            if graphs is not None:
+                graphs[i % n_rot].replay()
+            else:
+                lat.mvm(Vs[i % n_rot], out=outs[i % n_rot], mode=mode, blur=blur_arg)
+
+        ms = timed_steps(step, steps, warm, world, dev) / steps
+        strong = {"job": f"one {L}-column block, columns split {world} ways ({Lr} per rank)", "value": 1e3 / ms, "unit": UNIT,
+                  "ms_per_step": ms, "one_gpu_ms_per_step": ms_full_block, "speedup_vs_1": ms_full_block / ms,
+                  "limiter": "the per-point index streams (replay / row-sorted entries: 8.5-16 B per point-vertex) do not "
+                             "shrink with the column count; column sharding pays when M*L >> N*(d+1) (workload C)"}
+        del graphs, Vs, outs
+    # ---- correctness ----------------------------------------------------------------------------------------------
+    sums = torch.tensor([array_checksum(lat.replay), array_checksum(lat.keys), array_checksum(lat.nbr)], device=dev)
+    allsums = [torch.zeros_like(sums) for _ in range(world)]
+    dist.all_gather(allsums, sums)
+    same = all(bool(torch.equal(a, allsums[0])) for a in allsums)
+    gv = torch.Generator(device=dev).manual_seed(777)
+    V = torch.randn(N, L, generator=gv, device=dev)             # identical on every rank
+    want = lat.mvm(V).clone()
+    op = ColumnShardedOperator(lat)
+    full = op.matmul_full(V)
+    e_col = float((full - want).norm() / want.norm())
+    x = torch.randn(N, d, generator=torch.Generator().manual_seed(0)).to(dev)
+    ps = PointShardedLattice(x, coeffs)      # first use: communicator channels for all_gather, allocator
+    del ps
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    ps = PointShardedLattice(x, coeffs)
+    torch.cuda.synchronize()
+    ps_build_ms = (time.perf_counter() - t0) * 1e3
+    plo, phi = shard_points(N, world, rank)
+    mine = ps.mvm(V[plo:phi].contiguous())
+    e_pt = torch.tensor([float((mine - want[plo:phi]).norm() / want[plo:phi].norm())], device=dev, dtype=torch.float64)
+    dist.all_reduce(e_pt, op=dist.ReduceOp.MAX)
+    keys_same = torch.tensor([int(ps.M == lat.M and array_checksum(ps.local.keys) == int(allsums[0][1].item()))], device=dev)
+    dist.all_reduce(keys_same, op=dist.ReduceOp.MIN)
+    e_colt = torch.tensor([e_col], device=dev, dtype=torch.float64)
+    dist.all_reduce(e_colt, op=dist.ReduceOp.MAX)
+    check = {"broadcast_lattice_identical_on_all_ranks": bool(same),
+             "column_sharded_all_gather_rel_err": float(e_colt.item()),
+             "point_sharded_rel_err": float(e_pt.item()),
+             "point_sharded_build_keys_equal_rank0_build": bool(keys_same.item()),
+             "point_sharded_build_ms": ps_build_ms, "tolerance": 1e-5,
+             "ok": bool(same and float(e_colt.item()) < 1e-5 and float(e_pt.item()) < 1e-5 and bool(keys_same.item()))}
+    del ps, V, want, full, mine, x
+    return strong, check
+
+
+def run_point_sharded(args, w, world, rank, dev, placement):
+    """`--scaling point`: the POINTS are split over the ranks (BASELINE.json configs[4]).  Every rank builds the lattice
+    of its own points only, the key lists are merged (sharded build), and a step is: local splat of the rank's rows into
+    the full [M, L] lattice, NCCL all-reduce of M*L*4 bytes, blur (replicated), local slice.  `value` = whole-job MVM/s."""
+    import torch
+    import torch.distributed as dist
+
+    from simplex_gp_b200.distributed import PointShardedLattice, shard_points
+    N, d, L = w["N"], w["d"], w["L"]
+    coeffs = COEFFS[(w["kernel"], w["order"])]
+    steps, warm = args.steps, max(args.warmup, 3)
+    lo, hi = shard_points(N, world, rank)
+    g = torch.Generator().manual_seed(0)
+    # every rank draws the same stream and keeps its share (the whole set is only 4*N*d bytes on the host)
+    x_loc = torch.randn(N, d, generator=g)[lo:hi].contiguous().to(dev)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    ps = PointShardedLattice(x_loc, coeffs, x_is_local=True, build_nbr=w.get("build_nbr", True))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    build_ms = (time.perf_counter() - t0) * 1e3
+    M = ps.M
+    n_rot = 2
+    gv = torch.Generator(device=dev).manual_seed(1234 + rank)
+    Vs = [torch.randn(hi - lo, L, generator=gv, device=dev) for _ in range(n_rot)]
+    outs = [torch.empty(hi - lo, L, device=dev) for _ in range(n_rot)]
+
+    def step(i):
+        outs[i % n_rot] = ps.mvm(Vs[i % n_rot], out=outs[i % n_rot])
+
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    elapsed_ms = timed_steps(step, steps, warm, world, dev)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = elapsed_ms / steps
+    # the exchange step alone
+    vals = torch.zeros(M, (L + 3) // 4 * 4 if L > 4 else L, device=dev)
+
+    def ar(i):
+        if world > 1:
+            dist.all_reduce(vals)
+
+    ar_ms = timed_steps(ar, max(5, min(steps, 20)), 2, world, dev) / max(5, min(steps, 20)) if world > 1 else 0.0
+    peak, peak_src = load_peaks()
+    mem = torch.tensor([torch.cuda.max_memory_allocated(dev)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(mem, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        r = w["order"]
+        alg = 4 * (2 * N * L + 4 * N * (d + 1) + 2 * M * L + (d + 1) * (2 * M * L + 2 * r * M))
+        line = {
+            "metric": f"lattice MVM/s ({workload_name(w)})", "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(w), "M": M, "points_per_rank": hi - lo, "M_local_rank0": ps.M_local,
+                       "sharding": "points split over the ranks; sharded lattice build (per-rank build + key-list merge); "
+                                   "per step: local splat -> NCCL all-reduce of M*L*4 bytes -> replicated blur -> local slice",
+                       "l2": "inputs larger than L2 (index tables and lattice values exceed 126 MB)"},
+            "clocks": clocks, "gpu_launches": steps * (2 + (len(ps.local.groups["list"]) if ps.local.groups else d + 1)),
+            "lattice_build_ms": build_ms, "allreduce_bytes_per_step": int(vals.numel() * 4), "allreduce_ms": ar_ms,
+            "allreduce_share_of_step": ar_ms / ms_per_step if ms_per_step else None,
+            "peak_device_memory_gb": float(mem.item()) / 1e9,
+            "mvm_roofline": {"alg_bytes": alg, "achieved": alg / ms_per_step / 1e6, "peak": peak * world, "unit": "GB/s",
+                             "frac": alg / ms_per_step / 1e6 / (peak * world), "peak_source": peak_src,
+                             "note": "whole-job algorithmic bytes over the aggregate HBM peak of the ranks; the blur's "
+                                     "(d+1)(2ML+2rM) bytes are replicated on every rank, so they do not speed up"},
+            "limiter": "the replicated blur (every rank moves the whole lattice d+1 times) plus the all-reduce; only "
+                       "splat and slice shrink with the rank count",
+            "host_placement": placement,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def run_ours(args, w):
     import torch
     import torch.distributed as dist
@@ -214,12 +469,15 @@ def run_ours(args, w):
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    placement = pin_rank_to_gpu_numa(local) if not args.no_pin else "not pinned (--no-pin)"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     if args.gpus != world:
         if rank == 0:
             print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    if args.scaling == "point":
+        return run_point_sharded(args, w, world, rank, dev, placement)
 
     N, d, L = w["N"], w["d"], w["L"]
     L_job = L
@@ -248,14 +506,26 @@ def run_ours(args, w):
         e1.record()
         torch.cuda.synchronize()
         build_ms = e0.elapsed_time(e1)
+    bcast_cold_ms = None
     if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        lat = broadcast_lattice(lat, src=0, device=dev)
-        torch.cuda.synchronize()
-        dist.barrier()
-        bcast_ms = (time.perf_counter() - t0) * 1e3
+        # cold: first collective of the process (communicator set-up); warm: what a hyper-parameter step pays -- header +
+        # one byte buffer over NVLink, then the derived tables (blur groups, row-sorted entries) rebuilt on each rank
+        lat0 = lat
+        for attempt in range(2):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            lat = broadcast_lattice(lat0, src=0, device=dev)
+            torch.cuda.synchronize()
+            dist.barrier()
+            dt = (time.perf_counter() - t0) * 1e3
+            if attempt == 0:
+                bcast_cold_ms = dt
+                if rank != 0:
+                    del lat
+            else:
+                bcast_ms = dt
+        del lat0
     M = lat.M
 
     # --- this rank's RHS blocks -----------------------------------------------------------------------
@@ -286,30 +556,19 @@ def run_ours(args, w):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()   # sampled over warm-up + timed region (a 50-step timed region alone lasts only ~11 ms)
-    for i in range(warm):
-        step(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for i in range(steps):
-        step(i)
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    elapsed_ms = timed_steps(step, steps, warm, world, dev)
     clocks = sampler.stop() if rank == 0 else None
-    elapsed_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(elapsed_ms.item())
     ms_per_step = elapsed_ms / steps
     value = (1 if args.scaling == "strong" else world) * steps / (elapsed_ms * 1e-3)
 
+    # --- N > 1: the same 16-column job split over the ranks (strong), and NCCL correctness in the line -------------
+    strong = check = None
+    if world > 1 and args.scaling == "weak" and not args.no_multi_gpu_check:
+        strong, check = strong_and_check(args, w, lat, world, rank, dev, ms_per_step, mode, blur_arg, steps, warm)
+
     # --- per-stage device times (CUDA events on the launching stream), same buffers, rank 0 -----------
     peak, peak_src = load_peaks()
+    traffic, traffic_src = load_traffic()
     roofline = stages = None
     if rank == 0:
         lib = _capi.lib()
@@ -362,21 +621,24 @@ def run_ours(args, w):
         b_blur = (d + 1) * 4 * (2 * M * L + 2 * r * M)
         b_slice = 4 * (M * L + 2 * N * (d + 1) + N * L)
         splat_kernel = {_capi.MODE_ATOMIC: "sgp_splat_atomic_kernel", _capi.MODE_GATHER: "sgp_splat_gather_kernel",
-                        _capi.MODE_TILES: "sgp_splat_tiles_kernel", _capi.MODE_ROWS: "sgp_splat_rows_kernel"}[mode]
+                        _capi.MODE_TILES: "sgp_splat_tiles_kernel",
+                        _capi.MODE_ROWS: "sgp_splat_ring_kernel" if lib.sgp_ring_splat_enabled() else "sgp_splat_rows_kernel"}[mode]
         stages = {
             "splat": {"ms": t_splat, "launches": 1, "alg_bytes": b_splat, "gbs": b_splat / t_splat / 1e6,
                       "kernel": splat_kernel},
             "blur": {"ms": t_blur, "launches": n_blur, "alg_bytes": b_blur, "gbs": b_blur / t_blur / 1e6,
                      "kernel": "sgp_blur_group_kernel" if use_groups else "sgp_blur_kernel"},
             "slice": {"ms": t_slice, "launches": 1, "alg_bytes": b_slice, "gbs": b_slice / t_slice / 1e6,
-                      "kernel": "sgp_slice_tiles_kernel" if mode == _capi.MODE_TILES else "sgp_slice_kernel"},
+                      "kernel": "sgp_slice_tiles_kernel" if mode == _capi.MODE_TILES else
+                                ("sgp_slice_ring_kernel" if lib.sgp_ring_slice_enabled() else "sgp_slice_kernel")},
         }
         dom = max(stages, key=lambda k: stages[k]["ms"] / stages[k]["launches"])
         per_launch_bytes = stages[dom]["alg_bytes"] / stages[dom]["launches"]
         per_launch_ms = stages[dom]["ms"] / stages[dom]["launches"]
         achieved = per_launch_bytes / per_launch_ms / 1e6
         roofline = {"bound": "hbm", "kernel": stages[dom]["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": TRAFFIC_NCU.get(stages[dom]["kernel"]), "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic.get(stages[dom]["kernel"]), "traffic_source": traffic_src,
+                    "peak_source": peak_src,
                     "alg_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
                     "share_of_step": stages[dom]["ms"] / ms_per_step}
         n_launches = 1 + n_blur + 1
@@ -402,8 +664,39 @@ def run_ours(args, w):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * args.e2e_steps / float(dt.item()), "unit": UNIT,
                "h2d_bytes_per_step": 4 * (N * L + N * d), "d2h_bytes_per_step": 4 * N * L,
-               "call": "simplex_gp_b200.filter(src, ref, coeffs) with pinned host tensors: H2D, lattice build, MVM, D2H",
-               "steps": args.e2e_steps, "checksum": float(res.double().sum().item())}
+               "call": "simplex_gp_b200.filter(src, ref, coeffs) with pinned host tensors = ONE sgp_filter_host call: H2D, "
+                       "lattice build, MVM (atomic splat, per-axis blur, ring slice: one product per lattice), D2H",
+               "steps": args.e2e_steps, "ms_per_call": float(dt.item()) / args.e2e_steps * 1e3,
+               "checksum": float(res.double().sum().item())}
+        # where a call's time goes, each phase alone, MAX over ranks (all ranks run it at the same time, as in the call)
+        x_dev, v_dev = x_pin.to(dev), v_pin.to(dev)
+        out_pin = torch.empty(N, L).pin_memory()
+
+        def phase(fn, reps=5):
+            fn()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            t = torch.tensor([(time.perf_counter() - t0) / reps * 1e3], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        def h2d():
+            x_dev.copy_(x_pin, non_blocking=True)
+            v_dev.copy_(v_pin, non_blocking=True)
+
+        e2e["phases_ms"] = {
+            "h2d": phase(h2d),
+            "filter_on_device_tensors": phase(lambda: sg.filter(v_dev, x_dev, c_t)),
+            "d2h": phase(lambda: out_pin.copy_(outs[0], non_blocking=True)),
+        }
+        e2e["host_placement"] = placement
+        del x_dev, v_dev, out_pin
 
     # --- CPU baseline beside it (rank 0, N=1 only, bounded sample) ------------------------------------
     cpu_baseline = None
@@ -439,6 +732,7 @@ def run_ours(args, w):
             "mvm_roofline": {"alg_bytes": alg_bytes, "achieved": alg_bytes / ms_per_step / 1e6, "peak": peak,
                              "unit": "GB/s", "frac": alg_bytes / ms_per_step / 1e6 / peak},
             "stages": stages, "lattice_build_ms": build_ms, "lattice_broadcast_ms": bcast_ms,
+            "lattice_broadcast_cold_ms": bcast_cold_ms, "strong": strong, "multi_gpu_check": check,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -457,8 +751,12 @@ def main():
     ap.add_argument("--splat", default="auto", choices=["auto", "rows", "tiles", "atomic", "gather"],
                     help="splat form: row-sorted segmented gather (default), locality tiles, atomic scatter, ordered gather")
     ap.add_argument("--blur", default="groups", choices=["groups", "axis"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: one L-column RHS block per rank (default); strong: ONE L-column block split over the ranks")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong", "point"],
+                    help="weak: one L-column RHS block per rank (default, plus a `strong` block in the line when N > 1); "
+                         "strong: ONE L-column block split over the ranks; point: the POINTS split over the ranks "
+                         "(sharded lattice build, all-reduce of the lattice values between splat and blur)")
+    ap.add_argument("--no-pin", action="store_true", help="do not restrict the rank to the CPUs of its GPU's NUMA node")
+    ap.add_argument("--no-multi-gpu-check", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the MVM kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -3,6 +3,7 @@
 
     python profiles/summarize.py gpurun_out/mvm_r1e.ncu-rep profiles/r1_mvm_full.txt
     python profiles/summarize.py --launches gpurun_out/r1_launches.csv profiles/r1_launches.txt
+    python profiles/summarize.py --traffic gpurun_out/mvm_r2.ncu-rep          # -> profiles/traffic.json (read by bench.py)
 
 Needs the `ncu` CLI (present in the build container; no GPU required to read a report).
 """
@@ -63,8 +64,39 @@ def launches(path, out):
             f.write(f"{k[:64]:64s} {v[0]:8d} {v[1] / 1e3:12.1f} {v[1] / v[0] / 1e3:10.2f}\n")
 
 
+def traffic(rep):
+    """profiles/traffic.json: DRAM bytes per launch of every kernel in the report (the LAST launch of each kernel
+    name), stamped with the hash of the kernel sources it was captured from; bench.py reports a figure only while the
+    stamp matches the sources it runs."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    kernels = {}
+    for r in data:
+        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0]
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r[idx[m]]) * scale[units[idx[m]]]
+        kernels[name] = tot
+    out = {"report": os.path.basename(rep), "source_stamp": bench.kernel_source_stamp(),
+           "how": "ncu --set full --clock-control none python profiles/ncu_mvm.py; dram__bytes_read.sum + dram__bytes_write.sum per launch (cold cache)",
+           "kernels": kernels}
+    with open(os.path.join(root, "profiles", "traffic.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "--launches":
+    if sys.argv[1] == "--traffic":
+        traffic(sys.argv[2])
+    elif sys.argv[1] == "--launches":
         launches(sys.argv[2], sys.argv[3])
     else:
         report(sys.argv[1], sys.argv[2])

@@ -80,6 +80,15 @@ int filter_layout(int64_t N, int d, int L, int order, int64_t M_max, bool host, 
     return SGP_OK;
 }
 
+// [N, width] fp32 rows between pitched buffers: one flat copy when both sides are dense (the common case: the 2-D form
+// takes a slower path for large pinned transfers)
+cudaError_t copy_rows(float *dst, int64_t ldd, const float *src, int64_t lds, int width, int64_t N, cudaMemcpyKind kind,
+                      cudaStream_t st)
+{
+    if (ldd == width && lds == width) return cudaMemcpyAsync(dst, src, (size_t)N * width * 4, kind, st);
+    return cudaMemcpy2DAsync(dst, (size_t)ldd * 4, src, (size_t)lds * 4, (size_t)width * 4, (size_t)N, kind, st);
+}
+
 // one side stream per device for the host variant's second upload (created on first use, never destroyed)
 cudaStream_t copy_stream(int dev)
 {
@@ -205,7 +214,7 @@ extern "C" int sgp_filter_host(const float *src_host, int64_t lds, const float *
     CUDA_TRY(cudaGetDevice(&dev));
     // positions first (the lattice build needs them); the RHS block travels on a second stream while the lattice is
     // being built.  Pinned host memory is copied asynchronously, pageable memory through the driver's staging.
-    CUDA_TRY(cudaMemcpy2DAsync(ref_d, (size_t)d * 4, ref_host, (size_t)ldx * 4, (size_t)d * 4, (size_t)N, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(copy_rows(ref_d, d, ref_host, ldx, d, N, cudaMemcpyHostToDevice, st));
     cudaStream_t side = copy_stream(dev);
     cudaEvent_t fork = nullptr, ready = nullptr;
     if (side) {
@@ -221,13 +230,12 @@ extern "C" int sgp_filter_host(const float *src_host, int64_t lds, const float *
         CUDA_TRY(cudaEventRecord(fork, st));
         CUDA_TRY(cudaStreamWaitEvent(side, fork, 0));
     }
-    cudaError_t ce = cudaMemcpy2DAsync(src_d, (size_t)L * 4, src_host, (size_t)lds * 4, (size_t)L * 4, (size_t)N,
-                                       cudaMemcpyHostToDevice, up);
+    cudaError_t ce = copy_rows(src_d, L, src_host, lds, L, N, cudaMemcpyHostToDevice, up);
     if (ce == cudaSuccess && side) ce = cudaEventRecord(ready, side);
     if (ce == cudaSuccess)
         rc = filter_device(src_d, L, ref_d, d, coeffs, k, N, L, d, out_d, L, base, w, M_out, st, side ? ready : nullptr);
     if (ce == cudaSuccess && rc == SGP_OK)
-        ce = cudaMemcpy2DAsync(out_host, (size_t)ldo * 4, out_d, (size_t)L * 4, (size_t)L * 4, (size_t)N, cudaMemcpyDeviceToHost, st);
+        ce = copy_rows(out_host, ldo, out_d, L, L, N, cudaMemcpyDeviceToHost, st);
     if (side) cudaStreamSynchronize(side);   // also on the error paths: the upload must not outlive the call
     cudaError_t se = cudaStreamSynchronize(st);
     if (fork) cudaEventDestroy(fork);
