@@ -107,12 +107,13 @@ def build_model(train_x, train_y, nu: Optional[float], order: int, min_noise: fl
     return gp.ExactGPModel(train_x, train_y, kernel.to(train_x.device), min_noise=min_noise).to(train_x.device)
 
 
-def train(model, optim, probes, cg_iter: int = 500, cg_tol: float = 1.0) -> dict:
+def train(model, optim, probes, cg_iter: int = 500, cg_tol: float = 1.0, pre_size: int = 100) -> dict:
     """One optimiser step on the negative marginal log-likelihood (train_simplexgp.py:29-57)."""
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     optim.zero_grad()
-    res = model.mll(probes=probes, tol=cg_tol, max_iter=cg_iter) if model.train_x.shape[0] > model.max_cholesky_size \
+    res = model.mll(probes=probes, tol=cg_tol, max_iter=cg_iter, preconditioner_size=pre_size) \
+        if model.train_x.shape[0] > model.max_cholesky_size \
         else model.mll()
     value, surrogate = res if isinstance(res, tuple) else (float(res.detach()), res)
     torch.cuda.synchronize()
@@ -124,18 +125,19 @@ def train(model, optim, probes, cg_iter: int = 500, cg_tol: float = 1.0) -> dict
     return {"train/mll": float(value), "train/loss_ts": loss_ts, "train/bw_ts": total - loss_ts, "train/total_ts": total}
 
 
-def test(x, y, model, cg_iter: int = 500, cg_tol: float = 1e-2, label: str = "test", variance_points: int = 0) -> dict:
+def test(x, y, model, cg_iter: int = 500, cg_tol: float = 1e-2, label: str = "test", variance_points: int = 0,
+         pre_size: int = 100) -> dict:
     """RMSE / MAE of the posterior mean (train_simplexgp.py:60-84); the NLL on the first ``variance_points`` points
     when asked for (exact variance, one CG solve per 16 points)."""
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    mean = model.predict(x, tol=cg_tol, max_iter=cg_iter)
+    mean = model.predict(x, tol=cg_tol, max_iter=cg_iter, preconditioner_size=pre_size)
     torch.cuda.synchronize()
     out = {f"{label}/rmse": float((mean - y).pow(2).mean().sqrt()), f"{label}/mae": float((mean - y).abs().mean()),
            f"{label}/pred_ts": time.perf_counter() - t0}
     if variance_points > 0:
         k = min(int(variance_points), x.shape[0])
-        m, var = model.predict(x[:k].contiguous(), tol=cg_tol, max_iter=cg_iter, variance=True)
+        m, var = model.predict(x[:k].contiguous(), tol=cg_tol, max_iter=cg_iter, variance=True, preconditioner_size=pre_size)
         sd = (var + model.noise.detach()).sqrt()
         out[f"{label}/nll"] = float(-torch.distributions.Normal(m, sd).log_prob(y[:k]).mean())
     return out
@@ -144,7 +146,8 @@ def test(x, y, model, cg_iter: int = 500, cg_tol: float = 1e-2, label: str = "te
 def main(dataset: str = "elevators", data_dir: Optional[str] = None, log_int: int = 1, seed: Optional[int] = None,
          device: int = 0, epochs: int = 100, lr: float = 0.1, p_epochs: int = 200, n_probes: int = 10,
          cg_iter: int = 500, cg_tol: float = 1.0, cg_eval_tol: float = 1e-2, nu: Optional[float] = 1.5, order: int = 1,
-         min_noise: float = 0.1, max_n: Optional[int] = None, variance_points: int = 0, quiet: bool = False) -> dict:
+         min_noise: float = 0.1, max_n: Optional[int] = None, variance_points: int = 0, quiet: bool = False,
+         pre_size: int = 100) -> dict:
     if not torch.cuda.is_available():
         raise RuntimeError("experiments/train_simplexgp.py needs a CUDA device: the lattice operator has no CPU path")
     set_seeds(seed)
@@ -160,10 +163,10 @@ def main(dataset: str = "elevators", data_dir: Optional[str] = None, log_int: in
     probes = torch.randn(train_x.shape[0], n_probes, device=dev).sign()
     stopper = EarlyStopper(patience=p_epochs)
     for i in range(epochs):
-        rec = {"step": i + 1, **train(model, optim, probes, cg_iter=cg_iter, cg_tol=cg_tol)}
+        rec = {"step": i + 1, **train(model, optim, probes, cg_iter=cg_iter, cg_tol=cg_tol, pre_size=pre_size)}
         if i % log_int == 0:
-            rec.update(test(val_x, val_y, model, cg_iter, cg_eval_tol, "val"))
-            rec.update(test(test_x, test_y, model, cg_iter, cg_eval_tol, "test", variance_points))
+            rec.update(test(val_x, val_y, model, cg_iter, cg_eval_tol, "val", pre_size=pre_size))
+            rec.update(test(test_x, test_y, model, cg_iter, cg_eval_tol, "test", variance_points, pre_size=pre_size))
             rec.update({"param/noise": float(model.noise.detach()), "param/outputscale": float(model.outputscale.detach())})
             stopper(-rec["val/rmse"], {"state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
                                        "summary": {"test/best_rmse": rec["test/rmse"], "val/best_step": i + 1,

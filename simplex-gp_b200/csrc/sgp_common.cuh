@@ -11,6 +11,18 @@ int sgp_fail(int code, const char *fmt, ...);
 int sgp_pdl_enabled(void);   // SGP_PDL=0 turns programmatic dependent launch off (default on)
 int sgp_launch_ok(const char *what);
 
+// NVTX range per stage (the replacement for the reference's -DDEBUG stage timers, permutohedral.h:268-336): every stage
+// entry point opens a range named after itself when the environment says SGP_NVTX=1 (read once); otherwise one branch.
+int sgp_nvtx_enabled(void);
+void sgp_nvtx_push(const char *name);
+void sgp_nvtx_pop(void);
+struct SgpRange {
+    bool on;
+    explicit SgpRange(const char *name) : on(sgp_nvtx_enabled() != 0) { if (on) sgp_nvtx_push(name); }
+    ~SgpRange() { if (on) sgp_nvtx_pop(); }
+};
+#define SGP_RANGE(name) SgpRange sgp_range_guard_(name)
+
 #define CUDA_TRY(expr)                                                                        \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \

@@ -177,6 +177,7 @@ extern "C" int sgp_filter(const float *src, int64_t lds, const float *ref, int64
                           int64_t N, int L, int d, float *out, int64_t ldo, void *workspace, size_t workspace_bytes,
                           int64_t M_max, int64_t *M_out, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_filter");
     if (M_out) *M_out = 0;
     if (!coeffs || k < 1 || (k & 1) == 0) return fail(SGP_EINVAL, "sgp_filter: the stencil must have odd length >= 1");
     FilterWs w;
@@ -196,6 +197,7 @@ extern "C" int sgp_filter_host(const float *src_host, int64_t lds, const float *
                                int k, int64_t N, int L, int d, float *out_host, int64_t ldo, void *workspace,
                                size_t workspace_bytes, int64_t M_max, int64_t *M_out, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_filter_host");
     if (M_out) *M_out = 0;
     if (!coeffs || k < 1 || (k & 1) == 0) return fail(SGP_EINVAL, "sgp_filter_host: the stencil must have odd length >= 1");
     FilterWs w;

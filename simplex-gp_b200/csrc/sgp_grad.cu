@@ -132,6 +132,7 @@ extern "C" int sgp_grad_channels(int d, int nl) { return 2 * (d + 1) * nl; }
 extern "C" int sgp_grad_pack(const float *g, int64_t ldg, const float *v, int64_t ldv, const float *x, int64_t ldx,
                              int64_t N, int d, int l0, int nl, float *packed, int64_t ldp, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_grad_pack");
     int rc = check_common(N, d, l0, nl, ldp);
     if (rc) return rc;
     if (N == 0) return SGP_OK;
@@ -154,6 +155,7 @@ extern "C" int sgp_grad_contract(const float *filtered, int64_t ldp, const float
                                  int first, int last, float *grad_x, int64_t ldgx, float *grad_src, int64_t ldgs,
                                  sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_grad_contract");
     int rc = check_common(N, d, l0, nl, ldp);
     if (rc) return rc;
     if (N == 0) return SGP_OK;

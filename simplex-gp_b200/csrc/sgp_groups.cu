@@ -263,6 +263,7 @@ extern "C" int sgp_group_prepare(const int16_t *keys, int64_t M, int d, int j0, 
                                  uint32_t *class_start, void *workspace, size_t workspace_bytes, int64_t *max_class_out,
                                  sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_group_prepare");
     if (!keys || !order || !pos || !class_start || !workspace || !max_class_out || M <= 0 || d < 1 || d > SGP_MAX_DIM ||
         j0 < 0 || j1 <= j0 || j1 > d + 1)
         return fail(SGP_EINVAL, "sgp_group_prepare: bad argument");
@@ -311,6 +312,7 @@ extern "C" int sgp_group_finalize(const int32_t *nbr, const int16_t *keys, int d
                                   void *workspace, size_t workspace_bytes, int64_t *n_batches_out, int32_t *max_rows_out,
                                   sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_group_finalize");
     if (!nbr && (!keys || !table || capacity < 2 || (capacity & (capacity - 1)) != 0 || d < 1 || d > SGP_MAX_DIM))
         return fail(SGP_EINVAL, "sgp_group_finalize: needs either nbr or keys + hash table");
     if (!order || !pos || !class_start || !batch_begin || !src || !lnb || !workspace || !max_rows_out ||
@@ -562,6 +564,7 @@ extern "C" int sgp_blur_groups_channel_block(int L)
 extern "C" int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64_t M, int order, const float *coeffs,
                                int k, int L, float *buf0, float *buf1, int *result_in_buf1, int fast, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_blur_groups");
     if (!groups || n_groups < 1 || M < 0 || L < 1 || !coeffs || k != 2 * order + 1 || order < 1 || order > SGP_MAX_ORDER)
         return fail(SGP_EINVAL, "sgp_blur_groups: bad argument");
     if (result_in_buf1) *result_in_buf1 = 0;
@@ -618,6 +621,7 @@ extern "C" int sgp_mvm_rows_groups(const sgp_lattice_view *slice_view, const int
                                    const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1, int Lv,
                                    sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_mvm_rows_groups");
     if (!slice_view) return fail(SGP_EINVAL, "sgp_mvm_rows_groups: null view");
     if (Lv < L || (Lv != L && Lv % 4 != 0)) return fail(SGP_EINVAL, "sgp_mvm_rows_groups: Lv must be L or L rounded up to a multiple of 4");
     int rc = sgp_splat_rows(ent, seg_row, n_entries, slice_view->N, slice_view->M, src, lds, L, buf0, Lv, stream);

@@ -60,6 +60,19 @@ int sgp_pdl_enabled(void)
 #define fail sgp_fail
 #define launch_ok sgp_launch_ok
 
+#include <nvtx3/nvToolsExt.h>   // header-only: resolves the profiler's injection library at run time, no link dependency
+int sgp_nvtx_enabled(void)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SGP_NVTX");
+        v = e ? (atoi(e) != 0) : 0;
+    }
+    return v;
+}
+void sgp_nvtx_push(const char *name) { nvtxRangePushA(name); }
+void sgp_nvtx_pop(void) { nvtxRangePop(); }
+
 extern "C" int sgp_abi_version(void) { return SGP_ABI_VERSION; }
 extern "C" const char *sgp_last_error(void) { return g_err; }
 
@@ -984,6 +997,7 @@ extern "C" int sgp_build_points(const float *x, int64_t N, int d, int64_t ldx, c
                                 int16_t *greedy, int8_t *rank, int32_t *replay, int32_t *status_flags,
                                 sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_build_points");
     int rc = check_dims(N, d);
     if (rc) return rc;
     if (N == 0) return SGP_OK;
@@ -1009,6 +1023,7 @@ extern "C" int sgp_hash_insert(const int16_t *greedy, const int8_t *rank, int64_
                                uint64_t *table, int64_t capacity, uint32_t *slot_of,
                                int32_t *status_flags, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_hash_insert");
     int rc = check_dims(N, d);
     if (rc) return rc;
     if (N == 0) return SGP_OK;
@@ -1048,6 +1063,7 @@ extern "C" int sgp_count_points(const uint64_t *table, int64_t capacity, const u
                                 const int32_t *status_flags, int64_t *M_out, int32_t *flags_out,
                                 sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_count_points");
     int rc = check_dims(N, d);
     if (rc) return rc;
     if (!M_out || !flags_out) return fail(SGP_EINVAL, "sgp_count_points: null output");
@@ -1087,6 +1103,7 @@ extern "C" int sgp_number_points(uint64_t *table, int64_t capacity, const uint32
                                  const void *workspace, int64_t M, int32_t *replay, int16_t *keys,
                                  sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_number_points");
     int rc = check_dims(N, d);
     if (rc) return rc;
     if (N == 0) return SGP_OK;
@@ -1115,6 +1132,7 @@ static int check_capacity(int64_t capacity)
 extern "C" int sgp_hash_seed(const int16_t *keys, int64_t M, int d, uint64_t *table, int64_t capacity,
                              int32_t *status_flags, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_hash_seed");
     if (d < 1 || d > SGP_MAX_DIM) return fail(SGP_EUNSUPPORTED, "d=%d outside [1, %d]", d, SGP_MAX_DIM);
     if (M < 0 || M >= (1ll << 31)) return fail(SGP_EINVAL, "M=%lld out of range", (long long)M);
     int rc = check_capacity(capacity);
@@ -1143,6 +1161,7 @@ extern "C" int sgp_hash_extend(const int16_t *greedy_new, const int8_t *rank_new
                                const int16_t *keys, int64_t M_old, uint64_t *table, int64_t capacity,
                                uint32_t *slot_of, int32_t *status_flags, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_hash_extend");
     int rc = check_extension(N_new, d, M_old);
     if (rc) return rc;
     rc = check_capacity(capacity);
@@ -1162,6 +1181,7 @@ extern "C" int sgp_count_extension(const uint64_t *table, int64_t capacity, cons
                                    int d, void *workspace, size_t workspace_bytes, const int32_t *status_flags,
                                    int64_t *M_add_out, int32_t *flags_out, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_count_extension");
     int rc = check_extension(N_new, d, 0);
     if (rc) return rc;
     if (!M_add_out || !flags_out) return fail(SGP_EINVAL, "sgp_count_extension: null output");
@@ -1201,6 +1221,7 @@ extern "C" int sgp_number_extension(uint64_t *table, int64_t capacity, const uin
                                     const void *workspace, int64_t M_old, int64_t M_add, int32_t *replay_new,
                                     int16_t *keys, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_number_extension");
     int rc = check_extension(N_new, d, M_old);
     if (rc) return rc;
     if (N_new == 0) return SGP_OK;
@@ -1226,6 +1247,7 @@ extern "C" int sgp_hash_append_keys(const int16_t *new_keys, int64_t m_new, int 
                                     uint64_t *table, int64_t capacity, uint32_t *slot_of_new, int32_t *status_flags,
                                     sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_hash_append_keys");
     if (d < 1 || d > SGP_MAX_DIM) return fail(SGP_EUNSUPPORTED, "d=%d outside [1, %d]", d, SGP_MAX_DIM);
     if (m_new < 0 || M_old < 0 || M_old + m_new >= (1ll << 31))
         return fail(SGP_EOVERFLOW, "M_old + m_new does not fit 31-bit lattice indices");
@@ -1244,6 +1266,7 @@ extern "C" int sgp_count_appended(const uint64_t *table, int64_t capacity, const
                                   void *workspace, size_t workspace_bytes, const int32_t *status_flags,
                                   int64_t *M_add_out, int32_t *flags_out, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_count_appended");
     if (!M_add_out || !flags_out) return fail(SGP_EINVAL, "sgp_count_appended: null output");
     *M_add_out = 0;
     *flags_out = 0;
@@ -1278,6 +1301,7 @@ extern "C" int sgp_number_appended(uint64_t *table, int64_t capacity, const uint
                                    int64_t m_new, int d, const void *workspace, int64_t M_old, int64_t M_add,
                                    int32_t *map_out, int16_t *keys, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_number_appended");
     if (m_new == 0) return SGP_OK;
     if (!table || !slot_of_new || !new_keys || !workspace || !keys || d < 1 || d > SGP_MAX_DIM || m_new < 0 || M_old < 0 ||
         M_add < 0 || M_add > m_new)
@@ -1298,6 +1322,7 @@ extern "C" int sgp_build_neighbours(const int16_t *keys, int64_t M, int d, int o
                                     const uint64_t *table, int64_t capacity, int32_t *nbr,
                                     sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_build_neighbours");
     if (d < 1 || d > SGP_MAX_DIM) return fail(SGP_EUNSUPPORTED, "d=%d outside [1, %d]", d, SGP_MAX_DIM);
     if (order < 0 || order > SGP_MAX_ORDER) return fail(SGP_EUNSUPPORTED, "order=%d outside [0, %d]", order, SGP_MAX_ORDER);
     if (M == 0 || order == 0) return SGP_OK;
@@ -1340,6 +1365,7 @@ static inline int pick_vec(int L, int64_t ld_a, int64_t ld_b, const void *p0, co
 extern "C" int sgp_splat(const sgp_lattice_view *lat, const float *src, int64_t lds, int L,
                          float *values, int mode, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_splat");
     int rc = check_view(lat, L);
     if (rc) return rc;
     if (lat->M == 0) return SGP_OK;
@@ -1369,6 +1395,7 @@ extern "C" int sgp_splat(const sgp_lattice_view *lat, const float *src, int64_t 
 extern "C" int sgp_blur(const sgp_lattice_view *lat, const float *coeffs, int k, int L,
                         float *buf0, float *buf1, int *result_in_buf1, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_blur");
     int rc = check_view(lat, L);
     if (rc) return rc;
     if (!coeffs || k != 2 * lat->order + 1) return fail(SGP_EINVAL, "stencil length %d does not match order %d", k, lat->order);
@@ -1434,6 +1461,7 @@ extern "C" int sgp_blur(const sgp_lattice_view *lat, const float *coeffs, int k,
 extern "C" int sgp_slice(const sgp_lattice_view *lat, const float *values, int L, float *out,
                          int64_t ldo, int L_out, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_slice");
     int rc = check_view(lat, L);
     if (rc) return rc;
     if (lat->N == 0) return SGP_OK;

@@ -495,17 +495,18 @@ static int slice_geometry(int dp1, int chunks, int *ppp_out, int *passes_out)
 {
     if (chunks < 1 || chunks > 32) return 0;
     const int ppp = 32 / chunks;
-    // tiles are multiples of 16 bytes (ppp * passes * dp1 even) and at most 4.5 KB; two passes measured best at the
-    // metric shape (smaller stages = more resident warps, and the kernel's speed is proportional to those)
+    // tiles are multiples of 16 bytes (ppp * passes * dp1 even) and at most 2.25 KB: the kernel's speed is proportional
+    // to the resident warps (83 / 64 / 52 us at 24 / 32 / 40 warps per SM at the metric shape), and 2 stages x 8 warps x
+    // 2.25 KB still leaves shared memory for 6 CTAs; two passes of 8 points measured best at L = 16 (1152-byte stages)
     int passes = ring_env("SGP_SLICE_PASSES", 2);
     if (passes < 1) passes = 1;
     if ((ppp * passes * dp1) & 1) ++passes;
-    while (passes > 1 && (size_t)ppp * passes * dp1 * 8 > 4608) {
+    while (passes > 1 && (size_t)ppp * passes * dp1 * 8 > 2304) {
         --passes;
         if ((ppp * passes * dp1) & 1) --passes;
     }
     if (passes < 1) passes = ((ppp * dp1) & 1) ? 2 : 1;
-    if ((size_t)ppp * passes * dp1 * 8 > 9216) return 0;
+    if ((size_t)ppp * passes * dp1 * 8 > 3072) return 0;   // larger stages cost more occupancy than the prefetch gains: one-shot kernel
     *ppp_out = ppp;
     *passes_out = passes;
     return 1;
@@ -516,12 +517,16 @@ extern "C" int sgp_slice_ring_supported(const sgp_lattice_view *lat, const float
     if (!lat || lat->perm || lat->replay_transposed) return 0;
     const int vec = ring_vec(L, values);
     int ppp, passes;
-    return vec != 0 && slice_geometry(lat->d + 1, L / vec, &ppp, &passes);
+    if (vec == 0 || !slice_geometry(lat->d + 1, L / vec, &ppp, &passes)) return 0;
+    // narrow rows: with one or two channel chunks a warp instruction gathers 32 / 16 distinct rows and the one-shot
+    // kernel measures faster (L = 1 / 2 / 4 / 8: 28 / 33 / 38 / 45 us against 64 / 67 / 45 / 49 us; L = 12 / 16 / 32: 59 / 62 / 110 against 57 / 51 / 96); SGP_RING_FORCE=1 overrides (experiments)
+    return L / vec >= ring_env("SGP_RING_MIN_CHUNKS", 3) || ring_env("SGP_RING_FORCE", 0) != 0;
 }
 
 extern "C" int sgp_slice_ring(const sgp_lattice_view *lat, const float *values, int L, float *out, int64_t ldo,
                               int L_out, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_slice_ring");
     if (!lat || lat->N < 0 || lat->d < 1 || lat->d > SGP_MAX_DIM || L < 1) return fail(SGP_EINVAL, "sgp_slice_ring: bad view");
     if (lat->N == 0) return SGP_OK;
     if (!values || !out || !lat->replay || L_out < 1 || L_out > L || ldo < L_out)
@@ -569,6 +574,7 @@ extern "C" int sgp_splat_ring_supported(const float *values, int L) { return rin
 extern "C" int sgp_splat_rows_ring(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
                                    const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_splat_rows_ring");
     if (N == 0 || M == 0) return SGP_OK;
     if (!ent || !seg_row || !src || !values || N < 0 || M < 0 || n_entries < 16 || n_entries % 16 != 0 || L_src < 1 ||
         lds < L_src || L < L_src)

@@ -221,6 +221,7 @@ extern "C" size_t sgp_cg_scratch_floats(int L) { return (size_t)CG_MAX_BLOCKS * 
 extern "C" int sgp_cg_apply(float *AP, const float *P, const float *s, const float *noise, int64_t N, int L,
                             float *pAp, float *scratch, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_cg_apply");
     int rc = cg_check(N, L, AP, P, scratch);
     if (rc) return rc;
     if (!s || !noise || !pAp) return fail(SGP_EINVAL, "sgp_cg_apply: null pointer");
@@ -237,6 +238,7 @@ extern "C" int sgp_cg_update(float *X, float *R, const float *P, const float *AP
                              const float *bnorm, float tol, int64_t N, int L, float *alpha_out, float *beta_out,
                              int32_t *done, float *scratch, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_cg_update");
     int rc = cg_check(N, L, X, R, scratch);
     if (rc) return rc;
     if (!P || !AP || !rs || !pAp || !bnorm || !alpha_out || !beta_out || !done)
@@ -253,6 +255,7 @@ extern "C" int sgp_cg_update(float *X, float *R, const float *P, const float *AP
 
 extern "C" int sgp_cg_direction(float *P, const float *R, const float *beta, int64_t N, int L, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_cg_direction");
     if (N < 1 || L < 1 || L > CG_MAX_COLUMNS || !P || !R || !beta) return fail(SGP_EINVAL, "sgp_cg_direction: bad argument");
     const CgGeometry g = cg_geometry(N, L);
     sgp_cg_direction_kernel<<<g.blocks, CG_THREADS, 0, (cudaStream_t)stream>>>(P, R, beta, N * (int64_t)L, L, g.active,

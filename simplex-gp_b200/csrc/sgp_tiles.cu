@@ -175,6 +175,7 @@ extern "C" int sgp_tiles_prepare(const int32_t *replay, int64_t N, int d, int64_
                                  const uint32_t *perm, void *workspace, size_t workspace_bytes, int64_t *S_out,
                                  sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_tiles_prepare");
     if (!replay || !perm || !workspace || !S_out || N <= 0 || M <= 0 || d < 1 || d > SGP_MAX_DIM)
         return fail(SGP_EINVAL, "sgp_tiles_prepare: bad argument");
     if (tile_points < 1 || (int64_t)tile_points * (d + 1) > 65535)
@@ -222,6 +223,7 @@ extern "C" int sgp_tiles_finalize(const int32_t *replay, const uint32_t *perm, i
                                   int32_t *seg_row, int32_t *seg_ent, uint32_t *tile_seg_ptr, uint16_t *lidx,
                                   float *tile_w, int32_t *max_dict_out, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_tiles_finalize");
     if (!replay || !perm || !workspace || !seg_ptr || !seg_row || !seg_ent || !tile_seg_ptr || !lidx || !tile_w ||
         !max_dict_out || N <= 0 || S <= 0)
         return fail(SGP_EINVAL, "sgp_tiles_finalize: bad argument");
@@ -294,6 +296,7 @@ extern "C" size_t sgp_sort_points_workspace_bytes(int64_t N)
 extern "C" int sgp_sort_points(const int16_t *greedy, int64_t N, int d, uint32_t *perm, void *workspace,
                                size_t workspace_bytes, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_sort_points");
     if (!greedy || !perm || !workspace || N <= 0 || d < 1 || d > SGP_MAX_DIM) return fail(SGP_EINVAL, "sgp_sort_points: bad argument");
     if (workspace_bytes < sgp_sort_points_workspace_bytes(N)) return fail(SGP_EINVAL, "sgp_sort_points: workspace too small");
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -430,6 +433,7 @@ extern "C" int sgp_build_rowsorted(const int32_t *replay, int64_t N, int d, int6
                                    int32_t *ent_row, int32_t *seg_row, void *workspace, size_t workspace_bytes,
                                    sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_build_rowsorted");
     if (!replay || !ent || !seg_row || !workspace || N <= 0 || M <= 0 || d < 1) return fail(SGP_EINVAL, "sgp_build_rowsorted: bad argument");
     if (fill_rows != 0 && fill_rows != M) return fail(SGP_EINVAL, "sgp_build_rowsorted: fill_rows must be 0 or M");
     if (N >= (1ll << 31)) return fail(SGP_EOVERFLOW, "sgp_build_rowsorted: N does not fit 31 bits");
@@ -548,6 +552,7 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
 extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
                               const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_splat_rows");
     if (N == 0 || M == 0) return SGP_OK;
     if (!ent || !seg_row || !src || !values || N < 0 || M < 0 || n_entries < 0 || n_entries % ROWSEG != 0 || L_src < 1 ||
         lds < L_src || L < L_src)
@@ -786,6 +791,7 @@ static int check_tiles(const sgp_tiles_view *t, int L)
 extern "C" int sgp_splat_tiles(const sgp_tiles_view *t, const float *src, int64_t lds, int L, float *values,
                                sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_splat_tiles");
     int rc = check_tiles(t, L);
     if (rc) return rc;
     if (!src || !values || lds < L || !t->tile_piece_ptr || !t->piece_ptr || !t->piece_row || !t->seg_ent)
@@ -819,6 +825,7 @@ extern "C" int sgp_splat_tiles(const sgp_tiles_view *t, const float *src, int64_
 extern "C" int sgp_slice_tiles(const sgp_tiles_view *t, const float *values, int L, float *out, int64_t ldo,
                                int fast, sgp_stream_t stream)
 {
+    SGP_RANGE("sgp_slice_tiles");
     int rc = check_tiles(t, L);
     if (rc) return rc;
     if (!values || !out || ldo < L || !t->tile_seg_ptr || !t->seg_row || !t->lidx || !t->tile_w)

@@ -22,7 +22,8 @@ from typing import Callable, Optional
 
 import torch
 
-__all__ = ["mll_dense", "mll_cg", "mll_cg_sharded", "batched_cg", "ExactGPModel"]
+__all__ = ["mll_dense", "mll_cg", "mll_cg_sharded", "batched_cg", "ExactGPModel", "pivoted_cholesky",
+           "LowRankPreconditioner"]
 
 
 def mll_dense(matmul: Callable, y: torch.Tensor, mean: torch.Tensor, outputscale: torch.Tensor,
@@ -142,6 +143,68 @@ def _batched_cg_cuda(matmul: Callable, scale: torch.Tensor, shift: torch.Tensor,
     return X[:, :L0].contiguous(), alphas[:k, :L0].contiguous(), betas[:k, :L0].contiguous()
 
 
+@torch.no_grad()
+def pivoted_cholesky(matmul: Callable, n: int, diag_value, rank: int = 100, block: int = 16, rel_tol: float = 1e-3,
+                     device=None, dtype=torch.float32) -> torch.Tensor:
+    """Rank-``rank`` pivoted Cholesky factor ``Lm [n, rank]`` of ``K = diag_value-scaled operator``: ``K ~ Lm Lm^T``.
+
+    The reference's solver settings ask GPyTorch for this preconditioner (``max_preconditioner_size = 100``,
+    experiments/train_simplexgp.py:34-37,63-67).  GPyTorch's loop fetches one row of ``K`` per pivot -- for the lattice
+    operator a row is an MVM with a one-hot vector, and a 1-column MVM costs half of a 16-column one -- so the pivots are
+    taken ``block`` at a time: the ``block`` largest residual diagonals are chosen, their rows fetched by ONE
+    ``block``-column MVM, and the Cholesky updates run over them in order; a pivot whose residual has meanwhile dropped
+    under ``rel_tol * diag_value`` (it was close to an earlier pivot of the block) contributes a zero column.  Like
+    GPyTorch the residual starts from the operator's nominal diagonal (``LazyTensor.diag()``, ones for the lattice kernel:
+    bilateral_kernel.py:139-140, times the output scale).  No host synchronisation inside."""
+    dv = float(diag_value)
+    d = torch.full((n,), dv, device=device, dtype=dtype)
+    Lm = torch.zeros((n, rank), device=device, dtype=dtype)
+    k = 0
+    while k < rank:
+        b = min(block, rank - k)
+        piv = torch.topk(d, b).indices
+        E = torch.zeros((n, b), device=device, dtype=dtype)
+        E[piv, torch.arange(b, device=device)] = 1.0
+        R = matmul(E)                                   # rows K[piv, :] as columns (the operator is symmetric)
+        for j in range(b):
+            p = piv[j]
+            dp = d[p]
+            ok = (dp > rel_tol * dv).to(dtype)
+            col = R[:, j] - Lm[:, :k] @ Lm[p, :k] if k > 0 else R[:, j].clone()
+            col = col * (ok / torch.sqrt(dp.clamp_min(1e-30)))
+            Lm[:, k] = col
+            d = (d - col * col).clamp_min(0.0)
+            d[p] = 0.0
+            k += 1
+    return Lm
+
+
+class LowRankPreconditioner:
+    """``P = noise * I + Lm Lm^T`` through the thin eigen-decomposition ``Lm Lm^T = U diag(lam) U^T`` (``U [n, k]``
+    orthonormal): ``P^{-1/2} v = v / sqrt(noise) + U ((lam + noise)^{-1/2} - noise^{-1/2}) U^T v`` -- two skinny GEMMs.
+    CG then runs on ``P^{-1/2} A P^{-1/2}`` (symmetric preconditioning), which keeps the plain CG sweeps of
+    ``csrc/sgp_solver.cu`` and makes the Lanczos tridiagonals those of the preconditioned operator, so that
+    ``log|A| = log|P| + log|P^{-1/2} A P^{-1/2}|`` (GPyTorch corrects its log-determinant estimate the same way)."""
+
+    def __init__(self, Lm: torch.Tensor, noise):
+        n, k = Lm.shape
+        self.n, self.noise = n, float(noise)
+        G = (Lm.T @ Lm).double()
+        lam, Q = torch.linalg.eigh(G)
+        keep = lam > 1e-10 * lam.max().clamp_min(1e-30)
+        lam, Q = lam[keep], Q[:, keep]
+        self.lam = lam.to(Lm.dtype)
+        self.U = (Lm @ (Q / lam.sqrt()).to(Lm.dtype)).contiguous()
+        self.coef = ((self.lam + self.noise).rsqrt() - self.noise ** -0.5)
+
+    def inv_sqrt(self, V: torch.Tensor) -> torch.Tensor:
+        return V * (self.noise ** -0.5) + self.U @ (self.coef.unsqueeze(1) * (self.U.T @ V))
+
+    def logdet(self) -> float:
+        import math
+        return float((self.n - self.lam.numel()) * math.log(self.noise) + torch.log(self.lam.double() + self.noise).sum())
+
+
 def _lanczos_logdet(alphas: torch.Tensor, betas: torch.Tensor, n: int) -> torch.Tensor:
     """Stochastic Lanczos quadrature: mean over probe columns of ``n * e1^T log(T) e1``."""
     k, p = alphas.shape
@@ -164,9 +227,12 @@ def _lanczos_logdet(alphas: torch.Tensor, betas: torch.Tensor, n: int) -> torch.
 
 def mll_cg(matmul: Callable, y: torch.Tensor, mean: torch.Tensor, outputscale: torch.Tensor, noise: torch.Tensor,
            n_probes: int = 10, tol: float = 1e-4, max_iter: int = 500, generator: Optional[torch.Generator] = None,
-           probes: Optional[torch.Tensor] = None):
+           probes: Optional[torch.Tensor] = None, preconditioner_size: int = 0, stats: Optional[dict] = None):
     """Returns ``(mll_value, surrogate)``: ``mll_value`` is the (detached) per-datum MLL estimate, ``surrogate`` a scalar
-    whose gradient with respect to the hyper-parameters is the usual CG / stochastic-trace MLL gradient estimate."""
+    whose gradient with respect to the hyper-parameters is the usual CG / stochastic-trace MLL gradient estimate.
+
+    ``preconditioner_size = k > 0``: rank-``k`` pivoted-Cholesky preconditioner of the reference's solver settings
+    (``pivoted_cholesky`` / ``LowRankPreconditioner``).  ``stats`` (a dict) receives the CG iteration count."""
     n = y.shape[0]
     r = (y - mean)
     if probes is None:
@@ -179,10 +245,34 @@ def mll_cg(matmul: Callable, y: torch.Tensor, mean: torch.Tensor, outputscale: t
         with torch.no_grad():
             return outputscale.detach() * matmul(V) + noise.detach() * V
 
-    X, al, be = batched_cg(A, B, tol=tol, max_iter=max_iter, matmul=matmul, scale=outputscale, shift=noise)
+    pre = None
+    if preconditioner_size > 0:
+        with torch.no_grad():
+            s_ = outputscale.detach()
+            Lm = pivoted_cholesky(lambda V: s_ * matmul(V), n, float(s_), rank=int(preconditioner_size), device=y.device,
+                                  dtype=y.dtype)
+            pre = LowRankPreconditioner(Lm, float(noise.detach()))
+            del Lm
+    if pre is None:
+        X, al, be = batched_cg(A, B, tol=tol, max_iter=max_iter, matmul=matmul, scale=outputscale, shift=noise)
+        logdet_p = 0.0
+    else:
+        # symmetric preconditioning: CG on P^-1/2 A P^-1/2 with right-hand sides [P^-1/2 r | probes]; the probe columns
+        # are Rademacher in the preconditioned space (what the Lanczos quadrature needs), their images P^-1/2 z are the
+        # vectors the trace estimator pairs the solutions with (E[z~^T A~^-1 P^-1/2 dA P^-1/2 z~] = tr(A^-1 dA))
+        Bt = torch.cat([pre.inv_sqrt(B[:, :1]), B[:, 1:]], dim=1)
+        one, zero = torch.ones((), device=y.device, dtype=y.dtype), torch.zeros((), device=y.device, dtype=y.dtype)
+        At = lambda V: pre.inv_sqrt(A(pre.inv_sqrt(V)))
+        Xt, al, be = batched_cg(At, Bt, tol=tol, max_iter=max_iter, matmul=At, scale=one, shift=zero)
+        X = pre.inv_sqrt(Xt)
+        Z = pre.inv_sqrt(Z)
+        logdet_p = pre.logdet()
+    if stats is not None:
+        stats["cg_iterations"] = int(al.shape[0])
+        stats["preconditioner_rank"] = 0 if pre is None else int(pre.lam.numel())
     alpha, U = X[:, :1], X[:, 1:]
     quad = float((r.detach().unsqueeze(-1) * alpha).sum())
-    logdet = float(_lanczos_logdet(al[:, 1:], be[:, 1:], n))
+    logdet = logdet_p + float(_lanczos_logdet(al[:, 1:], be[:, 1:], n))
     value = (-0.5 * (quad + logdet + n * math.log(2 * math.pi))) / n
     # surrogate: d/dtheta [ -1/2 r^T K^-1 r - 1/2 log|K| ] = 1/2 a^T dK a - a^T dmu ... - 1/2 E[u^T dK z]
     V = torch.cat([alpha, Z], dim=1)
@@ -308,7 +398,8 @@ class ExactGPModel(torch.nn.Module):
         return mll_cg(matmul, self.train_y, self.raw_mean, self.outputscale, self.noise, **cg_kwargs)
 
     @torch.no_grad()
-    def predict(self, test_x, tol: float = 1e-2, max_iter: int = 1000, variance: bool = False, var_block: int = 16):
+    def predict(self, test_x, tol: float = 1e-2, max_iter: int = 1000, variance: bool = False, var_block: int = 16,
+                preconditioner_size: int = 100):
         """Posterior mean (and, on request, the latent variance) at ``test_x`` -- what ``model(test_x)`` of
         experiments/train_simplexgp.py:60-84 returns in evaluation mode.
 
@@ -316,7 +407,8 @@ class ExactGPModel(torch.nn.Module):
         ``tol`` (the reference's ``eval_cg_tolerance``); ``mean = mu + s K(test, train) alpha`` is ONE rectangular
         product on the training lattice extended by the test points.  The variance
         ``s - s^2 k_i^T (s K + noise I)^-1 k_i`` is exact up to ``tol`` and costs a solve with ``var_block`` columns per
-        ``var_block`` test points (the reference uses GPyTorch's LOVE approximation, ``fast_pred_var``, instead)."""
+        ``var_block`` test points (the reference uses GPyTorch's LOVE approximation, ``fast_pred_var``, instead).
+        ``preconditioner_size``: rank of the pivoted-Cholesky preconditioner of the CG solves (0 = none)."""
         op = self.operator()
         n = self.train_x.shape[0]
         s, noise, mu = self.outputscale, self.noise, self.raw_mean
@@ -328,11 +420,27 @@ class ExactGPModel(torch.nn.Module):
             eye = torch.eye(n, dtype=r.dtype, device=r.device)
             dense = torch.linalg.lu_factor(s * op.matmul(eye) + noise * eye)
 
+        pre = None
+        if dense is None and preconditioner_size > 0:
+            # the reference's evaluation settings: eval_cg_tolerance 1e-2 with a rank-100 pivoted-Cholesky preconditioner
+            # (experiments/train_simplexgp.py:63-67); built once per prediction, shared by every solve below
+            pre = LowRankPreconditioner(pivoted_cholesky(lambda V: s * op.matmul(V), n, float(s), rank=preconditioner_size,
+                                                         device=r.device, dtype=r.dtype), float(noise))
+        self.last_solve_iterations = []
+
         def solve(B):
             if dense is not None:
                 return torch.linalg.lu_solve(*dense, B)
-            return batched_cg(lambda V: s * op.matmul(V) + noise * V, B, tol=tol, max_iter=max_iter, matmul=op.matmul,
-                              scale=s, shift=noise)[0]
+            if pre is None:
+                X, al, _ = batched_cg(lambda V: s * op.matmul(V) + noise * V, B, tol=tol, max_iter=max_iter,
+                                      matmul=op.matmul, scale=s, shift=noise)
+            else:
+                At = lambda V: pre.inv_sqrt(s * op.matmul(pre.inv_sqrt(V)) + noise * pre.inv_sqrt(V))
+                one, zero = torch.ones((), device=B.device, dtype=B.dtype), torch.zeros((), device=B.device, dtype=B.dtype)
+                Xt, al, _ = batched_cg(At, pre.inv_sqrt(B), tol=tol, max_iter=max_iter, matmul=At, scale=one, shift=zero)
+                X = pre.inv_sqrt(Xt)
+            self.last_solve_iterations.append(int(al.shape[0]))
+            return X
 
         cross = self.kernel(test_x, self.train_x)              # K(test, train)
         mean = mu + s * cross.matmul(solve(r))[:, 0]
