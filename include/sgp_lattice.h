@@ -328,6 +328,18 @@ int sgp_mvm_rows_groups(const sgp_lattice_view *slice_view, const int32_t *ent, 
                         const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1, int Lv,
                         sgp_stream_t stream);
 
+/* The same chain with the memset of the splat buffer taken off the critical path.  flags: SGP_MVM_PREZEROED -- buf0
+ * holds zeros on entry (no memset in front of the splat); SGP_MVM_ZERO_AFTER -- buf0 is left zeroed on exit: with an
+ * odd number of group stages it is zeroed on an internal side stream while the slice runs (a parallel branch when the
+ * call is captured into a CUDA graph), with an even number after the slice.  A graph captured with both flags on
+ * private buffers (Lattice.capture) replays without ever waiting for the memset. */
+#define SGP_MVM_PREZEROED 1
+#define SGP_MVM_ZERO_AFTER 2
+int sgp_mvm_rows_groups_ex(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
+                           int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src, int64_t lds,
+                           int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1, int Lv,
+                           int flags, sgp_stream_t stream);
+
 /* ---- stage 5: lengthscale-gradient pass (bilateral_kernel.py:97-124) -------------------
  *
  * The reference filters one N x 2L(1+d) block [g | g(x)x | v | v(x)x] with the derivative stencil and

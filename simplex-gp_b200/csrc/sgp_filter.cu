@@ -23,6 +23,18 @@
 
 #define fail sgp_fail
 
+// one side stream per device (the host variant's second upload; the off-critical-path memset of sgp_mvm_rows_groups_ex):
+// created on first use, never destroyed
+cudaStream_t sgp_side_stream(int dev)
+{
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {};
+    if (dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
+    return streams[dev];
+}
+
 namespace {
 
 struct FilterWs {
@@ -89,16 +101,7 @@ cudaError_t copy_rows(float *dst, int64_t ldd, const float *src, int64_t lds, in
     return cudaMemcpy2DAsync(dst, (size_t)ldd * 4, src, (size_t)lds * 4, (size_t)width * 4, (size_t)N, kind, st);
 }
 
-// one side stream per device for the host variant's second upload (created on first use, never destroyed)
-cudaStream_t copy_stream(int dev)
-{
-    static std::mutex mu;
-    static cudaStream_t streams[64] = {};
-    if (dev < 0 || dev >= 64) return nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
-    return streams[dev];
-}
+cudaStream_t copy_stream(int dev) { return sgp_side_stream(dev); }
 
 int filter_device(const float *src, int64_t lds, const float *ref, int64_t ldx, const float *coeffs, int k, int64_t N,
                   int L, int d, float *out, int64_t ldo, char *base, const FilterWs &w, int64_t *M_out, cudaStream_t st,

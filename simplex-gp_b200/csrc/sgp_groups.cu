@@ -616,6 +616,60 @@ extern "C" int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64
 
 // The production chain in one call: row-sorted splat -> blur-group stages -> slice.  `slice_view->replay` must address
 // the lattice values in the order the last stage leaves them (sgp_permute_replay with that stage's pos).
+// flags: SGP_MVM_PREZEROED (1) buf0 holds zeros on entry (skip the memset in front of the splat);
+//        SGP_MVM_ZERO_AFTER (2) leave buf0 zeroed on exit.  With an odd number of stages buf0 is last read by the last
+//        stage, so it is zeroed on a side stream WHILE the slice runs (fork / join with events: also inside a stream
+//        capture, where it becomes a parallel branch of the graph); with an even number the slice itself reads buf0 and
+//        the zeroing follows it.  Replaying a graph captured with both flags keeps the 25.6 MB memset of the metric
+//        shape off the critical path of every product.
+extern "C" int sgp_mvm_rows_groups_ex(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
+                                      int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src,
+                                      int64_t lds, int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0,
+                                      float *buf1, int Lv, int flags, sgp_stream_t stream)
+{
+    SGP_RANGE("sgp_mvm_rows_groups_ex");
+    if (!slice_view) return fail(SGP_EINVAL, "sgp_mvm_rows_groups_ex: null view");
+    if (Lv < L || (Lv != L && Lv % 4 != 0)) return fail(SGP_EINVAL, "sgp_mvm_rows_groups_ex: Lv must be L or L rounded up to a multiple of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = (flags & 1) ? sgp_splat_rows_prezeroed(ent, seg_row, n_entries, slice_view->N, slice_view->M, src, lds, L, buf0, Lv, stream)
+                         : sgp_splat_rows(ent, seg_row, n_entries, slice_view->N, slice_view->M, src, lds, L, buf0, Lv, stream);
+    if (rc) return rc;
+    int in1 = 0;
+    rc = sgp_blur_groups(groups, n_groups, slice_view->M, slice_view->order, coeffs, k, Lv, buf0, buf1, &in1,
+                         slice_view->fast, stream);
+    if (rc) return rc;
+    const size_t zero_bytes = sizeof(float) * (size_t)slice_view->M * (size_t)Lv;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaStream_t side = nullptr;
+    if ((flags & 2) && in1 && slice_view->M > 0) {   // buf0 is dead: zero it next to the slice
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        side = sgp_side_stream(dev);
+        if (side && (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
+                     cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess)) {
+            if (fork) cudaEventDestroy(fork);
+            fork = join = nullptr;
+            side = nullptr;
+        }
+        if (side) {
+            CUDA_TRY(cudaEventRecord(fork, st));
+            CUDA_TRY(cudaStreamWaitEvent(side, fork, 0));
+            CUDA_TRY(cudaMemsetAsync(buf0, 0, zero_bytes, side));
+            CUDA_TRY(cudaEventRecord(join, side));
+        }
+    }
+    rc = sgp_slice(slice_view, in1 ? buf1 : buf0, Lv, out, ldo, L, stream);
+    if (side) {
+        cudaError_t e = cudaStreamWaitEvent(st, join, 0);
+        cudaEventDestroy(fork);
+        cudaEventDestroy(join);
+        if (e != cudaSuccess && !rc) return fail(SGP_ECUDA, "sgp_mvm_rows_groups_ex: %s", cudaGetErrorString(e));
+    } else if ((flags & 2) && !rc && slice_view->M > 0) {
+        CUDA_TRY(cudaMemsetAsync(buf0, 0, zero_bytes, st));
+    }
+    return rc;
+}
+
 extern "C" int sgp_mvm_rows_groups(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
                                    int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src, int64_t lds, int L,
                                    const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1, int Lv,

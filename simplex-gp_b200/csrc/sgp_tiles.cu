@@ -475,6 +475,13 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     if (prefetch_bytes > 0) {
         const int64_t line = tid * 128;
         if (line < prefetch_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)src + line));
+    } else if (prefetch_bytes < 0) {
+        // bulk form (TMA engine, no LSU work): the first CTAs each ask L2 for one 32 KB piece of src
+        const int64_t piece = 32768, off = (int64_t)blockIdx.x * piece;
+        if (threadIdx.x == 0 && off < -prefetch_bytes) {
+            const int64_t n = min(piece, -prefetch_bytes - off) & ~(int64_t)15;
+            if (n > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char *)src + off), "r"((uint32_t)n) : "memory");
+        }
     }
     pdl_launch_dependents();
     const int64_t seg = tid / chunks;
@@ -549,8 +556,26 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     if (single && !(prev_there && prev_key == key)) acc.red(values + (int64_t)row * L + c0);
 }
 
+static int splat_rows_impl(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
+                           const float *src, int64_t lds, int L_src, float *values, int L, bool prezeroed,
+                           sgp_stream_t stream);
+
 extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
                               const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream)
+{
+    return splat_rows_impl(ent, seg_row, n_entries, N, M, src, lds, L_src, values, L, false, stream);
+}
+
+// values must hold zeros on entry: the caller zeroed it off the critical path (sgp_mvm_rows_groups_ex)
+int sgp_splat_rows_prezeroed(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
+                             const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream)
+{
+    return splat_rows_impl(ent, seg_row, n_entries, N, M, src, lds, L_src, values, L, true, stream);
+}
+
+static int splat_rows_impl(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
+                           const float *src, int64_t lds, int L_src, float *values, int L, bool prezeroed,
+                           sgp_stream_t stream)
 {
     SGP_RANGE("sgp_splat_rows");
     if (N == 0 || M == 0) return SGP_OK;
@@ -559,7 +584,7 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_
         return fail(SGP_EINVAL, "sgp_splat_rows: bad argument");
     // production form: index stream through warp-private TMA rings, stores instead of reductions (sgp_ring.cu);
     // SGP_RING=0 selects the one-shot kernel below (kept for comparison)
-    if (sgp_ring_splat_enabled() && n_entries >= 16 && sgp_splat_ring_supported(values, L))
+    if (!prezeroed && sgp_ring_splat_enabled() && n_entries >= 16 && sgp_splat_ring_supported(values, L))
         return sgp_splat_rows_ring(ent, seg_row, n_entries, N, M, src, lds, L_src, values, L, stream);
     cudaStream_t st = (cudaStream_t)stream;
     static int seg_env = 0;   // tuning hook: SGP_ROWSEG=4|8|16 entries per thread
@@ -578,14 +603,17 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_
     const int chunks = L / vec;
     const char *dbg_e = getenv("SGP_SPLAT_DBG");   // experiments only: bit 0 no reductions, bit 1 no memset, bits 8+ fold
     const int dbg = dbg_e ? atoi(dbg_e) : 0;
-    if (!(dbg & 2)) CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)M * (size_t)L, st));
+    if (!(dbg & 2) && !prezeroed) CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)M * (size_t)L, st));
     const int64_t work = n_seg * chunks;
-    static int pref_env = -1;   // tuning hook: SGP_SPLAT_PREFETCH=1 enables an L2 prefetch of src (measured: no gain)
-    if (pref_env < 0) {
+    int pref_env = 0;   // tuning hook: SGP_SPLAT_PREFETCH=1|2 asks L2 for src up front (read on every call)
+    {
         const char *e = getenv("SGP_SPLAT_PREFETCH");
         pref_env = e ? atoi(e) : 0;
     }
-    const int64_t prefetch_bytes = pref_env ? (int64_t)N * lds * (int64_t)sizeof(float) : 0;
+    // SGP_SPLAT_PREFETCH: 1 = one prefetch.global.L2 per 128-byte line, 2 = cp.async.bulk.prefetch.L2 in 32 KB pieces
+    // (src must then be 16-byte aligned)
+    int64_t prefetch_bytes = pref_env ? (int64_t)N * lds * (int64_t)sizeof(float) : 0;
+    if (pref_env == 2) prefetch_bytes = al(src, 16) ? -prefetch_bytes : 0;
     // warp-level aggregation of whole-segment runs: lanes l, l + chunks, l + 2 chunks, ... hold the same channel chunk of
     // consecutive segments
     static int agg_env = -1;    // tuning hook: SGP_SPLAT_AGG=0 disables

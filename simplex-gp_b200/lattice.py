@@ -672,7 +672,7 @@ class Lattice:
     # ---- the MVM ------------------------------------------------------------------------------------
     def mvm(self, src: torch.Tensor, out: Optional[torch.Tensor] = None, coeffs=None,
             mode: int = _capi.SGP_SPLAT_AUTO, blur: str = "auto", sorted: Optional[bool] = None,
-            exact: Optional[bool] = None, after_splat=None, scratch=None) -> torch.Tensor:
+            exact: Optional[bool] = None, after_splat=None, scratch=None, zero_flags: int = 0) -> torch.Tensor:
         """``out[N, L] = slice(blur(splat(src[N, L])))`` on the built lattice.
 
         ``mode``   splat form: 0 auto (row-sorted segmented gather when built, else atomic scatter), 1 atomic scatter
@@ -689,7 +689,9 @@ class Lattice:
         ``after_splat`` optional callable invoked with the splatted lattice values ``[M, L]`` (in place) before the
                    blur: the exchange step of point sharding (an all-reduce over the ranks' partial splats).
         ``scratch`` a private pair of ``[M, ceil4(L)]`` work buffers instead of the lattice's shared ones (a captured CUDA
-                   graph owns its pair: its nodes must not point into buffers the lattice may free or reuse)."""
+                   graph owns its pair: its nodes must not point into buffers the lattice may free or reuse).
+        ``zero_flags`` (production chain only, private scratch): 1 = ``scratch[0]`` holds zeros on entry, 2 = leave it
+                   zeroed on exit, overlapped with the slice (``sgp_mvm_rows_groups_ex``; what ``capture`` uses)."""
         src = self._check_src(src)
         L = int(src.shape[1])
         c = self.coeffs if coeffs is None else _coeffs_np(coeffs)
@@ -733,11 +735,21 @@ class Lattice:
             arr = self.groups["array"]
             v_out = self._view(self._table(False, True), None, exact)
             with torch.cuda.device(self.device):
-                check(lib.sgp_mvm_rows_groups(C.byref(v_out), _ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]),
-                                              self.rows["n"], arr,
-                                              len(arr), _ptr(src), src.stride(0), L, _fp(c), c.shape[0], _ptr(out),
-                                              out.stride(0), _ptr(buf0), _ptr(buf1), Lv, st))
+                if zero_flags:
+                    if scratch is None:
+                        raise ValueError("zero_flags needs private scratch buffers")
+                    check(lib.sgp_mvm_rows_groups_ex(C.byref(v_out), _ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]),
+                                                     self.rows["n"], arr, len(arr), _ptr(src), src.stride(0), L, _fp(c),
+                                                     c.shape[0], _ptr(out), out.stride(0), _ptr(buf0), _ptr(buf1), Lv,
+                                                     int(zero_flags), st))
+                else:
+                    check(lib.sgp_mvm_rows_groups(C.byref(v_out), _ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]),
+                                                  self.rows["n"], arr,
+                                                  len(arr), _ptr(src), src.stride(0), L, _fp(c), c.shape[0], _ptr(out),
+                                                  out.stride(0), _ptr(buf0), _ptr(buf1), Lv, st))
             return out
+        if zero_flags:
+            raise ValueError("zero_flags applies to the production chain only (row-sorted splat + blur groups)")
         with torch.cuda.device(self.device):
             perm = self.sorted["perm"] if use_sorted else None
             if use_tiles:
@@ -786,16 +798,25 @@ class Lattice:
         Lv = (L + 3) // 4 * 4 if L > 4 else L
         if mvm_kwargs.get("mode", _capi.MODE_AUTO) not in (_capi.MODE_AUTO, _capi.MODE_ROWS) or self.rows is None:
             Lv = L
-        scratch = (torch.empty((max(self.M, 1), Lv), dtype=torch.float32, device=self.device),
+        scratch = (torch.zeros((max(self.M, 1), Lv), dtype=torch.float32, device=self.device),
                    torch.empty((max(self.M, 1), Lv), dtype=torch.float32, device=self.device))
+        # production chain on private buffers: the splat buffer is zeroed at the END of every product, next to the slice
+        # (a parallel branch of the graph), instead of in front of the splat: 4-6 us off the critical path at the
+        # metric shape.  SGP_GRAPH_ZERO_AFTER=0 keeps the memset in front.
+        import os
+        production = (mvm_kwargs.get("mode", _capi.MODE_AUTO) in (_capi.MODE_AUTO, _capi.MODE_ROWS) and self.rows is not None
+                      and self.groups is not None and mvm_kwargs.get("blur", "auto") in ("auto", "groups")
+                      and not mvm_kwargs.get("sorted") and mvm_kwargs.get("after_splat") is None
+                      and not _capi.lib().sgp_ring_splat_enabled() and os.environ.get("SGP_GRAPH_ZERO_AFTER", "1") != "0")
+        zf = 3 if production else 0
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):     # warm-up outside the capture: lazy tables, function attributes
-            self.mvm(src, out=out, scratch=scratch, **mvm_kwargs)
+            self.mvm(src, out=out, scratch=scratch, zero_flags=zf, **mvm_kwargs)
         torch.cuda.current_stream(self.device).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.mvm(src, out=out, scratch=scratch, **mvm_kwargs)
+            self.mvm(src, out=out, scratch=scratch, zero_flags=zf, **mvm_kwargs)
         graph._sgp_keepalive = (scratch, src, out, self)   # the graph's nodes point into these: keep them alive with it
         return graph
 
