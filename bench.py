@@ -575,8 +575,6 @@ def run_ours(args, w):
         buf0, buf1 = lat._scratch(L)
         cnp = lat.coeffs
         st = _stream_ptr(dev)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        acc = [0.0, 0.0, 0.0]
         reps = max(5, min(steps, 20))
         where = C.c_int(0)
         fast = 0 if lat.exact else 1
@@ -586,35 +584,59 @@ def run_ours(args, w):
         tv_in = lat._tiles_view(False) if mode == _capi.MODE_TILES else None
         tv_out = lat._tiles_view(use_groups) if mode == _capi.MODE_TILES else None
         garr = lat.groups["array"] if use_groups else None
-        for i in range(reps):
-            V, out = Vs[i % n_rot], outs[i % n_rot]
-            ev[0].record()
+        # Each stage is launched `reps` times back to back between two events (after two warm-up launches), so that the
+        # average is the kernel's device time and not the launch latency of an idle stream; V/out rotate as in the step.
+        def splat_stage(i):
+            V = Vs[i % n_rot]
             if mode == _capi.MODE_TILES:
                 _capi.check(lib.sgp_splat_tiles(C.byref(tv_in), _ptr(V), V.stride(0), L, _ptr(buf0), st))
+            elif mode == _capi.MODE_ROWS and not lib.sgp_ring_splat_enabled():
+                # the kernel alone (its memset is timed apart: in the MVM's graph it runs beside the previous slice);
+                # repeated launches keep accumulating into buf0, which is irrelevant for the timing
+                _capi.check(lib.sgp_mvm_stage_splat_prezeroed(_ptr(lat.rows["ent"]), _ptr(lat.rows["seg_row"]), lat.rows["n"], N,
+                                                              M, _ptr(V), V.stride(0), L, _ptr(buf0), L, st))
             elif mode == _capi.MODE_ROWS:
                 _capi.check(lib.sgp_splat_rows(_ptr(lat.rows["ent"]), _ptr(lat.rows["seg_row"]), lat.rows["n"], N, M, _ptr(V),
                                                V.stride(0), L, _ptr(buf0), L, st))
             else:
                 _capi.check(lib.sgp_splat(C.byref(v_in if mode == _capi.MODE_ATOMIC else v_axis), _ptr(V), V.stride(0), L,
                                           _ptr(buf0), mode, st))
-            ev[1].record()
+
+        def blur_stage(i):
             if use_groups:
                 _capi.check(lib.sgp_blur_groups(garr, len(garr), M, lat.order, _fp(cnp), cnp.shape[0], L, _ptr(buf0),
                                                 _ptr(buf1), C.byref(where), fast, st))
             else:
                 _capi.check(lib.sgp_blur(C.byref(v_axis), _fp(cnp), cnp.shape[0], L, _ptr(buf0), _ptr(buf1),
                                          C.byref(where), st))
-            ev[2].record()
+
+        def slice_stage(i):
+            out = outs[i % n_rot]
             res_buf = buf1 if where.value else buf0
             if mode == _capi.MODE_TILES:
                 _capi.check(lib.sgp_slice_tiles(C.byref(tv_out), _ptr(res_buf), L, _ptr(out), out.stride(0), fast, st))
             else:
                 _capi.check(lib.sgp_slice(C.byref(v_out), _ptr(res_buf), L, _ptr(out), out.stride(0), L, st))
-            ev[3].record()
+
+        def stage_ms(fn):
+            for i in range(2):
+                fn(i)
             torch.cuda.synchronize()
-            for k in range(3):
-                acc[k] += ev[k].elapsed_time(ev[k + 1])
-        t_splat, t_blur, t_slice = (a / reps for a in acc)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(reps):
+                fn(i)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        buf0.zero_()
+        t_splat = stage_ms(splat_stage)
+        memset_ms = stage_ms(lambda i: buf0.zero_()) if (mode == _capi.MODE_ROWS and not lib.sgp_ring_splat_enabled()) else None
+        buf0.normal_()
+        t_blur = stage_ms(blur_stage)
+        buf0.normal_(); buf1.normal_()
+        t_slice = stage_ms(slice_stage)
         r = lat.order
         n_blur = len(lat.groups["list"]) if use_groups else d + 1
         b_splat = 4 * (N * L + 2 * N * (d + 1) + M * L)
@@ -625,7 +647,7 @@ def run_ours(args, w):
                         _capi.MODE_ROWS: "sgp_splat_ring_kernel" if lib.sgp_ring_splat_enabled() else "sgp_splat_rows_kernel"}[mode]
         stages = {
             "splat": {"ms": t_splat, "launches": 1, "alg_bytes": b_splat, "gbs": b_splat / t_splat / 1e6,
-                      "kernel": splat_kernel},
+                      "kernel": splat_kernel, "memset_ms_timed_apart": memset_ms},
             "blur": {"ms": t_blur, "launches": n_blur, "alg_bytes": b_blur, "gbs": b_blur / t_blur / 1e6,
                      "kernel": "sgp_blur_group_kernel" if use_groups else "sgp_blur_kernel"},
             "slice": {"ms": t_slice, "launches": 1, "alg_bytes": b_slice, "gbs": b_slice / t_slice / 1e6,
@@ -668,6 +690,19 @@ def run_ours(args, w):
                        "lattice build, MVM (atomic splat, per-axis blur, ring slice: one product per lattice), D2H",
                "steps": args.e2e_steps, "ms_per_call": float(dt.item()) / args.e2e_steps * 1e3,
                "checksum": float(res.double().sum().item())}
+        if world > 1:
+            # the same loop with the odd ranks started half a call late: ranks that run in lockstep all upload and then
+            # all download, using one PCIe direction at a time; independent processes in production are not in lockstep
+            dist.barrier()
+            if rank % 2:
+                time.sleep(e2e["ms_per_call"] * 0.5e-3)
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                res = sg.filter(v_pin, x_pin, c_t, device=dev)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            e2e["value_staggered_start"] = world * args.e2e_steps / float(dt.item())
         # where a call's time goes, each phase alone, MAX over ranks (all ranks run it at the same time, as in the call)
         x_dev, v_dev = x_pin.to(dev), v_pin.to(dev)
         out_pin = torch.empty(N, L).pin_memory()

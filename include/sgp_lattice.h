@@ -333,6 +333,9 @@ int sgp_mvm_rows_groups(const sgp_lattice_view *slice_view, const int32_t *ent, 
  * odd number of group stages it is zeroed on an internal side stream while the slice runs (a parallel branch when the
  * call is captured into a CUDA graph), with an even number after the slice.  A graph captured with both flags on
  * private buffers (Lattice.capture) replays without ever waiting for the memset. */
+/* The splat stage of that chain alone: sgp_splat_rows without its memset -- `values` must hold zeros on entry. */
+int sgp_mvm_stage_splat_prezeroed(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
+                                  const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream);
 #define SGP_MVM_PREZEROED 1
 #define SGP_MVM_ZERO_AFTER 2
 int sgp_mvm_rows_groups_ex(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,

@@ -1,6 +1,6 @@
 """Minimal driver for ncu captures: build the config-A lattice, run a few MVMs.
 
-    ncu --set full --clock-control none --import-source on -k regex:sgp_ -s 11 -c 11 -o gpurun_out/mvm python profiles/ncu_mvm.py
+    ncu --set full --clock-control none --import-source on -k regex:"sgp_(splat|blur|slice)" -s 10 -c 5 -o gpurun_out/mvm python profiles/ncu_mvm.py
 """
 import os
 import sys
@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import simplex_gp_b200 as sg  # noqa: E402
 
 N, d, L = int(os.environ.get("SGP_N", 1_000_000)), int(os.environ.get("SGP_D", 8)), int(os.environ.get("SGP_L", 16))
-mode = int(os.environ.get("SGP_SPLAT", 1))
+mode = int(os.environ.get("SGP_SPLAT", 0))   # 0 = the production chain
 torch.manual_seed(0)
 x = torch.randn(N, d, device="cuda")
 v = torch.randn(N, L, device="cuda")

@@ -28,7 +28,7 @@ SYMBOLS = [
     "sgp_grad_channels", "sgp_grad_pack", "sgp_grad_contract",
     "sgp_group_workspace_bytes", "sgp_group_prepare", "sgp_group_max_batches", "sgp_group_finalize",
     "sgp_remap_replay",
-    "sgp_blur_groups_channel_block", "sgp_blur_groups", "sgp_mvm_rows_groups", "sgp_mvm_rows_groups_ex", "sgp_sort_points_workspace_bytes", "sgp_sort_points",
+    "sgp_blur_groups_channel_block", "sgp_blur_groups", "sgp_mvm_rows_groups", "sgp_mvm_rows_groups_ex", "sgp_mvm_stage_splat_prezeroed", "sgp_sort_points_workspace_bytes", "sgp_sort_points",
     "sgp_permute_replay", "sgp_rowsort_workspace_bytes", "sgp_rowsort_padded", "sgp_build_rowsorted",
     "sgp_splat_rows", "sgp_cg_scratch_floats", "sgp_cg_apply", "sgp_cg_update", "sgp_cg_direction",
     "sgp_ring_enabled", "sgp_ring_splat_enabled", "sgp_ring_slice_enabled", "sgp_splat_ring_supported", "sgp_slice_ring_supported", "sgp_splat_rows_ring", "sgp_slice_ring",
@@ -197,6 +197,8 @@ def lib() -> C.CDLL:
     L.sgp_blur_groups.argtypes = [C.POINTER(BlurGroup), i32, i64, i32, fp, i32, i32, vp, vp, C.POINTER(C.c_int), i32, vp]
     L.sgp_mvm_rows_groups.restype = i32
     L.sgp_mvm_rows_groups.argtypes = [pv, vp, vp, i64, C.POINTER(BlurGroup), i32, vp, i64, i32, fp, i32, vp, i64, vp, vp, i32, vp]
+    L.sgp_mvm_stage_splat_prezeroed.restype = i32
+    L.sgp_mvm_stage_splat_prezeroed.argtypes = [vp, vp, i64, i64, i64, vp, i64, i32, vp, i32, vp]
     L.sgp_mvm_rows_groups_ex.restype = i32
     L.sgp_mvm_rows_groups_ex.argtypes = [pv, vp, vp, i64, C.POINTER(BlurGroup), i32, vp, i64, i32, fp, i32, vp, i64, vp, vp, i32,
                                          i32, vp]

@@ -520,9 +520,19 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     // most-touched rows span hundreds of consecutive segments (1250 at the centre of the metric lattice), and that
     // many reductions to one address serialise in L2.  Singles of the same row and channel chunk that sit in the same
     // warp are summed with shuffles first and the first of them issues one reduction.
-    bool single = aggregate;
+    bool single = aggregate || (dbg & 4);
 #pragma unroll
     for (int i = 1; i < SEG; ++i) single = single && !(e[i].x < 0);
+    // Warp-uniform case (dbg bit 2, the default for 3+ channel chunks): all segments of the warp lie inside ONE lattice
+    // row -- the long rows at the centre of the data, where most reductions go.  Their partial sums are added across the
+    // warp's segments with a butterfly and the first segment issues one reduction per channel chunk: 8x fewer L2
+    // atomics for those warps, and nothing but one vote and one shuffle for all the others.
+    bool uniform = false;
+    if ((dbg & 4) && !aggregate) {
+        const int row_first = __shfl_sync(mask, row, 0);
+        uniform = mask == 0xffffffffu && __all_sync(mask, single && row == row_first) && (32 % chunks == 0);
+        single = uniform;   // non-uniform warps: every thread reduces its own runs, as before
+    }
     pdl_wait();   // the lattice values are zeroed (and last read) by the stream's previous work
 #pragma unroll
     for (int i = 0; i < SEG; ++i) {
@@ -535,6 +545,14 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
 #pragma unroll
             for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
         }
+    }
+    if (uniform) {
+        for (int step = chunks; step < 32; step <<= 1) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc.v[k] += __shfl_xor_sync(0xffffffffu, acc.v[k], step);
+        }
+        if ((threadIdx.x & 31) < chunks) acc.red(values + (int64_t)row * L + c0);
+        return;
     }
     if (!aggregate) return;
     // segmented sum over the lanes lane, lane + chunks, lane + 2 chunks, ... (same channel chunk, consecutive segments)
@@ -564,6 +582,13 @@ extern "C" int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_
                               const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream)
 {
     return splat_rows_impl(ent, seg_row, n_entries, N, M, src, lds, L_src, values, L, false, stream);
+}
+
+extern "C" int sgp_mvm_stage_splat_prezeroed(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N,
+                                             int64_t M, const float *src, int64_t lds, int L_src, float *values, int L,
+                                             sgp_stream_t stream)
+{
+    return splat_rows_impl(ent, seg_row, n_entries, N, M, src, lds, L_src, values, L, true, stream);
 }
 
 // values must hold zeros on entry: the caller zeroed it off the critical path (sgp_mvm_rows_groups_ex)
@@ -602,7 +627,7 @@ static int splat_rows_impl(const int32_t *ent, const int32_t *seg_row, int64_t n
     const bool ragged = vec > 1 && !(L_src == L && lds % vec == 0 && al(src, 4 * vec));
     const int chunks = L / vec;
     const char *dbg_e = getenv("SGP_SPLAT_DBG");   // experiments only: bit 0 no reductions, bit 1 no memset, bits 8+ fold
-    const int dbg = dbg_e ? atoi(dbg_e) : 0;
+    int dbg = dbg_e ? atoi(dbg_e) : 0;
     if (!(dbg & 2) && !prezeroed) CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)M * (size_t)L, st));
     const int64_t work = n_seg * chunks;
     int pref_env = 0;   // tuning hook: SGP_SPLAT_PREFETCH=1|2 asks L2 for src up front (read on every call)
@@ -625,6 +650,11 @@ static int splat_rows_impl(const int32_t *ent, const int32_t *seg_row, int64_t n
     // 32 / 16 segments of a row meet in a warp); neutral at 12 columns, 2 us slower at 16 (8 segments per warp do not pay
     // for the shuffles), so it is used for one or two chunks only.
     const bool aggregate = agg_env && chunks <= 2;
+    {
+        const char *e = getenv("SGP_SPLAT_UAGG");   // warp-uniform aggregation for wide rows (default on; power-of-two chunk counts)
+        const int uagg = e ? atoi(e) : 1;
+        if (uagg && !aggregate && (chunks & (chunks - 1)) == 0 && !(dbg & 1)) dbg |= 4;
+    }
     cudaError_t launch_err = cudaSuccess;
 #define SGP_ROWS_LAUNCH(VV, SS)                                                                                        \
     launch_err = ragged ? sgp_launch_pdl(sgp_splat_rows_kernel<VV, SS, true>, dim3(grid_for(work, 256)), dim3(256), 0,  \
