@@ -402,8 +402,10 @@ def run_point_sharded(args, w, world, rank, dev, placement):
     Vs = [torch.randn(hi - lo, L, generator=gv, device=dev) for _ in range(n_rot)]
     outs = [torch.empty(hi - lo, L, device=dev) for _ in range(n_rot)]
 
+    col_blur = world > 1 and L % world == 0 and ps.local.groups is not None and args.column_blur
+
     def step(i):
-        outs[i % n_rot] = ps.mvm(Vs[i % n_rot], out=outs[i % n_rot])
+        outs[i % n_rot] = ps.mvm(Vs[i % n_rot], out=outs[i % n_rot], column_blur=col_blur)
 
     sampler = ClockSampler(dev.index)
     if rank == 0:
@@ -431,8 +433,11 @@ def run_point_sharded(args, w, world, rank, dev, placement):
             "steps": steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(w), "M": M, "points_per_rank": hi - lo, "M_local_rank0": ps.M_local,
-                       "sharding": "points split over the ranks; sharded lattice build (per-rank build + key-list merge); "
-                                   "per step: local splat -> NCCL all-reduce of M*L*4 bytes -> replicated blur -> local slice",
+                       "sharding": "points split over the ranks; sharded lattice build (per-rank build + key-list merge); per step: "
+                                   + ("local splat -> NCCL reduce-scatter over column blocks -> blur of L/ranks columns -> "
+                                      "all-gather -> local slice (the same M*L*4 bytes on the wire as an all-reduce)" if col_blur
+                                      else "local splat -> NCCL all-reduce of M*L*4 bytes -> replicated blur -> local slice"),
+                       "blur": "column-sharded" if col_blur else "replicated",
                        "l2": "inputs larger than L2 (index tables and lattice values exceed 126 MB)"},
             "clocks": clocks, "gpu_launches": steps * (2 + (len(ps.local.groups["list"]) if ps.local.groups else d + 1)),
             "lattice_build_ms": build_ms, "allreduce_bytes_per_step": int(vals.numel() * 4), "allreduce_ms": ar_ms,
@@ -442,8 +447,10 @@ def run_point_sharded(args, w, world, rank, dev, placement):
                              "frac": alg / ms_per_step / 1e6 / (peak * world), "peak_source": peak_src,
                              "note": "whole-job algorithmic bytes over the aggregate HBM peak of the ranks; the blur's "
                                      "(d+1)(2ML+2rM) bytes are replicated on every rank, so they do not speed up"},
-            "limiter": "the replicated blur (every rank moves the whole lattice d+1 times) plus the all-reduce; only "
-                       "splat and slice shrink with the rank count",
+            "limiter": ("the exchange (reduce-scatter + all-gather of the lattice values and their two re-layout copies) and the "
+                        "narrow-row blur: its time falls less than linearly with the column count") if col_blur else
+                       ("the replicated blur (every rank moves the whole lattice d+1 times) plus the all-reduce; only "
+                        "splat and slice shrink with the rank count"),
             "host_placement": placement,
         }
         print(json.dumps(line), flush=True)
@@ -790,6 +797,9 @@ def main():
                     help="weak: one L-column RHS block per rank (default, plus a `strong` block in the line when N > 1); "
                          "strong: ONE L-column block split over the ranks; point: the POINTS split over the ranks "
                          "(sharded lattice build, all-reduce of the lattice values between splat and blur)")
+    ap.add_argument("--column-blur", action="store_true",
+                    help="--scaling point: reduce-scatter / column-sharded blur / all-gather instead of all-reduce + replicated "
+                         "blur (measured slower at D10 on 2 GPUs: 8.2 vs 6.2 ms)")
     ap.add_argument("--no-pin", action="store_true", help="do not restrict the rank to the CPUs of its GPU's NUMA node")
     ap.add_argument("--no-multi-gpu-check", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the MVM kernels eagerly instead of replaying a CUDA graph")

@@ -335,8 +335,68 @@ class PointShardedLattice:
                                          **lattice_kwargs)
         del mine, table
 
-    def mvm(self, V_local: torch.Tensor, **kw) -> torch.Tensor:
+    def mvm(self, V_local: torch.Tensor, out: Optional[torch.Tensor] = None, column_blur: Optional[bool] = None,
+            **kw) -> torch.Tensor:
+        """This rank's rows of the product.  ``column_blur=True`` (needs ``L % world == 0`` and the blur groups) replaces
+        the all-reduce + replicated blur by reduce-scatter over COLUMN blocks -> blur of this rank's ``L / world`` columns
+        -> all-gather: the same bytes on the wire, and the blur -- the part of the step that point sharding alone leaves
+        replicated -- is divided by the world size.  Off by default: measured SLOWER on 2 B200 at the stress shape D/10
+        (L = 4: 8.2 ms against 6.2 ms per MVM) -- the two re-layout copies move the lattice values in 8-byte pieces and
+        the blur-group kernel is row-count-bound, so two columns cost it almost what four do."""
         if V_local.shape[0] != self.hi - self.lo:
             raise ValueError(f"rank {self.rank} owns {self.hi - self.lo} points, got {V_local.shape[0]} rows")
+        L = int(V_local.shape[1])
+        lat = self.local
+        can = (self.world > 1 and L % self.world == 0 and lat.groups is not None and lat.rows is not None and not kw
+               and V_local.dtype == torch.float32)
+        if column_blur is None:
+            column_blur = False
+        if column_blur and not can:
+            raise ValueError("column_blur needs world > 1, L % world == 0, blur groups and row-sorted entries")
+        if column_blur:
+            return self._mvm_column_blur(V_local, out)
         hook = (lambda vals: allreduce_lattice_values(vals, group=self.group)) if self.world > 1 else None
-        return self.local.mvm(V_local, after_splat=hook, **kw)
+        return lat.mvm(V_local, out=out, after_splat=hook, **kw)
+
+    def _mvm_column_blur(self, V: torch.Tensor, out: Optional[torch.Tensor]) -> torch.Tensor:
+        import ctypes as C
+
+        from . import _capi
+        from .lattice import _fp, _ptr, _stream_ptr
+        lib, lat, G = _capi.lib(), self.local, self.world
+        dev, M, L = lat.device, lat.M, int(V.shape[1])
+        Lc = L // G
+        n_loc = int(V.shape[0])
+        if V.stride(1) != 1 and L > 1:
+            V = V.contiguous()
+        if out is None:
+            out = torch.empty((n_loc, L), dtype=torch.float32, device=dev)
+        key = ("colblur", L)
+        bufs = lat._bufs.get(key)
+        if bufs is None:
+            bufs = {"full": torch.empty((M, L), dtype=torch.float32, device=dev),
+                    "parts": torch.empty((G, M, Lc), dtype=torch.float32, device=dev),
+                    "b0": torch.empty((M, Lc), dtype=torch.float32, device=dev),
+                    "b1": torch.empty((M, Lc), dtype=torch.float32, device=dev)}
+            lat._bufs = {key: bufs}
+        full, parts, b0, b1 = bufs["full"], bufs["parts"], bufs["b0"], bufs["b1"]
+        c = lat.coeffs
+        where = C.c_int(0)
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            if n_loc > 0:
+                _capi.check(lib.sgp_splat_rows(_ptr(lat.rows["ent"]), _ptr(lat.rows["seg_row"]), lat.rows["n"], lat.N, M, _ptr(V),
+                                               V.stride(0), L, _ptr(full), L, st))
+            else:
+                full.zero_()
+            parts.copy_(full.view(M, G, Lc).permute(1, 0, 2))               # column blocks made contiguous
+            dist.reduce_scatter_tensor(b0, parts, group=self.group)         # this rank's columns, summed over the ranks
+            arr = lat.groups["array"]
+            _capi.check(lib.sgp_blur_groups(arr, len(arr), M, lat.order, _fp(c), c.shape[0], Lc, _ptr(b0), _ptr(b1),
+                                            C.byref(where), 0 if lat.exact else 1, st))
+            dist.all_gather_into_tensor(parts, b1 if where.value else b0, group=self.group)
+            full.view(M, G, Lc).copy_(parts.permute(1, 0, 2))               # back to [M, L] rows, last stage's order
+            if n_loc > 0:
+                v_out = lat._view(lat._table(False, True), None, lat.exact)
+                _capi.check(lib.sgp_slice(C.byref(v_out), _ptr(full), L, _ptr(out), out.stride(0), L, st))
+        return out

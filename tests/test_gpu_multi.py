@@ -49,8 +49,12 @@ def _worker(rank, world, port, q):
         # 2. point sharding: local splat, all-reduce of the lattice values, blur, local slice
         ps = PointShardedLattice(xd, MAT15_2)
         lo, hi = shard_points(N, world, rank)
-        mine = ps.mvm(vd[lo:hi].contiguous())
+        mine = ps.mvm(vd[lo:hi].contiguous(), column_blur=False)      # all-reduce, replicated blur
         e_pt = float((mine - want[lo:hi]).norm() / want[lo:hi].norm())
+        if world > 1:                                                   # reduce-scatter, column-sharded blur, all-gather
+            mine2 = ps.mvm(vd[lo:hi].contiguous(), column_blur=True)
+            e_pt = max(e_pt, float((mine2 - want[lo:hi]).norm() / want[lo:hi].norm()))
+            assert ps.M == ref_lat.M and torch.equal(ps.local.keys, ref_lat.keys)
         # 3. a CG training step with the probe / RHS columns sharded: value and lengthscale gradient equal the
         #    single-GPU ones (gradients summed over ranks)
         from simplex_gp_b200 import gp
