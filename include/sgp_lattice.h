@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SGP_ABI_VERSION 4
+#define SGP_ABI_VERSION 5
 
 #define SGP_OK 0
 #define SGP_EINVAL (-1)       /* bad argument */
@@ -199,6 +199,10 @@ typedef struct sgp_lattice_view {
                                 (differs by rounding only, ~1e-7 relative) */
     int32_t replay_transposed; /* 0: replay is [N, d+1, 2]; 1: [d+1, N, 2] (what sgp_permute_replay can produce: the
                                   points of a warp then read one contiguous run per vertex) */
+    int32_t replay_stride;     /* entries per point of a non-transposed replay table: 0 or d+1 = dense; d+2 for the
+                                  table sgp_permute_replay_padded makes when d+1 is odd (one {0, 0.0f} filler per point,
+                                  so that every point starts 16-byte aligned and the slice reads entry PAIRS) */
+    int32_t reserved_;
 } sgp_lattice_view;
 
 #define SGP_SPLAT_AUTO 0
@@ -461,6 +465,11 @@ int sgp_filter(const float *src, int64_t lds, const float *ref, int64_t ldx, con
 int sgp_filter_host(const float *src_host, int64_t lds, const float *ref_host, int64_t ldx, const float *coeffs,
                     int k, int64_t N, int L, int d, float *out_host, int64_t ldo, void *workspace,
                     size_t workspace_bytes, int64_t M_max, int64_t *M_out, sgp_stream_t stream);
+
+/* sgp_permute_replay with a row stride: replay_out is [N, stride, 2] with stride >= d+1, the entries past d+1 are
+ * {0, 0.0f}.  stride = d+1 rounded up to even gives the slice 16-byte aligned points (sgp_lattice_view.replay_stride). */
+int sgp_permute_replay_padded(const int32_t *replay, const uint32_t *perm, const uint32_t *pos, int64_t N, int d,
+                              int stride, int32_t *replay_out, sgp_stream_t stream);
 
 /* Test hook: number of fp32 bit patterns a in [lo, lo+count) for which the division-by-constant
  * used inside sgp_slice differs from the IEEE division a / sgp_slice_divisor(d).  Must be 0. */

@@ -29,7 +29,7 @@ SYMBOLS = [
     "sgp_group_workspace_bytes", "sgp_group_prepare", "sgp_group_max_batches", "sgp_group_finalize",
     "sgp_remap_replay",
     "sgp_blur_groups_channel_block", "sgp_blur_groups", "sgp_mvm_rows_groups", "sgp_mvm_rows_groups_ex", "sgp_mvm_stage_splat_prezeroed", "sgp_sort_points_workspace_bytes", "sgp_sort_points",
-    "sgp_permute_replay", "sgp_rowsort_workspace_bytes", "sgp_rowsort_padded", "sgp_build_rowsorted",
+    "sgp_permute_replay", "sgp_permute_replay_padded", "sgp_rowsort_workspace_bytes", "sgp_rowsort_padded", "sgp_build_rowsorted",
     "sgp_splat_rows", "sgp_cg_scratch_floats", "sgp_cg_apply", "sgp_cg_update", "sgp_cg_direction",
     "sgp_ring_enabled", "sgp_ring_splat_enabled", "sgp_ring_slice_enabled", "sgp_splat_ring_supported", "sgp_slice_ring_supported", "sgp_splat_rows_ring", "sgp_slice_ring",
     "sgp_hash_append_keys", "sgp_count_appended", "sgp_number_appended",
@@ -52,6 +52,8 @@ class LatticeView(C.Structure):
         ("perm", C.c_void_p),
         ("fast", C.c_int32),
         ("replay_transposed", C.c_int32),
+        ("replay_stride", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 
@@ -208,6 +210,8 @@ def lib() -> C.CDLL:
     L.sgp_sort_points.argtypes = [vp, i64, i32, vp, vp, sz, vp]
     L.sgp_permute_replay.restype = i32
     L.sgp_permute_replay.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
+    L.sgp_permute_replay_padded.restype = i32
+    L.sgp_permute_replay_padded.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
     L.sgp_rowsort_workspace_bytes.restype = sz
     L.sgp_rowsort_workspace_bytes.argtypes = [i64, i32, i64]
     L.sgp_rowsort_padded.restype = i64
@@ -243,8 +247,8 @@ def lib() -> C.CDLL:
         fn.argtypes = [vp, i64, vp, i64, fp, i32, i64, i32, i32, vp, i64, vp, sz, i64, C.POINTER(i64), vp]
     L.sgp_debug_division_mismatches.restype = i32
     L.sgp_debug_division_mismatches.argtypes = [i32, C.c_uint32, C.c_uint32, vp, vp]
-    if L.sgp_abi_version() != 4:
-        raise RuntimeError(f"{LIB_PATH}: ABI version {L.sgp_abi_version()} != 4, rebuild the library")
+    if L.sgp_abi_version() != 5:
+        raise RuntimeError(f"{LIB_PATH}: ABI version {L.sgp_abi_version()} != 5, rebuild the library")
     _lib = L
     return L
 

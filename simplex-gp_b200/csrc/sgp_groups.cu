@@ -105,35 +105,44 @@ sgp_group_pos_kernel(const uint32_t *__restrict__ order, const uint32_t *__restr
 // streams class_start through a window of PACK_WINDOW entries (coalesced loads by all threads), and the walker hops
 // inside the window at shared-memory latency (~30 cycles a hop instead of a ~500 ns global round trip).
 // out[0] = n_batches, out[1] = rows of the largest batch, out[2] = error flag.
-#define PACK_WINDOW 51200      /* 200 KB of dynamic shared memory: 8 window loads at M = 4e5 instead of 40 */
+#define PACK_WINDOW 25600      /* two windows of 100 KB of dynamic shared memory, used alternately */
 #define PACK_THREADS 1024
+// The walker (thread 0) reads class_start at the positions b + cap, which grow by at most cap <= 1024 per hop: the
+// block streams class_start through consecutive windows [cap + k W, cap + (k+1) W); while the walker hops inside window k
+// at shared-memory latency, all threads have the copy of window k+1 in flight (cp.async), so the global round trips of
+// the stream are hidden behind the walk instead of alternating with it (146 -> ~60 us per group at M = 4e5).
 __global__ void __launch_bounds__(PACK_THREADS)
 sgp_group_pack_kernel(const uint32_t *__restrict__ class_start, int64_t M, int64_t cap, int64_t max_batches,
                       uint32_t *__restrict__ batch_begin, uint32_t *__restrict__ out)
 {
-    extern __shared__ uint32_t win[];   // PACK_WINDOW entries
-    __shared__ long long s_begin, s_nb, s_w0;
-    __shared__ uint32_t s_max, s_err;
-    if (threadIdx.x == 0) { s_begin = 0; s_nb = 0; s_max = 0; s_err = 0; s_w0 = 0; }
-    __syncthreads();
-    while (true) {
-        const int64_t begin = s_begin;
-        if (begin >= M || s_nb >= max_batches || s_err) break;
-        // window = class_start[w0, w0 + PACK_WINDOW), starting at the first position the walker will read
-        const int64_t w0 = begin + cap < M ? begin + cap : M;
+    extern __shared__ __align__(16) uint32_t win[];   // 2 x PACK_WINDOW entries
+    __shared__ long long s_begin, s_nb;
+    __shared__ uint32_t s_max, s_err, s_done;
+    if (threadIdx.x == 0) { s_begin = 0; s_nb = 0; s_max = 0; s_err = 0; s_done = 0; }
+    const int64_t n_win = M > cap ? (M - cap + PACK_WINDOW - 1) / PACK_WINDOW : 0;
+    auto load = [&](int64_t k, uint32_t *dst) {     // window k = class_start[cap + k W, cap + (k+1) W) clipped to M
+        const int64_t w0 = cap + k * PACK_WINDOW;
         const int64_t wn = (M - w0 < PACK_WINDOW) ? M - w0 : PACK_WINDOW;
-        for (int64_t i = threadIdx.x; i < wn; i += PACK_THREADS) win[i] = class_start[w0 + i];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int64_t b = begin, nb = s_nb;
+        if (wn > 0) cta_copy_async(dst, class_start + w0, (int)(wn * 4), threadIdx.x, PACK_THREADS);
+    };
+    if (n_win > 0) load(0, win);
+    cp_async_wait_all();
+    __syncthreads();
+    for (int64_t k = 0; k <= n_win; ++k) {
+        uint32_t *cur = win + (k & 1) * PACK_WINDOW;
+        if (k + 1 < n_win) load(k + 1, win + ((k + 1) & 1) * PACK_WINDOW);
+        if (threadIdx.x == 0 && !s_done) {
+            const int64_t w0 = cap + k * PACK_WINDOW;
+            const int64_t w1 = (k < n_win) ? ((w0 + PACK_WINDOW < M) ? w0 + PACK_WINDOW : M) : M;   // window k covers [w0, w1)
+            int64_t b = s_begin, nb = s_nb;
             uint32_t mx = s_max;
             while (b < M && nb < max_batches) {
                 int64_t end = b + cap;
                 if (end >= M) {
                     end = M;
                 } else {
-                    if (end - w0 >= wn) break;            // next read is beyond the window: reload
-                    end = win[end - w0];                   // start of the class that position b + cap falls into
+                    if (end >= w1) break;                  // the next read lies in the next window
+                    end = cur[end - w0];                   // start of the class that position b + cap falls into
                     if (end <= b) { s_err = 1; break; }    // a class larger than cap (the caller checks max_class)
                 }
                 batch_begin[nb++] = (uint32_t)b;
@@ -141,8 +150,11 @@ sgp_group_pack_kernel(const uint32_t *__restrict__ class_start, int64_t M, int64
                 b = end;
             }
             s_begin = b; s_nb = nb; s_max = mx;
+            if (b >= M || nb >= max_batches || s_err) s_done = 1;
         }
+        cp_async_wait_all();
         __syncthreads();
+        if (s_done) break;
     }
     if (threadIdx.x == 0) {
         if (s_begin < M) s_err = 1;
@@ -328,8 +340,8 @@ extern "C" int sgp_group_finalize(const int32_t *nbr, const int16_t *keys, int d
     CUDA_TRY(cudaMemsetAsync(small, 0, 32, st));
     // the opt-in above 48 KB is per device (and cheap): set it on every call rather than caching it per process
     CUDA_TRY(cudaFuncSetAttribute(sgp_group_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(PACK_WINDOW * sizeof(uint32_t))));
-    sgp_group_pack_kernel<<<1, PACK_THREADS, PACK_WINDOW * sizeof(uint32_t), st>>>(class_start, M, cap, max_batches,
+                                  (int)(2 * PACK_WINDOW * sizeof(uint32_t))));
+    sgp_group_pack_kernel<<<1, PACK_THREADS, 2 * PACK_WINDOW * sizeof(uint32_t), st>>>(class_start, M, cap, max_batches,
                                                                                    batch_begin, small);
     rc = launch_ok("sgp_group_pack_kernel");
     if (rc) return rc;

@@ -245,6 +245,8 @@ sgp_points_kernel(const float *__restrict__ x, int64_t N, int d_rt, int64_t ldx,
     if (bad) atomicOr(flags, SGP_FLAG_KEY_RANGE);
 }
 
+#define SGP_MAX_PROBES 8192ull
+
 // ------------------------------------------------------------------------------------
 // stage 1b: lock-free hash insertion.  One thread per point-vertex pv = n*(d+1)+rem.
 // A slot is a 64-bit word {fingerprint:32 | owner pv:32}; it is claimed with one CAS and
@@ -279,7 +281,13 @@ sgp_insert_kernel(const int16_t *__restrict__ greedy, const int8_t *__restrict__
     uint64_t slot = h & mask;
     const unsigned long long mine = ((unsigned long long)fp << 32) | (uint32_t)pv;
 
-    for (uint64_t probe = 0; probe <= mask; ++probe) {
+    // A caller may size the table from the previous lattice of the same shape (4x its M instead of 2 N(d+1)); if this
+    // lattice outgrew it, give up quickly instead of scanning a full table from every thread: a probe sequence longer
+    // than SGP_MAX_PROBES never occurs below ~95 % load, and once one thread has raised the flag the others leave at
+    // their next check.
+    const uint64_t max_probes = mask + 1 < SGP_MAX_PROBES ? mask + 1 : SGP_MAX_PROBES;
+    for (uint64_t probe = 0; probe < max_probes; ++probe) {
+        if ((probe & 63) == 63 && (*((volatile int32_t *)flags) & SGP_FLAG_TABLE_FULL)) break;
         unsigned long long cur = *((volatile unsigned long long *)(table + slot));
         if (cur == SGP_EMPTY) {
             unsigned long long prev = atomicCAS(table + slot, SGP_EMPTY, mine);
@@ -1339,6 +1347,8 @@ extern "C" int sgp_build_neighbours(const int16_t *keys, int64_t M, int d, int o
 static int check_view(const sgp_lattice_view *lat, int L)
 {
     if (!lat) return fail(SGP_EINVAL, "null lattice view");
+    if (lat->replay_stride != 0 && (lat->replay_stride < lat->d + 1 || lat->replay_transposed))
+        return fail(SGP_EINVAL, "replay_stride must be 0 or >= d+1 (and the table not transposed)");
     if (lat->N < 0 || lat->M < 0 || lat->d < 1 || lat->d > SGP_MAX_DIM || lat->order < 0 || lat->order > SGP_MAX_ORDER)
         return fail(SGP_EINVAL, "bad lattice view (N=%lld M=%lld d=%d order=%d)", (long long)lat->N, (long long)lat->M,
                     lat->d, lat->order);
@@ -1386,7 +1396,7 @@ extern "C" int sgp_splat(const sgp_lattice_view *lat, const float *src, int64_t 
     CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)lat->M * (size_t)L, st));
     const int64_t work = lat->N * chunks;
     SGP_DISPATCH_VEC(vec, (sgp_splat_atomic_kernel<VV><<<grid_for(work, 256), 256, 0, st>>>(
-                              (const int2 *)lat->replay, lat->replay_transposed ? 1 : lat->d + 1,
+                              (const int2 *)lat->replay, lat->replay_transposed ? 1 : (lat->replay_stride > 0 ? lat->replay_stride : lat->d + 1),
                               lat->replay_transposed ? lat->N : 1, lat->perm, src, lds, lat->N, lat->d + 1, L, chunks,
                               values)));
     return launch_ok("sgp_splat_atomic_kernel");
@@ -1486,7 +1496,7 @@ extern "C" int sgp_slice(const sgp_lattice_view *lat, const float *values, int L
     }
 #define SGP_SLICE_LAUNCH(BB, FF, SS, RG)                                                                                     \
     SGP_DISPATCH_VEC(vec, (launch_err = sgp_launch_pdl(sgp_slice_kernel<VV, BB, FF, SS, RG>, dim3(grid_for(work, 256)), dim3(256), 0, st, \
-                              (const int2 *)lat->replay, (int64_t)(lat->replay_transposed ? 1 : lat->d + 1),             \
+                              (const int2 *)lat->replay, (int64_t)(lat->replay_transposed ? 1 : (lat->replay_stride > 0 ? lat->replay_stride : lat->d + 1)), \
                               (int64_t)(lat->replay_transposed ? lat->N : 1), lat->perm, values, lat->N, lat->d + 1, L, chunks, \
                               divisor, (float)rdivisor, out, ldo, L_out)))
     cudaError_t launch_err = cudaSuccess;

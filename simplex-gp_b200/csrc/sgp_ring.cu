@@ -109,14 +109,49 @@ __device__ __forceinline__ void slice_batch(const int2 *ep, const float *__restr
     }
 }
 
+// The same with the entries read in PAIRS (16-byte shared-memory loads): the table has an even number of entry slots per
+// point, so every point starts 16-byte aligned (sgp_permute_replay_padded).  S slots, the first `nreal` (S or S - 1) of
+// them real: half the shared-memory wavefronts of the 8-byte reads (18 -> 10 per pass at d = 8).
+template <int VEC, bool FAST, int S>
+__device__ __forceinline__ void slice_batch_pairs(const int4 *ep, int nreal, const float *__restrict__ values, int L, int c0,
+                                                  Vec<VEC> &acc, float divisor, float rdivisor)
+{
+    int idx[S];
+    float w[S];
+    Vec<VEC> v[S];
+#pragma unroll
+    for (int j = 0; j < S / 2; ++j) {
+        const int4 q = ep[j];
+        idx[2 * j] = q.x; w[2 * j] = __int_as_float(q.y);
+        idx[2 * j + 1] = q.z; w[2 * j + 1] = __int_as_float(q.w);
+    }
+    int lowest = idx[0];
+#pragma unroll
+    for (int b = 1; b < S; ++b) lowest = min(lowest, idx[b]);
+    if (lowest >= 0) {
+#pragma unroll
+        for (int b = 0; b < S; ++b)
+            if (b < S - 1 || nreal == S) v[b].load_ordered(values + (int64_t)idx[b] * L + c0);
+#pragma unroll
+        for (int b = 0; b < S; ++b) {
+            if (b < S - 1 || nreal == S) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    acc.v[k] = FAST ? __fmaf_rn(w[b], v[b].v[k], acc.v[k])
+                                    : __fadd_rn(acc.v[k], exact_div(__fmul_rn(w[b], v[b].v[k]), divisor, rdivisor));
+            }
+        }
+    }
+}
+
 // Persistent warps; warp w takes the tiles w, w + W, ... of P = ppp * passes points.  A tile's replay entries
 // ([P, d+1] {index, weight}: contiguous) arrive in the warp's ring by one bulk copy; in a pass the lanes are
 // (point, channel chunk): ppp = 32 / chunks points.
 template <int VEC, bool FAST, bool RAGGED>
 __global__ void __launch_bounds__(RING_THREADS)
-sgp_slice_ring_kernel(const int2 *__restrict__ replay, const float *__restrict__ values, int64_t N, int dp1, int L,
-                      int chunks, int ppp, int passes, int stages, uint32_t tile_stride, float divisor, float rdivisor,
-                      float *__restrict__ out, int64_t ldo, int L_out)
+sgp_slice_ring_kernel(const int2 *__restrict__ replay, const float *__restrict__ values, int64_t N, int dp1, int estride,
+                      int L, int chunks, int ppp, int passes, int stages, uint32_t tile_stride, float divisor,
+                      float rdivisor, float *__restrict__ out, int64_t ldo, int L_out)
 {
     extern __shared__ __align__(128) unsigned char ring_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,10 +171,10 @@ sgp_slice_ring_kernel(const int2 *__restrict__ replay, const float *__restrict__
     auto issue = [&](int64_t t, int s) {   // lane 0: stream tile t into stage s
         const int64_t p0 = t * P;
         const int np = (int)min((int64_t)P, N - p0);
-        const uint32_t bytes = (uint32_t)np * (uint32_t)dp1 * 8u;
+        const uint32_t bytes = (uint32_t)np * (uint32_t)estride * 8u;
         const uint32_t b16 = bytes & ~15u;
         unsigned char *dst = ring + (size_t)s * tile_stride;
-        const unsigned char *src = (const unsigned char *)(replay + p0 * dp1);
+        const unsigned char *src = (const unsigned char *)(replay + p0 * estride);
         if (bytes != b16) *(int2 *)(dst + b16) = __ldg((const int2 *)(src + b16));   // odd entry count: the last by hand
         mbar_arrive_expect_tx(bars + s, b16);
         bulk_g2s(dst, src, b16, bars + s, pol);
@@ -165,13 +200,22 @@ sgp_slice_ring_kernel(const int2 *__restrict__ replay, const float *__restrict__
         for (int pass = 0; pass < passes; ++pass) {
             const int lp = pass * ppp + sub;
             if (lane_on && lp < np) {
-                const int2 *ep = E + lp * dp1;
+                const int2 *ep = E + lp * estride;
                 Vec<VEC> acc;
                 vec_zero(acc);
                 int r0 = 0;
-                for (; r0 + 9 <= dp1; r0 += 9) slice_batch<VEC, FAST, 9>(ep + r0, values, L, c0, acc, divisor, rdivisor);
-                for (; r0 + 3 <= dp1; r0 += 3) slice_batch<VEC, FAST, 3>(ep + r0, values, L, c0, acc, divisor, rdivisor);
-                for (; r0 < dp1; ++r0) slice_batch<VEC, FAST, 1>(ep + r0, values, L, c0, acc, divisor, rdivisor);
+                if ((estride & 1) == 0) {   // 16-byte aligned points: entries in pairs
+                    for (; r0 + 10 <= estride; r0 += 10)
+                        slice_batch_pairs<VEC, FAST, 10>((const int4 *)(ep + r0), min(10, dp1 - r0), values, L, c0, acc, divisor, rdivisor);
+                    for (; r0 + 4 <= estride; r0 += 4)
+                        slice_batch_pairs<VEC, FAST, 4>((const int4 *)(ep + r0), min(4, dp1 - r0), values, L, c0, acc, divisor, rdivisor);
+                    for (; r0 + 2 <= estride; r0 += 2)
+                        slice_batch_pairs<VEC, FAST, 2>((const int4 *)(ep + r0), min(2, dp1 - r0), values, L, c0, acc, divisor, rdivisor);
+                } else {
+                    for (; r0 + 9 <= dp1; r0 += 9) slice_batch<VEC, FAST, 9>(ep + r0, values, L, c0, acc, divisor, rdivisor);
+                    for (; r0 + 3 <= dp1; r0 += 3) slice_batch<VEC, FAST, 3>(ep + r0, values, L, c0, acc, divisor, rdivisor);
+                    for (; r0 < dp1; ++r0) slice_batch<VEC, FAST, 1>(ep + r0, values, L, c0, acc, divisor, rdivisor);
+                }
                 if (FAST) {   // one division of the sum instead of one per term (differs from the reference by rounding only)
 #pragma unroll
                     for (int k = 0; k < VEC; ++k) acc.v[k] = exact_div(acc.v[k], divisor, rdivisor);
@@ -517,7 +561,9 @@ extern "C" int sgp_slice_ring_supported(const sgp_lattice_view *lat, const float
     if (!lat || lat->perm || lat->replay_transposed) return 0;
     const int vec = ring_vec(L, values);
     int ppp, passes;
-    if (vec == 0 || !slice_geometry(lat->d + 1, L / vec, &ppp, &passes)) return 0;
+    const int estride = lat->replay_stride > 0 ? lat->replay_stride : lat->d + 1;
+    if (estride > lat->d + 2) return 0;   // at most one filler slot per point
+    if (vec == 0 || !slice_geometry(estride, L / vec, &ppp, &passes)) return 0;
     // narrow rows: with one or two channel chunks a warp instruction gathers 32 / 16 distinct rows and the one-shot
     // kernel measures faster (L = 1 / 2 / 4 / 8: 28 / 33 / 38 / 45 us against 64 / 67 / 45 / 49 us; L = 12 / 16 / 32: 59 / 62 / 110 against 57 / 51 / 96); SGP_RING_FORCE=1 overrides (experiments)
     return L / vec >= ring_env("SGP_RING_MIN_CHUNKS", 3) || ring_env("SGP_RING_FORCE", 0) != 0;
@@ -538,8 +584,9 @@ extern "C" int sgp_slice_ring(const sgp_lattice_view *lat, const float *values, 
     if (vec == 1 && L_out != L) return fail(SGP_EUNSUPPORTED, "sgp_slice_ring: L_out < L needs vectorisable lattice rows");
     const int chunks = L / vec;
     const int dp1 = lat->d + 1;
+    const int estride = lat->replay_stride > 0 ? lat->replay_stride : dp1;
     int ppp = 0, passes = 0;
-    slice_geometry(dp1, chunks, &ppp, &passes);
+    slice_geometry(estride, chunks, &ppp, &passes);
     const int P = ppp * passes;
     const int64_t n_tiles = (lat->N + P - 1) / P;
     const float divisor = sgp_slice_divisor(lat->d);
@@ -549,10 +596,10 @@ extern "C" int sgp_slice_ring(const sgp_lattice_view *lat, const float *values, 
     cudaError_t le = cudaSuccess;
 #define SGP_SLICE_RING(VV, FF, RG)                                                                                     \
     do {                                                                                                               \
-        rc = ring_config(sgp_slice_ring_kernel<VV, FF, RG>, (uint32_t)P * dp1 * 8u, n_tiles, 2, "SGP_SLICE_STAGES", &rl); \
+        rc = ring_config(sgp_slice_ring_kernel<VV, FF, RG>, (uint32_t)P * estride * 8u, n_tiles, 2, "SGP_SLICE_STAGES", &rl); \
         if (rc) return rc;                                                                                             \
         le = sgp_launch_pdl(sgp_slice_ring_kernel<VV, FF, RG>, dim3(rl.grid), dim3(RING_THREADS), rl.smem, st,         \
-                            (const int2 *)lat->replay, values, lat->N, dp1, L, chunks, ppp, passes, rl.stages,         \
+                            (const int2 *)lat->replay, values, lat->N, dp1, estride, L, chunks, ppp, passes, rl.stages, \
                             rl.tile_stride, divisor, (float)rdivisor, out, ldo, L_out);                                \
     } while (0)
 #define SGP_SLICE_RING_V(VV)                                                                                           \

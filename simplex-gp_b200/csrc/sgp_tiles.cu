@@ -355,6 +355,33 @@ extern "C" int sgp_permute_replay(const int32_t *replay, const uint32_t *perm, c
     return launch_ok("sgp_permute_replay_kernel");
 }
 
+__global__ void __launch_bounds__(256)
+sgp_permute_replay_padded_kernel(const int2 *__restrict__ replay, const uint32_t *__restrict__ perm,
+                                 const uint32_t *__restrict__ pos, int64_t N, int dp1, int stride, int2 *__restrict__ out)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // output index
+    if (q >= N * stride) return;
+    const int64_t p = q / stride;
+    const int r = (int)(q - p * stride);
+    int2 e = make_int2(0, 0);
+    if (r < dp1) {
+        e = replay[(perm ? (int64_t)perm[p] : p) * dp1 + r];
+        if (pos) e.x = (int)pos[e.x];
+    }
+    out[q] = e;
+}
+
+extern "C" int sgp_permute_replay_padded(const int32_t *replay, const uint32_t *perm, const uint32_t *pos, int64_t N, int d,
+                                         int stride, int32_t *replay_out, sgp_stream_t stream)
+{
+    if (N == 0) return SGP_OK;
+    if (!replay || !replay_out || N < 0 || d < 1 || stride < d + 1) return fail(SGP_EINVAL, "sgp_permute_replay_padded: bad argument");
+    const int64_t total = N * (int64_t)stride;
+    sgp_permute_replay_padded_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const int2 *)replay, perm, pos, N,
+                                                                                              d + 1, stride, (int2 *)replay_out);
+    return launch_ok("sgp_permute_replay_padded_kernel");
+}
+
 // ------------------------------------------------------------------------------------
 // Row-sorted splat ("segmented gather").  The point-vertices are sorted once per lattice by the lattice row they
 // touch (stable radix sort: within a row they stay in point-vertex order, the reference's accumulation order).  A

@@ -65,6 +65,7 @@ def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
 
 
 _GROUP_HINTS = {}   # (d, order, rows per CTA) -> axis-range lengths of the last blur-group build of that shape
+_M_BUILD_HINT = {}  # (N, d) -> lattice points of the last build of that shape: sizes the next build's hash table
 
 
 class Lattice:
@@ -139,19 +140,42 @@ class Lattice:
             if N > 0:
                 check(lib.sgp_build_points(_ptr(x), N, d, x.stride(0), _fp(self.scale), _ptr(self.greedy),
                                            _ptr(self.rank), _ptr(self.replay), _ptr(flags), st))
-                cap = int(hash_capacity) if hash_capacity else int(lib.sgp_hash_capacity(total))
-                self.hash_capacity = cap
-                table = torch.full((cap,), -1, dtype=torch.int64, device=dev)
+                # The table only has to hold the DISTINCT keys (M of them, 4 % of the N(d+1) insertions at the metric
+                # shape), but M is not known before the insertion.  Successive hyper-parameter steps build almost the
+                # same lattice, so the table is sized for four times the M of the last build of this shape (8 MB instead
+                # of 268 MB at the metric shape: it then lives in L2 for the 9 M atomic probes, and the fill / re-target
+                # passes over it shrink with it); if the lattice outgrew that, the insertion reports a full table and is
+                # repeated at the safe size 2 N(d+1).  The numbering does not depend on the table's size or layout.
+                cap_full = int(lib.sgp_hash_capacity(total))
+                hint = _M_BUILD_HINT.get((N, d))
+                cap = int(hash_capacity) if hash_capacity else (
+                    min(cap_full, int(lib.sgp_hash_capacity(2 * hint))) if hint else cap_full)
                 slot_of = torch.empty(total, dtype=torch.int32, device=dev)
-                check(lib.sgp_hash_insert(_ptr(self.greedy), _ptr(self.rank), N, d, _ptr(table), cap, _ptr(slot_of),
-                                          _ptr(flags), st))
                 ws_bytes = int(lib.sgp_number_workspace_bytes(N, d))
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 M = C.c_int64(0)
                 fl = C.c_int32(0)
-                check(lib.sgp_count_points(_ptr(table), cap, _ptr(slot_of), N, d, _ptr(ws), ws_bytes, _ptr(flags),
-                                           C.byref(M), C.byref(fl), st))
+                while True:
+                    table = torch.full((cap,), -1, dtype=torch.int64, device=dev)
+                    check(lib.sgp_hash_insert(_ptr(self.greedy), _ptr(self.rank), N, d, _ptr(table), cap, _ptr(slot_of),
+                                              _ptr(flags), st))
+                    rc = lib.sgp_count_points(_ptr(table), cap, _ptr(slot_of), N, d, _ptr(ws), ws_bytes, _ptr(flags),
+                                              C.byref(M), C.byref(fl), st)
+                    if rc == -3 and (fl.value & 2) and cap < cap_full and not hash_capacity:   # SGP_FLAG_TABLE_FULL
+                        cap = cap_full
+                        flags.zero_()
+                        del table
+                        continue
+                    check(rc)
+                    if 2 * int(M.value) > cap and cap < cap_full and not hash_capacity:
+                        cap = cap_full       # over half full: the neighbour look-ups that follow would probe long chains
+                        flags.zero_()
+                        del table
+                        continue
+                    break
+                self.hash_capacity = cap
                 self.M = int(M.value)
+                _M_BUILD_HINT[(N, d)] = self.M
                 self._covers_all_rows = True      # every lattice point was created by one of these points
                 self.keys = torch.empty((self.M, d), dtype=torch.int16, device=dev)
                 check(lib.sgp_number_points(_ptr(table), cap, _ptr(slot_of), _ptr(self.greedy), _ptr(self.rank), N, d,
@@ -375,7 +399,8 @@ class Lattice:
             while mx.value > rows_limit and j1 - j0 > 1:      # shorten the range until its largest class fits
                 j1 -= 1
                 order_of, pos, cstart, mx = prepare(j0, j1)
-            if adaptive:
+            hinted = adaptive and len(groups) < len(hints) and j1 - j0 == hints[len(groups)]
+            if adaptive and not hinted:   # (a range that repeats the last build's length is not probed for one more axis)
                 # ... or lengthen it while it still does and the batch-local neighbour table stays at most 48 bytes a
                 # row (it shares the CTA's shared memory with the values: longer tables cost occupancy)
                 max_axes = max(3, 48 // (4 * r))
@@ -559,23 +584,35 @@ class Lattice:
             return self.replay
         t = self._tables.get(key)
         if t is None:
-            t = torch.empty((self.N, self.d + 1, 2), dtype=torch.int32, device=self.device)
             perm = self.sorted["perm"] if sorted else None
             pos = self.groups["final_pos"] if final else None
+            # an odd number of vertices per point gets one filler slot: every point of the table then starts 16-byte
+            # aligned and the ring slice reads its entries in pairs (SGP_REPLAY_PAD=0 keeps the dense table)
+            import os
+            stride = self.d + 1
+            if final and not sorted and stride % 2 == 1 and os.environ.get("SGP_REPLAY_PAD", "1") != "0":
+                stride += 1
+            t = torch.empty((self.N, stride, 2), dtype=torch.int32, device=self.device)
             with torch.cuda.device(self.device):
-                check(_capi.lib().sgp_permute_replay(_ptr(self.replay), _ptr(perm), _ptr(pos), self.N, self.d, 0, _ptr(t),
-                                                     _stream_ptr(self.device)))
+                if stride == self.d + 1:
+                    check(_capi.lib().sgp_permute_replay(_ptr(self.replay), _ptr(perm), _ptr(pos), self.N, self.d, 0, _ptr(t),
+                                                         _stream_ptr(self.device)))
+                else:
+                    check(_capi.lib().sgp_permute_replay_padded(_ptr(self.replay), _ptr(perm), _ptr(pos), self.N, self.d,
+                                                                stride, _ptr(t), _stream_ptr(self.device)))
             self._tables[key] = t
         return t
 
     def _view(self, replay: Optional[torch.Tensor] = None, perm: Optional[torch.Tensor] = None,
               exact: Optional[bool] = None, transposed: bool = False) -> LatticeView:
         exact = self.exact if exact is None else exact
-        return LatticeView(self.N, self.M, self.d, self.order, (self.replay if replay is None else replay).data_ptr(),
+        rp = self.replay if replay is None else replay
+        stride = int(rp.shape[1]) if (not transposed and rp.dim() == 3 and int(rp.shape[1]) != self.d + 1) else 0
+        return LatticeView(self.N, self.M, self.d, self.order, rp.data_ptr(),
                            self.nbr.data_ptr() if (self.nbr is not None and self.nbr.numel()) else 0,
                            self.csr_ptr.data_ptr() if self.csr_ptr is not None else 0,
                            self.csr_ent.data_ptr() if self.csr_ent is not None else 0,
-                           0 if perm is None else perm.data_ptr(), 0 if exact else 1, 1 if transposed else 0)
+                           0 if perm is None else perm.data_ptr(), 0 if exact else 1, 1 if transposed else 0, stride, 0)
 
     def _scratch(self, L: int):
         key = int(L)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(sg):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_capi.SYMBOLS) == declared, "python binding list out of sync with the header"
-    assert lib.sgp_abi_version() == 4
+    assert lib.sgp_abi_version() == 5
 
 
 @pytest.mark.parametrize("coeffs", [RBF1, RBF2, MAT15_2, MAT15_3, [1.0], [0.5, 1.0, 0.5]])

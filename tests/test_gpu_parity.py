@@ -397,3 +397,27 @@ def test_sharded_build_equals_full_build(sg, N, d, coeffs, shards):
             assert lean.nbr is None
             got = lean.mvm(vd[lo:hi].contiguous(), after_splat=lambda vals: vals[:, :6].copy_(total))
             assert float((got - want_out[lo:hi]).norm() / want_out[lo:hi].norm()) < 1e-5
+
+
+def test_hash_table_sized_from_the_previous_build(sg, oracle):
+    """The build sizes its hash table from the lattice of the last build of the same (N, d) (4x its M instead of
+    2 N(d+1)); a lattice that outgrew the hint fills the table, which the insertion reports quickly (bounded probing) and
+    the build repeats at the safe size.  Numbering never depends on the table."""
+    from simplex_gp_b200 import lattice as LT
+    LT._M_BUILD_HINT.clear()
+    x, v = make_inputs(20000, 4, 3, seed=91)
+    xd = x.cuda()
+    first = sg.Lattice(xd, RBF1)                      # no hint: safe size
+    again = sg.Lattice(xd.clone(), RBF1)              # hinted: small table
+    assert again.hash_capacity < first.hash_capacity
+    assert again.M == first.M and torch.equal(again.keys, first.keys) and torch.equal(again.replay, first.replay)
+    assert torch.equal(again.nbr, first.nbr)
+    big = sg.Lattice((xd * 6).contiguous(), RBF1)     # many more lattice points than the hint allows for
+    O = oracle.OracleLattice((x * 6).numpy(), RBF1)
+    assert big.M == O.M > 4 * first.M
+    assert np.array_equal(big.keys.cpu().numpy(), O.keys) and np.array_equal(big.offsets.cpu().numpy(), O.offsets)
+    assert np.array_equal(big.nbr.cpu().numpy(), O.nbr)
+    small = sg.Lattice((xd * 0.2).contiguous(), RBF1)  # far fewer: the hinted table is merely roomy
+    O = oracle.OracleLattice((x * 0.2).numpy(), RBF1)
+    assert small.M == O.M and np.array_equal(small.keys.cpu().numpy(), O.keys)
+    LT._M_BUILD_HINT.clear()
