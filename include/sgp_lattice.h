@@ -313,6 +313,20 @@ int sgp_group_finalize(const int32_t *nbr, const int16_t *keys, int d, const uin
                        int64_t cap, int64_t max_batches, uint32_t *batch_begin, int32_t *src, uint16_t *lnb,
                        void *workspace, size_t workspace_bytes, int64_t *n_batches_out, int32_t *max_rows_out,
                        sgp_stream_t stream);
+/* The same launches without the read-back: nothing synchronises, the figures land in `result` (device uint32[8]:
+ * [0] largest class, [1] batches, [2] rows of the largest batch, [3] != 0: the classes did not fit / max_batches too
+ * small, [4] != 0: a neighbour fell outside its batch).  A caller that knows the axis ranges (from the last lattice of
+ * the same shape) runs sgp_group_prepare_async for every range on one stream, sgp_group_finalize_async on a second one
+ * behind an event, and reads all results with ONE synchronisation; if a result is bad it falls back to the synchronous
+ * pair above.  sgp_group_prepare_async needs the workspace only until the next prepare may overwrite it;
+ * sgp_group_finalize_async needs none. */
+int sgp_group_prepare_async(const int16_t *keys, int64_t M, int d, int j0, int j1, uint32_t *order, uint32_t *pos,
+                            uint32_t *class_start, void *workspace, size_t workspace_bytes, uint32_t *result,
+                            sgp_stream_t stream);
+int sgp_group_finalize_async(const int32_t *nbr, const int16_t *keys, int d, const uint64_t *table, int64_t capacity,
+                             int64_t M, int order, int j0, int j1, const uint32_t *order_of, const uint32_t *pos,
+                             const uint32_t *class_start, const uint32_t *prev_pos, int64_t cap, int64_t max_batches,
+                             uint32_t *batch_begin, int32_t *src, uint16_t *lnb, uint32_t *result, sgp_stream_t stream);
 /* replay_out[q] = {pos[replay[q].index], replay[q].weight bits}, q < total */
 int sgp_remap_replay(const int32_t *replay, int64_t total, const uint32_t *pos, int32_t *replay_out,
                      sgp_stream_t stream);

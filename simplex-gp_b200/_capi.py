@@ -27,6 +27,7 @@ SYMBOLS = [
     "sgp_tiles_workspace_bytes", "sgp_tiles_prepare", "sgp_tiles_finalize", "sgp_splat_tiles", "sgp_slice_tiles",
     "sgp_grad_channels", "sgp_grad_pack", "sgp_grad_contract",
     "sgp_group_workspace_bytes", "sgp_group_prepare", "sgp_group_max_batches", "sgp_group_finalize",
+    "sgp_group_prepare_async", "sgp_group_finalize_async",
     "sgp_remap_replay",
     "sgp_blur_groups_channel_block", "sgp_blur_groups", "sgp_mvm_rows_groups", "sgp_mvm_rows_groups_ex", "sgp_mvm_stage_splat_prezeroed", "sgp_sort_points_workspace_bytes", "sgp_sort_points",
     "sgp_permute_replay", "sgp_permute_replay_padded", "sgp_rowsort_workspace_bytes", "sgp_rowsort_padded", "sgp_build_rowsorted",
@@ -189,6 +190,10 @@ def lib() -> C.CDLL:
     L.sgp_group_finalize.restype = i32
     L.sgp_group_finalize.argtypes = [vp, vp, i32, vp, i64, i64, i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, sz,
                                      C.POINTER(i64), C.POINTER(C.c_int32), vp]
+    L.sgp_group_prepare_async.restype = i32
+    L.sgp_group_prepare_async.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, sz, vp, vp]
+    L.sgp_group_finalize_async.restype = i32
+    L.sgp_group_finalize_async.argtypes = [vp, vp, i32, vp, i64, i64, i32, i32, i32, vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp]
     L.sgp_group_max_batches.restype = i64
     L.sgp_group_max_batches.argtypes = [i64, i64, i64]
     L.sgp_remap_replay.restype = i32

@@ -171,12 +171,14 @@ __global__ void __launch_bounds__(256)
 sgp_group_tables_kernel(const int32_t *__restrict__ nbr, const int16_t *__restrict__ keys, int d,
                         const unsigned long long *__restrict__ table, uint64_t mask, int64_t M, int order_r, int j0, int j1,
                         const uint32_t *__restrict__ order, const uint32_t *__restrict__ pos,
-                        const uint32_t *__restrict__ prev_pos, int64_t n_batches,
+                        const uint32_t *__restrict__ prev_pos, const uint32_t *__restrict__ n_batches_dev,
                         const uint32_t *__restrict__ batch_begin, uint32_t absent, int32_t *__restrict__ src,
                         uint16_t *__restrict__ lnb, int32_t *__restrict__ flags)
 {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= M) return;
+    const int64_t n_batches = (int64_t)__ldg(n_batches_dev);   // left by the pack kernel: no host round trip in between
+    if (n_batches < 1) return;                                  // (the pack failed: its error flag says so)
     const uint32_t row = order[p];
     src[p] = prev_pos ? (int32_t)prev_pos[row] : (int32_t)row;
     // batch of position p: last b with batch_begin[b] <= p
@@ -271,24 +273,25 @@ extern "C" size_t sgp_group_workspace_bytes(int64_t M)
     return w.bytes;
 }
 
-extern "C" int sgp_group_prepare(const int16_t *keys, int64_t M, int d, int j0, int j1, uint32_t *order, uint32_t *pos,
-                                 uint32_t *class_start, void *workspace, size_t workspace_bytes, int64_t *max_class_out,
-                                 sgp_stream_t stream)
+// result (device uint32[8], one per group): [0] largest class, [1] batches, [2] rows of the largest batch, [3] pack error,
+// [4] neighbour-outside-batch flag.  The *_async forms launch everything on the stream and never synchronise: a caller
+// that knows the axis ranges (from the last lattice of the same shape) builds all groups back to back and reads all the
+// results with ONE synchronisation; sgp_group_prepare / sgp_group_finalize are the same launches plus the read-back.
+static int group_prepare_launch(const int16_t *keys, int64_t M, int d, int j0, int j1, uint32_t *order, uint32_t *pos,
+                                uint32_t *class_start, void *workspace, size_t workspace_bytes, uint32_t *result,
+                                cudaStream_t st)
 {
-    SGP_RANGE("sgp_group_prepare");
-    if (!keys || !order || !pos || !class_start || !workspace || !max_class_out || M <= 0 || d < 1 || d > SGP_MAX_DIM ||
-        j0 < 0 || j1 <= j0 || j1 > d + 1)
+    if (!keys || !order || !pos || !class_start || !workspace || !result || M <= 0 || d < 1 || d > SGP_MAX_DIM || j0 < 0 ||
+        j1 <= j0 || j1 > d + 1)
         return fail(SGP_EINVAL, "sgp_group_prepare: bad argument");
     if (M >= (1ll << 32)) return fail(SGP_EOVERFLOW, "M does not fit 32 bits");
     GroupWs w;
     int rc = group_ws_layout(M, &w);
     if (rc) return rc;
     if (workspace_bytes < w.bytes) return fail(SGP_EINVAL, "group workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
-    cudaStream_t st = (cudaStream_t)stream;
     char *base = (char *)workspace;
     unsigned long long *ha = (unsigned long long *)(base + w.hash_a), *hb = (unsigned long long *)(base + w.hash_b);
     uint32_t *ids = (uint32_t *)(base + w.ids_a), *head = (uint32_t *)(base + w.head);
-    uint32_t *small = (uint32_t *)(base + w.small);
     size_t cub_bytes = w.cub_bytes;
     const int bits = group_hash_bits(M);
     sgp_group_hash_kernel<<<grid_for(M, 256), 256, 0, st>>>(keys, M, d, j0, j1, 64 - bits, ha, ids);
@@ -300,9 +303,68 @@ extern "C" int sgp_group_prepare(const int16_t *keys, int64_t M, int d, int j0, 
     if (rc) return rc;
     cub_bytes = w.cub_bytes;
     CUDA_TRY(cub::DeviceScan::InclusiveScan(base + w.cub, cub_bytes, head, class_start, cub::Max(), (int64_t)M, st));
-    CUDA_TRY(cudaMemsetAsync(small, 0, 16, st));
-    sgp_group_pos_kernel<<<grid_for(M, 256), 256, 0, st>>>(order, class_start, M, pos, small);
-    rc = launch_ok("sgp_group_pos_kernel");
+    CUDA_TRY(cudaMemsetAsync(result, 0, 32, st));
+    sgp_group_pos_kernel<<<grid_for(M, 256), 256, 0, st>>>(order, class_start, M, pos, result);
+    return launch_ok("sgp_group_pos_kernel");
+}
+
+static int group_finalize_launch(const int32_t *nbr, const int16_t *keys, int d, const uint64_t *table, int64_t capacity,
+                                 int64_t M, int order_r, int j0, int j1, const uint32_t *order, const uint32_t *pos,
+                                 const uint32_t *class_start, const uint32_t *prev_pos, int64_t cap, int64_t max_batches,
+                                 uint32_t *batch_begin, int32_t *src, uint16_t *lnb, uint32_t *result, cudaStream_t st)
+{
+    if (!nbr && (!keys || !table || capacity < 2 || (capacity & (capacity - 1)) != 0 || d < 1 || d > SGP_MAX_DIM))
+        return fail(SGP_EINVAL, "sgp_group_finalize: needs either nbr or keys + hash table");
+    if (!order || !pos || !class_start || !batch_begin || !src || !lnb || !result || M <= 0 || order_r < 1 ||
+        order_r > SGP_MAX_ORDER || j1 <= j0 || cap < 1 || cap > 1024 || max_batches < 1)
+        return fail(SGP_EINVAL, "sgp_group_finalize: bad argument");
+    // the opt-in above 48 KB is per device (and cheap): set it on every call rather than caching it per process
+    CUDA_TRY(cudaFuncSetAttribute(sgp_group_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(2 * PACK_WINDOW * sizeof(uint32_t))));
+    sgp_group_pack_kernel<<<1, PACK_THREADS, 2 * PACK_WINDOW * sizeof(uint32_t), st>>>(class_start, M, cap, max_batches,
+                                                                                       batch_begin, result + 1);
+    int rc = launch_ok("sgp_group_pack_kernel");
+    if (rc) return rc;
+    const uint32_t absent = cap > 512 ? 1024u : 512u;   // ROWS_MAX of the kernel variant that takes this group
+    sgp_group_tables_kernel<<<grid_for(M, 256), 256, 0, st>>>(nbr, keys, d, (const unsigned long long *)table,
+                                                               (uint64_t)(capacity - 1), M, order_r, j0, j1, order, pos, prev_pos,
+                                                               result + 1, batch_begin, absent, src, lnb, (int32_t *)(result + 4));
+    return launch_ok("sgp_group_tables_kernel");
+}
+
+extern "C" int sgp_group_prepare_async(const int16_t *keys, int64_t M, int d, int j0, int j1, uint32_t *order, uint32_t *pos,
+                                       uint32_t *class_start, void *workspace, size_t workspace_bytes, uint32_t *result,
+                                       sgp_stream_t stream)
+{
+    SGP_RANGE("sgp_group_prepare_async");
+    return group_prepare_launch(keys, M, d, j0, j1, order, pos, class_start, workspace, workspace_bytes, result,
+                                (cudaStream_t)stream);
+}
+
+extern "C" int sgp_group_finalize_async(const int32_t *nbr, const int16_t *keys, int d, const uint64_t *table,
+                                        int64_t capacity, int64_t M, int order_r, int j0, int j1, const uint32_t *order,
+                                        const uint32_t *pos, const uint32_t *class_start, const uint32_t *prev_pos,
+                                        int64_t cap, int64_t max_batches, uint32_t *batch_begin, int32_t *src, uint16_t *lnb,
+                                        uint32_t *result, sgp_stream_t stream)
+{
+    SGP_RANGE("sgp_group_finalize_async");
+    return group_finalize_launch(nbr, keys, d, table, capacity, M, order_r, j0, j1, order, pos, class_start, prev_pos, cap,
+                                 max_batches, batch_begin, src, lnb, result, (cudaStream_t)stream);
+}
+
+extern "C" int sgp_group_prepare(const int16_t *keys, int64_t M, int d, int j0, int j1, uint32_t *order, uint32_t *pos,
+                                 uint32_t *class_start, void *workspace, size_t workspace_bytes, int64_t *max_class_out,
+                                 sgp_stream_t stream)
+{
+    SGP_RANGE("sgp_group_prepare");
+    if (!max_class_out) return fail(SGP_EINVAL, "sgp_group_prepare: bad argument");
+    GroupWs w;
+    int rc = M > 0 ? group_ws_layout(M, &w) : fail(SGP_EINVAL, "sgp_group_prepare: bad argument");
+    if (rc) return rc;
+    if (!workspace || workspace_bytes < w.bytes) return fail(SGP_EINVAL, "group workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *small = (uint32_t *)((char *)workspace + w.small);
+    rc = group_prepare_launch(keys, M, d, j0, j1, order, pos, class_start, workspace, workspace_bytes, small, st);
     if (rc) return rc;
     uint32_t mx = 0;
     CUDA_TRY(cudaMemcpyAsync(&mx, small, sizeof(mx), cudaMemcpyDeviceToHost, st));
@@ -325,12 +387,7 @@ extern "C" int sgp_group_finalize(const int32_t *nbr, const int16_t *keys, int d
                                   sgp_stream_t stream)
 {
     SGP_RANGE("sgp_group_finalize");
-    if (!nbr && (!keys || !table || capacity < 2 || (capacity & (capacity - 1)) != 0 || d < 1 || d > SGP_MAX_DIM))
-        return fail(SGP_EINVAL, "sgp_group_finalize: needs either nbr or keys + hash table");
-    if (!order || !pos || !class_start || !batch_begin || !src || !lnb || !workspace || !max_rows_out ||
-        !n_batches_out || M <= 0 || order_r < 1 || order_r > SGP_MAX_ORDER || j1 <= j0 || cap < 1 || cap > 1024 ||
-        max_batches < 1)
-        return fail(SGP_EINVAL, "sgp_group_finalize: bad argument");
+    if (!workspace || !max_rows_out || !n_batches_out || M <= 0) return fail(SGP_EINVAL, "sgp_group_finalize: bad argument");
     GroupWs w;
     int rc = group_ws_layout(M, &w);
     if (rc) return rc;
@@ -338,30 +395,16 @@ extern "C" int sgp_group_finalize(const int32_t *nbr, const int16_t *keys, int d
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t *small = (uint32_t *)((char *)workspace + w.small);
     CUDA_TRY(cudaMemsetAsync(small, 0, 32, st));
-    // the opt-in above 48 KB is per device (and cheap): set it on every call rather than caching it per process
-    CUDA_TRY(cudaFuncSetAttribute(sgp_group_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(2 * PACK_WINDOW * sizeof(uint32_t))));
-    sgp_group_pack_kernel<<<1, PACK_THREADS, 2 * PACK_WINDOW * sizeof(uint32_t), st>>>(class_start, M, cap, max_batches,
-                                                                                   batch_begin, small);
-    rc = launch_ok("sgp_group_pack_kernel");
+    rc = group_finalize_launch(nbr, keys, d, table, capacity, M, order_r, j0, j1, order, pos, class_start, prev_pos, cap,
+                               max_batches, batch_begin, src, lnb, small, st);
     if (rc) return rc;
-    uint32_t host[4] = {0, 0, 0, 0};
+    uint32_t host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(host, small, sizeof(host), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (host[2] != 0) return fail(SGP_EINVAL, "blur group [%d,%d): classes do not fit %lld rows", j0, j1, (long long)cap);
-    const int64_t n_batches = host[0];
-    const uint32_t absent = cap > 512 ? 1024u : 512u;   // ROWS_MAX of the kernel variant that takes this group
-    sgp_group_tables_kernel<<<grid_for(M, 256), 256, 0, st>>>(nbr, keys, d, (const unsigned long long *)table,
-                                                               (uint64_t)(capacity - 1), M, order_r, j0, j1, order, pos, prev_pos, n_batches,
-                                                               batch_begin, absent, src, lnb, (int32_t *)(small + 4));
-    rc = launch_ok("sgp_group_tables_kernel");
-    if (rc) return rc;
-    uint32_t flag = 0;
-    CUDA_TRY(cudaMemcpyAsync(&flag, small + 4, sizeof(flag), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (flag != 0) return fail(SGP_EINVAL, "blur group [%d,%d): a neighbour fell outside its CTA batch", j0, j1);
-    *n_batches_out = n_batches;
-    *max_rows_out = (int32_t)host[1];
+    if (host[3] != 0) return fail(SGP_EINVAL, "blur group [%d,%d): classes do not fit %lld rows", j0, j1, (long long)cap);
+    if (host[4] != 0) return fail(SGP_EINVAL, "blur group [%d,%d): a neighbour fell outside its CTA batch", j0, j1);
+    *n_batches_out = host[1];
+    *max_rows_out = (int32_t)host[2];
     return SGP_OK;
 }
 

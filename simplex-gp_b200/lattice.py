@@ -206,8 +206,15 @@ class Lattice:
             self.nbr = None    # the blur groups are built straight from the hash table
         if build_csr:
             self._build_csr()
+        pending = None
         if build_groups and r >= 1 and self.M > 0:
-            self._build_groups(group_axes, group_rows, table=None if build_nbr else table)
+            # the axis ranges of the last lattice of this shape: every group launched back to back, no host round trip,
+            # the batch packing on a second stream beside the next group's class sort and the row sort below
+            pending = self._launch_groups_hinted(group_axes, group_rows, table=None if build_nbr else table)
+            if pending is not None and build_rows and self.rows is None and not (sort_points or build_tiles or build_csr):
+                self._build_rows()
+            if pending is None or not self._finish_groups_hinted(pending):
+                self._build_groups(group_axes, group_rows, table=None if build_nbr else table)
         if not build_nbr and build_groups and r >= 1 and self.groups is None:   # no groups (long 1-D lines): the per-axis blur needs nbr
             self.nbr = torch.empty((d + 1, self.M, 2 * r), dtype=torch.int32, device=dev)
             check(lib.sgp_build_neighbours(_ptr(self.keys), self.M, d, r, _ptr(table), cap, _ptr(self.nbr), st))
@@ -362,6 +369,72 @@ class Lattice:
                         self._build_rows()
         return self
 
+    def _launch_groups_hinted(self, group_axes, group_rows, table=None):
+        """Blur groups with the axis ranges of the last build of this (d, order, rows) -- no probing, no synchronisation:
+        returns the pending state for ``_finish_groups_hinted`` or None when there is no usable hint."""
+        import os
+        if not (group_axes is None or int(group_axes) <= 0) or os.environ.get("SGP_GROUP_FAST", "1") == "0":
+            return None
+        lib = _capi.lib()
+        dev, d, M, r = self.device, self.d, self.M, self.order
+        rows_limit = max(1, min(int(group_rows), 1024))
+        hint = _GROUP_HINTS.get((d, r, rows_limit))
+        if not isinstance(hint, dict) or sum(hint["lengths"]) != d + 1:
+            return None
+        lengths, mcs = hint["lengths"], hint["max_class"]
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        ws_bytes = int(lib.sgp_group_workspace_bytes(M))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        results = torch.zeros((len(lengths), 8), dtype=torch.int32, device=dev)
+        groups, keep, prev_pos, j0 = [], [ws, results, table], None, 0
+        for gi, (ln, mc) in enumerate(zip(lengths, mcs)):
+            j1 = j0 + ln
+            bound_class = min(rows_limit - 1, mc + max(64, mc // 4))    # room for the classes to grow since the last build
+            max_batches = int(lib.sgp_group_max_batches(M, rows_limit, bound_class))
+            if max_batches > max(M // 8, 1 << 16):      # (batch_begin would be out of proportion: probe the slow way)
+                return None
+            order_of = torch.empty(M, dtype=torch.int32, device=dev)
+            pos = torch.empty(M, dtype=torch.int32, device=dev)
+            cstart = torch.empty(M, dtype=torch.int32, device=dev)
+            g = {"j0": j0, "j1": j1, "batch_begin": torch.empty(max_batches + 1, dtype=torch.int32, device=dev),
+                 "src": torch.empty(M, dtype=torch.int32, device=dev),
+                 "lnb": torch.empty((M, j1 - j0, 2 * r), dtype=torch.int16, device=dev), "max_batches": max_batches}
+            check(lib.sgp_group_prepare_async(_ptr(self.keys), M, d, j0, j1, _ptr(order_of), _ptr(pos), _ptr(cstart), _ptr(ws),
+                                              ws_bytes, _ptr(results[gi]), C.c_void_p(main.cuda_stream)))
+            side.wait_stream(main)
+            check(lib.sgp_group_finalize_async(_ptr(self.nbr if table is None else None), _ptr(self.keys), d, _ptr(table),
+                                               0 if table is None else int(table.numel()), M, r, j0, j1, _ptr(order_of),
+                                               _ptr(pos), _ptr(cstart), _ptr(prev_pos), rows_limit, max_batches,
+                                               _ptr(g["batch_begin"]), _ptr(g["src"]), _ptr(g["lnb"]), _ptr(results[gi]),
+                                               C.c_void_p(side.cuda_stream)))
+            groups.append(g)
+            keep += [order_of, cstart, pos]
+            g["pos"] = pos
+            prev_pos = pos
+            j0 = j1
+        return {"groups": groups, "results": results, "keep": keep, "rows_limit": rows_limit, "side": side}
+
+    def _finish_groups_hinted(self, pending) -> bool:
+        """The one synchronisation of the hinted group build: read every group's figures, accept or reject them all."""
+        main = torch.cuda.current_stream(self.device)
+        main.wait_stream(pending["side"])
+        res = pending["results"].cpu().numpy().astype("int64") & 0xFFFFFFFF        # synchronises
+        rows_limit, groups = pending["rows_limit"], pending["groups"]
+        for g, r_ in zip(groups, res):
+            if not (0 < r_[0] <= rows_limit and r_[3] == 0 and r_[4] == 0 and 1 <= r_[1] <= g["max_batches"]):
+                return False
+        for g, r_ in zip(groups, res):
+            g["max_class"], g["n_batches"], g["rows_cap"] = int(r_[0]), int(r_[1]), int(r_[2])
+        arr = (_capi.BlurGroup * len(groups))()
+        for k, g in enumerate(groups):
+            arr[k] = _capi.BlurGroup(g["j0"], g["j1"], g["rows_cap"], 1024 if rows_limit > 512 else 512, g["n_batches"],
+                                     g["batch_begin"].data_ptr(), g["src"].data_ptr(), g["lnb"].data_ptr())
+        self.groups = {"list": groups, "array": arr, "final_pos": groups[-1]["pos"]}
+        _GROUP_HINTS[(self.d, self.order, rows_limit)] = {"lengths": [g["j1"] - g["j0"] for g in groups],
+                                                          "max_class": [g["max_class"] for g in groups]}
+        return True
+
     def _build_groups(self, group_axes: Optional[int] = None, group_rows: int = 512, table=None) -> None:
         """Blur groups (csrc/sgp_groups.cu): cover axes 0..d with ranges of consecutive axes whose classes fit
         ``group_rows`` rows of one CTA.  ``group_axes=None``: every range is made as long as it can be (3 axes at the
@@ -391,7 +464,8 @@ class Lattice:
         # same lattice, and on sparse high-dimensional lattices finding a 10-axis range one axis at a time costs more
         # than everything else in the build (16 sorts at d = 18)
         hint_key = (d, r, rows_limit)
-        hints = _GROUP_HINTS.get(hint_key, []) if adaptive else []
+        hint = _GROUP_HINTS.get(hint_key) if adaptive else None
+        hints = hint["lengths"] if isinstance(hint, dict) else []
         while j0 <= d:
             start = hints[len(groups)] if len(groups) < len(hints) else 3
             j1 = min(j0 + (start if adaptive else max(1, int(group_axes))), d + 1)
@@ -441,7 +515,8 @@ class Lattice:
                                      g["src"].data_ptr(), g["lnb"].data_ptr())
         self.groups = {"list": groups, "array": arr, "final_pos": prev_pos}
         if adaptive:
-            _GROUP_HINTS[hint_key] = [g["j1"] - g["j0"] for g in groups]
+            _GROUP_HINTS[hint_key] = {"lengths": [g["j1"] - g["j0"] for g in groups],
+                                      "max_class": [g["max_class"] for g in groups]}
 
     def _build_rows(self) -> None:
         """Point-vertices sorted by lattice row for the segmented-gather splat (csrc/sgp_tiles.cu, sgp_build_rowsorted):
@@ -948,3 +1023,15 @@ def lattice_filter(src: torch.Tensor, ref: torch.Tensor, coeffs, *, device=None)
                            C.c_void_p(out.data_ptr()), L), (_stream_ptr(dev),))
         del ws   # sgp_filter_host has synchronised: nothing is in flight on the workspace
     return out if out_dtype == torch.float32 else out.to(out_dtype)
+
+
+_side_streams = {}
+
+
+def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """One extra stream per device for build work that runs beside the main stream (batch packing of the blur groups)."""
+    s = _side_streams.get(dev.index)
+    if s is None:
+        s = torch.cuda.Stream(device=dev)
+        _side_streams[dev.index] = s
+    return s
