@@ -439,7 +439,7 @@ struct GroupCoeffs {
 //     does (permutohedral.h:545 substitutes a zero vector and still adds c*0): the passes are branch-free;
 //   * PASS_UNROLL rows are processed together -- their neighbour indices, then all their neighbour rows, are read
 //     before any arithmetic -- so that several shared-memory round trips overlap (warps issue in order).
-template <int VEC, int R, int CHUNKS, int THREADS, bool FAST>
+template <int VEC, int R, int CHUNKS, int THREADS, bool FAST, int ROWS_MAX_T = 2 * THREADS>
 __global__ void __launch_bounds__(THREADS)   // (capping registers for a fourth CTA per SM measured slower: 62 vs 56 us)
 sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *__restrict__ src,
                       const uint16_t *__restrict__ lnb, const float *__restrict__ in, float *__restrict__ out, int L,
@@ -449,7 +449,9 @@ sgp_blur_group_kernel(const uint32_t *__restrict__ batch_begin, const int32_t *_
     constexpr int CBT = CHUNKS * VEC;
     constexpr int RSTEP = THREADS / CHUNKS;
     constexpr int U = PASS_UNROLL;
-    constexpr int ROWS_MAX = THREADS * 2;                    // 512 rows at 256 threads, 1024 at 512 (host-checked)
+    constexpr int ROWS_MAX = ROWS_MAX_T;                     // 512 rows at 256 threads, 1024 at 512 (host-checked); (512 rows
+                                                             // on 128 threads for one-chunk rows measured no faster: the
+                                                             // narrow-row blur is bound by its neighbour tables)
     constexpr int MAXI = ROWS_MAX / RSTEP;                   // row slots per thread: 2 * CHUNKS
     constexpr int UU = MAXI < U ? MAXI : U;
     static_assert(MAXI % UU == 0, "row slots must split into whole unroll groups");
@@ -570,13 +572,13 @@ static size_t group_smem_bytes(int rows_cap, int rows_max, int cbt, int nax, int
            (((size_t)rows_cap * nax * 2 * order * sizeof(uint16_t) + 15) & ~(size_t)15) + (size_t)rows_cap * sizeof(int32_t);
 }
 
-template <int VEC, int CHUNKS, int THREADS, bool FAST>
+template <int VEC, int CHUNKS, int THREADS, bool FAST, int ROWS_MAX_T = 2 * THREADS>
 static int launch_group(const sgp_blur_group *g, int order, const GroupCoeffs &cf, int L, const float *in, float *out,
                         cudaStream_t st)
 {
     constexpr int CBT = VEC * CHUNKS;
     const int nax = g->j1 - g->j0;
-    const size_t smem = group_smem_bytes(g->rows_cap, THREADS * 2, CBT, nax, order);
+    const size_t smem = group_smem_bytes(g->rows_cap, ROWS_MAX_T, CBT, nax, order);
     if (smem > 227 * 1024)
         return fail(SGP_EUNSUPPORTED, "blur group needs %zu bytes of shared memory (%d rows x %d channels)", smem,
                     g->rows_cap, CBT);
@@ -586,9 +588,9 @@ static int launch_group(const sgp_blur_group *g, int order, const GroupCoeffs &c
         /* the opt-in above 48 KB is an attribute of (function, device): set it on every launch (a host-side call of  \
            about a microsecond) instead of caching it per process, so that a second device works too */              \
         if (smem > 48 * 1024)                                                                                         \
-            CUDA_TRY(cudaFuncSetAttribute(sgp_blur_group_kernel<VEC, RR, CHUNKS, THREADS, FAST>,                            \
+            CUDA_TRY(cudaFuncSetAttribute(sgp_blur_group_kernel<VEC, RR, CHUNKS, THREADS, FAST, ROWS_MAX_T>,                \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                   \
-        cudaError_t le = sgp_launch_pdl(sgp_blur_group_kernel<VEC, RR, CHUNKS, THREADS, FAST>, grid, dim3(THREADS), smem, st, \
+        cudaError_t le = sgp_launch_pdl(sgp_blur_group_kernel<VEC, RR, CHUNKS, THREADS, FAST, ROWS_MAX_T>, grid, dim3(THREADS), smem, st, \
                                         g->batch_begin, g->src, g->lnb, in, out, L, g->rows_cap, nax, order, cf);     \
         if (le != cudaSuccess) return fail(SGP_ECUDA, "launch of sgp_blur_group_kernel failed: %s", cudaGetErrorString(le)); \
     } while (0)
