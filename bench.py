@@ -63,7 +63,7 @@ def kernel_source_stamp():
     return h.hexdigest()[:16]
 
 
-def load_traffic():
+def load_traffic(workload="A"):
     """{kernel name: dram__bytes_read.sum + dram__bytes_write.sum per launch} from the committed `ncu --set full` capture
     (profiles/traffic.json, cold-cache replays of profiles/ncu_mvm.py), or {} when the capture is older than the
     kernels: a stale figure is reported as null, never as a number."""
@@ -74,6 +74,8 @@ def load_traffic():
         return {}, "no profiles/traffic.json"
     if t.get("source_stamp") != kernel_source_stamp():
         return {}, f"profiles/traffic.json is stale (captured for sources {t.get('source_stamp')})"
+    if t.get("workload", "A") != workload:
+        return {}, f"profiles/traffic.json was captured at workload {t.get('workload', 'A')}, not {workload}"
     return t.get("kernels", {}), f"profiles/traffic.json ({t.get('report')})"
 
 
@@ -578,7 +580,7 @@ def run_ours(args, w):
 
     # --- per-stage device times (CUDA events on the launching stream), same buffers, rank 0 -----------
     peak, peak_src = load_peaks()
-    traffic, traffic_src = load_traffic()
+    traffic, traffic_src = load_traffic(args.workload if L == w["L"] else None)
     roofline = stages = None
     if rank == 0:
         lib = _capi.lib()

@@ -92,7 +92,7 @@ def traffic(rep):
         for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(r[idx[m]]) * scale[units[idx[m]]]
         kernels[name] = tot
-    out = {"report": os.path.basename(rep), "source_stamp": bench.kernel_source_stamp(),
+    out = {"report": os.path.basename(rep), "source_stamp": bench.kernel_source_stamp(), "workload": "A",
            "how": "ncu --set full --clock-control none python profiles/ncu_mvm.py; dram__bytes_read.sum + dram__bytes_write.sum per launch (cold cache)",
            "kernels": kernels}
     with open(os.path.join(root, "profiles", "traffic.json"), "w") as f:

@@ -205,7 +205,9 @@ class LatticeFilterGeneral(Function):
         else:
             lat = Lattice(_to_device(reference.detach().float().contiguous(), dev), coeffs)
             ctx.lat = None
-        out = lat.mvm(_to_device(source.detach().float(), dev))
+        # the stencil is passed explicitly: the cache keys a lattice on the stencil's length and variance only, and two
+        # stencils can share both (the variance is scale-invariant)
+        out = lat.mvm(_to_device(source.detach().float(), dev), coeffs=coeffs)
         return out.to(device=source.device, dtype=source.dtype)
 
     @staticmethod
@@ -220,7 +222,7 @@ class LatticeFilterGeneral(Function):
                 # the operator is symmetric: grad_source = filter(g) with the forward stencil (:110-111)
                 lat = ctx.lat if ctx.lat is not None else Lattice(_to_device(ref.detach().float().contiguous(), dev),
                                                                   ctx.coeffs)
-                grad_source = lat.mvm(g).to(device=src.device, dtype=src.dtype)
+                grad_source = lat.mvm(g, coeffs=ctx.coeffs).to(device=src.device, dtype=src.dtype)
             if ctx.needs_input_grad[1]:
                 x_dev = ref.detach() if on_dev else _to_device(ref.detach().float().contiguous(), dev)
                 if on_dev:

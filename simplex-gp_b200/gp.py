@@ -95,6 +95,8 @@ def _batched_cg_cuda(matmul: Callable, scale: torch.Tensor, shift: torch.Tensor,
     lat = owner.lattice() if hasattr(owner, "lattice") else None
     if lat is not None and (lat.N != N or lat.device != dev):
         lat = None
+    # the operator's own stencil, passed to every product (the lattice cache keys on its length and variance only)
+    op_coeffs = owner.dkernel.get_coeffs() if (lat is not None and getattr(owner, "dkernel", None) is not None) else None
     L = (L0 + 3) // 4 * 4 if (lat is not None and L0 > 4) else L0
     if L > 256:
         L = L0
@@ -120,7 +122,7 @@ def _batched_cg_cuda(matmul: Callable, scale: torch.Tensor, shift: torch.Tensor,
         st = _stream_ptr(dev)
         for it in range(max_iter):
             if lat is not None:
-                lat.mvm(P, out=AP)
+                lat.mvm(P, out=AP, coeffs=op_coeffs)
             else:
                 AP = matmul(P)
                 if AP.dtype != torch.float32 or not AP.is_contiguous() or AP.data_ptr() == P.data_ptr():

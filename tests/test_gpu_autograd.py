@@ -190,3 +190,30 @@ def test_rectangular_operator_extends_the_cached_training_lattice(sg, oracle):
 def test_matern_nu_validation(sg):
     with pytest.raises(NotImplementedError):
         sg.MaternLattice(nu=0.7)
+
+
+def test_cached_lattice_serves_stencils_of_equal_variance(sg):
+    """The lattice cache keys on the stencil's length and variance, and the variance is scale-invariant: a second
+    kernel function whose stencil is a multiple of the first one's reuses the cached lattice and must still be applied
+    with ITS coefficients (every product passes the stencil explicitly)."""
+    class Scaled:
+        def __init__(self, c, dc):
+            self.c, self.dc = torch.tensor(c), torch.tensor(dc)
+
+        def get_coeffs(self):
+            return self.c
+
+        def get_deriv_coeffs(self):
+            return self.dc
+
+    d = 3
+    x, v = make_inputs(400, d, 2, seed=8)
+    xd, vd = x.cuda(), v.cuda()
+    base = Scaled(RBF1, RBF1)
+    twice = Scaled([2 * c for c in RBF1], [2 * c for c in RBF1])
+    sg.lattice_cache.clear()
+    builds = sg.lattice_cache.builds
+    a = sg.LatticeFilterGeneral.apply(vd, xd, base)
+    b = sg.LatticeFilterGeneral.apply(vd, xd, twice)
+    assert sg.lattice_cache.builds == builds + 1                 # one lattice, two stencils
+    assert float((b - 2.0 ** (d + 1) * a).norm() / b.norm()) < 1e-5   # d+1 blur passes, each doubled
