@@ -592,7 +592,7 @@ def run_ours(args, w):
         fast = 0 if lat.exact else 1
         v_in = lat._view(lat._table(False, False), None, lat.exact)
         v_axis = lat._view(exact=lat.exact)
-        v_out = lat._view(lat._table(False, use_groups), None, lat.exact)
+        v_out = lat._slice_view(L, use_groups, lat.exact)
         tv_in = lat._tiles_view(False) if mode == _capi.MODE_TILES else None
         tv_out = lat._tiles_view(use_groups) if mode == _capi.MODE_TILES else None
         garr = lat.groups["array"] if use_groups else None

@@ -650,14 +650,23 @@ class Lattice:
         """fp32 ``[N, d+1]``: barycentric weight of every simplex vertex (reference ``replay[].weight``)."""
         return self.replay[..., 1].view(torch.float32)
 
-    def _table(self, sorted: bool, final: bool) -> torch.Tensor:
+    def _table(self, sorted: bool, final: bool, transposed: bool = False) -> torch.Tensor:
         """Internal replay table ``[N, d+1, 2]``, built on first use: rows in the locality order when ``sorted``;
-        lattice indices mapped to the order the last blur-group stage leaves the lattice values in when ``final``.
-        (The transposed layout ``[d+1, N, 2]`` that ``sgp_permute_replay`` can also produce measured slower.)"""
-        key = (bool(sorted), bool(final))
-        if key == (False, False):
+        lattice indices mapped to the order the last blur-group stage leaves the lattice values in when ``final``;
+        ``transposed``: ``[d+1, N, 2]`` -- the layout for narrow rows (one or two channel chunks), where the lanes of a
+        warp are different points and read one contiguous run per vertex instead of 72-byte strides."""
+        key = (bool(sorted), bool(final), bool(transposed))
+        if key == (False, False, False):
             return self.replay
         t = self._tables.get(key)
+        if t is None and transposed:
+            perm = self.sorted["perm"] if sorted else None
+            pos = self.groups["final_pos"] if final else None
+            t = torch.empty((self.d + 1, self.N, 2), dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                check(_capi.lib().sgp_permute_replay(_ptr(self.replay), _ptr(perm), _ptr(pos), self.N, self.d, 1, _ptr(t),
+                                                     _stream_ptr(self.device)))
+            self._tables[key] = t
         if t is None:
             perm = self.sorted["perm"] if sorted else None
             pos = self.groups["final_pos"] if final else None
@@ -688,6 +697,16 @@ class Lattice:
                            self.csr_ptr.data_ptr() if self.csr_ptr is not None else 0,
                            self.csr_ent.data_ptr() if self.csr_ent is not None else 0,
                            0 if perm is None else perm.data_ptr(), 0 if exact else 1, 1 if transposed else 0, stride, 0)
+
+    def _slice_view(self, Lv: int, final: bool, exact: Optional[bool] = None) -> LatticeView:
+        """The view the slice of an ``Lv``-channel product reads: the dense / padded table for wide rows (several lanes
+        per point: TMA-ring slice), the transposed table for narrow ones (SGP_SLICE_TRANSPOSED_MAX_L, default 8: measured 24 / 30 / 36 / 39 us against
+        29 / 33 / 40 / 46 us at 1 / 2 / 4 / 8 channels, metric shape)."""
+        import os
+        narrow = int(Lv) <= int(os.environ.get("SGP_SLICE_TRANSPOSED_MAX_L", "8"))
+        if narrow:
+            return self._view(self._table(False, final, True), None, exact, transposed=True)
+        return self._view(self._table(False, final), None, exact)
 
     def _scratch(self, L: int):
         key = int(L)
@@ -845,7 +864,7 @@ class Lattice:
         if mode == _capi.MODE_ROWS and use_groups and not use_tiles and not use_sorted and after_splat is None:
             # the production chain, one call across the C ABI
             arr = self.groups["array"]
-            v_out = self._view(self._table(False, True), None, exact)
+            v_out = self._slice_view(Lv, True, exact)
             with torch.cuda.device(self.device):
                 if zero_flags:
                     if scratch is None:
@@ -890,7 +909,8 @@ class Lattice:
                 tv = self._tiles_view(use_groups)
                 check(lib.sgp_slice_tiles(C.byref(tv), _ptr(res), L, _ptr(out), out.stride(0), 0 if exact else 1, st))
             else:
-                v_out = self._view(self._table(use_sorted, use_groups), perm, exact)
+                v_out = self._view(self._table(use_sorted, use_groups), perm, exact) if use_sorted \
+                    else self._slice_view(Lv, use_groups, exact)
                 check(lib.sgp_slice(C.byref(v_out), _ptr(res), Lv, _ptr(out), out.stride(0), L, st))
         return out
 
