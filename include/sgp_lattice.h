@@ -189,9 +189,9 @@ typedef struct sgp_lattice_view {
     const int32_t *replay;   /* device [N, d+1, 2] {lattice index, weight bits} */
     const int32_t *nbr;      /* device [(d+1), M, 2r] */
     const uint32_t *csr_ptr; /* device [M+1] or NULL: row starts into csr_ent (ordered-gather splat) */
-    const int32_t *csr_ent;  /* device [N*(d+1), 2] or NULL: {point, weight bits} sorted by lattice row, point-vertex
-                                order inside a row -- the first N*(d+1) entries of sgp_build_rowsorted's `ent` (bit 31 of
-                                the point word is ignored) */
+    const int32_t *csr_ent;  /* device or NULL: {point, weight bits} sorted by lattice row, point-vertex order inside a
+                                row -- sgp_build_rowsorted's `ent`, in its interleaved storage order (csr_ptr holds
+                                row-sorted positions; bit 31 of the point word is ignored) */
     const uint32_t *perm;    /* device [N] or NULL.  When set, row p of replay describes point perm[p]: splat and
                                 slice walk the points in that (locality) order and address src / out rows through it */
     int32_t fast;            /* 0: the reference's arithmetic, one rounding per product and per sum (bit-exact on the
@@ -400,9 +400,12 @@ int sgp_cg_direction(float *P, const float *R, const float *beta, int64_t N, int
 
 /* ---- row-sorted splat ("segmented gather") -------------------------------------------------
  * The point-vertices sorted by lattice row, point-vertex order within a row (the reference's accumulation order),
- * padded with zero-weight entries to n_entries = sgp_rowsort_padded(N, d, fill_rows), a multiple of 16:
+ * padded with zero-weight entries to n_entries = sgp_rowsort_padded(N, d, fill_rows), a multiple of 64:
  *   ent      device [n_entries, 2] int32 {point | row-start flag in bit 31, weight bits}; the flag marks the first
- *            entry of a lattice row;
+ *            entry of a lattice row.  STORAGE ORDER: the splat consumes 8 entries per thread as four 16-byte pieces, and
+ *            the entries are stored in groups of 64 with the pieces interleaved over the group's 8 segments -- entry
+ *            e = 64 g + 8 s + 2 p + h lives at position 64 g + 16 p + 2 s + h -- so that a warp instruction reads one
+ *            contiguous 128-byte run;
  *   seg_row  device [n_entries / 4] int32: lattice row of every fourth entry;
  *   ent_row  optional (may be NULL) device [n_entries] int32: lattice row of every entry.
  * The encoding needs every lattice row 0..M-1 to own an entry.  That holds for the lattice of the points themselves

@@ -79,6 +79,18 @@ __device__ __forceinline__ float ldg_ordered_f1(const float *p)
     return v;
 }
 
+// ---- layout of the row-sorted entries ---------------------------------------------------------------------------
+// The entries {point | row-start flag, weight} are consumed 8 at a time (a "segment", one thread), as four 16-byte pieces.
+// They are stored in groups of 8 segments (64 entries, 512 bytes) with the pieces interleaved: [piece 0..3][segment 0..7],
+// so that the threads of a warp that read piece i of consecutive segments read ONE contiguous 128-byte run (linear
+// storage puts them 64 bytes apart: four 128-byte lines per instruction, and a 4-way bank conflict when staged in
+// shared memory).  sgp_entry_index(e) = position (in entries) of row-sorted entry e.
+__host__ __device__ __forceinline__ int64_t sgp_entry_index(int64_t e)
+{
+    return ((e >> 6) << 6) + (((e & 7) >> 1) << 4) + (((e >> 3) & 7) << 1) + (e & 1);
+}
+#define SGP_ENTRY_GROUP 64   /* entries per interleave group; the arrays are padded to a multiple of it */
+
 // ---- key hash table (shared by the lattice build and the blur-group build) ------------------------------
 // A slot is {fingerprint:32 | value:32}; after sgp_number_points the value is the lattice index of the key.
 #define SGP_EMPTY 0xFFFFFFFFFFFFFFFFull

@@ -790,7 +790,7 @@ sgp_splat_gather_kernel(const uint32_t *__restrict__ row_ptr, const int2 *__rest
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc.v[k] = 0.0f;
     for (uint32_t q = a; q < b; ++q) {
-        const int2 e = __ldg(entries + q);
+        const int2 e = __ldg(entries + sgp_entry_index(q));   // row-sorted position -> interleaved storage
         const float w = __int_as_float(e.y);
         Vec<VEC> v;
         v.load(src + (int64_t)(e.x & 0x7fffffff) * lds + c0);   // bit 31 is the row-start flag of the row-sorted entries

@@ -242,7 +242,7 @@ sgp_slice_ring_kernel(const int2 *__restrict__ replay, const float *__restrict__
 // =====================================================================================================
 // Tile geometry shared by the zero kernel and the splat: a pass covers spp = 32 / chunks segments of 8 entries.
 struct SplatTile {
-    int spp, passes, T;   // T = 8 * spp * passes entries per tile, a multiple of 16
+    int spp, passes, T;   // T = 8 * spp * passes entries per tile, a multiple of 64 (whole interleave groups)
 };
 static SplatTile splat_tile(int chunks)
 {
@@ -251,7 +251,7 @@ static SplatTile splat_tile(int chunks)
     if (g.spp < 1) g.spp = 1;
     int passes = 256 / (8 * g.spp);
     if (passes < 1) passes = 1;
-    if ((g.spp * passes) & 1) ++passes;   // T % 16 == 0
+    while ((g.spp * passes) & 7) ++passes;   // T % 64 == 0: whole interleave groups
     g.passes = passes;
     g.T = 8 * g.spp * passes;
     return g;
@@ -274,11 +274,10 @@ sgp_ring_zero_heads_kernel(const int2 *__restrict__ ent, const int32_t *__restri
     values[(int64_t)__ldg(seg_row + e0 / 4) * L + c] = 0.0f;
 }
 
-// Shared-memory layout of a tile's entries: blocks of 16 entries (128 bytes = two segments) 144 bytes apart.  The 16
-// bytes of padding put the 16-byte pieces that the segments of a pass read together on distinct bank groups (a
-// linear layout is a 4-way conflict: segments are 64 bytes apart).  One bulk copy per block, issued by lane `block`.
-#define ENT_BLOCK_STRIDE 144u
-__device__ __forceinline__ uint32_t ent_offset(int entry) { return (uint32_t)(entry >> 4) * ENT_BLOCK_STRIDE + (uint32_t)(entry & 15) * 8u; }
+// A tile is a whole number of interleave groups (64 entries, sgp_entry_index): one bulk copy brings it in as it lies in
+// global memory, and the 16-byte pieces that the segments of a pass read together are contiguous in shared memory too
+// (no bank conflict).  ent_offset(e) = byte offset of row-sorted entry e inside the tile.
+__device__ __forceinline__ uint32_t ent_offset(int entry) { return (uint32_t)sgp_entry_index(entry) * 8u; }
 
 // thread = (segment of 8 consecutive row-sorted entries, channel chunk) within a pass; see the file header.
 // RAGGED: src has L_src < L columns / arbitrary alignment and is read channel by channel (missing channels = 0).
@@ -293,7 +292,7 @@ sgp_splat_ring_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     extern __shared__ __align__(128) unsigned char ring_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = 8 * spp * passes;
-    const uint32_t ent_region = (uint32_t)(T / 16 + 1) * ENT_BLOCK_STRIDE;
+    const uint32_t ent_region = (uint32_t)(T + 2) * 8u;
     unsigned char *ring = ring_smem + (size_t)warp * stages * tile_stride;
     uint64_t *bars = (uint64_t *)(ring_smem + (size_t)RING_WARPS * stages * tile_stride) + warp * RING_MAX_STAGES;
     const int64_t n_tiles = (n_entries + T - 1) / T;
@@ -306,21 +305,16 @@ sgp_splat_ring_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     pdl_launch_dependents();
     const uint64_t pol = l2_policy_evict_first();
 
-    // whole warp: entries block by block (+ the first entry pair of the next tile: the look-ahead flag) and row ids
+    // lane 0: the tile's entries (+ the first entry pair of the next tile: the look-ahead flag) and its row ids
     auto issue = [&](int64_t t, int s) {
+        if (lane != 0) return;
         const int64_t e0 = t * (int64_t)T;
         const uint32_t ne = (uint32_t)min((int64_t)T, n_entries - e0);
         const uint32_t look = (SCAN && e0 + ne < n_entries) ? 16u : 0u;
         unsigned char *dst = ring + (size_t)s * tile_stride;
-        if (lane == 0) mbar_arrive_expect_tx(bars + s, ne * 8u + look + ne);
-        __syncwarp();
-        const uint32_t nblk = ne >> 4;
-        for (uint32_t b = lane; b < nblk; b += 32)
-            bulk_g2s(dst + b * ENT_BLOCK_STRIDE, ent + e0 + 16 * b, 128u, bars + s, pol);
-        if (lane == 31) {
-            if (look) bulk_g2s(dst + nblk * ENT_BLOCK_STRIDE, ent + e0 + ne, 16u, bars + s, pol);
-            bulk_g2s(dst + ent_region, seg_row + e0 / 4, ne, bars + s, pol);
-        }
+        mbar_arrive_expect_tx(bars + s, ne * 8u + look + ne);
+        bulk_g2s(dst, ent + e0, ne * 8u + look, bars + s, pol);
+        bulk_g2s(dst + ent_region, seg_row + e0 / 4, ne, bars + s, pol);
     };
     for (int k = 0; k < stages; ++k) {
         const int64_t t = gw + (int64_t)k * W;
@@ -361,7 +355,7 @@ sgp_splat_ring_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
                 float w[8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int4 q = ep[i];
+                    const int4 q = ep[8 * i];   // piece i of this segment (the 8 segments of a group are interleaved)
                     pt[2 * i] = q.x; w[2 * i] = __int_as_float(q.y);
                     pt[2 * i + 1] = q.z; w[2 * i + 1] = __int_as_float(q.w);
                 }
@@ -623,7 +617,7 @@ extern "C" int sgp_splat_rows_ring(const int32_t *ent, const int32_t *seg_row, i
 {
     SGP_RANGE("sgp_splat_rows_ring");
     if (N == 0 || M == 0) return SGP_OK;
-    if (!ent || !seg_row || !src || !values || N < 0 || M < 0 || n_entries < 16 || n_entries % 16 != 0 || L_src < 1 ||
+    if (!ent || !seg_row || !src || !values || N < 0 || M < 0 || n_entries < 64 || n_entries % 64 != 0 || L_src < 1 ||
         lds < L_src || L < L_src)
         return fail(SGP_EINVAL, "sgp_splat_rows_ring: bad argument");
     const int vec = ring_vec(L, values);
@@ -648,7 +642,7 @@ extern "C" int sgp_splat_rows_ring(const int32_t *ent, const int32_t *seg_row, i
                             (const int2 *)ent, seg_row, n_tiles, g.T, L, values);
         if (le != cudaSuccess) return fail(SGP_ECUDA, "launch of sgp_ring_zero_heads_kernel failed: %s", cudaGetErrorString(le));
     }
-    const uint32_t tile_bytes = (uint32_t)(g.T / 16 + 1) * 144u + (uint32_t)g.T;
+    const uint32_t tile_bytes = (uint32_t)(g.T + 2) * 8u + (uint32_t)g.T;
 #define SGP_SPLAT_RING(VV, RG, SC)                                                                                     \
     do {                                                                                                               \
         rc = ring_config(sgp_splat_ring_kernel<VV, RG, SC>, tile_bytes, n_tiles, 2, "SGP_SPLAT_STAGES", &rl);          \

@@ -394,7 +394,7 @@ extern "C" int sgp_permute_replay_padded(const int32_t *replay, const uint32_t *
 #ifndef SGP_LDCS
 #define SGP_LDCS 1
 #endif
-#define ROWSEG 16   /* padding granularity of the row-sorted arrays; the kernel takes SEG = 4, 8 or 16 entries per thread */
+#define ROWSEG SGP_ENTRY_GROUP   /* padding granularity of the row-sorted arrays (sgp_entry_index, sgp_common.cuh) */
 
 // q < total: a point-vertex, keyed by its lattice row.  total <= q < total + fill: one weightless filler per lattice
 // row 0..fill-1 (value 0xFFFFFFFF), for lattices whose points do not touch every row (a rank's share of the points
@@ -429,10 +429,11 @@ sgp_rowsort_fill_kernel(const int2 *__restrict__ replay, const uint32_t *__restr
         const uint32_t q = sorted_pv[k];
         row = sorted_row[k];
         const uint32_t start = (k > 0 && sorted_row[k - 1] != row) ? SGP_ROW_START : 0u;
-        ent[k] = q == SGP_ROW_FILLER ? make_int2((int)start, 0) : make_int2((int)((q / (uint32_t)dp1) | start), replay[q].y);
+        ent[sgp_entry_index(k)] = q == SGP_ROW_FILLER ? make_int2((int)start, 0)
+                                                      : make_int2((int)((q / (uint32_t)dp1) | start), replay[q].y);
     } else {   // padding: weight 0 on the last row
         row = sorted_row[total - 1];
-        ent[k] = make_int2(0, 0);
+        ent[sgp_entry_index(k)] = make_int2(0, 0);
     }
     if (ent_row) ent_row[k] = (int32_t)row;
     if (k % SGP_ROW_GRAIN == 0) seg_row[k / SGP_ROW_GRAIN] = (int32_t)row;
@@ -517,11 +518,13 @@ sgp_splat_rows_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     const int c0 = (int)(tid - seg * chunks) * VEC;
     int2 e[SEG];
     Vec<VEC> v[SEG];
-    const int4 *ep = (const int4 *)(ent + seg * SEG);     // SEG entries = SEG/2 16-byte loads
+    static_assert(SEG == 8, "the entry layout interleaves segments of 8 entries");
+    // piece i of segment seg: the segments of a group of 8 are interleaved piece by piece (sgp_entry_index)
+    const int4 *ep = (const int4 *)ent + ((seg >> 3) << 5) + (seg & 7);
     int row = __ldg(seg_row + seg * (SEG / SGP_ROW_GRAIN));   // lattice row of the first entry
 #pragma unroll
     for (int i = 0; i < SEG / 2; ++i) {
-        const int4 t = SGP_LDCS ? __ldcs(ep + i) : __ldg(ep + i);   // read once: streaming, keeps src and the lattice in L2
+        const int4 t = SGP_LDCS ? __ldcs(ep + 8 * i) : __ldg(ep + 8 * i);   // read once: streaming, keeps src and the lattice in L2
         e[2 * i] = make_int2(t.x, t.y);
         e[2 * i + 1] = make_int2(t.z, t.w);
     }
@@ -639,12 +642,7 @@ static int splat_rows_impl(const int32_t *ent, const int32_t *seg_row, int64_t n
     if (!prezeroed && sgp_ring_splat_enabled() && n_entries >= 16 && sgp_splat_ring_supported(values, L))
         return sgp_splat_rows_ring(ent, seg_row, n_entries, N, M, src, lds, L_src, values, L, stream);
     cudaStream_t st = (cudaStream_t)stream;
-    static int seg_env = 0;   // tuning hook: SGP_ROWSEG=4|8|16 entries per thread
-    if (seg_env == 0) {
-        const char *e = getenv("SGP_ROWSEG");
-        seg_env = e ? atoi(e) : 8;
-        if (seg_env != 4 && seg_env != 16) seg_env = 8;
-    }
+    const int seg_env = 8;
     const int64_t n_seg = n_entries / seg_env;
     auto al = [](const void *p, int bytes) { return ((uintptr_t)p % bytes) == 0; };
     // the lattice side decides the vector width; src is read channel by channel when it does not match it
@@ -690,12 +688,7 @@ static int splat_rows_impl(const int32_t *ent, const int32_t *seg_row, int64_t n
                         : sgp_launch_pdl(sgp_splat_rows_kernel<VV, SS, false>, dim3(grid_for(work, 256)), dim3(256), 0, \
                                          st, (const int2 *)ent, seg_row, n_seg, src, lds, L, L_src, chunks,            \
                                          prefetch_bytes, aggregate, values, dbg)
-#define SGP_ROWS_SEG(VV)                                                                                               \
-    do {                                                                                                               \
-        if (seg_env == 4) SGP_ROWS_LAUNCH(VV, 4);                                                                      \
-        else if (seg_env == 16) SGP_ROWS_LAUNCH(VV, 16);                                                               \
-        else SGP_ROWS_LAUNCH(VV, 8);                                                                                   \
-    } while (0)
+#define SGP_ROWS_SEG(VV) SGP_ROWS_LAUNCH(VV, 8)
     if (vec == 4) SGP_ROWS_SEG(4);
     else if (vec == 2) SGP_ROWS_SEG(2);
     else SGP_ROWS_SEG(1);

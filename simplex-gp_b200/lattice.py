@@ -541,7 +541,7 @@ class Lattice:
         rows = build(0)
         if not getattr(self, "_covers_all_rows", False):
             # wrapped arrays: do the points touch every row?  (row starts = flags + the first entry)
-            starts = int((rows["ent"][:total, 0] < 0).sum()) + 1
+            starts = int((rows["ent"][:, 0] < 0).sum()) + 1      # (padding entries carry no flag; the storage is interleaved)
             if starts != M:
                 rows = build(M)
         self.rows = rows
@@ -632,7 +632,12 @@ class Lattice:
         if self.rows is None:
             self._build_rows()
         total = self.rows["entries"]
-        starts = torch.nonzero(self.rows["ent"][:total, 0] < 0).flatten().to(torch.int32)   # row-start flags
+        # row-start flags; the entries are stored interleaved in groups of 64 (csrc/sgp_common.cuh, sgp_entry_index):
+        # storage position j holds row-sorted entry  group*64 + segment*8 + piece*2 + half
+        j = torch.nonzero(self.rows["ent"][:, 0] < 0).flatten()
+        within = j % 64
+        lin = (j // 64) * 64 + ((within % 16) // 2) * 8 + (within // 16) * 2 + (within % 2)
+        starts = torch.sort(lin).values.to(torch.int32)
         ends = torch.tensor([total], dtype=torch.int32, device=self.device)
         self.csr_ptr = torch.cat([torch.zeros(1, dtype=torch.int32, device=self.device), starts, ends]).contiguous()
         if self.csr_ptr.numel() != self.M + 1:
