@@ -602,14 +602,11 @@ def run_ours(args, w):
             V = Vs[i % n_rot]
             if mode == _capi.MODE_TILES:
                 _capi.check(lib.sgp_splat_tiles(C.byref(tv_in), _ptr(V), V.stride(0), L, _ptr(buf0), st))
-            elif mode == _capi.MODE_ROWS and not lib.sgp_ring_splat_enabled():
+            elif mode == _capi.MODE_ROWS:
                 # the kernel alone (its memset is timed apart: in the MVM's graph it runs beside the previous slice);
                 # repeated launches keep accumulating into buf0, which is irrelevant for the timing
                 _capi.check(lib.sgp_mvm_stage_splat_prezeroed(_ptr(lat.rows["ent"]), _ptr(lat.rows["seg_row"]), lat.rows["n"], N,
                                                               M, _ptr(V), V.stride(0), L, _ptr(buf0), L, st))
-            elif mode == _capi.MODE_ROWS:
-                _capi.check(lib.sgp_splat_rows(_ptr(lat.rows["ent"]), _ptr(lat.rows["seg_row"]), lat.rows["n"], N, M, _ptr(V),
-                                               V.stride(0), L, _ptr(buf0), L, st))
             else:
                 _capi.check(lib.sgp_splat(C.byref(v_in if mode == _capi.MODE_ATOMIC else v_axis), _ptr(V), V.stride(0), L,
                                           _ptr(buf0), mode, st))
@@ -644,7 +641,7 @@ def run_ours(args, w):
 
         buf0.zero_()
         t_splat = stage_ms(splat_stage)
-        memset_ms = stage_ms(lambda i: buf0.zero_()) if (mode == _capi.MODE_ROWS and not lib.sgp_ring_splat_enabled()) else None
+        memset_ms = stage_ms(lambda i: buf0.zero_()) if mode == _capi.MODE_ROWS else None
         buf0.normal_()
         t_blur = stage_ms(blur_stage)
         buf0.normal_(); buf1.normal_()
@@ -656,7 +653,8 @@ def run_ours(args, w):
         b_slice = 4 * (M * L + 2 * N * (d + 1) + N * L)
         splat_kernel = {_capi.MODE_ATOMIC: "sgp_splat_atomic_kernel", _capi.MODE_GATHER: "sgp_splat_gather_kernel",
                         _capi.MODE_TILES: "sgp_splat_tiles_kernel",
-                        _capi.MODE_ROWS: "sgp_splat_ring_kernel" if lib.sgp_ring_splat_enabled() else "sgp_splat_rows_kernel"}[mode]
+                        _capi.MODE_ROWS: "sgp_splat_ring_kernel" if (lib.sgp_ring_splat_enabled() and lat.rows["n"] >= 8 * M
+                                                                       and lat.rows["n"] >= (1 << 21)) else "sgp_splat_rows_kernel"}[mode]
         stages = {
             "splat": {"ms": t_splat, "launches": 1, "alg_bytes": b_splat, "gbs": b_splat / t_splat / 1e6,
                       "kernel": splat_kernel, "memset_ms_timed_apart": memset_ms},

@@ -430,7 +430,7 @@ int sgp_splat_rows(const int32_t *ent, const int32_t *seg_row, int64_t n_entries
  * mbarrier; sgp_splat_rows_ring writes every lattice row that lies inside one warp tile with a plain store and zeroes
  * (then reduces into) only the rows that cross a tile boundary -- `values` is NOT memset. */
 int sgp_ring_enabled(void);        /* SGP_RING (default 1) */
-int sgp_ring_splat_enabled(void);  /* ... and SGP_RING_SPLAT (default 0: measured slower) */
+int sgp_ring_splat_enabled(void);  /* ... and SGP_RING_SPLAT (default 1; used for dense lattices only) */
 int sgp_ring_slice_enabled(void);  /* ... and SGP_RING_SLICE (default 1) */
 int sgp_splat_ring_supported(const float *values, int L);
 int sgp_slice_ring_supported(const sgp_lattice_view *lat, const float *values, int L);

@@ -128,16 +128,15 @@ def main():
                     print(json.dumps({"variant": f"slice stages={stg} passes={ps}", "error": str(exc)}), flush=True)
         env(SGP_SLICE_STAGES=None, SGP_SLICE_PASSES=None, SGP_RING_OCC=None)
     # graph replay of the whole product, both forms
-    for pf, za in ((0, 0), (0, 1), (2, 0), (2, 1), (1, 1)):
-        env(SGP_RING=1, SGP_RING_SPLAT=0, SGP_RING_SLICE=1, SGP_SPLAT_PREFETCH=pf, SGP_GRAPH_ZERO_AFTER=za)
-        report(f"splat prefetch={pf}", splat_us=timed(splat, args.reps))
+    for rs in (0, 1):
+        env(SGP_RING=1, SGP_RING_SPLAT=rs, SGP_RING_SLICE=1, SGP_SPLAT_PREFETCH=None, SGP_GRAPH_ZERO_AFTER=None)
+        report(f"splat ring={rs}", splat_us=timed(splat, args.reps))
         graphs = [lat.capture(Vs[k], outs[k]) for k in range(4)]
         for k in range(4):
             graphs[k].replay()
         torch.cuda.synchronize()
         ok = float((outs[1] - ref_mvm).norm() / ref_mvm.norm())
-        report(f"graph prefetch={pf} zero_after={za}", mvm_us=timed(lambda i: graphs[i % 4].replay(), max(args.reps, 300), warm=20),
-               rel=ok * 1e6)
+        report(f"graph splat ring={rs}", mvm_us=timed(lambda i: graphs[i % 4].replay(), max(args.reps, 300), warm=20), rel=ok * 1e6)
         del graphs
 
 

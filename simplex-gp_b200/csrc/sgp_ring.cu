@@ -393,12 +393,29 @@ sgp_splat_ring_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
                             vec_zero(acc);
                         }
                     }
-                    if (!SCAN) acc.red(values + (int64_t)(row0 + k) * L + c0);
                     tail = acc;
                     reset = (k > 0) || f0;
                 }
             }
-            if (!SCAN) continue;
+            if (!SCAN) {
+                // Reductions: one per run and thread -- except in the warp-uniform case, where every segment of the pass
+                // lies inside ONE lattice row (the long rows at the centre of the data, where most reductions go): the
+                // partial sums are added across the segments with a butterfly and one lane group reduces (8x fewer L2
+                // atomics for those passes; every other pass pays one vote).
+                const bool pow2 = (chunks & (chunks - 1)) == 0;
+                const int row_first = __shfl_sync(0xffffffffu, row0, 0);
+                const bool uniform = pow2 && __all_sync(0xffffffffu, act && k == 0 && row0 == row_first);
+                if (uniform) {
+                    for (int step = chunks; step < 32; step <<= 1) {
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) tail.v[q] += __shfl_xor_sync(0xffffffffu, tail.v[q], step);
+                    }
+                    if (lane < chunks) tail.red(values + (int64_t)row0 * L + c0);
+                } else if (act) {
+                    tail.red(values + (int64_t)(row0 + k) * L + c0);
+                }
+                continue;
+            }
             // inclusive segmented scan of (tail, reset) over the segments of the pass, per channel chunk
             Vec<VEC> sv = tail;
             bool sr = reset;
@@ -476,10 +493,11 @@ static int ring_env(const char *name, int dflt)
 
 // read on every call (a getenv, ~100 ns): a process can switch between the two forms, e.g. to compare them
 extern "C" int sgp_ring_enabled(void) { return ring_env("SGP_RING", 1) != 0; }
-// The ring splat is off by default: at the metric shape it measures 93 us (97 us with the scan) against 86 us for the
-// one-shot kernel -- the splat is bound by its reductions / memset (20 us) and by V rows that miss L2 (16 us), not by
-// the latency of its index stream (profiles/r2_splat_decomposition.txt); the ring slice gains 15 % (61 -> 52 us).
-extern "C" int sgp_ring_splat_enabled(void) { return sgp_ring_enabled() && ring_env("SGP_RING_SPLAT", 0) != 0; }
+// The ring splat: first measured slower than the one-shot kernel (93 vs 86 us at the metric shape) with entries stored
+// linearly (18 bulk copies per tile and padded shared-memory blocks); with the interleaved entry layout (one bulk copy per
+// tile, conflict-free reads) and the warp-uniform aggregation of long rows it measures 74.7 us and the MVM 178.5 us
+// (188.8 with the one-shot splat).  sgp_splat_rows selects it for dense lattices only (see there).
+extern "C" int sgp_ring_splat_enabled(void) { return sgp_ring_enabled() && ring_env("SGP_RING_SPLAT", 1) != 0; }
 extern "C" int sgp_ring_slice_enabled(void) { return sgp_ring_enabled() && ring_env("SGP_RING_SLICE", 1) != 0; }
 
 struct RingLaunch {
@@ -612,8 +630,26 @@ extern "C" int sgp_slice_ring(const sgp_lattice_view *lat, const float *values, 
 
 extern "C" int sgp_splat_ring_supported(const float *values, int L) { return ring_vec(L, values) != 0; }
 
+static int splat_rows_ring_impl(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
+                                const float *src, int64_t lds, int L_src, float *values, int L, bool prezeroed,
+                                sgp_stream_t stream);
+
 extern "C" int sgp_splat_rows_ring(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
                                    const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream)
+{
+    return splat_rows_ring_impl(ent, seg_row, n_entries, N, M, src, lds, L_src, values, L, false, stream);
+}
+
+// values already holds zeros (the caller zeroed it off the critical path); reductions form only
+int sgp_splat_rows_ring_prezeroed(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
+                                  const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream)
+{
+    return splat_rows_ring_impl(ent, seg_row, n_entries, N, M, src, lds, L_src, values, L, true, stream);
+}
+
+static int splat_rows_ring_impl(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
+                                const float *src, int64_t lds, int L_src, float *values, int L, bool prezeroed,
+                                sgp_stream_t stream)
 {
     SGP_RANGE("sgp_splat_rows_ring");
     if (N == 0 || M == 0) return SGP_OK;
@@ -633,9 +669,9 @@ extern "C" int sgp_splat_rows_ring(const int32_t *ent, const int32_t *seg_row, i
     cudaError_t le = cudaSuccess;
     // SGP_SPLAT_SCAN=1: runs combined across the threads of a tile and stored, no memset (the shuffles of the scan cost
     // as many L1 data-pipe wavefronts as a third of the row gathers: measured slower at the metric shape, 93 vs 8x us)
-    const bool scan = ring_env("SGP_SPLAT_SCAN", 0) != 0;
+    const bool scan = !prezeroed && ring_env("SGP_SPLAT_SCAN", 0) != 0;
     if (!scan) {
-        CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)M * (size_t)L, st));
+        if (!prezeroed) CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)M * (size_t)L, st));
     } else if (n_tiles > 1) {
         const int64_t work = (n_tiles - 1) * L;
         le = sgp_launch_pdl(sgp_ring_zero_heads_kernel, dim3(sgp_grid_for(work, 256)), dim3(256), 0, st,

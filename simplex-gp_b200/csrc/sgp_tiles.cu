@@ -637,10 +637,15 @@ static int splat_rows_impl(const int32_t *ent, const int32_t *seg_row, int64_t n
     if (!ent || !seg_row || !src || !values || N < 0 || M < 0 || n_entries < 0 || n_entries % ROWSEG != 0 || L_src < 1 ||
         lds < L_src || L < L_src)
         return fail(SGP_EINVAL, "sgp_splat_rows: bad argument");
-    // production form: index stream through warp-private TMA rings, stores instead of reductions (sgp_ring.cu);
-    // SGP_RING=0 selects the one-shot kernel below (kept for comparison)
-    if (!prezeroed && sgp_ring_splat_enabled() && n_entries >= 16 && sgp_splat_ring_supported(values, L))
-        return sgp_splat_rows_ring(ent, seg_row, n_entries, N, M, src, lds, L_src, values, L, stream);
+    // production form for dense lattices: index stream through warp-private TMA rings (sgp_ring.cu); SGP_RING=0 or
+    // SGP_RING_SPLAT=0 selects the one-shot kernel below
+    // ... where it wins: long rows (a dense lattice: the metric shape has 22 entries per lattice row) and enough tiles to
+    // keep every persistent warp busy.  Measured: config A 86.3 -> 74.7 us; config C (1.5 entries per row) 434 -> 510 us
+    // and config B (16.6 k points) 8 -> 19 us, which therefore keep the one-shot kernel.  SGP_RING_FORCE=1 overrides.
+    const bool ring_pays = (n_entries >= 8 * M && n_entries >= (1 << 21)) || (getenv("SGP_RING_FORCE") && atoi(getenv("SGP_RING_FORCE")));
+    if (sgp_ring_splat_enabled() && ring_pays && n_entries >= 64 && sgp_splat_ring_supported(values, L))
+        return prezeroed ? sgp_splat_rows_ring_prezeroed(ent, seg_row, n_entries, N, M, src, lds, L_src, values, L, stream)
+                         : sgp_splat_rows_ring(ent, seg_row, n_entries, N, M, src, lds, L_src, values, L, stream);
     cudaStream_t st = (cudaStream_t)stream;
     const int seg_env = 8;
     const int64_t n_seg = n_entries / seg_env;

@@ -944,7 +944,7 @@ class Lattice:
         production = (mvm_kwargs.get("mode", _capi.MODE_AUTO) in (_capi.MODE_AUTO, _capi.MODE_ROWS) and self.rows is not None
                       and self.groups is not None and mvm_kwargs.get("blur", "auto") in ("auto", "groups")
                       and not mvm_kwargs.get("sorted") and mvm_kwargs.get("after_splat") is None
-                      and not _capi.lib().sgp_ring_splat_enabled() and os.environ.get("SGP_GRAPH_ZERO_AFTER", "1") != "0")
+                      and os.environ.get("SGP_GRAPH_ZERO_AFTER", "1") != "0")
         zf = 3 if production else 0
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))

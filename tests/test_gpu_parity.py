@@ -421,3 +421,33 @@ def test_hash_table_sized_from_the_previous_build(sg, oracle):
     O = oracle.OracleLattice((x * 0.2).numpy(), RBF1)
     assert small.M == O.M and np.array_equal(small.keys.cpu().numpy(), O.keys)
     LT._M_BUILD_HINT.clear()
+
+
+@pytest.mark.parametrize("N,d,L,coeffs", [(5000, 8, 16, RBF1), (3000, 5, 11, MAT15_2), (2000, 3, 4, RBF1), (900, 2, 1, RBF2),
+                                           (70, 8, 16, RBF1), (4097, 11, 32, RBF1)])
+@pytest.mark.parametrize("scan", [0, 1])
+def test_ring_kernels_forced_at_small_sizes(sg, oracle, N, d, L, coeffs, scan):
+    """The TMA-ring splat / slice (csrc/sgp_ring.cu) are selected for large dense lattices and wide rows only; here they
+    are forced (SGP_RING_FORCE) on small and ragged shapes -- partial tiles, 11 -> 12 padded channels, one channel chunk,
+    fewer tiles than warps -- in both reduction forms (per-run reductions + warp-uniform aggregation; tile scan + stores)."""
+    import os
+    x, v = make_inputs(N, d, L, seed=N + L + scan)
+    want = oracle.OracleLattice(x.numpy(), coeffs).mvm(v.numpy())
+    lat = sg.Lattice(x.cuda(), coeffs)
+    old = {k: os.environ.get(k) for k in ("SGP_RING_FORCE", "SGP_SPLAT_SCAN")}
+    os.environ.update(SGP_RING_FORCE="1", SGP_SPLAT_SCAN=str(scan))
+    try:
+        got = lat.mvm(v.cuda()).cpu().numpy()
+        graph_out = torch.empty(N, L, device="cuda")
+        graph = lat.capture(v.cuda(), graph_out)
+        for _ in range(3):       # the splat buffer is re-zeroed at the end of every replay
+            graph.replay()
+        torch.cuda.synchronize()
+    finally:
+        for k, val in old.items():
+            if val is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = val
+    assert _rel(got, want) < REL_TOL
+    assert _rel(graph_out.cpu().numpy(), want) < REL_TOL
