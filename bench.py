@@ -34,6 +34,8 @@ WORKLOADS = {
     "A": dict(N=1_000_000, d=8, L=16, kernel="rbf", order=1),
     # the other BASELINE.json configurations: parity-test cases, timed for information only (--workload)
     "A1": dict(N=1_000_000, d=8, L=1, kernel="rbf", order=1),   # configs[1]: the single-RHS MVM
+    "A11": dict(N=1_000_000, d=8, L=11, kernel="rbf", order=1),  # the training step's block [y | 10 probes] on the metric lattice
+    "A12": dict(N=1_000_000, d=8, L=12, kernel="rbf", order=1),  # ... as the solver pads it (16-byte vectors)
     "B": dict(N=16_600, d=18, L=11, kernel="rbf", order=1),
     "C": dict(N=2_050_000, d=11, L=16, kernel="matern1.5", order=2),
     "D10": dict(N=1_000_000, d=24, L=4, kernel="matern1.5", order=3),

@@ -286,9 +286,12 @@ __device__ __forceinline__ uint32_t ent_offset(int entry) { return (uint32_t)sgp
 template <int VEC, bool RAGGED, bool SCAN>
 __global__ void __launch_bounds__(RING_THREADS, SCAN ? 3 : 4)
 sgp_splat_ring_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ seg_row, int64_t n_entries,
-                      const float *__restrict__ src, int64_t lds, int L, int L_src, int chunks, int spp, int passes,
+                      const float *__restrict__ src, int64_t lds, int L, int L_src, int chunks, int live, int spp, int passes,
                       int stages, uint32_t tile_stride, float *__restrict__ values)
 {
+    // chunks = lane slots per segment (the lane layout and the shuffle strides), live <= chunks = the channel chunks that
+    // exist: with 3 (5, 6, 7) chunks per row the segments still sit at power-of-two lane strides and the spare lanes idle,
+    // which keeps the warp-uniform aggregation below (idle lanes cost no memory wavefronts, and issue slots are not the limit)
     extern __shared__ __align__(128) unsigned char ring_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = 8 * spp * passes;
@@ -323,7 +326,7 @@ sgp_splat_ring_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
     const int sub = lane / chunks;
     const int cl = lane - sub * chunks;
     const int c0 = cl * VEC;
-    const bool lane_on = sub < spp;
+    const bool lane_on = sub < spp && cl < live;
     const int last_src = (spp - 1) * chunks + cl;   // the lane holding this chunk of the pass's last segment
     pdl_wait();   // values is zeroed (SCAN: its boundary rows are) by the stream's previous work
 
@@ -404,13 +407,13 @@ sgp_splat_ring_kernel(const int2 *__restrict__ ent, const int32_t *__restrict__ 
                 // atomics for those passes; every other pass pays one vote).
                 const bool pow2 = (chunks & (chunks - 1)) == 0;
                 const int row_first = __shfl_sync(0xffffffffu, row0, 0);
-                const bool uniform = pow2 && __all_sync(0xffffffffu, act && k == 0 && row0 == row_first);
+                const bool uniform = pow2 && __all_sync(0xffffffffu, cl >= live || (act && k == 0 && row0 == row_first));
                 if (uniform) {
                     for (int step = chunks; step < 32; step <<= 1) {
 #pragma unroll
                         for (int q = 0; q < VEC; ++q) tail.v[q] += __shfl_xor_sync(0xffffffffu, tail.v[q], step);
                     }
-                    if (lane < chunks) tail.red(values + (int64_t)row0 * L + c0);
+                    if (lane < live) tail.red(values + (int64_t)row0 * L + c0);
                 } else if (act) {
                     tail.red(values + (int64_t)(row0 + k) * L + c0);
                 }
@@ -661,15 +664,19 @@ static int splat_rows_ring_impl(const int32_t *ent, const int32_t *seg_row, int6
     cudaStream_t st = (cudaStream_t)stream;
     auto al = [](const void *p, int bytes) { return ((uintptr_t)p % bytes) == 0; };
     const bool ragged = !(L_src == L && lds % vec == 0 && al(src, 4 * vec));
-    const int chunks = L / vec;
-    const SplatTile g = splat_tile(chunks);
-    const int64_t n_tiles = (n_entries + g.T - 1) / g.T;
+    const int live = L / vec;
     RingLaunch rl;
     int rc;
     cudaError_t le = cudaSuccess;
     // SGP_SPLAT_SCAN=1: runs combined across the threads of a tile and stored, no memset (the shuffles of the scan cost
     // as many L1 data-pipe wavefronts as a third of the row gathers: measured slower at the metric shape, 93 vs 8x us)
     const bool scan = !prezeroed && ring_env("SGP_SPLAT_SCAN", 0) != 0;
+    // lane slots per segment: rounded up to a power of two in the reductions form (see the kernel), SGP_SPLAT_SLOTS=0: not
+    int chunks = live;
+    if (!scan && live <= 16 && ring_env("SGP_SPLAT_SLOTS", 1) != 0)
+        while (chunks & (chunks - 1)) ++chunks;
+    const SplatTile g = splat_tile(chunks);
+    const int64_t n_tiles = (n_entries + g.T - 1) / g.T;
     if (!scan) {
         if (!prezeroed) CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)M * (size_t)L, st));
     } else if (n_tiles > 1) {
@@ -684,7 +691,7 @@ static int splat_rows_ring_impl(const int32_t *ent, const int32_t *seg_row, int6
         rc = ring_config(sgp_splat_ring_kernel<VV, RG, SC>, tile_bytes, n_tiles, 2, "SGP_SPLAT_STAGES", &rl);          \
         if (rc) return rc;                                                                                             \
         le = sgp_launch_pdl(sgp_splat_ring_kernel<VV, RG, SC>, dim3(rl.grid), dim3(RING_THREADS), rl.smem, st,         \
-                            (const int2 *)ent, seg_row, n_entries, src, lds, L, L_src, chunks, g.spp, g.passes,        \
+                            (const int2 *)ent, seg_row, n_entries, src, lds, L, L_src, chunks, live, g.spp, g.passes,  \
                             rl.stages, rl.tile_stride, values);                                                        \
     } while (0)
 #define SGP_SPLAT_RING_S(VV, RG) do { if (scan) SGP_SPLAT_RING(VV, RG, true); else SGP_SPLAT_RING(VV, RG, false); } while (0)

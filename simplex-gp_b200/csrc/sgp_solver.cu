@@ -29,16 +29,21 @@
 #define CG_MAX_COLUMNS CG_THREADS
 
 struct CgGeometry {
-    int active;      // threads that take part: the largest multiple of L not above CG_THREADS
+    int vec;         // floats per thread and access: 4 (16-byte vectors) when L % 4 == 0 and the blocks are 16-byte aligned, else 1
+    int active;      // threads that take part: the largest multiple of L / vec not above CG_THREADS
+    int active2;     // threads of the one-block second stage: the largest multiple of L not above CG_THREADS
     int blocks;
-    int64_t per_block;   // elements per block, a multiple of `active`
+    int64_t per_block;   // vec-float elements per block, a multiple of `active`
 };
 
-static CgGeometry cg_geometry(int64_t N, int L)
+static CgGeometry cg_geometry(int64_t N, int L, bool aligned16)
 {
     CgGeometry g;
-    g.active = (CG_THREADS / L) * L;
-    const int64_t total = N * (int64_t)L;
+    g.vec = (L % 4 == 0 && aligned16) ? 4 : 1;
+    const int lanes = L / g.vec;
+    g.active = (CG_THREADS / lanes) * lanes;
+    g.active2 = (CG_THREADS / L) * L;
+    const int64_t total = N * (int64_t)lanes;
     int64_t blocks = (total + (int64_t)g.active * 2 * CG_UNROLL - 1) / ((int64_t)g.active * 2 * CG_UNROLL);
     if (blocks > CG_MAX_BLOCKS) blocks = CG_MAX_BLOCKS;
     if (blocks < 1) blocks = 1;
@@ -49,15 +54,46 @@ static CgGeometry cg_geometry(int64_t N, int L)
     return g;
 }
 
-// sum the per-thread partials of equal column (thread t holds column t % L) and store them at partial[block, :]
-__device__ __forceinline__ void cg_block_columns(float acc, int active, int L, float *__restrict__ partial)
+// V floats of one row: a thread's unit of work.  V = 4 moves 16-byte vectors (one request per 512 bytes and warp instead
+// of four); streaming loads (every block is read once per sweep and is larger than what stays in L2 next to the lattice)
+template <int V> struct CgVec {
+    float v[V];
+};
+template <int V> __device__ __forceinline__ CgVec<V> cg_load(const float *p)
 {
-    __shared__ float s_acc[CG_THREADS];
-    s_acc[threadIdx.x] = threadIdx.x < active ? acc : 0.0f;
+    CgVec<V> r;
+    if (V == 4) {
+        const float4 t = __ldcs((const float4 *)p);
+        r.v[0] = t.x; r.v[1 % V] = t.y; r.v[2 % V] = t.z; r.v[3 % V] = t.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) r.v[k] = __ldcs(p + k);
+    }
+    return r;
+}
+template <int V> __device__ __forceinline__ void cg_store(float *p, const CgVec<V> &a)
+{
+    if (V == 4) {
+        *(float4 *)p = make_float4(a.v[0], a.v[1 % V], a.v[2 % V], a.v[3 % V]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) p[k] = a.v[k];
+    }
+}
+
+// sum the per-thread partials of equal column (thread t holds columns (t % (L / V)) * V ... + V - 1) and store them at
+// partial[block, :]
+template <int V>
+__device__ __forceinline__ void cg_block_columns(const float (&acc)[V], int active, int L, float *__restrict__ partial)
+{
+    __shared__ float s_acc[V][CG_THREADS];
+#pragma unroll
+    for (int k = 0; k < V; ++k) s_acc[k][threadIdx.x] = threadIdx.x < active ? acc[k] : 0.0f;
     __syncthreads();
     if (threadIdx.x < L) {
+        const int lanes = L / V, g = threadIdx.x / V, c = threadIdx.x % V;
         float t = 0.0f;
-        for (int k = threadIdx.x; k < active; k += L) t += s_acc[k];
+        for (int k = g; k < active; k += lanes) t += s_acc[c][k];
         partial[(int64_t)blockIdx.x * L + threadIdx.x] = t;
     }
 }
@@ -93,36 +129,50 @@ __device__ __forceinline__ float cg_sum_partials(const float *__restrict__ parti
     return total;
 }
 
+template <int V>
 __global__ void __launch_bounds__(CG_THREADS)
 sgp_cg_apply_kernel(float *__restrict__ AP, const float *__restrict__ P, const float *__restrict__ s_ptr,
                     const float *__restrict__ noise_ptr, int64_t total, int L, int active, int64_t per_block,
                     float *__restrict__ partial)
 {
-    const float s = __ldg(s_ptr), noise = __ldg(noise_ptr);
-    float acc = 0.0f;
+    // total, per_block and the indices below count V-float elements
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.0f;
     if (threadIdx.x < active) {
+        const float s = __ldg(s_ptr), noise = __ldg(noise_ptr);
         const int64_t lo = (int64_t)blockIdx.x * per_block;
         const int64_t hi = min(lo + per_block, total);
         int64_t i = lo + threadIdx.x;
         for (; i + (int64_t)(CG_UNROLL - 1) * active < hi; i += (int64_t)CG_UNROLL * active) {
-            float p[CG_UNROLL], kp[CG_UNROLL];
-#pragma unroll
-            for (int u = 0; u < CG_UNROLL; ++u) { p[u] = __ldcs(P + i + (int64_t)u * active); kp[u] = __ldcs(AP + i + (int64_t)u * active); }
+            CgVec<V> p[CG_UNROLL], kp[CG_UNROLL];
 #pragma unroll
             for (int u = 0; u < CG_UNROLL; ++u) {
-                const float ap = fmaf(s, kp[u], noise * p[u]);
-                AP[i + (int64_t)u * active] = ap;
-                acc = fmaf(p[u], ap, acc);
+                const int64_t q = (i + (int64_t)u * active) * V;
+                p[u] = cg_load<V>(P + q); kp[u] = cg_load<V>(AP + q);
+            }
+#pragma unroll
+            for (int u = 0; u < CG_UNROLL; ++u) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    kp[u].v[k] = fmaf(s, kp[u].v[k], noise * p[u].v[k]);
+                    acc[k] = fmaf(p[u].v[k], kp[u].v[k], acc[k]);
+                }
+                cg_store<V>(AP + (i + (int64_t)u * active) * V, kp[u]);
             }
         }
         for (; i < hi; i += active) {
-            const float p = P[i];
-            const float ap = fmaf(s, AP[i], noise * p);
-            AP[i] = ap;
-            acc = fmaf(p, ap, acc);
+            const CgVec<V> p = cg_load<V>(P + i * V);
+            CgVec<V> kp = cg_load<V>(AP + i * V);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                kp.v[k] = fmaf(s, kp.v[k], noise * p.v[k]);
+                acc[k] = fmaf(p.v[k], kp.v[k], acc[k]);
+            }
+            cg_store<V>(AP + i * V, kp);
         }
     }
-    cg_block_columns(acc, active, L, partial);
+    cg_block_columns<V>(acc, active, L, partial);
 }
 
 __global__ void __launch_bounds__(CG_THREADS)
@@ -132,44 +182,64 @@ sgp_cg_reduce_kernel(const float *__restrict__ partial, int blocks, int L, int a
     if (threadIdx.x < L) out[threadIdx.x] = t;
 }
 
+template <int V>
 __global__ void __launch_bounds__(CG_THREADS)
 sgp_cg_update_kernel(float *__restrict__ X, float *__restrict__ R, const float *__restrict__ P,
                      const float *__restrict__ AP, const float *__restrict__ rs, const float *__restrict__ pAp,
                      int64_t total, int L, int active, int64_t per_block, float *__restrict__ alpha_out,
                      float *__restrict__ partial)
 {
-    float acc = 0.0f;
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.0f;
     if (threadIdx.x < active) {
-        const int col = threadIdx.x % L;
-        const float alpha = __ldg(rs + col) / fmaxf(__ldg(pAp + col), 1e-30f);
-        if (blockIdx.x == 0 && threadIdx.x < L) alpha_out[col] = alpha;
+        const int col = (threadIdx.x % (L / V)) * V;
+        float alpha[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) alpha[k] = __ldg(rs + col + k) / fmaxf(__ldg(pAp + col + k), 1e-30f);
+        if (blockIdx.x == 0 && threadIdx.x < L / V) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) alpha_out[col + k] = alpha[k];
+        }
         const int64_t lo = (int64_t)blockIdx.x * per_block;
         const int64_t hi = min(lo + per_block, total);
         int64_t i = lo + threadIdx.x;
-        for (; i + (int64_t)(CG_UNROLL - 1) * active < hi; i += (int64_t)CG_UNROLL * active) {
-            float xv[CG_UNROLL], rv[CG_UNROLL], pv[CG_UNROLL], av[CG_UNROLL];
+        // V = 4: two elements per trip (8 vector loads in flight per thread, as many bytes as the scalar form's 16 x 2)
+        constexpr int U = V == 4 ? 2 : CG_UNROLL;
+        for (; i + (int64_t)(U - 1) * active < hi; i += (int64_t)U * active) {
+            CgVec<V> xv[U], rv[U], pv[U], av[U];
 #pragma unroll
-            for (int u = 0; u < CG_UNROLL; ++u) {
-                const int64_t q = i + (int64_t)u * active;
-                xv[u] = __ldcs(X + q); rv[u] = __ldcs(R + q); pv[u] = __ldcs(P + q); av[u] = __ldcs(AP + q);
+            for (int u = 0; u < U; ++u) {
+                const int64_t q = (i + (int64_t)u * active) * V;
+                xv[u] = cg_load<V>(X + q); rv[u] = cg_load<V>(R + q); pv[u] = cg_load<V>(P + q); av[u] = cg_load<V>(AP + q);
             }
 #pragma unroll
-            for (int u = 0; u < CG_UNROLL; ++u) {
-                const int64_t q = i + (int64_t)u * active;
-                X[q] = fmaf(alpha, pv[u], xv[u]);
-                const float r = fmaf(-alpha, av[u], rv[u]);
-                R[q] = r;
-                acc = fmaf(r, r, acc);
+            for (int u = 0; u < U; ++u) {
+                const int64_t q = (i + (int64_t)u * active) * V;
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    xv[u].v[k] = fmaf(alpha[k], pv[u].v[k], xv[u].v[k]);
+                    rv[u].v[k] = fmaf(-alpha[k], av[u].v[k], rv[u].v[k]);
+                    acc[k] = fmaf(rv[u].v[k], rv[u].v[k], acc[k]);
+                }
+                cg_store<V>(X + q, xv[u]);
+                cg_store<V>(R + q, rv[u]);
             }
         }
         for (; i < hi; i += active) {
-            X[i] = fmaf(alpha, P[i], X[i]);
-            const float r = fmaf(-alpha, AP[i], R[i]);
-            R[i] = r;
-            acc = fmaf(r, r, acc);
+            CgVec<V> xv = cg_load<V>(X + i * V), rv = cg_load<V>(R + i * V);
+            const CgVec<V> pv = cg_load<V>(P + i * V), av = cg_load<V>(AP + i * V);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                xv.v[k] = fmaf(alpha[k], pv.v[k], xv.v[k]);
+                rv.v[k] = fmaf(-alpha[k], av.v[k], rv.v[k]);
+                acc[k] = fmaf(rv.v[k], rv.v[k], acc[k]);
+            }
+            cg_store<V>(X + i * V, xv);
+            cg_store<V>(R + i * V, rv);
         }
     }
-    cg_block_columns(acc, active, L, partial);
+    cg_block_columns<V>(acc, active, L, partial);
 }
 
 // one block: rs_new from the partials, beta, the convergence flag; rs <- rs_new
@@ -190,24 +260,43 @@ sgp_cg_beta_kernel(const float *__restrict__ partial, int blocks, int L, int act
     if (threadIdx.x == 0) *done = s_open == 0 ? 1 : 0;
 }
 
+template <int V>
 __global__ void __launch_bounds__(CG_THREADS)
 sgp_cg_direction_kernel(float *__restrict__ P, const float *__restrict__ R, const float *__restrict__ beta,
                         int64_t total, int L, int active, int64_t per_block)
 {
     if (threadIdx.x >= active) return;
-    const float b = __ldg(beta + threadIdx.x % L);
+    const int col = (threadIdx.x % (L / V)) * V;
+    float b[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) b[k] = __ldg(beta + col + k);
     const int64_t lo = (int64_t)blockIdx.x * per_block;
     const int64_t hi = min(lo + per_block, total);
     int64_t i = lo + threadIdx.x;
     for (; i + (int64_t)(CG_UNROLL - 1) * active < hi; i += (int64_t)CG_UNROLL * active) {
-        float pv[CG_UNROLL], rv[CG_UNROLL];
+        CgVec<V> pv[CG_UNROLL], rv[CG_UNROLL];
 #pragma unroll
-        for (int u = 0; u < CG_UNROLL; ++u) { pv[u] = __ldcs(P + i + (int64_t)u * active); rv[u] = __ldcs(R + i + (int64_t)u * active); }
+        for (int u = 0; u < CG_UNROLL; ++u) {
+            const int64_t q = (i + (int64_t)u * active) * V;
+            pv[u] = cg_load<V>(P + q); rv[u] = cg_load<V>(R + q);
+        }
 #pragma unroll
-        for (int u = 0; u < CG_UNROLL; ++u) P[i + (int64_t)u * active] = fmaf(b, pv[u], rv[u]);
+        for (int u = 0; u < CG_UNROLL; ++u) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) pv[u].v[k] = fmaf(b[k], pv[u].v[k], rv[u].v[k]);
+            cg_store<V>(P + (i + (int64_t)u * active) * V, pv[u]);
+        }
     }
-    for (; i < hi; i += active) P[i] = fmaf(b, P[i], R[i]);
+    for (; i < hi; i += active) {
+        CgVec<V> pv = cg_load<V>(P + i * V);
+        const CgVec<V> rv = cg_load<V>(R + i * V);
+#pragma unroll
+        for (int k = 0; k < V; ++k) pv.v[k] = fmaf(b[k], pv.v[k], rv.v[k]);
+        cg_store<V>(P + i * V, pv);
+    }
 }
+
+static bool cg_aligned16(const void *a, const void *b) { return (((uintptr_t)a | (uintptr_t)b) & 15) == 0; }
 
 static int cg_check(int64_t N, int L, const void *a, const void *b, const void *scratch)
 {
@@ -225,12 +314,14 @@ extern "C" int sgp_cg_apply(float *AP, const float *P, const float *s, const flo
     int rc = cg_check(N, L, AP, P, scratch);
     if (rc) return rc;
     if (!s || !noise || !pAp) return fail(SGP_EINVAL, "sgp_cg_apply: null pointer");
-    const CgGeometry g = cg_geometry(N, L);
+    const CgGeometry g = cg_geometry(N, L, cg_aligned16(AP, P));
     cudaStream_t st = (cudaStream_t)stream;
-    sgp_cg_apply_kernel<<<g.blocks, CG_THREADS, 0, st>>>(AP, P, s, noise, N * (int64_t)L, L, g.active, g.per_block, scratch);
+    const int64_t total = N * (int64_t)(L / g.vec);
+    if (g.vec == 4) sgp_cg_apply_kernel<4><<<g.blocks, CG_THREADS, 0, st>>>(AP, P, s, noise, total, L, g.active, g.per_block, scratch);
+    else sgp_cg_apply_kernel<1><<<g.blocks, CG_THREADS, 0, st>>>(AP, P, s, noise, total, L, g.active, g.per_block, scratch);
     rc = launch_ok("sgp_cg_apply_kernel");
     if (rc) return rc;
-    sgp_cg_reduce_kernel<<<1, CG_THREADS, 0, st>>>(scratch, g.blocks, L, g.active, pAp);
+    sgp_cg_reduce_kernel<<<1, CG_THREADS, 0, st>>>(scratch, g.blocks, L, g.active2, pAp);
     return launch_ok("sgp_cg_reduce_kernel");
 }
 
@@ -243,13 +334,16 @@ extern "C" int sgp_cg_update(float *X, float *R, const float *P, const float *AP
     if (rc) return rc;
     if (!P || !AP || !rs || !pAp || !bnorm || !alpha_out || !beta_out || !done)
         return fail(SGP_EINVAL, "sgp_cg_update: null pointer");
-    const CgGeometry g = cg_geometry(N, L);
+    const CgGeometry g = cg_geometry(N, L, cg_aligned16(X, R) && cg_aligned16(P, AP));
     cudaStream_t st = (cudaStream_t)stream;
-    sgp_cg_update_kernel<<<g.blocks, CG_THREADS, 0, st>>>(X, R, P, AP, rs, pAp, N * (int64_t)L, L, g.active, g.per_block,
-                                                          alpha_out, scratch);
+    const int64_t total = N * (int64_t)(L / g.vec);
+    if (g.vec == 4)
+        sgp_cg_update_kernel<4><<<g.blocks, CG_THREADS, 0, st>>>(X, R, P, AP, rs, pAp, total, L, g.active, g.per_block, alpha_out, scratch);
+    else
+        sgp_cg_update_kernel<1><<<g.blocks, CG_THREADS, 0, st>>>(X, R, P, AP, rs, pAp, total, L, g.active, g.per_block, alpha_out, scratch);
     rc = launch_ok("sgp_cg_update_kernel");
     if (rc) return rc;
-    sgp_cg_beta_kernel<<<1, CG_THREADS, 0, st>>>(scratch, g.blocks, L, g.active, rs, bnorm, tol, beta_out, done);
+    sgp_cg_beta_kernel<<<1, CG_THREADS, 0, st>>>(scratch, g.blocks, L, g.active2, rs, bnorm, tol, beta_out, done);
     return launch_ok("sgp_cg_beta_kernel");
 }
 
@@ -257,8 +351,9 @@ extern "C" int sgp_cg_direction(float *P, const float *R, const float *beta, int
 {
     SGP_RANGE("sgp_cg_direction");
     if (N < 1 || L < 1 || L > CG_MAX_COLUMNS || !P || !R || !beta) return fail(SGP_EINVAL, "sgp_cg_direction: bad argument");
-    const CgGeometry g = cg_geometry(N, L);
-    sgp_cg_direction_kernel<<<g.blocks, CG_THREADS, 0, (cudaStream_t)stream>>>(P, R, beta, N * (int64_t)L, L, g.active,
-                                                                              g.per_block);
+    const CgGeometry g = cg_geometry(N, L, cg_aligned16(P, R));
+    const int64_t total = N * (int64_t)(L / g.vec);
+    if (g.vec == 4) sgp_cg_direction_kernel<4><<<g.blocks, CG_THREADS, 0, (cudaStream_t)stream>>>(P, R, beta, total, L, g.active, g.per_block);
+    else sgp_cg_direction_kernel<1><<<g.blocks, CG_THREADS, 0, (cudaStream_t)stream>>>(P, R, beta, total, L, g.active, g.per_block);
     return launch_ok("sgp_cg_direction_kernel");
 }

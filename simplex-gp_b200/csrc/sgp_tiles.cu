@@ -640,9 +640,14 @@ static int splat_rows_impl(const int32_t *ent, const int32_t *seg_row, int64_t n
     // production form for dense lattices: index stream through warp-private TMA rings (sgp_ring.cu); SGP_RING=0 or
     // SGP_RING_SPLAT=0 selects the one-shot kernel below
     // ... where it wins: long rows (a dense lattice: the metric shape has 22 entries per lattice row) and enough tiles to
-    // keep every persistent warp busy.  Measured: config A 86.3 -> 74.7 us; config C (1.5 entries per row) 434 -> 510 us
-    // and config B (16.6 k points) 8 -> 19 us, which therefore keep the one-shot kernel.  SGP_RING_FORCE=1 overrides.
-    const bool ring_pays = (n_entries >= 8 * M && n_entries >= (1 << 21)) || (getenv("SGP_RING_FORCE") && atoi(getenv("SGP_RING_FORCE")));
+    // keep every persistent warp busy, and 2 to 16 float4 chunks per row (3, 5, 6, 7, 9+ chunks run on power-of-two lane
+    // slots with idle lanes, which keeps the warp-uniform aggregation).  Measured (profiles/exp_splat_L.py, metric
+    // lattice, one-shot -> ring): L = 8: 59.5 -> 57.8 us, 12: 83.4 -> 75.3, 16: 86.5 -> 73.6, 20: 126.1 -> 111.0,
+    // 24: 142.0 -> 121.4, 28: 176.0 -> 150.4, 32: 160.8 -> 120.0, 40: 241.5 -> 219.6; but L = 1: 42.2 -> 49.4,
+    // L = 4: 49.6 -> 53.7; config C (1.5 entries per row) 434 -> 510 us and config B (16.6 k points) 8 -> 19 us: those
+    // keep the one-shot kernel.  SGP_RING_FORCE=1 overrides.
+    const bool ring_pays = (n_entries >= 8 * M && n_entries >= (1 << 21) && L % 4 == 0 && L >= 8 && L <= 64) ||
+                           (getenv("SGP_RING_FORCE") && atoi(getenv("SGP_RING_FORCE")));
     if (sgp_ring_splat_enabled() && ring_pays && n_entries >= 64 && sgp_splat_ring_supported(values, L))
         return prezeroed ? sgp_splat_rows_ring_prezeroed(ent, seg_row, n_entries, N, M, src, lds, L_src, values, L, stream)
                          : sgp_splat_rows_ring(ent, seg_row, n_entries, N, M, src, lds, L_src, values, L, stream);

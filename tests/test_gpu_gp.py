@@ -210,7 +210,7 @@ def test_experiment_harness_learns_on_toy_shape(sg):
     assert len(summary["lengthscale"]) == 3
 
 
-@pytest.mark.parametrize("n,L", [(5000, 11), (777, 1), (3000, 16), (1200, 37), (40, 256)])
+@pytest.mark.parametrize("n,L", [(5000, 11), (777, 1), (3000, 16), (1200, 37), (40, 256), (2001, 12), (13, 8), (9000, 4)])
 def test_cuda_cg_sweeps_match_tensor_expressions(sg, n, L):
     """batched_cg on the sweeps of csrc/sgp_solver.cu against the same iteration written with tensor expressions, on a
     dense SPD operator (so that only the vector updates differ)."""
