@@ -396,6 +396,15 @@ int sgp_cg_apply(float *AP, const float *P, const float *s, const float *noise, 
 int sgp_cg_update(float *X, float *R, const float *P, const float *AP, float *rs, const float *pAp,
                   const float *bnorm, float tol, int64_t N, int L, float *alpha_out, float *beta_out,
                   int32_t *done, float *scratch, sgp_stream_t stream);
+/* ... with the stopping rule chosen: SGP_CG_ALL_COLUMNS as above; SGP_CG_MEAN: *done = mean over the columns with a
+ * non-zero right-hand side (bnorm > 1e-29) of sqrt(rs_new[l])/bnorm[l] < tol -- the rule of GPyTorch's linear_cg
+ * (residual_norm.mean() < tolerance), which the reference's cg_tolerance setting refers to
+ * (experiments/train_simplexgp.py:34-37). */
+#define SGP_CG_ALL_COLUMNS 0
+#define SGP_CG_MEAN 1
+int sgp_cg_update_ex(float *X, float *R, const float *P, const float *AP, float *rs, const float *pAp,
+                     const float *bnorm, float tol, int criterion, int64_t N, int L, float *alpha_out,
+                     float *beta_out, int32_t *done, float *scratch, sgp_stream_t stream);
 int sgp_cg_direction(float *P, const float *R, const float *beta, int64_t N, int L, sgp_stream_t stream);
 
 /* ---- row-sorted splat ("segmented gather") -------------------------------------------------

@@ -242,22 +242,38 @@ sgp_cg_update_kernel(float *__restrict__ X, float *__restrict__ R, const float *
     cg_block_columns<V>(acc, active, L, partial);
 }
 
-// one block: rs_new from the partials, beta, the convergence flag; rs <- rs_new
+// one block: rs_new from the partials, beta, the convergence flag; rs <- rs_new.
+// criterion 0: every column's relative residual sqrt(rs_new) / bnorm is below tol; 1: their mean over the columns with a
+// non-zero right-hand side is (GPyTorch's linear_cg stops on residual_norm.mean() < tolerance)
 __global__ void __launch_bounds__(CG_THREADS)
 sgp_cg_beta_kernel(const float *__restrict__ partial, int blocks, int L, int active, float *__restrict__ rs,
-                   const float *__restrict__ bnorm, float tol, float *__restrict__ beta_out, int32_t *__restrict__ done)
+                   const float *__restrict__ bnorm, float tol, int criterion, float *__restrict__ beta_out,
+                   int32_t *__restrict__ done)
 {
     __shared__ int s_open;
+    __shared__ float s_rel[CG_THREADS];
     if (threadIdx.x == 0) s_open = 0;
     const float rs_new = cg_sum_partials(partial, blocks, L, active);   // contains a __syncthreads
     __syncthreads();
     if (threadIdx.x < L) {
         beta_out[threadIdx.x] = rs_new / fmaxf(rs[threadIdx.x], 1e-30f);
         rs[threadIdx.x] = rs_new;
-        if (!(sqrtf(rs_new) / bnorm[threadIdx.x] < tol)) atomicAdd(&s_open, 1);
+        const float rel = sqrtf(rs_new) / bnorm[threadIdx.x];
+        s_rel[threadIdx.x] = rel;
+        if (criterion == 0 && !(rel < tol)) atomicAdd(&s_open, 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) *done = s_open == 0 ? 1 : 0;
+    if (threadIdx.x == 0) {
+        if (criterion == 0) {
+            *done = s_open == 0 ? 1 : 0;
+        } else {
+            float sum = 0.0f;
+            int cols = 0;
+            for (int l = 0; l < L; ++l)
+                if (bnorm[l] > 1e-29f) { sum += s_rel[l]; ++cols; }   // (bnorm is clamped to 1e-30 for zero columns)
+            *done = (cols == 0 || sum / (float)cols < tol) ? 1 : 0;
+        }
+    }
 }
 
 template <int V>
@@ -329,11 +345,19 @@ extern "C" int sgp_cg_update(float *X, float *R, const float *P, const float *AP
                              const float *bnorm, float tol, int64_t N, int L, float *alpha_out, float *beta_out,
                              int32_t *done, float *scratch, sgp_stream_t stream)
 {
+    return sgp_cg_update_ex(X, R, P, AP, rs, pAp, bnorm, tol, SGP_CG_ALL_COLUMNS, N, L, alpha_out, beta_out, done, scratch, stream);
+}
+
+extern "C" int sgp_cg_update_ex(float *X, float *R, const float *P, const float *AP, float *rs, const float *pAp,
+                                const float *bnorm, float tol, int criterion, int64_t N, int L, float *alpha_out,
+                                float *beta_out, int32_t *done, float *scratch, sgp_stream_t stream)
+{
     SGP_RANGE("sgp_cg_update");
     int rc = cg_check(N, L, X, R, scratch);
     if (rc) return rc;
     if (!P || !AP || !rs || !pAp || !bnorm || !alpha_out || !beta_out || !done)
         return fail(SGP_EINVAL, "sgp_cg_update: null pointer");
+    if (criterion != SGP_CG_ALL_COLUMNS && criterion != SGP_CG_MEAN) return fail(SGP_EINVAL, "sgp_cg_update: unknown criterion %d", criterion);
     const CgGeometry g = cg_geometry(N, L, cg_aligned16(X, R) && cg_aligned16(P, AP));
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = N * (int64_t)(L / g.vec);
@@ -343,7 +367,7 @@ extern "C" int sgp_cg_update(float *X, float *R, const float *P, const float *AP
         sgp_cg_update_kernel<1><<<g.blocks, CG_THREADS, 0, st>>>(X, R, P, AP, rs, pAp, total, L, g.active, g.per_block, alpha_out, scratch);
     rc = launch_ok("sgp_cg_update_kernel");
     if (rc) return rc;
-    sgp_cg_beta_kernel<<<1, CG_THREADS, 0, st>>>(scratch, g.blocks, L, g.active2, rs, bnorm, tol, beta_out, done);
+    sgp_cg_beta_kernel<<<1, CG_THREADS, 0, st>>>(scratch, g.blocks, L, g.active2, rs, bnorm, tol, criterion, beta_out, done);
     return launch_ok("sgp_cg_beta_kernel");
 }
 

@@ -42,24 +42,35 @@ def mll_dense(matmul: Callable, y: torch.Tensor, mean: torch.Tensor, outputscale
 
 @torch.no_grad()
 def batched_cg(A: Callable, B: torch.Tensor, tol: float = 1e-4, max_iter: int = 500, *, matmul: Optional[Callable] = None,
-               scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None):
+               scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None, stop: str = "all",
+               min_iter: int = 0):
     """Solve ``A X = B`` column-wise (A symmetric positive definite, given as ``A(V)``).  Returns ``X`` and the CG
     coefficients ``(alphas[k, L], betas[k, L])`` from which the Lanczos tridiagonal of every column follows.
 
     When the operator is also given in parts, ``A(V) = scale * matmul(V) + shift * V``, and ``B`` is a float32 CUDA
     block of at most 256 columns, the three vector sweeps of an iteration run as one launch each with their dot products
     folded in (``csrc/sgp_solver.cu``) instead of ~17 tensor expressions -- at N = 1M, L = 11 those cost more device
-    time than the lattice MVM between them."""
+    time than the lattice MVM between them.
+
+    ``stop``: ``"all"`` -- every column's relative residual is below ``tol``; ``"mean"`` -- their mean over the non-zero
+    columns is, the rule of GPyTorch's ``linear_cg`` (``residual_norm.mean() < tolerance``), which is what the
+    reference's ``cg_tolerance`` settings mean (experiments/train_simplexgp.py:34-37,63-67).  ``min_iter``: iterations
+    run whatever the residual (GPyTorch: 10, and ``max_lanczos_quadrature_iterations`` = 20 when the coefficients feed
+    a log-determinant)."""
+    if stop not in ("all", "mean"):
+        raise ValueError(f"stop must be 'all' or 'mean', got {stop!r}")
+    min_iter = min(int(min_iter), max(int(max_iter) - 1, 0))
     if (matmul is not None and scale is not None and shift is not None and B.is_cuda and B.dtype == torch.float32
             and B.dim() == 2 and 1 <= B.shape[1] <= 256 and B.shape[0] >= 1):
-        return _batched_cg_cuda(matmul, scale, shift, B, tol, max_iter)
+        return _batched_cg_cuda(matmul, scale, shift, B, tol, max_iter, stop, min_iter)
     X = torch.zeros_like(B)
     R = B.clone()
     P = R.clone()
     rs = (R * R).sum(0)
     b_norm = rs.sqrt().clamp_min(1e-30)
     alphas, betas = [], []
-    for _ in range(max_iter):
+    nonzero = rs > 0
+    for it in range(max_iter):
         AP = A(P)
         pAp = (P * AP).sum(0)
         alpha = rs / pAp.clamp_min(1e-30)
@@ -69,7 +80,9 @@ def batched_cg(A: Callable, B: torch.Tensor, tol: float = 1e-4, max_iter: int = 
         beta = rs_new / rs.clamp_min(1e-30)
         alphas.append(alpha)
         betas.append(beta)
-        if bool(((rs_new.sqrt() / b_norm) < tol).all()):
+        rel = rs_new.sqrt() / b_norm
+        converged = bool((rel < tol).all()) if stop == "all" else (not bool(nonzero.any()) or bool(rel[nonzero].mean() < tol))
+        if converged and it + 1 >= min_iter:
             break
         P = R + P * beta
         rs = rs_new
@@ -77,7 +90,7 @@ def batched_cg(A: Callable, B: torch.Tensor, tol: float = 1e-4, max_iter: int = 
 
 
 def _batched_cg_cuda(matmul: Callable, scale: torch.Tensor, shift: torch.Tensor, B: torch.Tensor, tol: float,
-                     max_iter: int):
+                     max_iter: int, stop: str = "all", min_iter: int = 0):
     """The same iteration as above on the sweeps of ``csrc/sgp_solver.cu`` (``sgp_cg_apply / update / direction``).
 
     * A lattice operator is driven through its ``Lattice`` directly (no autograd node per product, output written in
@@ -118,6 +131,7 @@ def _batched_cg_cuda(matmul: Callable, scale: torch.Tensor, shift: torch.Tensor,
     nz = shift.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
     AP = torch.empty((N, L), dtype=torch.float32, device=dev) if lat is not None else None
     k = 0
+    criterion = 1 if stop == "mean" else 0   # SGP_CG_MEAN / SGP_CG_ALL_COLUMNS
     with torch.cuda.device(dev):
         st = _stream_ptr(dev)
         for it in range(max_iter):
@@ -128,15 +142,15 @@ def _batched_cg_cuda(matmul: Callable, scale: torch.Tensor, shift: torch.Tensor,
                 if AP.dtype != torch.float32 or not AP.is_contiguous() or AP.data_ptr() == P.data_ptr():
                     AP = AP.to(torch.float32).contiguous().clone()
             _capi.check(lib.sgp_cg_apply(_ptr(AP), _ptr(P), _ptr(s), _ptr(nz), N, L, _ptr(pAp), _ptr(scratch), st))
-            _capi.check(lib.sgp_cg_update(_ptr(X), _ptr(R), _ptr(P), _ptr(AP), _ptr(rs), _ptr(pAp), _ptr(bnorm),
-                                          float(tol), N, L, _ptr(alphas[it]), _ptr(betas[it]), _ptr(done[it:]),
-                                          _ptr(scratch), st))
+            _capi.check(lib.sgp_cg_update_ex(_ptr(X), _ptr(R), _ptr(P), _ptr(AP), _ptr(rs), _ptr(pAp), _ptr(bnorm),
+                                             float(tol), criterion, N, L, _ptr(alphas[it]), _ptr(betas[it]),
+                                             _ptr(done[it:]), _ptr(scratch), st))
             done_host[it:it + 1].copy_(done[it:it + 1], non_blocking=True)
             events[it & 1].record()
             k = it + 1
             if it > 0:
                 events[(it - 1) & 1].synchronize()      # iteration it-1 finished long ago; iteration it is running
-                if int(done_host[it - 1]):
+                if int(done_host[it - 1]) and it >= min_iter:   # (iteration it - 1 is the it-th one)
                     break
             if it + 1 < max_iter:
                 _capi.check(lib.sgp_cg_direction(_ptr(P), _ptr(R), _ptr(betas[it]), N, L, st))
@@ -229,12 +243,15 @@ def _lanczos_logdet(alphas: torch.Tensor, betas: torch.Tensor, n: int) -> torch.
 
 def mll_cg(matmul: Callable, y: torch.Tensor, mean: torch.Tensor, outputscale: torch.Tensor, noise: torch.Tensor,
            n_probes: int = 10, tol: float = 1e-4, max_iter: int = 500, generator: Optional[torch.Generator] = None,
-           probes: Optional[torch.Tensor] = None, preconditioner_size: int = 0, stats: Optional[dict] = None):
+           probes: Optional[torch.Tensor] = None, preconditioner_size: int = 0, stats: Optional[dict] = None,
+           stop: str = "all", min_iter: int = 0):
     """Returns ``(mll_value, surrogate)``: ``mll_value`` is the (detached) per-datum MLL estimate, ``surrogate`` a scalar
     whose gradient with respect to the hyper-parameters is the usual CG / stochastic-trace MLL gradient estimate.
 
     ``preconditioner_size = k > 0``: rank-``k`` pivoted-Cholesky preconditioner of the reference's solver settings
-    (``pivoted_cholesky`` / ``LowRankPreconditioner``).  ``stats`` (a dict) receives the CG iteration count."""
+    (``pivoted_cholesky`` / ``LowRankPreconditioner``).  ``stats`` (a dict) receives the CG iteration count.
+    ``stop`` / ``min_iter``: the stopping rule of ``batched_cg``; GPyTorch's own (what the reference trains with) is
+    ``stop="mean", min_iter=20``."""
     n = y.shape[0]
     r = (y - mean)
     if probes is None:
@@ -256,7 +273,8 @@ def mll_cg(matmul: Callable, y: torch.Tensor, mean: torch.Tensor, outputscale: t
             pre = LowRankPreconditioner(Lm, float(noise.detach()))
             del Lm
     if pre is None:
-        X, al, be = batched_cg(A, B, tol=tol, max_iter=max_iter, matmul=matmul, scale=outputscale, shift=noise)
+        X, al, be = batched_cg(A, B, tol=tol, max_iter=max_iter, matmul=matmul, scale=outputscale, shift=noise,
+                               stop=stop, min_iter=min_iter)
         logdet_p = 0.0
     else:
         # symmetric preconditioning: CG on P^-1/2 A P^-1/2 with right-hand sides [P^-1/2 r | probes]; the probe columns
@@ -265,7 +283,8 @@ def mll_cg(matmul: Callable, y: torch.Tensor, mean: torch.Tensor, outputscale: t
         Bt = torch.cat([pre.inv_sqrt(B[:, :1]), B[:, 1:]], dim=1)
         one, zero = torch.ones((), device=y.device, dtype=y.dtype), torch.zeros((), device=y.device, dtype=y.dtype)
         At = lambda V: pre.inv_sqrt(A(pre.inv_sqrt(V)))
-        Xt, al, be = batched_cg(At, Bt, tol=tol, max_iter=max_iter, matmul=At, scale=one, shift=zero)
+        Xt, al, be = batched_cg(At, Bt, tol=tol, max_iter=max_iter, matmul=At, scale=one, shift=zero, stop=stop,
+                                min_iter=min_iter)
         X = pre.inv_sqrt(Xt)
         Z = pre.inv_sqrt(Z)
         logdet_p = pre.logdet()

@@ -306,3 +306,34 @@ def test_pivoted_cholesky_preconditioner_over_the_lattice_operator(sg):
     it0 = list(model.last_solve_iterations)
     m1 = model.predict(xt, preconditioner_size=100)
     assert float((m0 - m1).abs().max()) < 0.1 and model.last_solve_iterations[0] <= it0[0], (it0, model.last_solve_iterations)
+
+
+@pytest.mark.parametrize("stop,min_iter", [("mean", 0), ("mean", 20), ("all", 7)])
+def test_cuda_cg_stopping_rules_match_tensor_expressions(sg, stop, min_iter):
+    """The stopping rule of GPyTorch's linear_cg (mean relative residual over the non-zero columns, a minimum number of
+    iterations) on the device sweeps against the tensor-expression iteration: same iteration count (the device flag is
+    read one iteration late) and the same solution.  One right-hand side is zero and one converges much later than the
+    others, so 'mean' and 'all' stop at different iterations."""
+    from simplex_gp_b200 import gp
+    n, L = 1500, 8
+    g = torch.Generator().manual_seed(5)
+    Q = torch.randn(n, 48, generator=g).cuda()
+    Kmat = Q @ Q.T / 48
+    B = torch.randn(n, L, generator=g).cuda()
+    B[:, 3] = 0.0
+    B[:, 5] = Q[:, 0] * 30.0        # lies in the span of the large eigenvalues: slow to converge relative to its norm
+    s, noise = torch.tensor(1.0, device="cuda"), torch.tensor(0.05, device="cuda")
+    matmul = lambda V: Kmat @ V
+    A = lambda V: s * matmul(V) + noise * V
+    tol = 0.05
+    X0, a0, _ = gp.batched_cg(A, B, tol=tol, max_iter=300, stop=stop, min_iter=min_iter)
+    X1, a1, _ = gp.batched_cg(A, B, tol=tol, max_iter=300, matmul=matmul, scale=s, shift=noise, stop=stop, min_iter=min_iter)
+    assert a0.shape[0] >= min_iter and a1.shape[0] >= min_iter
+    assert 0 <= a1.shape[0] - a0.shape[0] <= 1
+    assert float((X0 - X1).norm() / X0.norm()) < 2e-2          # one iteration apart at a loose tolerance
+    assert float(X1[:, 3].abs().max()) == 0.0
+    if stop == "mean" and min_iter == 0:
+        Xa, aa, _ = gp.batched_cg(A, B, tol=tol, max_iter=300, matmul=matmul, scale=s, shift=noise, stop="all")
+        assert aa.shape[0] >= a1.shape[0]
+    with pytest.raises(ValueError):
+        gp.batched_cg(A, B, stop="median")

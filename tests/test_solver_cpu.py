@@ -62,3 +62,23 @@ def test_preconditioned_cg_same_answer_fewer_iterations():
                            + n * math.log(2 * math.pi))) / n)
     # the quadratic term is exact on both sides; the log-determinant is a 20-probe stochastic estimate
     assert abs(v0 - exact) < 0.03 and abs(v1 - exact) < 0.03
+
+
+def test_cg_stopping_rules_on_cpu():
+    """stop="mean" (GPyTorch's rule) never runs longer than stop="all"; min_iter is honoured; a zero right-hand side stays
+    zero and does not hold the mean rule up."""
+    from simplex_gp_b200 import gp
+    g = torch.Generator().manual_seed(3)
+    Q = torch.randn(300, 40, generator=g)
+    K = Q @ Q.T / 40 + 0.05 * torch.eye(300)
+    B = torch.randn(300, 5, generator=g)
+    B[:, 2] = 0.0
+    A = lambda V: K @ V
+    _, a_all, _ = gp.batched_cg(A, B, tol=0.05, max_iter=200, stop="all")
+    X, a_mean, _ = gp.batched_cg(A, B, tol=0.05, max_iter=200, stop="mean")
+    assert 1 <= a_mean.shape[0] <= a_all.shape[0]
+    assert float(X[:, 2].abs().max()) == 0.0
+    _, a_min, _ = gp.batched_cg(A, B, tol=0.5, max_iter=200, stop="mean", min_iter=20)
+    assert a_min.shape[0] == 20
+    _, a_cap, _ = gp.batched_cg(A, B, tol=0.5, max_iter=5, stop="mean", min_iter=20)
+    assert a_cap.shape[0] <= 5
