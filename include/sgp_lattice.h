@@ -350,12 +350,16 @@ int sgp_mvm_rows_groups(const sgp_lattice_view *slice_view, const int32_t *ent, 
  * holds zeros on entry (no memset in front of the splat); SGP_MVM_ZERO_AFTER -- buf0 is left zeroed on exit: with an
  * odd number of group stages it is zeroed on an internal side stream while the slice runs (a parallel branch when the
  * call is captured into a CUDA graph), with an even number after the slice.  A graph captured with both flags on
- * private buffers (Lattice.capture) replays without ever waiting for the memset. */
+ * private buffers (Lattice.capture) replays without ever waiting for the memset.
+ * SGP_MVM_SRC_PADDED -- src has Lv columns (lds >= Lv; columns L..Lv-1 zero) while out has L: what a caller passes after
+ * copying a ragged block (L = 11: the reference's training block [y | 10 probes]) into a zero-padded one, so that the
+ * splat gathers 16-byte vectors (config A with 11 columns: 236 -> 224 us per MVM including the copy). */
 /* The splat stage of that chain alone: sgp_splat_rows without its memset -- `values` must hold zeros on entry. */
 int sgp_mvm_stage_splat_prezeroed(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
                                   const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream);
 #define SGP_MVM_PREZEROED 1
 #define SGP_MVM_ZERO_AFTER 2
+#define SGP_MVM_SRC_PADDED 4
 int sgp_mvm_rows_groups_ex(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
                            int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src, int64_t lds,
                            int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1, int Lv,

@@ -679,6 +679,7 @@ extern "C" int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64
 //        capture, where it becomes a parallel branch of the graph); with an even number the slice itself reads buf0 and
 //        the zeroing follows it.  Replaying a graph captured with both flags keeps the 25.6 MB memset of the metric
 //        shape off the critical path of every product.
+//        SGP_MVM_SRC_PADDED (4) src has Lv columns (the caller's ragged block copied into a zero-padded one).
 extern "C" int sgp_mvm_rows_groups_ex(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
                                       int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src,
                                       int64_t lds, int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0,
@@ -688,8 +689,12 @@ extern "C" int sgp_mvm_rows_groups_ex(const sgp_lattice_view *slice_view, const 
     if (!slice_view) return fail(SGP_EINVAL, "sgp_mvm_rows_groups_ex: null view");
     if (Lv < L || (Lv != L && Lv % 4 != 0)) return fail(SGP_EINVAL, "sgp_mvm_rows_groups_ex: Lv must be L or L rounded up to a multiple of 4");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = (flags & 1) ? sgp_splat_rows_prezeroed(ent, seg_row, n_entries, slice_view->N, slice_view->M, src, lds, L, buf0, Lv, stream)
-                         : sgp_splat_rows(ent, seg_row, n_entries, slice_view->N, slice_view->M, src, lds, L, buf0, Lv, stream);
+    // SGP_MVM_SRC_PADDED (4): src is a zero-padded copy with Lv columns (lds >= Lv) of the caller's L-column block, so the
+    // splat gathers 16-byte vectors instead of reading ragged rows channel by channel; out keeps its L columns
+    if ((flags & 4) && lds < Lv) return fail(SGP_EINVAL, "sgp_mvm_rows_groups_ex: SGP_MVM_SRC_PADDED needs lds >= Lv");
+    const int L_src = (flags & 4) ? Lv : L;
+    int rc = (flags & 1) ? sgp_splat_rows_prezeroed(ent, seg_row, n_entries, slice_view->N, slice_view->M, src, lds, L_src, buf0, Lv, stream)
+                         : sgp_splat_rows(ent, seg_row, n_entries, slice_view->N, slice_view->M, src, lds, L_src, buf0, Lv, stream);
     if (rc) return rc;
     int in1 = 0;
     rc = sgp_blur_groups(groups, n_groups, slice_view->M, slice_view->order, coeffs, k, Lv, buf0, buf1, &in1,

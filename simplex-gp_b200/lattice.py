@@ -724,6 +724,24 @@ class Lattice:
             self._bufs[key] = b
         return b
 
+    def _pads_ragged_src(self) -> bool:
+        """Copy a ragged right-hand-side block into a zero-padded one in front of the splat?  Pays once the splat is
+        bound by its gathers (SGP_PAD_SRC=0/1 forces)."""
+        import os
+        e = os.environ.get("SGP_PAD_SRC")
+        if e is not None:
+            return e != "0"
+        return self.N * (self.d + 1) >= (1 << 20)
+
+    def _src_pad(self, Lv: int) -> torch.Tensor:
+        p = self._bufs.get(("pad", Lv))
+        if p is None:
+            for k in [k for k in self._bufs if isinstance(k, tuple)]:
+                del self._bufs[k]
+            p = torch.zeros((self.N, Lv), dtype=torch.float32, device=self.device)
+            self._bufs[("pad", Lv)] = p
+        return p
+
     def _check_src(self, src: torch.Tensor) -> torch.Tensor:
         if src.dim() != 2 or src.shape[0] != self.N:
             raise ValueError(f"Incompatible shapes {tuple(src.shape)}, and {(self.N, self.d)}")
@@ -854,7 +872,7 @@ class Lattice:
         # 16-byte vectors (L = 11, the CG block of a training step: 301 us on the scalar path at the metric shape);
         # the row-sorted splat and the slice read / write the caller's ragged rows channel by channel.
         Lv = (L + 3) // 4 * 4 if (mode == _capi.MODE_ROWS and L > 4) else L
-        buf0, buf1 = self._scratch(Lv) if scratch is None else scratch
+        buf0, buf1 = self._scratch(Lv) if scratch is None else scratch[:2]
         if tuple(buf0.shape) != (max(self.M, 1), Lv) or tuple(buf1.shape) != (max(self.M, 1), Lv):
             raise ValueError(f"scratch buffers must be [{max(self.M, 1)}, {Lv}]")
         use_sorted = False if sorted is None else bool(sorted)   # measured slower than the input order on B200
@@ -870,14 +888,22 @@ class Lattice:
             # the production chain, one call across the C ABI
             arr = self.groups["array"]
             v_out = self._slice_view(Lv, True, exact)
+            flags = int(zero_flags)
+            if zero_flags and scratch is None:
+                raise ValueError("zero_flags needs private scratch buffers")
             with torch.cuda.device(self.device):
-                if zero_flags:
-                    if scratch is None:
-                        raise ValueError("zero_flags needs private scratch buffers")
+                if Lv != L and self._pads_ragged_src():
+                    # ragged rows (L = 11: 44 bytes) can only be gathered channel by channel -- four times the L1
+                    # wavefronts of 16-byte vectors, nine times per point; one coalesced copy into a zero-padded block
+                    # is cheaper (config A, 11 columns: 236 -> 224 us per MVM; 187 us when the caller's block has 12)
+                    pad = scratch[2] if (scratch is not None and len(scratch) > 2) else self._src_pad(Lv)
+                    pad[:, :L].copy_(src)
+                    src, flags = pad, flags | 4      # SGP_MVM_SRC_PADDED
+                if flags:
                     check(lib.sgp_mvm_rows_groups_ex(C.byref(v_out), _ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]),
                                                      self.rows["n"], arr, len(arr), _ptr(src), src.stride(0), L, _fp(c),
                                                      c.shape[0], _ptr(out), out.stride(0), _ptr(buf0), _ptr(buf1), Lv,
-                                                     int(zero_flags), st))
+                                                     flags, st))
                 else:
                     check(lib.sgp_mvm_rows_groups(C.byref(v_out), _ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]),
                                                   self.rows["n"], arr,
@@ -937,6 +963,8 @@ class Lattice:
             Lv = L
         scratch = (torch.zeros((max(self.M, 1), Lv), dtype=torch.float32, device=self.device),
                    torch.empty((max(self.M, 1), Lv), dtype=torch.float32, device=self.device))
+        if Lv != L:
+            scratch = scratch + (torch.zeros((self.N, Lv), dtype=torch.float32, device=self.device),)   # zero-padded copy of src
         # production chain on private buffers: the splat buffer is zeroed at the END of every product, next to the slice
         # (a parallel branch of the graph), instead of in front of the splat: 4-6 us off the critical path at the
         # metric shape.  SGP_GRAPH_ZERO_AFTER=0 keeps the memset in front.
