@@ -586,7 +586,16 @@ def run_ours(args, w):
     roofline = stages = None
     if rank == 0:
         lib = _capi.lib()
-        buf0, buf1 = lat._scratch(L)
+        # as Lattice.mvm: lattice rows padded to a multiple of four channels, ragged right-hand sides through a
+        # zero-padded copy where that pays
+        Lv = (L + 3) // 4 * 4 if (mode == _capi.MODE_ROWS and L > 4) else L
+        buf0, buf1 = lat._scratch(Lv)
+        pad_src = Lv != L and lat._pads_ragged_src()
+        Vs_pad = None
+        if pad_src:
+            Vs_pad = [torch.zeros((N, Lv), dtype=torch.float32, device=dev) for _ in Vs]
+            for vp_, v_ in zip(Vs_pad, Vs):
+                vp_[:, :L].copy_(v_)
         cnp = lat.coeffs
         st = _stream_ptr(dev)
         reps = max(5, min(steps, 20))
@@ -594,31 +603,31 @@ def run_ours(args, w):
         fast = 0 if lat.exact else 1
         v_in = lat._view(lat._table(False, False), None, lat.exact)
         v_axis = lat._view(exact=lat.exact)
-        v_out = lat._slice_view(L, use_groups, lat.exact)
+        v_out = lat._slice_view(Lv, use_groups, lat.exact)
         tv_in = lat._tiles_view(False) if mode == _capi.MODE_TILES else None
         tv_out = lat._tiles_view(use_groups) if mode == _capi.MODE_TILES else None
         garr = lat.groups["array"] if use_groups else None
         # Each stage is launched `reps` times back to back between two events (after two warm-up launches), so that the
         # average is the kernel's device time and not the launch latency of an idle stream; V/out rotate as in the step.
         def splat_stage(i):
-            V = Vs[i % n_rot]
+            V = Vs_pad[i % n_rot] if pad_src else Vs[i % n_rot]
             if mode == _capi.MODE_TILES:
                 _capi.check(lib.sgp_splat_tiles(C.byref(tv_in), _ptr(V), V.stride(0), L, _ptr(buf0), st))
             elif mode == _capi.MODE_ROWS:
                 # the kernel alone (its memset is timed apart: in the MVM's graph it runs beside the previous slice);
                 # repeated launches keep accumulating into buf0, which is irrelevant for the timing
                 _capi.check(lib.sgp_mvm_stage_splat_prezeroed(_ptr(lat.rows["ent"]), _ptr(lat.rows["seg_row"]), lat.rows["n"], N,
-                                                              M, _ptr(V), V.stride(0), L, _ptr(buf0), L, st))
+                                                              M, _ptr(V), V.stride(0), int(V.shape[1]), _ptr(buf0), Lv, st))
             else:
                 _capi.check(lib.sgp_splat(C.byref(v_in if mode == _capi.MODE_ATOMIC else v_axis), _ptr(V), V.stride(0), L,
                                           _ptr(buf0), mode, st))
 
         def blur_stage(i):
             if use_groups:
-                _capi.check(lib.sgp_blur_groups(garr, len(garr), M, lat.order, _fp(cnp), cnp.shape[0], L, _ptr(buf0),
+                _capi.check(lib.sgp_blur_groups(garr, len(garr), M, lat.order, _fp(cnp), cnp.shape[0], Lv, _ptr(buf0),
                                                 _ptr(buf1), C.byref(where), fast, st))
             else:
-                _capi.check(lib.sgp_blur(C.byref(v_axis), _fp(cnp), cnp.shape[0], L, _ptr(buf0), _ptr(buf1),
+                _capi.check(lib.sgp_blur(C.byref(v_axis), _fp(cnp), cnp.shape[0], Lv, _ptr(buf0), _ptr(buf1),
                                          C.byref(where), st))
 
         def slice_stage(i):
@@ -627,7 +636,7 @@ def run_ours(args, w):
             if mode == _capi.MODE_TILES:
                 _capi.check(lib.sgp_slice_tiles(C.byref(tv_out), _ptr(res_buf), L, _ptr(out), out.stride(0), fast, st))
             else:
-                _capi.check(lib.sgp_slice(C.byref(v_out), _ptr(res_buf), L, _ptr(out), out.stride(0), L, st))
+                _capi.check(lib.sgp_slice(C.byref(v_out), _ptr(res_buf), Lv, _ptr(out), out.stride(0), L, st))
 
         def stage_ms(fn):
             for i in range(2):
@@ -655,8 +664,10 @@ def run_ours(args, w):
         b_slice = 4 * (M * L + 2 * N * (d + 1) + N * L)
         splat_kernel = {_capi.MODE_ATOMIC: "sgp_splat_atomic_kernel", _capi.MODE_GATHER: "sgp_splat_gather_kernel",
                         _capi.MODE_TILES: "sgp_splat_tiles_kernel",
+                        # the selection rule of csrc/sgp_tiles.cu::splat_rows_impl
                         _capi.MODE_ROWS: "sgp_splat_ring_kernel" if (lib.sgp_ring_splat_enabled() and lat.rows["n"] >= 8 * M
-                                                                       and lat.rows["n"] >= (1 << 21)) else "sgp_splat_rows_kernel"}[mode]
+                                                                       and lat.rows["n"] >= (1 << 21) and Lv % 4 == 0
+                                                                       and 8 <= Lv <= 64) else "sgp_splat_rows_kernel"}[mode]
         stages = {
             "splat": {"ms": t_splat, "launches": 1, "alg_bytes": b_splat, "gbs": b_splat / t_splat / 1e6,
                       "kernel": splat_kernel, "memset_ms_timed_apart": memset_ms},
@@ -664,7 +675,9 @@ def run_ours(args, w):
                      "kernel": "sgp_blur_group_kernel" if use_groups else "sgp_blur_kernel"},
             "slice": {"ms": t_slice, "launches": 1, "alg_bytes": b_slice, "gbs": b_slice / t_slice / 1e6,
                       "kernel": "sgp_slice_tiles_kernel" if mode == _capi.MODE_TILES else
-                                ("sgp_slice_ring_kernel" if lib.sgp_ring_slice_enabled() else "sgp_slice_kernel")},
+                                ("sgp_slice_ring_kernel" if (lib.sgp_ring_slice_enabled() and
+                                                            lib.sgp_slice_ring_supported(C.byref(v_out), _ptr(buf0), Lv))
+                                 else "sgp_slice_kernel")},
         }
         dom = max(stages, key=lambda k: stages[k]["ms"] / stages[k]["launches"])
         per_launch_bytes = stages[dom]["alg_bytes"] / stages[dom]["launches"]

@@ -451,3 +451,35 @@ def test_ring_kernels_forced_at_small_sizes(sg, oracle, N, d, L, coeffs, scan):
                 os.environ[k] = val
     assert _rel(got, want) < REL_TOL
     assert _rel(graph_out.cpu().numpy(), want) < REL_TOL
+
+
+@pytest.mark.parametrize("L", [5, 11])
+def test_ragged_right_hand_sides_through_the_padded_copy(sg, oracle, L):
+    """L = 11 (the reference's training block [y | 10 probes]): at large N the MVM copies the block into a zero-padded
+    one so that the splat gathers 16-byte vectors (SGP_MVM_SRC_PADDED); forced here at a size the oracle finishes, eager
+    and captured, and compared with the channel-by-channel path."""
+    import os
+    N, d = 3000, 6
+    x, v = make_inputs(N, d, L, seed=L)
+    want = oracle.OracleLattice(x.numpy(), RBF1).mvm(v.numpy())
+    lat = sg.Lattice(x.cuda(), RBF1)
+    old = os.environ.get("SGP_PAD_SRC")
+    try:
+        os.environ["SGP_PAD_SRC"] = "0"
+        plain = lat.mvm(v.cuda()).cpu().numpy()
+        os.environ["SGP_PAD_SRC"] = "1"
+        src = v.cuda()
+        got = lat.mvm(src).cpu().numpy()
+        out = torch.empty(N, L, device="cuda")
+        graph = lat.capture(src, out)
+        src.mul_(2.0)                      # the graph reads the caller's buffer at replay time, not a stale copy
+        graph.replay()
+        graph.replay()
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("SGP_PAD_SRC", None)
+        else:
+            os.environ["SGP_PAD_SRC"] = old
+    assert _rel(got, want) < REL_TOL and _rel(plain, want) < REL_TOL
+    assert _rel(out.cpu().numpy(), 2.0 * want) < REL_TOL
