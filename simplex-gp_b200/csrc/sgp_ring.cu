@@ -13,11 +13,15 @@
 // its indices sit in shared memory: the only exposed latency is the row gather, and the index stream costs no LSU
 // wavefronts on the global path.  No CTA-wide barrier anywhere: warps never wait for each other.
 //
-// The splat additionally combines runs of equal lattice row across the threads of a warp tile (segmented scan with
-// shuffles, carried from pass to pass), so every lattice row that lies inside one tile is written with a plain
-// store; only a row that crosses a tile boundary is reduced into memory (at most two vector reductions per tile,
-// 2 x 35 k instead of 1.5 M at the metric shape), and only those rows are zeroed beforehand (sgp_ring_zero_heads_kernel)
-// -- the 25.6 MB memset of the lattice values is gone.
+// The splat (production form for dense lattices at 8..64 columns, see sgp_tiles.cu::splat_rows_impl): a tile is 256
+// row-sorted entries in the interleaved storage order (sgp_entry_index: the eight lane groups of a warp read eight
+// consecutive 16-byte words) plus its 32 segment rows, delivered by ONE bulk copy pair; every thread reduces its runs
+// of equal lattice row into the (pre-zeroed) values with red.global.add.v4.f32, except that a pass whose segments all
+// lie inside one lattice row -- the long rows at the centre of the data -- is first summed across the warp with a
+// butterfly (segments sit at power-of-two lane strides; with 3, 5, 6, 7 chunks per row the spare lanes idle).
+// Optional form (SGP_SPLAT_SCAN=1, measured slower): runs are combined across the threads of a tile with a segmented
+// scan and stored; only rows that cross a tile boundary are reduced (and only those are zeroed beforehand,
+// sgp_ring_zero_heads_kernel), so the memset of the lattice values is gone -- at the price of 25 shuffles per pass.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -244,12 +248,12 @@ sgp_slice_ring_kernel(const int2 *__restrict__ replay, const float *__restrict__
 struct SplatTile {
     int spp, passes, T;   // T = 8 * spp * passes entries per tile, a multiple of 64 (whole interleave groups)
 };
-static SplatTile splat_tile(int chunks)
+static SplatTile splat_tile(int chunks, int target)
 {
     SplatTile g;
     g.spp = 32 / chunks;
     if (g.spp < 1) g.spp = 1;
-    int passes = 256 / (8 * g.spp);
+    int passes = target / (8 * g.spp);
     if (passes < 1) passes = 1;
     while ((g.spp * passes) & 7) ++passes;   // T % 64 == 0: whole interleave groups
     g.passes = passes;
@@ -675,7 +679,28 @@ static int splat_rows_ring_impl(const int32_t *ent, const int32_t *seg_row, int6
     int chunks = live;
     if (!scan && live <= 16 && ring_env("SGP_SPLAT_SLOTS", 1) != 0)
         while (chunks & (chunks - 1)) ++chunks;
-    const SplatTile g = splat_tile(chunks);
+    // Entries per tile.  A persistent warp takes the tiles w, w + W, ...: with 256-entry tiles the metric shape has 7.4
+    // tiles per warp and the last round runs with 42 % of the warps (67.9 us); 192-entry tiles make it 9.9 (61.9 us),
+    // 128: 14.9 (63.3 us), 64: 70 us (profiles/exp_splat_tile.py).  Pick the size whose last round is fullest, smaller
+    // tiles paying a little for their extra bulk copies and waits.  SGP_SPLAT_TILE fixes it.
+    int target = ring_env("SGP_SPLAT_TILE", 0);
+    if (target < 64) {
+        int dev = 0, sms = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const double W = (double)sms * 4 * RING_WARPS;   // 4 CTAs per SM (registers)
+        const int cand[3] = {192, 256, 128};
+        const double penalty[3] = {0.005, 0.0, 0.02};
+        double best = -1.0;
+        target = 256;
+        for (int c = 0; c < 3; ++c) {
+            const SplatTile t = splat_tile(chunks, cand[c]);
+            const double rounds = (double)((n_entries + t.T - 1) / t.T) / W;
+            const double fill = rounds <= 1.0 ? 1.0 : rounds / (double)(int64_t)(rounds + 0.999999);
+            if (fill - penalty[c] > best) { best = fill - penalty[c]; target = cand[c]; }
+        }
+    }
+    const SplatTile g = splat_tile(chunks, target);
     const int64_t n_tiles = (n_entries + g.T - 1) / g.T;
     if (!scan) {
         if (!prezeroed) CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)M * (size_t)L, st));
