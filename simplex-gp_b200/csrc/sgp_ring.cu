@@ -560,8 +560,9 @@ static int slice_geometry(int dp1, int chunks, int *ppp_out, int *passes_out)
     const int ppp = 32 / chunks;
     // tiles are multiples of 16 bytes (ppp * passes * dp1 even) and at most 2.25 KB: the kernel's speed is proportional
     // to the resident warps (83 / 64 / 52 us at 24 / 32 / 40 warps per SM at the metric shape), and 2 stages x 8 warps x
-    // 2.25 KB still leaves shared memory for 6 CTAs; two passes of 8 points measured best at L = 16 (1152-byte stages)
-    int passes = ring_env("SGP_SLICE_PASSES", 2);
+    // 2.25 KB still leaves shared memory for 6 CTAs; at L = 16 two to four passes of 8 points measure alike kernel-only
+    // (52.7 / 52.0 / 52.1 us), three or four are 1.5 us better inside the MVM's graph (172.2 -> 170.7 us)
+    int passes = ring_env("SGP_SLICE_PASSES", 3);
     if (passes < 1) passes = 1;
     if ((ppp * passes * dp1) & 1) ++passes;
     while (passes > 1 && (size_t)ppp * passes * dp1 * 8 > 2304) {
