@@ -23,6 +23,25 @@ for (N, d, L, c) in ((3000, 8, 16, [0.34608543, 1.0, 0.34608543]), (1500, 5, 3, 
         assert err < 1e-5, (N, d, kw, err)
     g = lat.capture(v, torch.empty_like(v))
     g.replay()
+    # the TMA-ring splat / slice forced onto these small shapes (both reduction forms), ragged blocks through the
+    # zero-padded copy, eager and captured; then the one-call C entries (device and host pointers)
+    os.environ.update(SGP_RING_FORCE="1", SGP_PAD_SRC="1")
+    for scan in ("0", "1"):
+        os.environ["SGP_SPLAT_SCAN"] = scan
+        out = lat.mvm(v)
+        err = float((out - ref).norm() / ref.norm())
+        assert err < 1e-5, (N, d, "ring", scan, err)
+        o2 = torch.empty_like(v)
+        g2 = lat.capture(v, o2)
+        g2.replay()
+        g2.replay()
+        torch.cuda.synchronize()
+        assert float((o2 - ref).norm() / ref.norm()) < 1e-5, (N, d, "ring graph", scan)
+    for k_ in ("SGP_RING_FORCE", "SGP_PAD_SRC", "SGP_SPLAT_SCAN"):
+        os.environ.pop(k_)
+    f1 = sg.filter(v, x, torch.tensor(c))
+    f2 = sg.filter(v.cpu(), x.cpu(), torch.tensor(c))
+    assert float((f1 - ref).norm() / ref.norm()) < 1e-5 and float((f2.cuda() - ref).norm() / ref.norm()) < 1e-5
 
     class KF:
         def get_coeffs(self):

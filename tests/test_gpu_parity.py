@@ -483,3 +483,53 @@ def test_ragged_right_hand_sides_through_the_padded_copy(sg, oracle, L):
             os.environ["SGP_PAD_SRC"] = old
     assert _rel(got, want) < REL_TOL and _rel(plain, want) < REL_TOL
     assert _rel(out.cpu().numpy(), 2.0 * want) < REL_TOL
+
+
+@pytest.mark.parametrize("N,d,L", [(1000, 4, 16), (333, 7, 12), (77, 3, 8), (2049, 8, 20)])
+def test_ring_kernels_stay_inside_their_buffers(sg, N, d, L):
+    """Guard bands around every buffer the TMA-ring kernels write (compute-sanitizer is not available on the GPU pool):
+    lattice values and outputs are views into the middle of larger NaN-filled allocations; after the forced ring splat
+    and slice (partial tiles, entry counts that are not a multiple of the tile) the bands are untouched, and so is the
+    zero-padded copy of a ragged block."""
+    import ctypes as C
+    import os
+    from simplex_gp_b200 import _capi
+    from simplex_gp_b200.lattice import _ptr, _stream_ptr
+    x, v = make_inputs(N, d, L, seed=3 * N + L)
+    lat = sg.Lattice(x.cuda(), RBF1)
+    lat.mvm(v.cuda())                      # builds the lazy tables
+    lib, st, M, rows = _capi.lib(), _stream_ptr(lat.device), lat.M, lat.rows
+    G = 4096                                # guard floats either side
+    nan = float("nan")
+    vals_all = torch.full((G + M * L + G,), nan, device="cuda")
+    out_all = torch.full((G + N * L + G,), nan, device="cuda")
+    vals = vals_all[G:G + M * L].view(M, L)
+    out = out_all[G:G + N * L].view(N, L)
+    src = v.cuda()
+    old = {k: os.environ.get(k) for k in ("SGP_RING_FORCE", "SGP_SPLAT_SCAN")}
+    try:
+        os.environ["SGP_RING_FORCE"] = "1"
+        want = None
+        for scan in ("0", "1"):
+            os.environ["SGP_SPLAT_SCAN"] = scan
+            vals.fill_(nan)
+            _capi.check(lib.sgp_splat_rows(_ptr(rows["ent"]), _ptr(rows["seg_row"]), rows["n"], N, M, _ptr(src), src.stride(0),
+                                           L, _ptr(vals), L, st))
+            torch.cuda.synchronize()
+            assert torch.isnan(vals_all[:G]).all() and torch.isnan(vals_all[G + M * L:]).all()
+            assert not torch.isnan(vals).any()
+            if want is None:
+                want = vals.clone()
+            else:
+                assert float((vals - want).abs().max()) <= 1e-5 * float(want.abs().max())
+        v_out = lat._view(lat._table(False, True), None, lat.exact)     # slice of values held in lattice-index order
+        _capi.check(lib.sgp_slice(C.byref(v_out), _ptr(vals), L, _ptr(out), out.stride(0), L, st))
+        torch.cuda.synchronize()
+        assert torch.isnan(out_all[:G]).all() and torch.isnan(out_all[G + N * L:]).all()
+        assert not torch.isnan(out).any()
+    finally:
+        for k, val in old.items():
+            if val is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = val
