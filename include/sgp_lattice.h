@@ -364,6 +364,20 @@ int sgp_mvm_rows_groups_ex(const sgp_lattice_view *slice_view, const int32_t *en
                            int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src, int64_t lds,
                            int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1, int Lv,
                            int flags, sgp_stream_t stream);
+/* One CG iteration's product AND the sweep that follows it (sgp_cg_apply below): out = s*K*src + noise*src,
+ * pAp[l] = sum_n src[n,l]*out[n,l].  With the TMA-ring slice the sweep runs in the slice's epilogue (the point's row of
+ * src is read there, s*K*src + noise*src is what gets stored, per-CTA partial dot products are summed by a one-block
+ * second stage); otherwise the slice is followed by sgp_cg_apply.  Unpadded blocks only: lds = ldo = Lv = L; s, noise:
+ * device scalars; pAp: device [L]; scratch: device [sgp_cg_scratch_floats(L)]; flags: SGP_MVM_PREZEROED / ZERO_AFTER. */
+int sgp_mvm_rows_groups_cg(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
+                           int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src, int64_t lds,
+                           int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0, float *buf1, int Lv,
+                           int flags, const float *s, const float *noise, float *pAp, float *scratch, sgp_stream_t stream);
+/* The slice of that chain alone, and whether it applies to a shape (16-byte vectors, ring slice selected). */
+int sgp_slice_ring_cg_supported(const sgp_lattice_view *lat, const float *values, int L, const float *out, int64_t ldo,
+                                const float *P, int64_t ldp);
+int sgp_slice_ring_cg(const sgp_lattice_view *lat, const float *values, int L, float *out, int64_t ldo, const float *P,
+                      int64_t ldp, const float *s, const float *noise, float *pAp, float *scratch, sgp_stream_t stream);
 
 /* ---- stage 5: lengthscale-gradient pass (bilateral_kernel.py:97-124) -------------------
  *
@@ -410,6 +424,26 @@ int sgp_cg_update_ex(float *X, float *R, const float *P, const float *AP, float 
                      const float *bnorm, float tol, int criterion, int64_t N, int L, float *alpha_out,
                      float *beta_out, int32_t *done, float *scratch, sgp_stream_t stream);
 int sgp_cg_direction(float *P, const float *R, const float *beta, int64_t N, int L, sgp_stream_t stream);
+/* The same iteration with X += alpha*P moved from the update sweep into the direction sweep (which reads P anyway):
+ *   sgp_cg_update_r     alpha = rs/max(pAp,1e-30);  R -= alpha*AP;  rs_new, beta, done as sgp_cg_update_ex
+ *   sgp_cg_direction_x  X += alpha*P;  P = R + beta*P
+ * eight passes over [N, L] per iteration instead of nine, the same arithmetic in the same order.  When the iteration
+ * stops after an update the caller adds the last alpha*P to X itself. */
+int sgp_cg_update_r(float *R, const float *AP, float *rs, const float *pAp, const float *bnorm, float tol,
+                    int criterion, int64_t N, int L, float *alpha_out, float *beta_out, int32_t *done, float *scratch,
+                    sgp_stream_t stream);
+int sgp_cg_direction_x(float *P, const float *R, float *X, const float *alpha, const float *beta, int64_t N, int L,
+                       sgp_stream_t stream);
+/* One whole CG iteration on the production chain (row-sorted splat -> blur groups -> slice with the CG epilogue ->
+ * sgp_cg_update_r -> sgp_cg_direction_x) enqueued by one call; iteration `it` writes alphas[it, :], betas[it, :],
+ * done[it] and copies done[it] to done_host[it] (pinned host memory, may be NULL) on the stream.  Blocks are unpadded
+ * [N, L] (L % 4 == 0 or L <= 4 for the lattice side); buf0 / buf1: [M, L] work buffers; flags as sgp_mvm_rows_groups_ex;
+ * X is complete after every call (the deferred X += alpha P is part of it). */
+int sgp_cg_iteration(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row, int64_t n_entries,
+                     const sgp_blur_group *groups, int n_groups, const float *coeffs, int k, float *buf0, float *buf1,
+                     int flags, float *X, float *R, float *P, float *AP, float *rs, float *pAp, const float *bnorm,
+                     const float *s, const float *noise, float tol, int criterion, int L, float *alphas, float *betas,
+                     int32_t *done, int32_t *done_host, int it, float *scratch, sgp_stream_t stream);
 
 /* ---- row-sorted splat ("segmented gather") -------------------------------------------------
  * The point-vertices sorted by lattice row, point-vertex order within a row (the reference's accumulation order),

@@ -31,7 +31,7 @@ SYMBOLS = [
     "sgp_remap_replay",
     "sgp_blur_groups_channel_block", "sgp_blur_groups", "sgp_mvm_rows_groups", "sgp_mvm_rows_groups_ex", "sgp_mvm_stage_splat_prezeroed", "sgp_sort_points_workspace_bytes", "sgp_sort_points",
     "sgp_permute_replay", "sgp_permute_replay_padded", "sgp_rowsort_workspace_bytes", "sgp_rowsort_padded", "sgp_build_rowsorted",
-    "sgp_splat_rows", "sgp_cg_scratch_floats", "sgp_cg_apply", "sgp_cg_update", "sgp_cg_update_ex", "sgp_cg_direction",
+    "sgp_splat_rows", "sgp_cg_scratch_floats", "sgp_cg_apply", "sgp_cg_update", "sgp_cg_update_ex", "sgp_cg_direction", "sgp_cg_update_r", "sgp_cg_direction_x", "sgp_mvm_rows_groups_cg", "sgp_slice_ring_cg", "sgp_slice_ring_cg_supported", "sgp_cg_iteration",
     "sgp_ring_enabled", "sgp_ring_splat_enabled", "sgp_ring_slice_enabled", "sgp_splat_ring_supported", "sgp_slice_ring_supported", "sgp_splat_rows_ring", "sgp_slice_ring",
     "sgp_hash_append_keys", "sgp_count_appended", "sgp_number_appended",
     "sgp_filter_workspace_bytes", "sgp_filter_host_workspace_bytes", "sgp_filter", "sgp_filter_host",
@@ -209,6 +209,16 @@ def lib() -> C.CDLL:
     L.sgp_mvm_rows_groups_ex.restype = i32
     L.sgp_mvm_rows_groups_ex.argtypes = [pv, vp, vp, i64, C.POINTER(BlurGroup), i32, vp, i64, i32, fp, i32, vp, i64, vp, vp, i32,
                                          i32, vp]
+    L.sgp_mvm_rows_groups_cg.restype = i32
+    L.sgp_mvm_rows_groups_cg.argtypes = [pv, vp, vp, i64, C.POINTER(BlurGroup), i32, vp, i64, i32, fp, i32, vp, i64, vp, vp, i32,
+                                         i32, vp, vp, vp, vp, vp]
+    L.sgp_cg_iteration.restype = i32
+    L.sgp_cg_iteration.argtypes = [pv, vp, vp, i64, C.POINTER(BlurGroup), i32, fp, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp,
+                                   vp, vp, C.c_float, i32, i32, vp, vp, vp, vp, i32, vp, vp]
+    L.sgp_slice_ring_cg_supported.restype = i32
+    L.sgp_slice_ring_cg_supported.argtypes = [pv, vp, i32, vp, i64, vp, i64]
+    L.sgp_slice_ring_cg.restype = i32
+    L.sgp_slice_ring_cg.argtypes = [pv, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp, vp]
     L.sgp_sort_points_workspace_bytes.restype = sz
     L.sgp_sort_points_workspace_bytes.argtypes = [i64]
     L.sgp_sort_points.restype = i32
@@ -233,6 +243,10 @@ def lib() -> C.CDLL:
     L.sgp_cg_update_ex.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_float, i32, i64, i32, vp, vp, vp, vp, vp]
     L.sgp_cg_direction.restype = i32
     L.sgp_cg_direction.argtypes = [vp, vp, vp, i64, i32, vp]
+    L.sgp_cg_update_r.restype = i32
+    L.sgp_cg_update_r.argtypes = [vp, vp, vp, vp, vp, C.c_float, i32, i64, i32, vp, vp, vp, vp, vp]
+    L.sgp_cg_direction_x.restype = i32
+    L.sgp_cg_direction_x.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]
     L.sgp_splat_rows.restype = i32
     L.sgp_splat_rows.argtypes = [vp, vp, i64, i64, i64, vp, i64, i32, vp, i32, vp]
     for fn in (L.sgp_ring_enabled, L.sgp_ring_splat_enabled, L.sgp_ring_slice_enabled):

@@ -39,6 +39,7 @@ int sgp_exclusive_scan_u32(uint32_t *data, int64_t n, uint32_t *tile_sums, unsig
 
 int sgp_splat_rows_prezeroed(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
                              const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream);
+int sgp_cg_reduce_partials(const float *partial, int blocks, int L, float *out, sgp_stream_t stream);
 int sgp_splat_rows_ring_prezeroed(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
                                   const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream);
 cudaStream_t sgp_side_stream(int dev);   // one internal non-blocking stream per device (created on first use)

@@ -680,10 +680,76 @@ extern "C" int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64
 //        the zeroing follows it.  Replaying a graph captured with both flags keeps the 25.6 MB memset of the metric
 //        shape off the critical path of every product.
 //        SGP_MVM_SRC_PADDED (4) src has Lv columns (the caller's ragged block copied into a zero-padded one).
+struct CgEpilogue {          // sgp_mvm_rows_groups_cg: the sweep after the product, folded into the slice where possible
+    const float *s, *noise;
+    float *pAp, *scratch;
+};
+
+static int mvm_rows_groups_impl(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
+                                int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src,
+                                int64_t lds, int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0,
+                                float *buf1, int Lv, int flags, const CgEpilogue *cg, sgp_stream_t stream);
+
 extern "C" int sgp_mvm_rows_groups_ex(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
                                       int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src,
                                       int64_t lds, int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0,
                                       float *buf1, int Lv, int flags, sgp_stream_t stream)
+{
+    return mvm_rows_groups_impl(slice_view, ent, seg_row, n_entries, groups, n_groups, src, lds, L, coeffs, k, out, ldo, buf0,
+                                buf1, Lv, flags, nullptr, stream);
+}
+
+// out = s * K src + noise * src and pAp[l] = sum_n src[n, l] * out[n, l]: one CG iteration's product and the sweep that
+// follows it (sgp_cg_apply), the sweep folded into the slice's epilogue when the TMA-ring slice applies (else it runs as
+// its own launch).  out and src are [N, L] blocks with ld = L (what sgp_cg_apply expects); s, noise: device scalars;
+// scratch: sgp_cg_scratch_floats(L) floats.
+extern "C" int sgp_mvm_rows_groups_cg(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
+                                      int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src,
+                                      int64_t lds, int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0,
+                                      float *buf1, int Lv, int flags, const float *s, const float *noise, float *pAp,
+                                      float *scratch, sgp_stream_t stream)
+{
+    if (!s || !noise || !pAp || !scratch) return fail(SGP_EINVAL, "sgp_mvm_rows_groups_cg: null pointer");
+    if (lds != L || ldo != L || Lv != L || (flags & 4))
+        return fail(SGP_EINVAL, "sgp_mvm_rows_groups_cg: needs unpadded [N, L] blocks (lds = ldo = Lv = L)");
+    const CgEpilogue cg{s, noise, pAp, scratch};
+    return mvm_rows_groups_impl(slice_view, ent, seg_row, n_entries, groups, n_groups, src, lds, L, coeffs, k, out, ldo, buf0,
+                                buf1, Lv, flags, &cg, stream);
+}
+
+// One whole CG iteration on the production chain, enqueued by ONE call (a Python loop that issues the product and the
+// three sweeps one by one costs ~500 us of host time per iteration at N = 1M -- more than the 290 us the device needs):
+//   AP = s K P + noise P, pAp            (sgp_mvm_rows_groups_cg)
+//   alpha = rs / pAp; R -= alpha AP; rs_new, beta, done[it]      (sgp_cg_update_r; done[it] also copied to done_host[it])
+//   X += alpha P; P = R + beta P         (sgp_cg_direction_x)
+// alphas / betas / done: device [max_iter, L] / [max_iter, L] / [max_iter]; done_host: pinned host [max_iter] or NULL.
+// The caller synchronises on an event recorded after the call before it reads done_host[it].
+extern "C" int sgp_cg_iteration(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
+                                int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *coeffs, int k,
+                                float *buf0, float *buf1, int flags, float *X, float *R, float *P, float *AP, float *rs,
+                                float *pAp, const float *bnorm, const float *s, const float *noise, float tol,
+                                int criterion, int L, float *alphas, float *betas, int32_t *done, int32_t *done_host,
+                                int it, float *scratch, sgp_stream_t stream)
+{
+    SGP_RANGE("sgp_cg_iteration");
+    if (!slice_view || !X || !R || !P || !AP || !alphas || !betas || !done || it < 0)
+        return fail(SGP_EINVAL, "sgp_cg_iteration: bad argument");
+    const int64_t N = slice_view->N;
+    int rc = sgp_mvm_rows_groups_cg(slice_view, ent, seg_row, n_entries, groups, n_groups, P, L, L, coeffs, k, AP, L, buf0, buf1,
+                                    L, flags, s, noise, pAp, scratch, stream);
+    if (rc) return rc;
+    float *alpha = alphas + (size_t)it * L, *beta = betas + (size_t)it * L;
+    rc = sgp_cg_update_r(R, AP, rs, pAp, bnorm, tol, criterion, N, L, alpha, beta, done + it, scratch, stream);
+    if (rc) return rc;
+    if (done_host)
+        CUDA_TRY(cudaMemcpyAsync(done_host + it, done + it, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return sgp_cg_direction_x(P, R, X, alpha, beta, N, L, stream);
+}
+
+static int mvm_rows_groups_impl(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
+                                int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src,
+                                int64_t lds, int L, const float *coeffs, int k, float *out, int64_t ldo, float *buf0,
+                                float *buf1, int Lv, int flags, const CgEpilogue *cg, sgp_stream_t stream)
 {
     SGP_RANGE("sgp_mvm_rows_groups_ex");
     if (!slice_view) return fail(SGP_EINVAL, "sgp_mvm_rows_groups_ex: null view");
@@ -720,7 +786,13 @@ extern "C" int sgp_mvm_rows_groups_ex(const sgp_lattice_view *slice_view, const 
             CUDA_TRY(cudaEventRecord(join, side));
         }
     }
-    rc = sgp_slice(slice_view, in1 ? buf1 : buf0, Lv, out, ldo, L, stream);
+    const float *res = in1 ? buf1 : buf0;
+    if (cg && sgp_slice_ring_cg_supported(slice_view, res, Lv, out, ldo, src, lds)) {
+        rc = sgp_slice_ring_cg(slice_view, res, Lv, out, ldo, src, lds, cg->s, cg->noise, cg->pAp, cg->scratch, stream);
+    } else {
+        rc = sgp_slice(slice_view, res, Lv, out, ldo, L, stream);
+        if (cg && !rc) rc = sgp_cg_apply(out, src, cg->s, cg->noise, slice_view->N, L, cg->pAp, cg->scratch, stream);
+    }
     if (side) {
         cudaError_t e = cudaStreamWaitEvent(st, join, 0);
         cudaEventDestroy(fork);

@@ -151,11 +151,22 @@ __device__ __forceinline__ void slice_batch_pairs(const int4 *ep, int nreal, con
 // Persistent warps; warp w takes the tiles w, w + W, ... of P = ppp * passes points.  A tile's replay entries
 // ([P, d+1] {index, weight}: contiguous) arrive in the warp's ring by one bulk copy; in a pass the lanes are
 // (point, channel chunk): ppp = 32 / chunks points.
-template <int VEC, bool FAST, bool RAGGED>
-__global__ void __launch_bounds__(RING_THREADS)
+// EPI (the CG form, sgp_slice_ring_cg): the sweep that follows the product in a CG iteration -- AP = s * KP + noise * P,
+// pAp[l] = sum_n P * AP (sgp_cg_apply) -- runs in the epilogue: the point's row of P is read (coalesced), AP is stored
+// instead of KP, and the per-thread dot products are combined per CTA in a fixed order into epi.partial[blockIdx.x, :]
+// (a one-block second stage sums those).  Saves a launch and two passes over [N, L] per iteration.
+struct SliceEpilogue {
+    const float *p;          // P [N, ldp]: the operand of the product
+    int64_t ldp;
+    const float *s, *noise;  // device scalars
+    float *partial;          // [gridDim.x, L]
+};
+
+template <int VEC, bool FAST, bool RAGGED, bool EPI = false>
+__global__ void __launch_bounds__(RING_THREADS, EPI ? 3 : 0)   // (0 = unspecified: the plain form takes 80 registers by itself)
 sgp_slice_ring_kernel(const int2 *__restrict__ replay, const float *__restrict__ values, int64_t N, int dp1, int estride,
                       int L, int chunks, int ppp, int passes, int stages, uint32_t tile_stride, float divisor,
-                      float rdivisor, float *__restrict__ out, int64_t ldo, int L_out)
+                      float rdivisor, float *__restrict__ out, int64_t ldo, int L_out, SliceEpilogue epi)
 {
     extern __shared__ __align__(128) unsigned char ring_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -192,6 +203,10 @@ sgp_slice_ring_kernel(const int2 *__restrict__ replay, const float *__restrict__
     const int sub = lane / chunks;
     const int c0 = (lane - sub * chunks) * VEC;
     const bool lane_on = sub < ppp;
+    Vec<VEC> dot;
+    vec_zero(dot);
+    float epi_s = 0.0f, epi_noise = 0.0f;
+    if (EPI) { epi_s = __ldg(epi.s); epi_noise = __ldg(epi.noise); }
     pdl_wait();   // everything above read build-time tables only; the lattice values are the predecessor's output
 
     int s = 0;
@@ -225,7 +240,16 @@ sgp_slice_ring_kernel(const int2 *__restrict__ replay, const float *__restrict__
                     for (int k = 0; k < VEC; ++k) acc.v[k] = exact_div(acc.v[k], divisor, rdivisor);
                 }
                 float *orow = out + (p0 + lp) * ldo + c0;
-                if (RAGGED) {
+                if (EPI) {
+                    Vec<VEC> pv;   // (requesting it ahead of the row gathers measured slower: 16 more bytes of spills)
+                    pv.load_plain(epi.p + (p0 + lp) * epi.ldp + c0);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) {
+                        acc.v[k] = fmaf(epi_s, acc.v[k], epi_noise * pv.v[k]);
+                        dot.v[k] = fmaf(pv.v[k], acc.v[k], dot.v[k]);
+                    }
+                    acc.store(orow);   // read again by the next sweep: no streaming hint
+                } else if (RAGGED) {
 #pragma unroll
                     for (int k = 0; k < VEC; ++k)
                         if (c0 + k < L_out) __stcs(orow + k, acc.v[k]);
@@ -238,6 +262,20 @@ sgp_slice_ring_kernel(const int2 *__restrict__ replay, const float *__restrict__
         const int64_t tn = t + (int64_t)stages * W;
         if (lane == 0 && tn < n_tiles) issue(tn, s);
         if (++s == stages) { s = 0; phase ^= 1u; }
+    }
+    if (EPI) {
+        // per CTA and column: the threads' dot products in thread order (deterministic: the tile assignment is static)
+        __shared__ float s_dot[VEC][RING_THREADS];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) s_dot[k][threadIdx.x] = lane_on ? dot.v[k] : 0.0f;
+        __syncthreads();
+        if ((int)threadIdx.x < L) {
+            const int chunk = threadIdx.x / VEC, kk = threadIdx.x % VEC;
+            float t = 0.0f;
+            for (int w = 0; w < RING_WARPS; ++w)
+                for (int sb = 0; sb < ppp; ++sb) t += s_dot[kk][w * 32 + sb * chunks + chunk];
+            epi.partial[(int64_t)blockIdx.x * L + threadIdx.x] = t;
+        }
     }
 }
 
@@ -620,7 +658,7 @@ extern "C" int sgp_slice_ring(const sgp_lattice_view *lat, const float *values, 
         if (rc) return rc;                                                                                             \
         le = sgp_launch_pdl(sgp_slice_ring_kernel<VV, FF, RG>, dim3(rl.grid), dim3(RING_THREADS), rl.smem, st,         \
                             (const int2 *)lat->replay, values, lat->N, dp1, estride, L, chunks, ppp, passes, rl.stages, \
-                            rl.tile_stride, divisor, (float)rdivisor, out, ldo, L_out);                                \
+                            rl.tile_stride, divisor, (float)rdivisor, out, ldo, L_out, SliceEpilogue{});               \
     } while (0)
 #define SGP_SLICE_RING_V(VV)                                                                                           \
     do {                                                                                                               \
@@ -634,6 +672,60 @@ extern "C" int sgp_slice_ring(const sgp_lattice_view *lat, const float *values, 
 #undef SGP_SLICE_RING
     if (le != cudaSuccess) return fail(SGP_ECUDA, "launch of sgp_slice_ring_kernel failed: %s", cudaGetErrorString(le));
     return launch_ok("sgp_slice_ring_kernel");
+}
+
+// The CG form: out = s * slice(values) + noise * P, pAp[l] = sum_n P[n, l] * out[n, l] (sgp_cg_apply fused into the
+// slice).  16-byte vectors only: L % 4 == 0, out / P aligned with ldo, ldp % 4 == 0.  scratch: sgp_cg_scratch_floats(L).
+extern "C" int sgp_slice_ring_cg_supported(const sgp_lattice_view *lat, const float *values, int L, const float *out,
+                                           int64_t ldo, const float *P, int64_t ldp)
+{
+    auto al16 = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
+    return sgp_ring_slice_enabled() && sgp_slice_ring_supported(lat, values, L) && ring_vec(L, values) == 4 && al16(out) &&
+           al16(P) && ldo % 4 == 0 && ldp % 4 == 0 && ldo >= L && ldp >= L && L <= RING_THREADS;
+}
+
+extern "C" int sgp_slice_ring_cg(const sgp_lattice_view *lat, const float *values, int L, float *out, int64_t ldo,
+                                 const float *P, int64_t ldp, const float *s, const float *noise, float *pAp,
+                                 float *scratch, sgp_stream_t stream)
+{
+    SGP_RANGE("sgp_slice_ring_cg");
+    if (!lat || lat->N < 0 || lat->d < 1 || lat->d > SGP_MAX_DIM || L < 1) return fail(SGP_EINVAL, "sgp_slice_ring_cg: bad view");
+    if (!values || !out || !P || !s || !noise || !pAp || !scratch || !lat->replay)
+        return fail(SGP_EINVAL, "sgp_slice_ring_cg: null pointer");
+    if (lat->N == 0) return SGP_OK;
+    if (!sgp_slice_ring_cg_supported(lat, values, L, out, ldo, P, ldp))
+        return fail(SGP_EUNSUPPORTED, "sgp_slice_ring_cg: shape not supported");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunks = L / 4;
+    const int dp1 = lat->d + 1;
+    const int estride = lat->replay_stride > 0 ? lat->replay_stride : dp1;
+    int ppp = 0, passes = 0;
+    slice_geometry(estride, chunks, &ppp, &passes);
+    const int P_tile = ppp * passes;
+    const int64_t n_tiles = (lat->N + P_tile - 1) / P_tile;
+    const float divisor = sgp_slice_divisor(lat->d);
+    volatile float rdivisor = 1.0f / divisor;
+    RingLaunch rl;
+    int rc;
+    cudaError_t le = cudaSuccess;
+    SliceEpilogue epi{P, ldp, s, noise, scratch};
+#define SGP_SLICE_RING_CG(FF)                                                                                          \
+    do {                                                                                                               \
+        rc = ring_config(sgp_slice_ring_kernel<4, FF, false, true>, (uint32_t)P_tile * estride * 8u, n_tiles, 2,       \
+                         "SGP_SLICE_STAGES", &rl);                                                                     \
+        if (rc) return rc;                                                                                             \
+        if ((size_t)rl.grid * (size_t)L > sgp_cg_scratch_floats(L))                                                    \
+            return fail(SGP_EUNSUPPORTED, "sgp_slice_ring_cg: %u CTAs exceed the scratch", rl.grid);                   \
+        le = sgp_launch_pdl(sgp_slice_ring_kernel<4, FF, false, true>, dim3(rl.grid), dim3(RING_THREADS), rl.smem, st, \
+                            (const int2 *)lat->replay, values, lat->N, dp1, estride, L, chunks, ppp, passes, rl.stages, \
+                            rl.tile_stride, divisor, (float)rdivisor, out, ldo, L, epi);                               \
+    } while (0)
+    if (lat->fast) SGP_SLICE_RING_CG(true); else SGP_SLICE_RING_CG(false);
+#undef SGP_SLICE_RING_CG
+    if (le != cudaSuccess) return fail(SGP_ECUDA, "launch of sgp_slice_ring_kernel (CG form) failed: %s", cudaGetErrorString(le));
+    rc = launch_ok("sgp_slice_ring_kernel");
+    if (rc) return rc;
+    return sgp_cg_reduce_partials(scratch, (int)rl.grid, L, pAp, stream);
 }
 
 extern "C" int sgp_splat_ring_supported(const float *values, int L) { return ring_vec(L, values) != 0; }

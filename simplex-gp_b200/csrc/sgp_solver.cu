@@ -312,6 +312,110 @@ sgp_cg_direction_kernel(float *__restrict__ P, const float *__restrict__ R, cons
     }
 }
 
+// ---- the same iteration with the update of X deferred into the direction sweep -------------------------------------
+// X += alpha P reads P, which the direction sweep P <- R + beta P reads anyway: moving it there makes the update sweep
+// three passes over [N, L] (read R, AP; write R) and the direction sweep five (read R, P, X; write P, X) -- eight
+// instead of nine per iteration, same arithmetic in the same order.  The caller applies the last X += alpha P itself
+// when the iteration stops after an update.
+template <int V>
+__global__ void __launch_bounds__(CG_THREADS)
+sgp_cg_update_r_kernel(float *__restrict__ R, const float *__restrict__ AP, const float *__restrict__ rs,
+                       const float *__restrict__ pAp, int64_t total, int L, int active, int64_t per_block,
+                       float *__restrict__ alpha_out, float *__restrict__ partial)
+{
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.0f;
+    if (threadIdx.x < active) {
+        const int col = (threadIdx.x % (L / V)) * V;
+        float alpha[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) alpha[k] = __ldg(rs + col + k) / fmaxf(__ldg(pAp + col + k), 1e-30f);
+        if (blockIdx.x == 0 && threadIdx.x < L / V) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) alpha_out[col + k] = alpha[k];
+        }
+        const int64_t lo = (int64_t)blockIdx.x * per_block;
+        const int64_t hi = min(lo + per_block, total);
+        int64_t i = lo + threadIdx.x;
+        for (; i + (int64_t)(CG_UNROLL - 1) * active < hi; i += (int64_t)CG_UNROLL * active) {
+            CgVec<V> rv[CG_UNROLL], av[CG_UNROLL];
+#pragma unroll
+            for (int u = 0; u < CG_UNROLL; ++u) {
+                const int64_t q = (i + (int64_t)u * active) * V;
+                rv[u] = cg_load<V>(R + q); av[u] = cg_load<V>(AP + q);
+            }
+#pragma unroll
+            for (int u = 0; u < CG_UNROLL; ++u) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    rv[u].v[k] = fmaf(-alpha[k], av[u].v[k], rv[u].v[k]);
+                    acc[k] = fmaf(rv[u].v[k], rv[u].v[k], acc[k]);
+                }
+                cg_store<V>(R + (i + (int64_t)u * active) * V, rv[u]);
+            }
+        }
+        for (; i < hi; i += active) {
+            CgVec<V> rv = cg_load<V>(R + i * V);
+            const CgVec<V> av = cg_load<V>(AP + i * V);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                rv.v[k] = fmaf(-alpha[k], av.v[k], rv.v[k]);
+                acc[k] = fmaf(rv.v[k], rv.v[k], acc[k]);
+            }
+            cg_store<V>(R + i * V, rv);
+        }
+    }
+    cg_block_columns<V>(acc, active, L, partial);
+}
+
+template <int V>
+__global__ void __launch_bounds__(CG_THREADS)
+sgp_cg_direction_x_kernel(float *__restrict__ P, const float *__restrict__ R, float *__restrict__ X,
+                          const float *__restrict__ alpha, const float *__restrict__ beta, int64_t total, int L,
+                          int active, int64_t per_block)
+{
+    if (threadIdx.x >= active) return;
+    const int col = (threadIdx.x % (L / V)) * V;
+    float a[V], b[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { a[k] = __ldg(alpha + col + k); b[k] = __ldg(beta + col + k); }
+    const int64_t lo = (int64_t)blockIdx.x * per_block;
+    const int64_t hi = min(lo + per_block, total);
+    int64_t i = lo + threadIdx.x;
+    constexpr int U = V == 4 ? 2 : CG_UNROLL;
+    for (; i + (int64_t)(U - 1) * active < hi; i += (int64_t)U * active) {
+        CgVec<V> pv[U], rv[U], xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = (i + (int64_t)u * active) * V;
+            pv[u] = cg_load<V>(P + q); rv[u] = cg_load<V>(R + q); xv[u] = cg_load<V>(X + q);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = (i + (int64_t)u * active) * V;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                xv[u].v[k] = fmaf(a[k], pv[u].v[k], xv[u].v[k]);
+                pv[u].v[k] = fmaf(b[k], pv[u].v[k], rv[u].v[k]);
+            }
+            cg_store<V>(X + q, xv[u]);
+            cg_store<V>(P + q, pv[u]);
+        }
+    }
+    for (; i < hi; i += active) {
+        CgVec<V> pv = cg_load<V>(P + i * V), xv = cg_load<V>(X + i * V);
+        const CgVec<V> rv = cg_load<V>(R + i * V);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            xv.v[k] = fmaf(a[k], pv.v[k], xv.v[k]);
+            pv.v[k] = fmaf(b[k], pv.v[k], rv.v[k]);
+        }
+        cg_store<V>(X + i * V, xv);
+        cg_store<V>(P + i * V, pv);
+    }
+}
+
 static bool cg_aligned16(const void *a, const void *b) { return (((uintptr_t)a | (uintptr_t)b) & 15) == 0; }
 
 static int cg_check(int64_t N, int L, const void *a, const void *b, const void *scratch)
@@ -322,6 +426,14 @@ static int cg_check(int64_t N, int L, const void *a, const void *b, const void *
 }
 
 extern "C" size_t sgp_cg_scratch_floats(int L) { return (size_t)CG_MAX_BLOCKS * (size_t)(L > 0 ? L : 1); }
+
+// second stage alone: out[l] = sum_b partial[b, l] in a fixed order (used by the slice's CG epilogue, sgp_ring.cu)
+int sgp_cg_reduce_partials(const float *partial, int blocks, int L, float *out, sgp_stream_t stream)
+{
+    if (!partial || !out || blocks < 1 || L < 1 || L > CG_MAX_COLUMNS) return fail(SGP_EINVAL, "sgp_cg_reduce_partials: bad argument");
+    sgp_cg_reduce_kernel<<<1, CG_THREADS, 0, (cudaStream_t)stream>>>(partial, blocks, L, (CG_THREADS / L) * L, out);
+    return launch_ok("sgp_cg_reduce_kernel");
+}
 
 extern "C" int sgp_cg_apply(float *AP, const float *P, const float *s, const float *noise, int64_t N, int L,
                             float *pAp, float *scratch, sgp_stream_t stream)
@@ -380,4 +492,37 @@ extern "C" int sgp_cg_direction(float *P, const float *R, const float *beta, int
     if (g.vec == 4) sgp_cg_direction_kernel<4><<<g.blocks, CG_THREADS, 0, (cudaStream_t)stream>>>(P, R, beta, total, L, g.active, g.per_block);
     else sgp_cg_direction_kernel<1><<<g.blocks, CG_THREADS, 0, (cudaStream_t)stream>>>(P, R, beta, total, L, g.active, g.per_block);
     return launch_ok("sgp_cg_direction_kernel");
+}
+
+extern "C" int sgp_cg_update_r(float *R, const float *AP, float *rs, const float *pAp, const float *bnorm, float tol,
+                               int criterion, int64_t N, int L, float *alpha_out, float *beta_out, int32_t *done,
+                               float *scratch, sgp_stream_t stream)
+{
+    SGP_RANGE("sgp_cg_update_r");
+    int rc = cg_check(N, L, R, AP, scratch);
+    if (rc) return rc;
+    if (!rs || !pAp || !bnorm || !alpha_out || !beta_out || !done) return fail(SGP_EINVAL, "sgp_cg_update_r: null pointer");
+    if (criterion != SGP_CG_ALL_COLUMNS && criterion != SGP_CG_MEAN) return fail(SGP_EINVAL, "sgp_cg_update_r: unknown criterion %d", criterion);
+    const CgGeometry g = cg_geometry(N, L, cg_aligned16(R, AP));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = N * (int64_t)(L / g.vec);
+    if (g.vec == 4) sgp_cg_update_r_kernel<4><<<g.blocks, CG_THREADS, 0, st>>>(R, AP, rs, pAp, total, L, g.active, g.per_block, alpha_out, scratch);
+    else sgp_cg_update_r_kernel<1><<<g.blocks, CG_THREADS, 0, st>>>(R, AP, rs, pAp, total, L, g.active, g.per_block, alpha_out, scratch);
+    rc = launch_ok("sgp_cg_update_r_kernel");
+    if (rc) return rc;
+    sgp_cg_beta_kernel<<<1, CG_THREADS, 0, st>>>(scratch, g.blocks, L, g.active2, rs, bnorm, tol, criterion, beta_out, done);
+    return launch_ok("sgp_cg_beta_kernel");
+}
+
+extern "C" int sgp_cg_direction_x(float *P, const float *R, float *X, const float *alpha, const float *beta, int64_t N,
+                                  int L, sgp_stream_t stream)
+{
+    SGP_RANGE("sgp_cg_direction_x");
+    if (N < 1 || L < 1 || L > CG_MAX_COLUMNS || !P || !R || !X || !alpha || !beta)
+        return fail(SGP_EINVAL, "sgp_cg_direction_x: bad argument");
+    const CgGeometry g = cg_geometry(N, L, cg_aligned16(P, R) && cg_aligned16(X, X));
+    const int64_t total = N * (int64_t)(L / g.vec);
+    if (g.vec == 4) sgp_cg_direction_x_kernel<4><<<g.blocks, CG_THREADS, 0, (cudaStream_t)stream>>>(P, R, X, alpha, beta, total, L, g.active, g.per_block);
+    else sgp_cg_direction_x_kernel<1><<<g.blocks, CG_THREADS, 0, (cudaStream_t)stream>>>(P, R, X, alpha, beta, total, L, g.active, g.per_block);
+    return launch_ok("sgp_cg_direction_x_kernel");
 }

@@ -132,31 +132,88 @@ def _batched_cg_cuda(matmul: Callable, scale: torch.Tensor, shift: torch.Tensor,
     AP = torch.empty((N, L), dtype=torch.float32, device=dev) if lat is not None else None
     k = 0
     criterion = 1 if stop == "mean" else 0   # SGP_CG_MEAN / SGP_CG_ALL_COLUMNS
+    import os
+    fuse = os.environ.get("SGP_CG_FUSE", "1") != "0"   # 0: the sweep after the product as its own launch (experiments)
+    one_call = None
+    if lat is not None and fuse and (L % 4 == 0 or L <= 4):
+        one_call = _cg_one_call_setup(lat, op_coeffs, L)
+    if one_call is not None:
+        # the whole iteration (product, its epilogue sweep, update, direction) enqueued by ONE C call: issued piece by
+        # piece from Python an iteration costs ~500 us of host time at N = 1M, more than the ~290 us the device needs
+        import ctypes as C
+        v_out, ent, seg, n_ent, arr, coeffs_np, bufs = one_call
+        args_head = (C.byref(v_out), _ptr(ent), _ptr(seg), n_ent, arr, len(arr), _capi_fp(coeffs_np), coeffs_np.shape[0],
+                     _ptr(bufs[0]), _ptr(bufs[1]), 3, _ptr(X), _ptr(R), _ptr(P), _ptr(AP), _ptr(rs), _ptr(pAp), _ptr(bnorm),
+                     _ptr(s), _ptr(nz), float(tol), criterion, L, _ptr(alphas), _ptr(betas), _ptr(done),
+                     C.c_void_p(done_host.data_ptr()))
+        flags_np = done_host.numpy()
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            for it in range(max_iter):
+                _capi.check(lib.sgp_cg_iteration(*args_head, it, _ptr(scratch), st))
+                events[it & 1].record()
+                k = it + 1
+                if it > 0:
+                    events[(it - 1) & 1].synchronize()      # iteration it-1 finished long ago; iteration it is running
+                    if int(flags_np[it - 1]) and it >= min_iter:
+                        break
+        return X[:, :L0].contiguous(), alphas[:k, :L0].contiguous(), betas[:k, :L0].contiguous()
     with torch.cuda.device(dev):
         st = _stream_ptr(dev)
         for it in range(max_iter):
             if lat is not None:
-                lat.mvm(P, out=AP, coeffs=op_coeffs)
+                # the product and the sweep after it (AP = s K P + noise P, pAp = sum P * AP) in one call: the sweep runs
+                # in the slice's epilogue where the TMA-ring slice applies
+                if fuse:
+                    lat.mvm(P, out=AP, coeffs=op_coeffs, cg=(s, nz, pAp, scratch))
+                else:
+                    lat.mvm(P, out=AP, coeffs=op_coeffs)
+                    _capi.check(lib.sgp_cg_apply(_ptr(AP), _ptr(P), _ptr(s), _ptr(nz), N, L, _ptr(pAp), _ptr(scratch), st))
             else:
                 AP = matmul(P)
                 if AP.dtype != torch.float32 or not AP.is_contiguous() or AP.data_ptr() == P.data_ptr():
                     AP = AP.to(torch.float32).contiguous().clone()
-            _capi.check(lib.sgp_cg_apply(_ptr(AP), _ptr(P), _ptr(s), _ptr(nz), N, L, _ptr(pAp), _ptr(scratch), st))
-            _capi.check(lib.sgp_cg_update_ex(_ptr(X), _ptr(R), _ptr(P), _ptr(AP), _ptr(rs), _ptr(pAp), _ptr(bnorm),
-                                             float(tol), criterion, N, L, _ptr(alphas[it]), _ptr(betas[it]),
-                                             _ptr(done[it:]), _ptr(scratch), st))
+                _capi.check(lib.sgp_cg_apply(_ptr(AP), _ptr(P), _ptr(s), _ptr(nz), N, L, _ptr(pAp), _ptr(scratch), st))
+            # X += alpha P is deferred into the direction sweep (which reads P anyway): 8 passes over [N, L] per iteration
+            # instead of 9; when the loop stops after an update, the last alpha P is added here
+            _capi.check(lib.sgp_cg_update_r(_ptr(R), _ptr(AP), _ptr(rs), _ptr(pAp), _ptr(bnorm), float(tol), criterion,
+                                            N, L, _ptr(alphas[it]), _ptr(betas[it]), _ptr(done[it:]), _ptr(scratch), st))
             done_host[it:it + 1].copy_(done[it:it + 1], non_blocking=True)
             events[it & 1].record()
             k = it + 1
-            if it > 0:
+            stop_now = it + 1 >= max_iter
+            if it > 0 and not stop_now:
                 events[(it - 1) & 1].synchronize()      # iteration it-1 finished long ago; iteration it is running
-                if int(done_host[it - 1]) and it >= min_iter:   # (iteration it - 1 is the it-th one)
-                    break
-            if it + 1 < max_iter:
-                _capi.check(lib.sgp_cg_direction(_ptr(P), _ptr(R), _ptr(betas[it]), N, L, st))
-        else:
-            k = max_iter
+                stop_now = bool(int(done_host[it - 1])) and it >= min_iter   # (iteration it - 1 is the it-th one)
+            if stop_now:
+                X.addcmul_(P, alphas[it].unsqueeze(0))
+                break
+            _capi.check(lib.sgp_cg_direction_x(_ptr(P), _ptr(R), _ptr(X), _ptr(alphas[it]), _ptr(betas[it]), N, L, st))
     return X[:, :L0].contiguous(), alphas[:k, :L0].contiguous(), betas[:k, :L0].contiguous()
+
+
+def _capi_fp(a):
+    from .lattice import _fp
+    return _fp(a)
+
+
+def _cg_one_call_setup(lat, op_coeffs, L: int):
+    """Tables and private work buffers for ``sgp_cg_iteration`` on ``lat`` (production chain), or ``None`` when the
+    lattice has no row-sorted entries / blur groups."""
+    from .lattice import _coeffs_np
+    lazy = getattr(lat, "_lazy", None)
+    if lazy is not None:            # many products follow: build the postponed tables now
+        lazy["calls"] = lazy["after"]
+        lat._count_product()
+    if lat.rows is None or lat.groups is None or lat.N == 0 or lat.M == 0:
+        return None
+    c = lat.coeffs if op_coeffs is None else _coeffs_np(op_coeffs)
+    if c.shape[0] != 2 * lat.order + 1:
+        return None
+    v_out = lat._slice_view(L, True, lat.exact)
+    bufs = (torch.zeros((lat.M, L), dtype=torch.float32, device=lat.device),
+            torch.empty((lat.M, L), dtype=torch.float32, device=lat.device))
+    return v_out, lat.rows["ent"], lat.rows["seg_row"], lat.rows["n"], lat.groups["array"], c, bufs
 
 
 @torch.no_grad()

@@ -826,7 +826,7 @@ class Lattice:
     # ---- the MVM ------------------------------------------------------------------------------------
     def mvm(self, src: torch.Tensor, out: Optional[torch.Tensor] = None, coeffs=None,
             mode: int = _capi.SGP_SPLAT_AUTO, blur: str = "auto", sorted: Optional[bool] = None,
-            exact: Optional[bool] = None, after_splat=None, scratch=None, zero_flags: int = 0) -> torch.Tensor:
+            exact: Optional[bool] = None, after_splat=None, scratch=None, zero_flags: int = 0, cg=None) -> torch.Tensor:
         """``out[N, L] = slice(blur(splat(src[N, L])))`` on the built lattice.
 
         ``mode``   splat form: 0 auto (row-sorted segmented gather when built, else atomic scatter), 1 atomic scatter
@@ -845,7 +845,11 @@ class Lattice:
         ``scratch`` a private pair of ``[M, ceil4(L)]`` work buffers instead of the lattice's shared ones (a captured CUDA
                    graph owns its pair: its nodes must not point into buffers the lattice may free or reuse).
         ``zero_flags`` (production chain only, private scratch): 1 = ``scratch[0]`` holds zeros on entry, 2 = leave it
-                   zeroed on exit, overlapped with the slice (``sgp_mvm_rows_groups_ex``; what ``capture`` uses)."""
+                   zeroed on exit, overlapped with the slice (``sgp_mvm_rows_groups_ex``; what ``capture`` uses).
+        ``cg``     ``(s, noise, pAp, scratch)`` device tensors: also run the sweep that follows the product in a CG
+                   iteration -- ``out = s * K src + noise * src``, ``pAp[l] = sum_n src * out`` (``sgp_cg_apply``) -- folded
+                   into the slice's epilogue on the production chain (``sgp_mvm_rows_groups_cg``), as its own launch
+                   otherwise.  Needs ``L % 4 == 0`` or ``L <= 4`` (no channel padding) and contiguous blocks."""
         src = self._check_src(src)
         L = int(src.shape[1])
         c = self.coeffs if coeffs is None else _coeffs_np(coeffs)
@@ -891,8 +895,16 @@ class Lattice:
             flags = int(zero_flags)
             if zero_flags and scratch is None:
                 raise ValueError("zero_flags needs private scratch buffers")
+            if cg is not None and Lv == L and src.stride(0) == L and out.stride(0) == L:
+                cs, cn, cp, cscr = cg
+                with torch.cuda.device(self.device):
+                    check(lib.sgp_mvm_rows_groups_cg(C.byref(v_out), _ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]),
+                                                     self.rows["n"], arr, len(arr), _ptr(src), src.stride(0), L, _fp(c),
+                                                     c.shape[0], _ptr(out), out.stride(0), _ptr(buf0), _ptr(buf1), Lv,
+                                                     flags, _ptr(cs), _ptr(cn), _ptr(cp), _ptr(cscr), st))
+                return out
             with torch.cuda.device(self.device):
-                if Lv != L and self._pads_ragged_src():
+                if Lv != L and self._pads_ragged_src() and cg is None:
                     # ragged rows (L = 11: 44 bytes) can only be gathered channel by channel -- four times the L1
                     # wavefronts of 16-byte vectors, nine times per point; one coalesced copy into a zero-padded block
                     # is cheaper (config A, 11 columns: 236 -> 224 us per MVM; 187 us when the caller's block has 12)
@@ -909,6 +921,11 @@ class Lattice:
                                                   self.rows["n"], arr,
                                                   len(arr), _ptr(src), src.stride(0), L, _fp(c), c.shape[0], _ptr(out),
                                                   out.stride(0), _ptr(buf0), _ptr(buf1), Lv, st))
+                if cg is not None:      # padded lattice rows (ragged L): the sweep as its own launch
+                    if out.stride(0) != L or src.stride(0) != L:
+                        raise ValueError("cg needs contiguous [N, L] blocks")
+                    cs, cn, cp, cscr = cg
+                    check(lib.sgp_cg_apply(_ptr(out), _ptr(src), _ptr(cs), _ptr(cn), self.N, L, _ptr(cp), _ptr(cscr), st))
             return out
         if zero_flags:
             raise ValueError("zero_flags applies to the production chain only (row-sorted splat + blur groups)")
@@ -943,6 +960,11 @@ class Lattice:
                 v_out = self._view(self._table(use_sorted, use_groups), perm, exact) if use_sorted \
                     else self._slice_view(Lv, use_groups, exact)
                 check(lib.sgp_slice(C.byref(v_out), _ptr(res), Lv, _ptr(out), out.stride(0), L, st))
+            if cg is not None:      # not the production chain: the sweep as its own launch
+                if out.stride(0) != L or src.stride(0) != L:
+                    raise ValueError("cg needs contiguous [N, L] blocks")
+                cs, cn, cp, cscr = cg
+                check(lib.sgp_cg_apply(_ptr(out), _ptr(src), _ptr(cs), _ptr(cn), self.N, L, _ptr(cp), _ptr(cscr), st))
         return out
 
     def capture(self, src: torch.Tensor, out: torch.Tensor, **mvm_kwargs) -> "torch.cuda.CUDAGraph":

@@ -337,3 +337,38 @@ def test_cuda_cg_stopping_rules_match_tensor_expressions(sg, stop, min_iter):
         assert aa.shape[0] >= a1.shape[0]
     with pytest.raises(ValueError):
         gp.batched_cg(A, B, stop="median")
+
+
+@pytest.mark.parametrize("N,d,L", [(6000, 6, 16), (5000, 8, 12), (3000, 5, 8), (2500, 4, 11), (1200, 3, 1), (4100, 7, 32)])
+def test_cg_sweep_folded_into_the_slice(sg, N, d, L):
+    """Lattice.mvm(cg=...) -- AP = s K P + noise P and pAp = sum_n P * AP, the sweep in the ring slice's epilogue where
+    that kernel applies (L >= 12), as its own launch elsewhere -- against the product followed by the tensor expressions."""
+    import os
+    from simplex_gp_b200 import _capi
+    g = torch.Generator().manual_seed(N + L)
+    x = torch.randn(N, d, generator=g).cuda()
+    P = torch.randn(N, L, generator=g).cuda()
+    lat = sg.Lattice(x, [0.34608543, 1.0, 0.34608543])
+    s, noise = torch.tensor([0.7], device="cuda"), torch.tensor([0.3], device="cuda")
+    KP = lat.mvm(P)
+    want = 0.7 * KP + 0.3 * P
+    want_dot = (P.double() * want.double()).sum(0)
+    lib = _capi.lib()
+    scratch = torch.empty(int(lib.sgp_cg_scratch_floats(L)), device="cuda")
+    for force in ("0", "1"):
+        os.environ["SGP_RING_FORCE"] = force           # 1: the epilogue form also on narrow rows
+        try:
+            AP = torch.full((N, L), float("nan"), device="cuda")
+            pAp = torch.full((L,), float("nan"), device="cuda")
+            lat.mvm(P, out=AP, cg=(s, noise, pAp, scratch))
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("SGP_RING_FORCE")
+        assert float((AP - want).norm() / want.norm()) < 1e-6
+        assert float(((pAp.double() - want_dot) / want_dot.abs().clamp_min(1e-12)).abs().max()) < 1e-4
+    # plain chain (atomic splat, per-axis blur): the sweep as its own launch
+    AP = torch.empty((N, L), device="cuda")
+    pAp = torch.empty((L,), device="cuda")
+    lat.mvm(P, out=AP, mode=1, blur="axis", cg=(s, noise, pAp, scratch))
+    assert float((AP - want).norm() / want.norm()) < 1e-5
+    assert float(((pAp.double() - want_dot) / want_dot.abs().clamp_min(1e-12)).abs().max()) < 1e-4
