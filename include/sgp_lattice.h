@@ -353,10 +353,13 @@ int sgp_mvm_rows_groups(const sgp_lattice_view *slice_view, const int32_t *ent, 
  * private buffers (Lattice.capture) replays without ever waiting for the memset.
  * SGP_MVM_SRC_PADDED -- src has Lv columns (lds >= Lv; columns L..Lv-1 zero) while out has L: what a caller passes after
  * copying a ragged block (L = 11: the reference's training block [y | 10 probes]) into a zero-padded one, so that the
- * splat gathers 16-byte vectors (config A with 11 columns: 236 -> 224 us per MVM including the copy). */
+ * splat gathers 16-byte vectors (config A with 11 columns: 236 -> 200 us per MVM including the copy, sgp_pad_columns). */
 /* The splat stage of that chain alone: sgp_splat_rows without its memset -- `values` must hold zeros on entry. */
 int sgp_mvm_stage_splat_prezeroed(const int32_t *ent, const int32_t *seg_row, int64_t n_entries, int64_t N, int64_t M,
                                   const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream);
+/* The zero-padded copy SGP_MVM_SRC_PADDED refers to: dst[n, 0..Lv) = src[n, 0..L), then zeros.  Lv % 4 == 0, dst 16-byte
+ * aligned, ldd % 4 == 0. */
+int sgp_pad_columns(const float *src, int64_t lds, int L, float *dst, int64_t ldd, int Lv, int64_t N, sgp_stream_t stream);
 #define SGP_MVM_PREZEROED 1
 #define SGP_MVM_ZERO_AFTER 2
 #define SGP_MVM_SRC_PADDED 4

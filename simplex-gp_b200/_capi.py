@@ -31,7 +31,7 @@ SYMBOLS = [
     "sgp_remap_replay",
     "sgp_blur_groups_channel_block", "sgp_blur_groups", "sgp_mvm_rows_groups", "sgp_mvm_rows_groups_ex", "sgp_mvm_stage_splat_prezeroed", "sgp_sort_points_workspace_bytes", "sgp_sort_points",
     "sgp_permute_replay", "sgp_permute_replay_padded", "sgp_rowsort_workspace_bytes", "sgp_rowsort_padded", "sgp_build_rowsorted",
-    "sgp_splat_rows", "sgp_cg_scratch_floats", "sgp_cg_apply", "sgp_cg_update", "sgp_cg_update_ex", "sgp_cg_direction", "sgp_cg_update_r", "sgp_cg_direction_x", "sgp_mvm_rows_groups_cg", "sgp_slice_ring_cg", "sgp_slice_ring_cg_supported", "sgp_cg_iteration",
+    "sgp_splat_rows", "sgp_cg_scratch_floats", "sgp_cg_apply", "sgp_cg_update", "sgp_cg_update_ex", "sgp_cg_direction", "sgp_cg_update_r", "sgp_cg_direction_x", "sgp_mvm_rows_groups_cg", "sgp_slice_ring_cg", "sgp_slice_ring_cg_supported", "sgp_cg_iteration", "sgp_pad_columns",
     "sgp_ring_enabled", "sgp_ring_splat_enabled", "sgp_ring_slice_enabled", "sgp_splat_ring_supported", "sgp_slice_ring_supported", "sgp_splat_rows_ring", "sgp_slice_ring",
     "sgp_hash_append_keys", "sgp_count_appended", "sgp_number_appended",
     "sgp_filter_workspace_bytes", "sgp_filter_host_workspace_bytes", "sgp_filter", "sgp_filter_host",
@@ -212,6 +212,8 @@ def lib() -> C.CDLL:
     L.sgp_mvm_rows_groups_cg.restype = i32
     L.sgp_mvm_rows_groups_cg.argtypes = [pv, vp, vp, i64, C.POINTER(BlurGroup), i32, vp, i64, i32, fp, i32, vp, i64, vp, vp, i32,
                                          i32, vp, vp, vp, vp, vp]
+    L.sgp_pad_columns.restype = i32
+    L.sgp_pad_columns.argtypes = [vp, i64, i32, vp, i64, i32, i64, vp]
     L.sgp_cg_iteration.restype = i32
     L.sgp_cg_iteration.argtypes = [pv, vp, vp, i64, C.POINTER(BlurGroup), i32, fp, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp,
                                    vp, vp, C.c_float, i32, i32, vp, vp, vp, vp, i32, vp, vp]

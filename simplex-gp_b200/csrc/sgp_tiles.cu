@@ -382,6 +382,38 @@ extern "C" int sgp_permute_replay_padded(const int32_t *replay, const uint32_t *
     return launch_ok("sgp_permute_replay_padded_kernel");
 }
 
+// dst[n, 0..Lv) = src[n, 0..L) followed by zeros (Lv % 4 == 0, dst 16-byte aligned with ldd % 4 == 0): the zero-padded
+// copy of a ragged right-hand-side block that lets the splat gather 16-byte vectors (SGP_MVM_SRC_PADDED).  One thread
+// per 16-byte piece of dst: coalesced scalar reads of the contiguous source rows, one vector store.
+__global__ void __launch_bounds__(256)
+sgp_pad_columns_kernel(const float *__restrict__ src, int64_t lds, int L, float *__restrict__ dst, int64_t ldd, int Lv, int64_t N)
+{
+    const int pieces = Lv >> 2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * pieces) return;
+    const int64_t n = t / pieces;
+    const int c = (int)(t - n * pieces) << 2;
+    const float *s = src + n * lds + c;
+    float4 v;
+    v.x = c + 0 < L ? __ldcs(s + 0) : 0.0f;
+    v.y = c + 1 < L ? __ldcs(s + 1) : 0.0f;
+    v.z = c + 2 < L ? __ldcs(s + 2) : 0.0f;
+    v.w = c + 3 < L ? __ldcs(s + 3) : 0.0f;
+    *(float4 *)(dst + n * ldd + c) = v;
+}
+
+extern "C" int sgp_pad_columns(const float *src, int64_t lds, int L, float *dst, int64_t ldd, int Lv, int64_t N,
+                               sgp_stream_t stream)
+{
+    if (N == 0) return SGP_OK;
+    if (!src || !dst || N < 0 || L < 1 || Lv < L || Lv % 4 != 0 || lds < L || ldd < Lv || ldd % 4 != 0 ||
+        ((uintptr_t)dst & 15) != 0)
+        return fail(SGP_EINVAL, "sgp_pad_columns: bad argument");
+    const int64_t work = N * (int64_t)(Lv / 4);
+    sgp_pad_columns_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, L, dst, ldd, Lv, N);
+    return launch_ok("sgp_pad_columns_kernel");
+}
+
 // ------------------------------------------------------------------------------------
 // Row-sorted splat ("segmented gather").  The point-vertices are sorted once per lattice by the lattice row they
 // touch (stable radix sort: within a row they stay in point-vertex order, the reference's accumulation order).  A

@@ -907,9 +907,9 @@ class Lattice:
                 if Lv != L and self._pads_ragged_src() and cg is None:
                     # ragged rows (L = 11: 44 bytes) can only be gathered channel by channel -- four times the L1
                     # wavefronts of 16-byte vectors, nine times per point; one coalesced copy into a zero-padded block
-                    # is cheaper (config A, 11 columns: 236 -> 224 us per MVM; 187 us when the caller's block has 12)
+                    # is cheaper (config A, 11 columns: 236 -> 200 us per MVM; 181 us when the caller's block has 12)
                     pad = scratch[2] if (scratch is not None and len(scratch) > 2) else self._src_pad(Lv)
-                    pad[:, :L].copy_(src)
+                    check(lib.sgp_pad_columns(_ptr(src), src.stride(0), L, _ptr(pad), pad.stride(0), Lv, self.N, st))
                     src, flags = pad, flags | 4      # SGP_MVM_SRC_PADDED
                 if flags:
                     check(lib.sgp_mvm_rows_groups_ex(C.byref(v_out), _ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]),
