@@ -588,12 +588,12 @@ def run_ours(args, w):
         lib = _capi.lib()
         # as Lattice.mvm: lattice rows padded to a multiple of four channels, ragged right-hand sides through a
         # zero-padded copy where that pays
-        Lv = (L + 3) // 4 * 4 if (mode == _capi.MODE_ROWS and L > 4) else L
+        Lv = lat.lattice_width(L) if mode == _capi.MODE_ROWS else L
         buf0, buf1 = lat._scratch(Lv)
-        pad_src = Lv != L and lat._pads_ragged_src()
+        pad_src = mode == _capi.MODE_ROWS and L > 4 and L % 4 != 0 and lat._pads_ragged_src()
         Vs_pad = None
         if pad_src:
-            Vs_pad = [torch.zeros((N, Lv), dtype=torch.float32, device=dev) for _ in Vs]
+            Vs_pad = [torch.zeros((N, (L + 3) // 4 * 4), dtype=torch.float32, device=dev) for _ in Vs]
             for vp_, v_ in zip(Vs_pad, Vs):
                 vp_[:, :L].copy_(v_)
         cnp = lat.coeffs

@@ -351,7 +351,8 @@ int sgp_mvm_rows_groups(const sgp_lattice_view *slice_view, const int32_t *ent, 
  * odd number of group stages it is zeroed on an internal side stream while the slice runs (a parallel branch when the
  * call is captured into a CUDA graph), with an even number after the slice.  A graph captured with both flags on
  * private buffers (Lattice.capture) replays without ever waiting for the memset.
- * SGP_MVM_SRC_PADDED -- src has Lv columns (lds >= Lv; columns L..Lv-1 zero) while out has L: what a caller passes after
+ * SGP_MVM_SRC_PADDED -- src has L rounded up to a multiple of 4 columns (lds >= that; the extra columns zero) while out
+ * has L: what a caller passes after
  * copying a ragged block (L = 11: the reference's training block [y | 10 probes]) into a zero-padded one, so that the
  * splat gathers 16-byte vectors (config A with 11 columns: 236 -> 200 us per MVM including the copy, sgp_pad_columns). */
 /* The splat stage of that chain alone: sgp_splat_rows without its memset -- `values` must hold zeros on entry. */
@@ -359,6 +360,8 @@ int sgp_mvm_stage_splat_prezeroed(const int32_t *ent, const int32_t *seg_row, in
                                   const float *src, int64_t lds, int L_src, float *values, int L, sgp_stream_t stream);
 /* The zero-padded copy SGP_MVM_SRC_PADDED refers to: dst[n, 0..Lv) = src[n, 0..L), then zeros.  Lv % 4 == 0, dst 16-byte
  * aligned, ldd % 4 == 0. */
+/* Lv may exceed L rounded up to a multiple of 4: 12 (or 9-11) columns on 16-channel lattice rows keep every 64-byte row
+ * gather inside one 128-byte line (config A: 181 -> see DESIGN.md section 4); splat and slice then leave the spare lanes idle. */
 int sgp_pad_columns(const float *src, int64_t lds, int L, float *dst, int64_t ldd, int Lv, int64_t N, sgp_stream_t stream);
 #define SGP_MVM_PREZEROED 1
 #define SGP_MVM_ZERO_AFTER 2
@@ -370,7 +373,8 @@ int sgp_mvm_rows_groups_ex(const sgp_lattice_view *slice_view, const int32_t *en
 /* One CG iteration's product AND the sweep that follows it (sgp_cg_apply below): out = s*K*src + noise*src,
  * pAp[l] = sum_n src[n,l]*out[n,l].  With the TMA-ring slice the sweep runs in the slice's epilogue (the point's row of
  * src is read there, s*K*src + noise*src is what gets stored, per-CTA partial dot products are summed by a one-block
- * second stage); otherwise the slice is followed by sgp_cg_apply.  Unpadded blocks only: lds = ldo = Lv = L; s, noise:
+ * second stage); otherwise the slice is followed by sgp_cg_apply.  Contiguous blocks only: lds = ldo = L, and Lv = L or
+ * (L % 4 == 0) a multiple of 4 above it -- 12 columns on 16-channel lattice rows, see sgp_mvm_rows_groups_ex; s, noise:
  * device scalars; pAp: device [L]; scratch: device [sgp_cg_scratch_floats(L)]; flags: SGP_MVM_PREZEROED / ZERO_AFTER. */
 int sgp_mvm_rows_groups_cg(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row,
                            int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *src, int64_t lds,
@@ -378,9 +382,10 @@ int sgp_mvm_rows_groups_cg(const sgp_lattice_view *slice_view, const int32_t *en
                            int flags, const float *s, const float *noise, float *pAp, float *scratch, sgp_stream_t stream);
 /* The slice of that chain alone, and whether it applies to a shape (16-byte vectors, ring slice selected). */
 int sgp_slice_ring_cg_supported(const sgp_lattice_view *lat, const float *values, int L, const float *out, int64_t ldo,
-                                const float *P, int64_t ldp);
-int sgp_slice_ring_cg(const sgp_lattice_view *lat, const float *values, int L, float *out, int64_t ldo, const float *P,
-                      int64_t ldp, const float *s, const float *noise, float *pAp, float *scratch, sgp_stream_t stream);
+                                int L_out, const float *P, int64_t ldp);
+int sgp_slice_ring_cg(const sgp_lattice_view *lat, const float *values, int L, float *out, int64_t ldo, int L_out,
+                      const float *P, int64_t ldp, const float *s, const float *noise, float *pAp, float *scratch,
+                      sgp_stream_t stream);
 
 /* ---- stage 5: lengthscale-gradient pass (bilateral_kernel.py:97-124) -------------------
  *
@@ -440,13 +445,13 @@ int sgp_cg_direction_x(float *P, const float *R, float *X, const float *alpha, c
 /* One whole CG iteration on the production chain (row-sorted splat -> blur groups -> slice with the CG epilogue ->
  * sgp_cg_update_r -> sgp_cg_direction_x) enqueued by one call; iteration `it` writes alphas[it, :], betas[it, :],
  * done[it] and copies done[it] to done_host[it] (pinned host memory, may be NULL) on the stream.  Blocks are unpadded
- * [N, L] (L % 4 == 0 or L <= 4 for the lattice side); buf0 / buf1: [M, L] work buffers; flags as sgp_mvm_rows_groups_ex;
+ * [N, L] (L % 4 == 0 or L <= 4 for the lattice side); buf0 / buf1: [M, Lv] work buffers; flags as sgp_mvm_rows_groups_ex;
  * X is complete after every call (the deferred X += alpha P is part of it). */
 int sgp_cg_iteration(const sgp_lattice_view *slice_view, const int32_t *ent, const int32_t *seg_row, int64_t n_entries,
                      const sgp_blur_group *groups, int n_groups, const float *coeffs, int k, float *buf0, float *buf1,
                      int flags, float *X, float *R, float *P, float *AP, float *rs, float *pAp, const float *bnorm,
-                     const float *s, const float *noise, float tol, int criterion, int L, float *alphas, float *betas,
-                     int32_t *done, int32_t *done_host, int it, float *scratch, sgp_stream_t stream);
+                     const float *s, const float *noise, float tol, int criterion, int L, int Lv, float *alphas,
+                     float *betas, int32_t *done, int32_t *done_host, int it, float *scratch, sgp_stream_t stream);
 
 /* ---- row-sorted splat ("segmented gather") -------------------------------------------------
  * The point-vertices sorted by lattice row, point-vertex order within a row (the reference's accumulation order),

@@ -216,11 +216,11 @@ def lib() -> C.CDLL:
     L.sgp_pad_columns.argtypes = [vp, i64, i32, vp, i64, i32, i64, vp]
     L.sgp_cg_iteration.restype = i32
     L.sgp_cg_iteration.argtypes = [pv, vp, vp, i64, C.POINTER(BlurGroup), i32, fp, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp,
-                                   vp, vp, C.c_float, i32, i32, vp, vp, vp, vp, i32, vp, vp]
+                                   vp, vp, C.c_float, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]
     L.sgp_slice_ring_cg_supported.restype = i32
-    L.sgp_slice_ring_cg_supported.argtypes = [pv, vp, i32, vp, i64, vp, i64]
+    L.sgp_slice_ring_cg_supported.argtypes = [pv, vp, i32, vp, i64, i32, vp, i64]
     L.sgp_slice_ring_cg.restype = i32
-    L.sgp_slice_ring_cg.argtypes = [pv, vp, i32, vp, i64, vp, i64, vp, vp, vp, vp, vp]
+    L.sgp_slice_ring_cg.argtypes = [pv, vp, i32, vp, i64, i32, vp, i64, vp, vp, vp, vp, vp]
     L.sgp_sort_points_workspace_bytes.restype = sz
     L.sgp_sort_points_workspace_bytes.argtypes = [i64]
     L.sgp_sort_points.restype = i32

@@ -679,7 +679,8 @@ extern "C" int sgp_blur_groups(const sgp_blur_group *groups, int n_groups, int64
 //        capture, where it becomes a parallel branch of the graph); with an even number the slice itself reads buf0 and
 //        the zeroing follows it.  Replaying a graph captured with both flags keeps the 25.6 MB memset of the metric
 //        shape off the critical path of every product.
-//        SGP_MVM_SRC_PADDED (4) src has Lv columns (the caller's ragged block copied into a zero-padded one).
+//        SGP_MVM_SRC_PADDED (4) src has L rounded up to a multiple of 4 columns (the caller's ragged block copied into a
+//        zero-padded one).
 struct CgEpilogue {          // sgp_mvm_rows_groups_cg: the sweep after the product, folded into the slice where possible
     const float *s, *noise;
     float *pAp, *scratch;
@@ -710,8 +711,8 @@ extern "C" int sgp_mvm_rows_groups_cg(const sgp_lattice_view *slice_view, const 
                                       float *scratch, sgp_stream_t stream)
 {
     if (!s || !noise || !pAp || !scratch) return fail(SGP_EINVAL, "sgp_mvm_rows_groups_cg: null pointer");
-    if (lds != L || ldo != L || Lv != L || (flags & 4))
-        return fail(SGP_EINVAL, "sgp_mvm_rows_groups_cg: needs unpadded [N, L] blocks (lds = ldo = Lv = L)");
+    if (lds != L || ldo != L || (flags & 4) || (Lv != L && (L % 4 != 0 || Lv % 4 != 0 || Lv < L)))
+        return fail(SGP_EINVAL, "sgp_mvm_rows_groups_cg: needs contiguous [N, L] blocks (lds = ldo = L) and Lv = L or, for L % 4 == 0, a multiple of 4 above it");
     const CgEpilogue cg{s, noise, pAp, scratch};
     return mvm_rows_groups_impl(slice_view, ent, seg_row, n_entries, groups, n_groups, src, lds, L, coeffs, k, out, ldo, buf0,
                                 buf1, Lv, flags, &cg, stream);
@@ -728,15 +729,15 @@ extern "C" int sgp_cg_iteration(const sgp_lattice_view *slice_view, const int32_
                                 int64_t n_entries, const sgp_blur_group *groups, int n_groups, const float *coeffs, int k,
                                 float *buf0, float *buf1, int flags, float *X, float *R, float *P, float *AP, float *rs,
                                 float *pAp, const float *bnorm, const float *s, const float *noise, float tol,
-                                int criterion, int L, float *alphas, float *betas, int32_t *done, int32_t *done_host,
-                                int it, float *scratch, sgp_stream_t stream)
+                                int criterion, int L, int Lv, float *alphas, float *betas, int32_t *done,
+                                int32_t *done_host, int it, float *scratch, sgp_stream_t stream)
 {
     SGP_RANGE("sgp_cg_iteration");
     if (!slice_view || !X || !R || !P || !AP || !alphas || !betas || !done || it < 0)
         return fail(SGP_EINVAL, "sgp_cg_iteration: bad argument");
     const int64_t N = slice_view->N;
     int rc = sgp_mvm_rows_groups_cg(slice_view, ent, seg_row, n_entries, groups, n_groups, P, L, L, coeffs, k, AP, L, buf0, buf1,
-                                    L, flags, s, noise, pAp, scratch, stream);
+                                    Lv, flags, s, noise, pAp, scratch, stream);
     if (rc) return rc;
     float *alpha = alphas + (size_t)it * L, *beta = betas + (size_t)it * L;
     rc = sgp_cg_update_r(R, AP, rs, pAp, bnorm, tol, criterion, N, L, alpha, beta, done + it, scratch, stream);
@@ -753,12 +754,13 @@ static int mvm_rows_groups_impl(const sgp_lattice_view *slice_view, const int32_
 {
     SGP_RANGE("sgp_mvm_rows_groups_ex");
     if (!slice_view) return fail(SGP_EINVAL, "sgp_mvm_rows_groups_ex: null view");
-    if (Lv < L || (Lv != L && Lv % 4 != 0)) return fail(SGP_EINVAL, "sgp_mvm_rows_groups_ex: Lv must be L or L rounded up to a multiple of 4");
+    if (Lv < L || (Lv != L && Lv % 4 != 0)) return fail(SGP_EINVAL, "sgp_mvm_rows_groups_ex: Lv must be L or a multiple of 4 above it");
     cudaStream_t st = (cudaStream_t)stream;
-    // SGP_MVM_SRC_PADDED (4): src is a zero-padded copy with Lv columns (lds >= Lv) of the caller's L-column block, so the
+    // SGP_MVM_SRC_PADDED (4): src is a zero-padded copy with ceil4(L) columns (lds >= that) of the caller's L-column block, so the
     // splat gathers 16-byte vectors instead of reading ragged rows channel by channel; out keeps its L columns
-    if ((flags & 4) && lds < Lv) return fail(SGP_EINVAL, "sgp_mvm_rows_groups_ex: SGP_MVM_SRC_PADDED needs lds >= Lv");
-    const int L_src = (flags & 4) ? Lv : L;
+    const int L_src = (flags & 4) ? (L + 3) / 4 * 4 : L;
+    if ((flags & 4) && (lds < L_src || Lv < L_src))
+        return fail(SGP_EINVAL, "sgp_mvm_rows_groups_ex: SGP_MVM_SRC_PADDED needs lds >= L rounded up to a multiple of 4 and Lv >= that");
     int rc = (flags & 1) ? sgp_splat_rows_prezeroed(ent, seg_row, n_entries, slice_view->N, slice_view->M, src, lds, L_src, buf0, Lv, stream)
                          : sgp_splat_rows(ent, seg_row, n_entries, slice_view->N, slice_view->M, src, lds, L_src, buf0, Lv, stream);
     if (rc) return rc;
@@ -787,8 +789,8 @@ static int mvm_rows_groups_impl(const sgp_lattice_view *slice_view, const int32_
         }
     }
     const float *res = in1 ? buf1 : buf0;
-    if (cg && sgp_slice_ring_cg_supported(slice_view, res, Lv, out, ldo, src, lds)) {
-        rc = sgp_slice_ring_cg(slice_view, res, Lv, out, ldo, src, lds, cg->s, cg->noise, cg->pAp, cg->scratch, stream);
+    if (cg && sgp_slice_ring_cg_supported(slice_view, res, Lv, out, ldo, L, src, lds)) {
+        rc = sgp_slice_ring_cg(slice_view, res, Lv, out, ldo, L, src, lds, cg->s, cg->noise, cg->pAp, cg->scratch, stream);
     } else {
         rc = sgp_slice(slice_view, res, Lv, out, ldo, L, stream);
         if (cg && !rc) rc = sgp_cg_apply(out, src, cg->s, cg->noise, slice_view->N, L, cg->pAp, cg->scratch, stream);
@@ -811,7 +813,7 @@ extern "C" int sgp_mvm_rows_groups(const sgp_lattice_view *slice_view, const int
 {
     SGP_RANGE("sgp_mvm_rows_groups");
     if (!slice_view) return fail(SGP_EINVAL, "sgp_mvm_rows_groups: null view");
-    if (Lv < L || (Lv != L && Lv % 4 != 0)) return fail(SGP_EINVAL, "sgp_mvm_rows_groups: Lv must be L or L rounded up to a multiple of 4");
+    if (Lv < L || (Lv != L && Lv % 4 != 0)) return fail(SGP_EINVAL, "sgp_mvm_rows_groups: Lv must be L or a multiple of 4 above it");
     int rc = sgp_splat_rows(ent, seg_row, n_entries, slice_view->N, slice_view->M, src, lds, L, buf0, Lv, stream);
     if (rc) return rc;
     int in1 = 0;

@@ -202,7 +202,7 @@ sgp_slice_ring_kernel(const int2 *__restrict__ replay, const float *__restrict__
     }
     const int sub = lane / chunks;
     const int c0 = (lane - sub * chunks) * VEC;
-    const bool lane_on = sub < ppp;
+    const bool lane_on = sub < ppp && (RAGGED || c0 < L_out);   // (out narrower than the lattice rows by whole vectors)
     Vec<VEC> dot;
     vec_zero(dot);
     float epi_s = 0.0f, epi_noise = 0.0f;
@@ -269,12 +269,12 @@ sgp_slice_ring_kernel(const int2 *__restrict__ replay, const float *__restrict__
 #pragma unroll
         for (int k = 0; k < VEC; ++k) s_dot[k][threadIdx.x] = lane_on ? dot.v[k] : 0.0f;
         __syncthreads();
-        if ((int)threadIdx.x < L) {
+        if ((int)threadIdx.x < L_out) {
             const int chunk = threadIdx.x / VEC, kk = threadIdx.x % VEC;
             float t = 0.0f;
             for (int w = 0; w < RING_WARPS; ++w)
                 for (int sb = 0; sb < ppp; ++sb) t += s_dot[kk][w * 32 + sb * chunks + chunk];
-            epi.partial[(int64_t)blockIdx.x * L + threadIdx.x] = t;
+            epi.partial[(int64_t)blockIdx.x * L_out + threadIdx.x] = t;
         }
     }
 }
@@ -638,7 +638,7 @@ extern "C" int sgp_slice_ring(const sgp_lattice_view *lat, const float *values, 
     if (!sgp_slice_ring_supported(lat, values, L)) return fail(SGP_EUNSUPPORTED, "sgp_slice_ring: shape not supported");
     cudaStream_t st = (cudaStream_t)stream;
     const int vec = ring_vec(L, values);
-    const bool ragged = vec > 1 && !(L_out == L && ldo % vec == 0 && ((uintptr_t)out % (4 * vec)) == 0);
+    const bool ragged = vec > 1 && !(L_out % vec == 0 && ldo % vec == 0 && ((uintptr_t)out % (4 * vec)) == 0);
     if (vec == 1 && L_out != L) return fail(SGP_EUNSUPPORTED, "sgp_slice_ring: L_out < L needs vectorisable lattice rows");
     const int chunks = L / vec;
     const int dp1 = lat->d + 1;
@@ -677,15 +677,16 @@ extern "C" int sgp_slice_ring(const sgp_lattice_view *lat, const float *values, 
 // The CG form: out = s * slice(values) + noise * P, pAp[l] = sum_n P[n, l] * out[n, l] (sgp_cg_apply fused into the
 // slice).  16-byte vectors only: L % 4 == 0, out / P aligned with ldo, ldp % 4 == 0.  scratch: sgp_cg_scratch_floats(L).
 extern "C" int sgp_slice_ring_cg_supported(const sgp_lattice_view *lat, const float *values, int L, const float *out,
-                                           int64_t ldo, const float *P, int64_t ldp)
+                                           int64_t ldo, int L_out, const float *P, int64_t ldp)
 {
     auto al16 = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
     return sgp_ring_slice_enabled() && sgp_slice_ring_supported(lat, values, L) && ring_vec(L, values) == 4 && al16(out) &&
-           al16(P) && ldo % 4 == 0 && ldp % 4 == 0 && ldo >= L && ldp >= L && L <= RING_THREADS;
+           al16(P) && ldo % 4 == 0 && ldp % 4 == 0 && L_out >= 4 && L_out <= L && L_out % 4 == 0 && ldo >= L_out &&
+           ldp >= L_out && L_out <= RING_THREADS;
 }
 
 extern "C" int sgp_slice_ring_cg(const sgp_lattice_view *lat, const float *values, int L, float *out, int64_t ldo,
-                                 const float *P, int64_t ldp, const float *s, const float *noise, float *pAp,
+                                 int L_out, const float *P, int64_t ldp, const float *s, const float *noise, float *pAp,
                                  float *scratch, sgp_stream_t stream)
 {
     SGP_RANGE("sgp_slice_ring_cg");
@@ -693,7 +694,7 @@ extern "C" int sgp_slice_ring_cg(const sgp_lattice_view *lat, const float *value
     if (!values || !out || !P || !s || !noise || !pAp || !scratch || !lat->replay)
         return fail(SGP_EINVAL, "sgp_slice_ring_cg: null pointer");
     if (lat->N == 0) return SGP_OK;
-    if (!sgp_slice_ring_cg_supported(lat, values, L, out, ldo, P, ldp))
+    if (!sgp_slice_ring_cg_supported(lat, values, L, out, ldo, L_out, P, ldp))
         return fail(SGP_EUNSUPPORTED, "sgp_slice_ring_cg: shape not supported");
     cudaStream_t st = (cudaStream_t)stream;
     const int chunks = L / 4;
@@ -714,18 +715,18 @@ extern "C" int sgp_slice_ring_cg(const sgp_lattice_view *lat, const float *value
         rc = ring_config(sgp_slice_ring_kernel<4, FF, false, true>, (uint32_t)P_tile * estride * 8u, n_tiles, 2,       \
                          "SGP_SLICE_STAGES", &rl);                                                                     \
         if (rc) return rc;                                                                                             \
-        if ((size_t)rl.grid * (size_t)L > sgp_cg_scratch_floats(L))                                                    \
+        if ((size_t)rl.grid * (size_t)L_out > sgp_cg_scratch_floats(L_out))                                            \
             return fail(SGP_EUNSUPPORTED, "sgp_slice_ring_cg: %u CTAs exceed the scratch", rl.grid);                   \
         le = sgp_launch_pdl(sgp_slice_ring_kernel<4, FF, false, true>, dim3(rl.grid), dim3(RING_THREADS), rl.smem, st, \
                             (const int2 *)lat->replay, values, lat->N, dp1, estride, L, chunks, ppp, passes, rl.stages, \
-                            rl.tile_stride, divisor, (float)rdivisor, out, ldo, L, epi);                               \
+                            rl.tile_stride, divisor, (float)rdivisor, out, ldo, L_out, epi);                           \
     } while (0)
     if (lat->fast) SGP_SLICE_RING_CG(true); else SGP_SLICE_RING_CG(false);
 #undef SGP_SLICE_RING_CG
     if (le != cudaSuccess) return fail(SGP_ECUDA, "launch of sgp_slice_ring_kernel (CG form) failed: %s", cudaGetErrorString(le));
     rc = launch_ok("sgp_slice_ring_kernel");
     if (rc) return rc;
-    return sgp_cg_reduce_partials(scratch, (int)rl.grid, L, pAp, stream);
+    return sgp_cg_reduce_partials(scratch, (int)rl.grid, L_out, pAp, stream);
 }
 
 extern "C" int sgp_splat_ring_supported(const float *values, int L) { return ring_vec(L, values) != 0; }
@@ -760,17 +761,20 @@ static int splat_rows_ring_impl(const int32_t *ent, const int32_t *seg_row, int6
     if (!vec) return fail(SGP_EUNSUPPORTED, "sgp_splat_rows_ring: %d channels do not fit a warp", L);
     cudaStream_t st = (cudaStream_t)stream;
     auto al = [](const void *p, int bytes) { return ((uintptr_t)p % bytes) == 0; };
-    const bool ragged = !(L_src == L && lds % vec == 0 && al(src, 4 * vec));
-    const int live = L / vec;
+    // src narrower than the lattice rows by whole vectors (a 12-column block on 16-channel lattice rows, which keeps every
+    // row gather inside one 128-byte line): the spare lane slots idle, no channel-by-channel path needed
+    const bool whole_chunks = L_src % vec == 0 && lds % vec == 0 && al(src, 4 * vec);
+    const bool ragged = !whole_chunks;
+    const int live = whole_chunks ? L_src / vec : L / vec;
     RingLaunch rl;
     int rc;
     cudaError_t le = cudaSuccess;
     // SGP_SPLAT_SCAN=1: runs combined across the threads of a tile and stored, no memset (the shuffles of the scan cost
     // as many L1 data-pipe wavefronts as a third of the row gathers: measured slower at the metric shape, 93 vs 8x us)
-    const bool scan = !prezeroed && ring_env("SGP_SPLAT_SCAN", 0) != 0;
+    const bool scan = !prezeroed && ring_env("SGP_SPLAT_SCAN", 0) != 0 && live == L / vec;   // (the store form writes every channel)
     // lane slots per segment: rounded up to a power of two in the reductions form (see the kernel), SGP_SPLAT_SLOTS=0: not
-    int chunks = live;
-    if (!scan && live <= 16 && ring_env("SGP_SPLAT_SLOTS", 1) != 0)
+    int chunks = L / vec;
+    if (!scan && chunks <= 16 && ring_env("SGP_SPLAT_SLOTS", 1) != 0)
         while (chunks & (chunks - 1)) ++chunks;
     // Entries per tile.  A persistent warp takes the tiles w, w + W, ...: with 256-entry tiles the metric shape has 7.4
     // tiles per warp and the last round runs with 42 % of the warps (67.9 us); 192-entry tiles make it 9.9 (61.9 us),

@@ -144,7 +144,7 @@ def _batched_cg_cuda(matmul: Callable, scale: torch.Tensor, shift: torch.Tensor,
         v_out, ent, seg, n_ent, arr, coeffs_np, bufs = one_call
         args_head = (C.byref(v_out), _ptr(ent), _ptr(seg), n_ent, arr, len(arr), _capi_fp(coeffs_np), coeffs_np.shape[0],
                      _ptr(bufs[0]), _ptr(bufs[1]), 3, _ptr(X), _ptr(R), _ptr(P), _ptr(AP), _ptr(rs), _ptr(pAp), _ptr(bnorm),
-                     _ptr(s), _ptr(nz), float(tol), criterion, L, _ptr(alphas), _ptr(betas), _ptr(done),
+                     _ptr(s), _ptr(nz), float(tol), criterion, L, int(bufs[0].shape[1]), _ptr(alphas), _ptr(betas), _ptr(done),
                      C.c_void_p(done_host.data_ptr()))
         flags_np = done_host.numpy()
         with torch.cuda.device(dev):
@@ -210,9 +210,10 @@ def _cg_one_call_setup(lat, op_coeffs, L: int):
     c = lat.coeffs if op_coeffs is None else _coeffs_np(op_coeffs)
     if c.shape[0] != 2 * lat.order + 1:
         return None
-    v_out = lat._slice_view(L, True, lat.exact)
-    bufs = (torch.zeros((lat.M, L), dtype=torch.float32, device=lat.device),
-            torch.empty((lat.M, L), dtype=torch.float32, device=lat.device))
+    Lv = lat.lattice_width(L)
+    v_out = lat._slice_view(Lv, True, lat.exact)
+    bufs = (torch.zeros((lat.M, Lv), dtype=torch.float32, device=lat.device),
+            torch.empty((lat.M, Lv), dtype=torch.float32, device=lat.device))
     return v_out, lat.rows["ent"], lat.rows["seg_row"], lat.rows["n"], lat.groups["array"], c, bufs
 
 

@@ -724,6 +724,22 @@ class Lattice:
             self._bufs[key] = b
         return b
 
+    def lattice_width(self, L: int) -> int:
+        """Channels of the lattice value rows for an ``L``-column block on the row-sorted chain: ``L`` rounded up to a
+        multiple of four (16-byte vectors between splat and slice), and 16 instead of 12 on large dense lattices --
+        48-byte rows straddle 128-byte lines, so every fourth row gather costs two L1 wavefronts; on 64-byte rows the
+        spare lanes idle and splat, blur and slice are all faster (config A, 12 columns: 181 -> 170 us per MVM).
+        ``SGP_LV16=0`` turns that off, ``SGP_LV16=2`` applies it whatever the lattice (tests)."""
+        if L <= 4:
+            return L
+        Lv = (L + 3) // 4 * 4
+        if Lv == 12 and self.rows is not None:
+            import os
+            e = os.environ.get("SGP_LV16", "1")
+            if e == "2" or (e != "0" and self.rows["n"] >= 8 * self.M and self.rows["n"] >= (1 << 21)):
+                Lv = 16
+        return Lv
+
     def _pads_ragged_src(self) -> bool:
         """Copy a ragged right-hand-side block into a zero-padded one in front of the splat?  Pays once the splat is
         bound by its gathers (SGP_PAD_SRC=0/1 forces)."""
@@ -875,7 +891,7 @@ class Lattice:
         # Lattice rows are padded to a multiple of 4 channels so that everything between splat and slice moves
         # 16-byte vectors (L = 11, the CG block of a training step: 301 us on the scalar path at the metric shape);
         # the row-sorted splat and the slice read / write the caller's ragged rows channel by channel.
-        Lv = (L + 3) // 4 * 4 if (mode == _capi.MODE_ROWS and L > 4) else L
+        Lv = self.lattice_width(L) if mode == _capi.MODE_ROWS else L
         buf0, buf1 = self._scratch(Lv) if scratch is None else scratch[:2]
         if tuple(buf0.shape) != (max(self.M, 1), Lv) or tuple(buf1.shape) != (max(self.M, 1), Lv):
             raise ValueError(f"scratch buffers must be [{max(self.M, 1)}, {Lv}]")
@@ -895,7 +911,7 @@ class Lattice:
             flags = int(zero_flags)
             if zero_flags and scratch is None:
                 raise ValueError("zero_flags needs private scratch buffers")
-            if cg is not None and Lv == L and src.stride(0) == L and out.stride(0) == L:
+            if cg is not None and (Lv == L or L % 4 == 0) and src.stride(0) == L and out.stride(0) == L:
                 cs, cn, cp, cscr = cg
                 with torch.cuda.device(self.device):
                     check(lib.sgp_mvm_rows_groups_cg(C.byref(v_out), _ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]),
@@ -904,12 +920,13 @@ class Lattice:
                                                      flags, _ptr(cs), _ptr(cn), _ptr(cp), _ptr(cscr), st))
                 return out
             with torch.cuda.device(self.device):
-                if Lv != L and self._pads_ragged_src() and cg is None:
+                if L % 4 and L > 4 and self._pads_ragged_src() and cg is None:
                     # ragged rows (L = 11: 44 bytes) can only be gathered channel by channel -- four times the L1
                     # wavefronts of 16-byte vectors, nine times per point; one coalesced copy into a zero-padded block
                     # is cheaper (config A, 11 columns: 236 -> 200 us per MVM; 181 us when the caller's block has 12)
-                    pad = scratch[2] if (scratch is not None and len(scratch) > 2) else self._src_pad(Lv)
-                    check(lib.sgp_pad_columns(_ptr(src), src.stride(0), L, _ptr(pad), pad.stride(0), Lv, self.N, st))
+                    Lp = (L + 3) // 4 * 4
+                    pad = scratch[2] if (scratch is not None and len(scratch) > 2) else self._src_pad(Lp)
+                    check(lib.sgp_pad_columns(_ptr(src), src.stride(0), L, _ptr(pad), pad.stride(0), Lp, self.N, st))
                     src, flags = pad, flags | 4      # SGP_MVM_SRC_PADDED
                 if flags:
                     check(lib.sgp_mvm_rows_groups_ex(C.byref(v_out), _ptr(self.rows["ent"]), _ptr(self.rows["seg_row"]),
@@ -980,13 +997,13 @@ class Lattice:
         if out.shape != src.shape or out.dtype != torch.float32 or out.device != self.device or out.stride(1) != 1:
             raise ValueError("out must be a float32 [N, L] tensor on the lattice's device with unit column stride")
         L = int(src.shape[1])
-        Lv = (L + 3) // 4 * 4 if L > 4 else L
+        Lv = self.lattice_width(L)
         if mvm_kwargs.get("mode", _capi.MODE_AUTO) not in (_capi.MODE_AUTO, _capi.MODE_ROWS) or self.rows is None:
             Lv = L
         scratch = (torch.zeros((max(self.M, 1), Lv), dtype=torch.float32, device=self.device),
                    torch.empty((max(self.M, 1), Lv), dtype=torch.float32, device=self.device))
-        if Lv != L:
-            scratch = scratch + (torch.zeros((self.N, Lv), dtype=torch.float32, device=self.device),)   # zero-padded copy of src
+        if L % 4 and L > 4:
+            scratch = scratch + (torch.zeros((self.N, (L + 3) // 4 * 4), dtype=torch.float32, device=self.device),)   # zero-padded copy of src
         # production chain on private buffers: the splat buffer is zeroed at the END of every product, next to the slice
         # (a parallel branch of the graph), instead of in front of the splat: 4-6 us off the critical path at the
         # metric shape.  SGP_GRAPH_ZERO_AFTER=0 keeps the memset in front.

@@ -533,3 +533,51 @@ def test_ring_kernels_stay_inside_their_buffers(sg, N, d, L):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = val
+
+
+@pytest.mark.parametrize("L", [9, 11, 12])
+@pytest.mark.parametrize("ring", ["0", "1"])
+def test_twelve_columns_on_sixteen_channel_lattice_rows(sg, oracle, L, ring):
+    """9-12 column blocks run on 16-channel lattice rows on large dense lattices (Lattice.lattice_width): the splat's and the
+    slice's spare lanes idle.  Forced here at a size the oracle finishes (SGP_LV16=2), with the one-shot and the ring
+    kernels, eager, captured, and through the CG form (sweep folded into the slice)."""
+    import os
+    from simplex_gp_b200 import _capi
+    N, d = 4000, 5
+    x, v = make_inputs(N, d, L, seed=40 + L)
+    want = oracle.OracleLattice(x.numpy(), RBF1).mvm(v.numpy())
+    lat = sg.Lattice(x.cuda(), RBF1)
+    src = v.cuda()
+    lat.mvm(src)
+    old = {k: os.environ.get(k) for k in ("SGP_LV16", "SGP_RING_FORCE", "SGP_PAD_SRC")}
+    os.environ.update(SGP_LV16="2", SGP_RING_FORCE=ring, SGP_PAD_SRC="1")
+    try:
+        assert lat.lattice_width(L) == 16
+        got = lat.mvm(src).cpu().numpy()
+        out = torch.empty(N, L, device="cuda")
+        graph = lat.capture(src, out)
+        graph.replay()
+        graph.replay()
+        torch.cuda.synchronize()
+        cg_out = cg_dot = None
+        if L % 4 == 0:
+            lib = _capi.lib()
+            s, noise = torch.tensor([0.5], device="cuda"), torch.tensor([0.25], device="cuda")
+            cg_out = torch.empty(N, L, device="cuda")
+            cg_dot = torch.empty(L, device="cuda")
+            scratch = torch.empty(int(lib.sgp_cg_scratch_floats(L)), device="cuda")
+            lat.mvm(src, out=cg_out, cg=(s, noise, cg_dot, scratch))
+            torch.cuda.synchronize()
+    finally:
+        for k, val in old.items():
+            if val is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = val
+    assert _rel(got, want) < REL_TOL
+    assert _rel(out.cpu().numpy(), want) < REL_TOL
+    if cg_out is not None:
+        ap = 0.5 * want + 0.25 * v.numpy()
+        assert _rel(cg_out.cpu().numpy(), ap) < REL_TOL
+        dots = (v.numpy().astype(np.float64) * ap.astype(np.float64)).sum(0)
+        assert np.abs(cg_dot.cpu().numpy() - dots).max() <= 1e-4 * np.abs(dots).max()
