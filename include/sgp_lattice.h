@@ -361,7 +361,7 @@ int sgp_mvm_stage_splat_prezeroed(const int32_t *ent, const int32_t *seg_row, in
 /* The zero-padded copy SGP_MVM_SRC_PADDED refers to: dst[n, 0..Lv) = src[n, 0..L), then zeros.  Lv % 4 == 0, dst 16-byte
  * aligned, ldd % 4 == 0. */
 /* Lv may exceed L rounded up to a multiple of 4: 12 (or 9-11) columns on 16-channel lattice rows keep every 64-byte row
- * gather inside one 128-byte line (config A: 181 -> see DESIGN.md section 4); splat and slice then leave the spare lanes idle. */
+ * gather inside one 128-byte line (config A, 12 columns: 181 -> 172 us per MVM); splat and slice then leave the spare lanes idle. */
 int sgp_pad_columns(const float *src, int64_t lds, int L, float *dst, int64_t ldd, int Lv, int64_t N, sgp_stream_t stream);
 #define SGP_MVM_PREZEROED 1
 #define SGP_MVM_ZERO_AFTER 2
