@@ -164,3 +164,40 @@ def test_metric_configuration_against_oracle_at_full_size(sg, oracle, L):
         with open(os.path.join(out_dir, f"parity_full_size_L{L}.json"), "w") as f:
             json.dump(rec, f, indent=1)
     print(json.dumps(rec))
+
+
+@pytest.mark.parametrize("L", [11, 12])
+def test_training_block_at_full_size(sg, oracle, L):
+    """The reference's training block ([y | 10 probes]: 11 columns; 12 as this package's solver pads it) at the metric
+    shape, ALL points: here the production chain runs on 16-channel lattice rows (Lattice.lattice_width), the 11-column
+    block through the zero-padded copy; eager, captured and, for 12 columns, the CG form with the sweep folded into the
+    slice -- all within the north star's 1e-5 of the oracle."""
+    from simplex_gp_b200 import _capi
+    N, d = 1_000_000, 8
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N, d, generator=g)
+    v = torch.randn(N, L, generator=g)
+    want = oracle.OracleLattice(x.numpy(), RBF1).mvm(v.numpy()).astype(np.float64)
+    lat = sg.Lattice(x.cuda(), RBF1)
+    vd = v.cuda()
+    lat.mvm(vd)                                   # builds the postponed tables
+    assert lat.lattice_width(L) == 16
+    prod = lat.mvm(vd).cpu().numpy().astype(np.float64)
+    assert float(np.linalg.norm(prod - want) / np.linalg.norm(want)) < 1e-5
+    out = torch.empty(N, L, device="cuda")
+    graph = lat.capture(vd, out)
+    graph.replay()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert float(np.linalg.norm(out.cpu().numpy() - want) / np.linalg.norm(want)) < 1e-5
+    if L % 4 == 0:
+        lib = _capi.lib()
+        s, noise = torch.tensor([0.5], device="cuda"), torch.tensor([0.25], device="cuda")
+        ap = torch.empty(N, L, device="cuda")
+        dots = torch.empty(L, device="cuda")
+        scratch = torch.empty(int(lib.sgp_cg_scratch_floats(L)), device="cuda")
+        lat.mvm(vd, out=ap, cg=(s, noise, dots, scratch))
+        ref_ap = 0.5 * want + 0.25 * v.numpy().astype(np.float64)
+        assert float(np.linalg.norm(ap.cpu().numpy() - ref_ap) / np.linalg.norm(ref_ap)) < 1e-5
+        ref_dots = (v.numpy().astype(np.float64) * ref_ap).sum(0)
+        assert float(np.abs(dots.cpu().numpy() - ref_dots).max() / np.abs(ref_dots).max()) < 1e-4
