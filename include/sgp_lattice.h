@@ -208,6 +208,8 @@ typedef struct sgp_lattice_view {
 #define SGP_SPLAT_AUTO 0
 #define SGP_SPLAT_ATOMIC 1 /* vectorised red.global.add scatter */
 #define SGP_SPLAT_GATHER 2 /* CSR gather, deterministic, reference accumulation order */
+#define SGP_SPLAT_ATOMIC_ACCUMULATE 5 /* as ATOMIC, but adds to `values` as they are (no memset): the view of a point
+                                         range contributes its part of a splat that is fed chunk by chunk */
 
 /* values[M, L] = sum_{point-vertices} weight * src[n, :]   (permutohedral.h:478-479) */
 int sgp_splat(const sgp_lattice_view *lat, const float *src, int64_t lds, int L,

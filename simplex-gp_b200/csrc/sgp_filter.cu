@@ -103,9 +103,29 @@ cudaError_t copy_rows(float *dst, int64_t ldd, const float *src, int64_t lds, in
 
 cudaStream_t copy_stream(int dev) { return sgp_side_stream(dev); }
 
+// How the host entry pipelines the product with its copies: the rows of src arrive in `n_chunks` pieces (ready[c] fires
+// when piece c is on the device) and are splatted as they come; after the blur the slice runs piece by piece and each
+// piece of the result starts its way back (on `down`) while the next one is still being sliced.
+// first point of piece c of C: multiples of 32 points, so that a piece's rows of the replay table, of src and of out keep
+// the 16-byte alignment the kernels' vector loads count on
+inline int64_t filter_chunk_begin(int64_t N, int c, int C)
+{
+    if (c >= C) return N;
+    return ((N * (int64_t)c) / C) & ~(int64_t)31;
+}
+
+struct FilterPipe {
+    int n_chunks;
+    const cudaEvent_t *ready;   // [n_chunks]
+    cudaStream_t down;          // stream of the device -> host copies
+    float *out_host;
+    int64_t ldo_host;
+    cudaEvent_t sliced;         // scratch event
+};
+
 int filter_device(const float *src, int64_t lds, const float *ref, int64_t ldx, const float *coeffs, int k, int64_t N,
                   int L, int d, float *out, int64_t ldo, char *base, const FilterWs &w, int64_t *M_out, cudaStream_t st,
-                  cudaEvent_t src_ready)
+                  const FilterPipe *pipe)
 {
     const int order = k / 2;
     float var = 0.0f;
@@ -151,13 +171,46 @@ int filter_device(const float *src, int64_t lds, const float *ref, int64_t ldx, 
     v.replay = replay;
     v.nbr = order > 0 ? nbr : nullptr;
     v.fast = 1;
-    if (src_ready) CUDA_TRY(cudaStreamWaitEvent(st, src_ready, 0));
-    rc = sgp_splat(&v, src, lds, L, buf0, SGP_SPLAT_ATOMIC, s);   // (buf0/buf1 overwrite the build scratch: stream order)
-    if (rc) return rc;
+    if (!pipe) {
+        rc = sgp_splat(&v, src, lds, L, buf0, SGP_SPLAT_ATOMIC, s);   // (buf0/buf1 overwrite the build scratch: stream order)
+        if (rc) return rc;
+        int in1 = 0;
+        rc = sgp_blur(&v, coeffs, k, L, buf0, buf1, &in1, s);
+        if (rc) return rc;
+        return sgp_slice(&v, in1 ? buf1 : buf0, L, out, ldo, L, s);
+    }
+    // pipelined with the copies: views of point ranges (the replay table is [N, d+1, 2], point-major)
+    const int C = pipe->n_chunks;
+    auto chunk_begin = [&](int c) { return filter_chunk_begin(N, c, C); };
+    CUDA_TRY(cudaMemsetAsync(buf0, 0, sizeof(float) * (size_t)M * (size_t)L, st));
+    for (int c = 0; c < C; ++c) {
+        const int64_t p0 = chunk_begin(c), p1 = chunk_begin(c + 1);
+        if (p1 == p0) continue;
+        CUDA_TRY(cudaStreamWaitEvent(st, pipe->ready[c], 0));
+        sgp_lattice_view vc = v;
+        vc.N = p1 - p0;
+        vc.replay = replay + p0 * (int64_t)(d + 1) * 2;
+        rc = sgp_splat(&vc, src + p0 * lds, lds, L, buf0, SGP_SPLAT_ATOMIC_ACCUMULATE, s);
+        if (rc) return rc;
+    }
     int in1 = 0;
     rc = sgp_blur(&v, coeffs, k, L, buf0, buf1, &in1, s);
     if (rc) return rc;
-    return sgp_slice(&v, in1 ? buf1 : buf0, L, out, ldo, L, s);
+    for (int c = 0; c < C; ++c) {
+        const int64_t p0 = chunk_begin(c), p1 = chunk_begin(c + 1);
+        if (p1 == p0) continue;
+        sgp_lattice_view vc = v;
+        vc.N = p1 - p0;
+        vc.replay = replay + p0 * (int64_t)(d + 1) * 2;
+        rc = sgp_slice(&vc, in1 ? buf1 : buf0, L, out + p0 * ldo, ldo, L, s);
+        if (rc) return rc;
+        // this piece of the result leaves while the next one is sliced (stream order on `down` keeps the event reusable)
+        CUDA_TRY(cudaEventRecord(pipe->sliced, st));
+        CUDA_TRY(cudaStreamWaitEvent(pipe->down, pipe->sliced, 0));
+        CUDA_TRY(copy_rows(pipe->out_host + p0 * pipe->ldo_host, pipe->ldo_host, out + p0 * ldo, ldo, L, p1 - p0,
+                           cudaMemcpyDeviceToHost, pipe->down));
+    }
+    return SGP_OK;
 }
 
 }   // namespace
@@ -220,31 +273,56 @@ extern "C" int sgp_filter_host(const float *src_host, int64_t lds, const float *
     // positions first (the lattice build needs them); the RHS block travels on a second stream while the lattice is
     // being built.  Pinned host memory is copied asynchronously, pageable memory through the driver's staging.
     CUDA_TRY(copy_rows(ref_d, d, ref_host, ldx, d, N, cudaMemcpyHostToDevice, st));
+    // ... in SGP_FILTER_CHUNKS pieces of rows (default 4), each splatted as soon as it has arrived; after the blur the
+    // result is sliced piece by piece and every piece starts its way back while the next one is sliced: the product
+    // hides behind the copies except for the blur.
     cudaStream_t side = copy_stream(dev);
-    cudaEvent_t fork = nullptr, ready = nullptr;
-    if (side) {
-        if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ready, cudaEventDisableTiming) != cudaSuccess) {
-            if (fork) cudaEventDestroy(fork);
-            fork = ready = nullptr;
-            side = nullptr;
-        }
+    constexpr int MAX_CHUNKS = 16;
+    int n_chunks = 4;
+    if (const char *e = getenv("SGP_FILTER_CHUNKS")) n_chunks = atoi(e);
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > MAX_CHUNKS) n_chunks = MAX_CHUNKS;
+    if ((int64_t)n_chunks > N) n_chunks = (int)N;
+    cudaEvent_t fork = nullptr, sliced = nullptr, ready[MAX_CHUNKS] = {};
+    bool ok = side != nullptr && cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&sliced, cudaEventDisableTiming) == cudaSuccess;
+    for (int c = 0; ok && c < n_chunks; ++c) ok = cudaEventCreateWithFlags(&ready[c], cudaEventDisableTiming) == cudaSuccess;
+    auto destroy_events = [&]() {
+        if (fork) cudaEventDestroy(fork);
+        if (sliced) cudaEventDestroy(sliced);
+        for (int c = 0; c < MAX_CHUNKS; ++c)
+            if (ready[c]) cudaEventDestroy(ready[c]);
+    };
+    cudaError_t ce = cudaSuccess;
+    if (!ok) {
+        // no second stream / events: everything in order on the caller's stream
+        destroy_events();
+        ce = copy_rows(src_d, L, src_host, lds, L, N, cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) rc = filter_device(src_d, L, ref_d, d, coeffs, k, N, L, d, out_d, L, base, w, M_out, st, nullptr);
+        if (ce == cudaSuccess && rc == SGP_OK) ce = copy_rows(out_host, ldo, out_d, L, L, N, cudaMemcpyDeviceToHost, st);
+        cudaError_t se0 = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) return fail(SGP_ECUDA, "sgp_filter_host: copy failed: %s", cudaGetErrorString(ce));
+        if (rc) return rc;
+        if (se0 != cudaSuccess) return fail(SGP_ECUDA, "sgp_filter_host: %s", cudaGetErrorString(se0));
+        return SGP_OK;
     }
-    cudaStream_t up = side ? side : st;
-    if (side) {   // the workspace may still be in use by earlier work of the caller's stream
-        CUDA_TRY(cudaEventRecord(fork, st));
-        CUDA_TRY(cudaStreamWaitEvent(side, fork, 0));
+    // the workspace may still be in use by earlier work of the caller's stream
+    ce = cudaEventRecord(fork, st);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(side, fork, 0);
+    for (int c = 0; ce == cudaSuccess && c < n_chunks; ++c) {
+        const int64_t p0 = filter_chunk_begin(N, c, n_chunks), p1 = filter_chunk_begin(N, c + 1, n_chunks);
+        if (p1 > p0)
+            ce = copy_rows(src_d + p0 * L, L, src_host + p0 * lds, lds, L, p1 - p0, cudaMemcpyHostToDevice, side);
+        if (ce == cudaSuccess) ce = cudaEventRecord(ready[c], side);
     }
-    cudaError_t ce = copy_rows(src_d, L, src_host, lds, L, N, cudaMemcpyHostToDevice, up);
-    if (ce == cudaSuccess && side) ce = cudaEventRecord(ready, side);
-    if (ce == cudaSuccess)
-        rc = filter_device(src_d, L, ref_d, d, coeffs, k, N, L, d, out_d, L, base, w, M_out, st, side ? ready : nullptr);
-    if (ce == cudaSuccess && rc == SGP_OK)
-        ce = copy_rows(out_host, ldo, out_d, L, L, N, cudaMemcpyDeviceToHost, st);
-    if (side) cudaStreamSynchronize(side);   // also on the error paths: the upload must not outlive the call
+    if (ce == cudaSuccess) {
+        FilterPipe pipe{n_chunks, ready, side, out_host, ldo, sliced};
+        rc = filter_device(src_d, L, ref_d, d, coeffs, k, N, L, d, out_d, L, base, w, M_out, st, &pipe);
+    }
+    cudaStreamSynchronize(side);   // also on the error paths: neither the uploads nor the downloads may outlive the call
     cudaError_t se = cudaStreamSynchronize(st);
-    if (fork) cudaEventDestroy(fork);
-    if (ready) cudaEventDestroy(ready);
+    if (se == cudaSuccess) se = cudaStreamSynchronize(side);   // (downloads enqueued behind work of st)
+    destroy_events();
     if (ce != cudaSuccess) return fail(SGP_ECUDA, "sgp_filter_host: copy failed: %s", cudaGetErrorString(ce));
     if (rc) return rc;
     if (se != cudaSuccess) return fail(SGP_ECUDA, "sgp_filter_host: %s", cudaGetErrorString(se));

@@ -1382,6 +1382,10 @@ extern "C" int sgp_splat(const sgp_lattice_view *lat, const float *src, int64_t 
     if (!src || !values || !lat->replay || lds < L) return fail(SGP_EINVAL, "sgp_splat: null pointer or lds < L");
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == SGP_SPLAT_AUTO) mode = (lat->csr_ptr && lat->csr_ent) ? SGP_SPLAT_GATHER : SGP_SPLAT_ATOMIC;
+    // accumulate: scatter into `values` as they are (no memset) -- a view of a point range adds its part to a splat that
+    // is fed chunk by chunk (sgp_filter_host: the rows of src are splatted while later rows are still being uploaded)
+    const bool accumulate = mode == SGP_SPLAT_ATOMIC_ACCUMULATE;
+    if (accumulate) mode = SGP_SPLAT_ATOMIC;
     const int vec = pick_vec(L, lds, L, src, values, values);
     const int chunks = L / vec;
     if (mode == SGP_SPLAT_GATHER) {
@@ -1393,7 +1397,7 @@ extern "C" int sgp_splat(const sgp_lattice_view *lat, const float *src, int64_t 
         return launch_ok("sgp_splat_gather_kernel");
     }
     if (mode != SGP_SPLAT_ATOMIC) return fail(SGP_EINVAL, "unknown splat mode %d", mode);
-    CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)lat->M * (size_t)L, st));
+    if (!accumulate) CUDA_TRY(cudaMemsetAsync(values, 0, sizeof(float) * (size_t)lat->M * (size_t)L, st));
     const int64_t work = lat->N * chunks;
     SGP_DISPATCH_VEC(vec, (sgp_splat_atomic_kernel<VV><<<grid_for(work, 256), 256, 0, st>>>(
                               (const int2 *)lat->replay, lat->replay_transposed ? 1 : (lat->replay_stride > 0 ? lat->replay_stride : lat->d + 1),
